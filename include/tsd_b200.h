@@ -1,0 +1,197 @@
+/*
+ * tsd_b200 - C ABI of the B200-native Tiny-Stable-Diffusion denoising path.
+ *
+ * The reference (lrmantovani10/Stable-Diffusion.mojo) has no FFI/plugin interface: its
+ * boundary is the Mojo struct API  X(...).forward(Matrix) -> Matrix.  Every entry point below
+ * names the reference method it replaces (file:line into the reference tree).  A Mojo shim
+ * binds these with sys.ffi.DLHandle / external_call; this repo's tests
+ * bind them with Python ctypes.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types.  Host entry points take host float32
+ *    buffers in the reference's layouts: Matrix = 3-D row-major (dim0, dim1, dim2)
+ *    (helpers/utils.mojo:521-524, index = z*dim1*dim2 + y*dim2 + x, :805-811); images are
+ *    (C, H, W), sequences (1, T, C); conv kernels OIHW (Matrix_Array, :1718); linear weights
+ *    [out][in] (:1943).  `_dev` variants take device pointers in the same layouts.
+ *  - every function returns int32 status: 0 = OK.  Nothing throws.  The message of the last
+ *    failure is tsd_last_error(ctx).  The reference's convention "print + return the null
+ *    Matrix(0,0,0)" (e.g. helpers/utils.mojo:1551-1552, 1848-1853, 1956-1957) maps to a
+ *    non-zero status; the shim prints tsd_last_error and returns Matrix(0,0,0).
+ *  - there is NO CPU fallback: without an sm_100 device tsd_init fails (TSD_ERR_NO_DEVICE).
+ *  - a context owns one CUDA stream; calls on one context are serialised by an internal mutex,
+ *    distinct contexts may be used from different threads.
+ */
+#ifndef TSD_B200_H
+#define TSD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(TSD_BUILD)
+#pragma GCC visibility push(default)
+#endif
+
+#define TSD_OK 0
+#define TSD_ERR_INVALID 1   /* bad shape / argument */
+#define TSD_ERR_CUDA 2      /* CUDA runtime or driver error */
+#define TSD_ERR_NO_DEVICE 3 /* no sm_100 (B200) device */
+#define TSD_ERR_OOM 4
+#define TSD_ERR_STATE 5     /* e.g. forward before load_weights */
+
+typedef struct tsd_ctx tsd_ctx;             /* device + stream + workspace */
+typedef struct tsd_diffusion tsd_diffusion; /* Diffusion (diffusion.mojo:294-318) */
+typedef struct tsd_decoder tsd_decoder;     /* VAE Decoder (vae.mojo:162-250) */
+
+/* ---- context ------------------------------------------------------------------------ */
+int32_t tsd_init(int32_t device, tsd_ctx** out);
+int32_t tsd_shutdown(tsd_ctx* ctx);
+const char* tsd_last_error(const tsd_ctx* ctx); /* ctx may be NULL: last tsd_init failure */
+int32_t tsd_synchronize(tsd_ctx* ctx);
+/* Semantic switches of SURVEY.md section 0 and engine knobs:
+ *   "softmax_axis"     0 = query axis, as reference Softmax(dim=2) (utils.mojo:435-445) [default]
+ *                      1 = key axis (standard attention)
+ *   "layernorm_mode"   0 = one mean/std over the whole (C,T) tensor, as reference
+ *                          LayerNorm = GroupNorm(1,C) (utils.mojo:2052-2061) [default]
+ *                      1 = per token
+ *   "fused_attention"  1 = fused tcgen05 attention kernel [default], 0 = GEMM+softmax+GEMM
+ *   "cuda_graph"       1 = replay model forwards from a captured CUDA graph [default], 0 = eager
+ */
+int32_t tsd_set_option(tsd_ctx* ctx, const char* name, int32_t value);
+int32_t tsd_get_option(tsd_ctx* ctx, const char* name, int32_t* value);
+/* number of kernels launched through ctx since creation (bench "gpu_launches") */
+int64_t tsd_launch_count(const tsd_ctx* ctx);
+
+/* ---- op level (host buffers, reference layouts) ---------------------------------------- */
+/* Conv2D.forward, helpers/utils.mojo:1738-1811.  x (cin,h,w); weight OIHW (cout,cin,k,k);
+ * bias (cout) or NULL; out (cout, ho, wo), ho = floor((h+2*pad-k)/stride)+1.  n images batched. */
+int32_t tsd_conv2d(tsd_ctx* ctx, const float* x, int32_t n, int32_t cin, int32_t h, int32_t w,
+                   const float* weight, const float* bias, int32_t cout, int32_t k, int32_t pad,
+                   int32_t stride, float* out);
+/* Linear.forward, helpers/utils.mojo:1954-1976 (bias added to every column).
+ * x (b,t,in_f); weight (out_f,in_f); bias (out_f) or NULL; out (b,t,out_f). */
+int32_t tsd_linear(tsd_ctx* ctx, const float* x, int32_t b, int32_t t, int32_t in_f,
+                   const float* weight, const float* bias, int32_t out_f, float* out);
+/* Matrix.matmul, helpers/utils.mojo:1549-1569: out[c] = a[c] (m,k) x b[c] (k,n). */
+int32_t tsd_matmul(tsd_ctx* ctx, const float* a, const float* b, int32_t c, int32_t m, int32_t k,
+                   int32_t n, float* out);
+/* GroupNorm.forward, helpers/utils.mojo:1845-1885: (x-mean)/(std+eps)*gamma, biased std,
+ * scalar gamma = 1, no beta.  x,out (c,h,w) x n images.  gamma/beta: optional per-channel
+ * vectors (superset for real checkpoints), NULL = reference behaviour. */
+int32_t tsd_groupnorm(tsd_ctx* ctx, const float* x, int32_t n, int32_t c, int32_t h, int32_t w,
+                      int32_t groups, float eps, const float* gamma, const float* beta, float* out);
+/* LayerNorm.forward, helpers/utils.mojo:2052-2061, on a (c,t,1) Matrix; eps = 1e-5. */
+int32_t tsd_layernorm(tsd_ctx* ctx, const float* x, int32_t c, int32_t t, float* out);
+/* SiLU.forward :1892-1902 / Gelu.forward :1908-1919 (tanh form); n elements. */
+int32_t tsd_silu(tsd_ctx* ctx, const float* x, int64_t n, float* out);
+int32_t tsd_gelu(tsd_ctx* ctx, const float* x, int64_t n, float* out);
+/* Upsample.forward, helpers/utils.mojo:1989-2010 under contract Q8: nearest x2 spatial. */
+int32_t tsd_upsample2x(tsd_ctx* ctx, const float* x, int32_t c, int32_t h, int32_t w, float* out);
+/* Softmax, helpers/utils.mojo:411-448. x,out (c,r,cc).  dim follows the reference numbering:
+ * dim=2 normalises every column over the rows (Q3), dim=1 every row over the columns. */
+int32_t tsd_softmax(tsd_ctx* ctx, const float* x, int32_t c, int32_t r, int32_t cc, int32_t dim,
+                    float* out);
+/* Self_Attention.forward, helpers/attention.mojo:26-65.  x,out (1,t,c); w_in (3c,c), b_in (3c)
+ * or NULL; w_out (c,c), b_out (c) or NULL.  Head split by raw reshape (Q4); softmax axis per
+ * the "softmax_axis" option. */
+int32_t tsd_self_attention(tsd_ctx* ctx, const float* x, int32_t t, int32_t c, int32_t n_heads,
+                           const float* w_in, const float* b_in, const float* w_out,
+                           const float* b_out, float* out);
+/* Cross_Attention.forward, helpers/attention.mojo:96-118.  x,out (1,t,c); context (1,tk,dc). */
+int32_t tsd_cross_attention(tsd_ctx* ctx, const float* x, int32_t t, int32_t c, const float* context,
+                            int32_t tk, int32_t dc, int32_t n_heads, const float* wq,
+                            const float* bq, const float* wk, const float* bk, const float* wv,
+                            const float* bv, const float* wo, const float* bo, float* out);
+/* Attention core only (config 5 sweep): q (h,tq,d), k,v (h,tk,d) -> out (tq, h*d) merged. */
+int32_t tsd_attention_core(tsd_ctx* ctx, const float* q, const float* k, const float* v, int32_t h,
+                           int32_t tq, int32_t tk, int32_t d, float* out);
+/* DDPMSampler.step, sampler.mojo:75-109 (+ CFG combine pipeline.mojo:117-119 when eps_uncond
+ * is non-NULL).  Scalars are the schedule values the host sampler computes (see
+ * tsd_b200.DDPMSampler): x0 = (x - sqrt_1mab*eps)/sqrt_ab ; out = c0*x0 + c1*x + sigma*noise. */
+int32_t tsd_sampler_step(tsd_ctx* ctx, const float* latents, const float* eps_cond,
+                         const float* eps_uncond, float cfg_scale, const float* noise, float sqrt_ab,
+                         float sqrt_1mab, float c0, float c1, float sigma, int64_t n, float* out);
+
+/* ---- Diffusion (time embedding MLP + UNet + output layer), diffusion.mojo:294-318 --------- */
+typedef struct tsd_diffusion_config {
+  int32_t latent_h, latent_w; /* 64 x 64 for 512 x 512 images (pipeline.mojo:60) */
+  int32_t max_batch;          /* latents evaluated per forward (CFG = 2) */
+  int32_t context_len;        /* 77 */
+  int32_t context_dim;        /* 768 */
+  int32_t mojo_alias_time;    /* 0 [default]; 1 reproduces SiLU^k(t_emb) aliasing */
+} tsd_diffusion_config;
+int32_t tsd_diffusion_create(tsd_ctx* ctx, const tsd_diffusion_config* cfg, tsd_diffusion** out);
+int32_t tsd_diffusion_destroy(tsd_diffusion* m);
+/* number of float32 values tsd_diffusion_load_weights expects */
+int64_t tsd_diffusion_num_params(const tsd_diffusion* m);
+/* Flat fp32 blob: every parameter tensor in struct-declaration order, depth first, each layer
+ * (weight, bias), in the reference layouts (diffusion.mojo:295-297,
+ * 151-173, 25-30, 76-85).  The exact tensor list: tsd_diffusion_param_name(). */
+int32_t tsd_diffusion_load_weights(tsd_diffusion* m, const float* blob, int64_t n_floats);
+/* Deterministic synthetic weights generated on the device with the reference's init ranges
+ * (conv U(+-1/sqrt(fan_in)), utils.mojo:1722-1724; linear U(+-1/sqrt(in))). */
+int32_t tsd_diffusion_init_random(tsd_diffusion* m, uint64_t seed);
+int32_t tsd_diffusion_param_count(const tsd_diffusion* m);
+const char* tsd_diffusion_param_name(const tsd_diffusion* m, int32_t i, int64_t* offset,
+                                     int64_t* numel);
+/* copies parameter tensor i (reference layout) back to the host - used to feed the oracle */
+int32_t tsd_diffusion_get_param(const tsd_diffusion* m, int32_t i, float* out);
+/* Diffusion.forward, diffusion.mojo:309-318.  x,out (n,4,H,W); context (n_ctx,77,768) with
+ * n_ctx = 1 (shared) or n; time (n_time,320) with n_time = 1 or n. */
+int32_t tsd_diffusion_forward(tsd_diffusion* m, const float* x, const float* context, int32_t n_ctx,
+                              const float* time, int32_t n_time, int32_t n, float* out);
+int32_t tsd_diffusion_forward_dev(tsd_diffusion* m, const float* x, const float* context,
+                                  int32_t n_ctx, const float* time, int32_t n_time, int32_t n,
+                                  float* out);
+/* per-family device time of the last profiled forward: families 0 gemm/conv, 1 attention,
+ * 2 norm, 3 other.  ms[f], flops[f], launches[f] arrays of 4. */
+int32_t tsd_diffusion_profile(tsd_diffusion* m, const float* x_dev, const float* context_dev,
+                              int32_t n_ctx, const float* time_dev, int32_t n_time, int32_t n,
+                              float* out_dev, double* ms, double* flops, int64_t* launches);
+
+/* ---- VAE decoder, vae.mojo:221-250 (+ rescale/clamp pipeline.mojo:127 when rescale != 0) --- */
+int32_t tsd_decoder_create(tsd_ctx* ctx, int32_t latent_h, int32_t latent_w, int32_t max_batch,
+                           tsd_decoder** out);
+int32_t tsd_decoder_destroy(tsd_decoder* m);
+int64_t tsd_decoder_num_params(const tsd_decoder* m);
+int32_t tsd_decoder_load_weights(tsd_decoder* m, const float* blob, int64_t n_floats);
+int32_t tsd_decoder_init_random(tsd_decoder* m, uint64_t seed);
+int32_t tsd_decoder_param_count(const tsd_decoder* m);
+const char* tsd_decoder_param_name(const tsd_decoder* m, int32_t i, int64_t* offset, int64_t* numel);
+int32_t tsd_decoder_get_param(const tsd_decoder* m, int32_t i, float* out);
+/* z (n,4,H,W) -> img (n,3,8H,8W) */
+int32_t tsd_decoder_forward(tsd_decoder* m, const float* z, int32_t n, int32_t rescale, float* img);
+int32_t tsd_decoder_forward_dev(tsd_decoder* m, const float* z, int32_t n, int32_t rescale,
+                                float* img);
+
+/* ---- whole denoising loop on the device, pipeline.mojo:86-122 ------------------------------- */
+typedef struct tsd_loop_params {
+  int32_t steps;           /* inference steps */
+  int32_t cfg;             /* 0 / 1 */
+  float cfg_scale;         /* pipeline.mojo:17 */
+  const int32_t* timesteps;/* [steps]           (DDPMSampler.set_inference_timesteps) */
+  const float* time_emb;   /* [steps][320]      (get_time_embedding, utils.mojo:353-370) */
+  const float* coef;       /* [steps][5]: sqrt_ab, sqrt_1mab, c0, c1, sigma */
+  const float* noise;      /* [steps][n][4*H*W] host, or NULL for no noise */
+} tsd_loop_params;
+/* latents (n,4,H,W) in/out; context (n_ctx,77,768): cond rows first, then (if cfg) uncond rows */
+int32_t tsd_generate_latents(tsd_diffusion* m, const tsd_loop_params* lp, const float* latents_in,
+                             const float* context, int32_t n_ctx, int32_t n, float* latents_out);
+
+/* ---- tuning probes (synthetic device-resident operands, CUDA-event ms per launch) ------------ */
+int32_t tsd_bench_gemm(tsd_ctx* ctx, int32_t m, int32_t n, int32_t k, int32_t batch, int32_t geglu,
+                       int32_t force_bn, int32_t force_splits, int32_t iters, double* ms_out);
+int32_t tsd_bench_conv(tsd_ctx* ctx, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                       int32_t k, int32_t stride, int32_t force_bn, int32_t force_splits,
+                       int32_t iters, double* ms_out);
+
+#if defined(TSD_BUILD)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSD_B200_H */

@@ -1,0 +1,24 @@
+#!/usr/bin/env bash
+# Builds libtsd_b200.so in-tree for sm_100a (B200).  nvcc cross-compiles without a GPU.
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -Wno-deprecated-gpu-targets -std=c++17 -Xcompiler -fPIC
+       -Xcompiler -fvisibility=hidden -DTSD_BUILD)
+mkdir -p build
+SRCS=(gemm_tcgen05.cu attention_tcgen05.cu elementwise.cu runtime.cu models.cu c_api.cu c_api_models.cu)
+pids=()
+for s in "${SRCS[@]}"; do
+  [ -f "$s" ] || continue
+  o="build/${s%.cu}.o"
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ -n "$(find . -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer "$o" -print -quit)" ] \
+     || [ ../../include/tsd_b200.h -nt "$o" ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+OBJS=()
+for s in "${SRCS[@]}"; do [ -f "build/${s%.cu}.o" ] && OBJS+=("build/${s%.cu}.o"); done
+"$NVCC" -Wno-deprecated-gpu-targets -shared -o libtsd_b200.so "${OBJS[@]}" -lcudart_static -lpthread -ldl -lrt
+echo "built $(pwd)/libtsd_b200.so"

@@ -1,0 +1,659 @@
+// K5..K9 kernel bodies - see elementwise.cuh.
+#include "elementwise.cuh"
+
+#include <cfloat>
+
+namespace tsd {
+
+namespace {
+
+constexpr int kSMs = 148;
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)kSMs * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_f(float x) {
+  const float k = 0.7978845608028654f;
+  return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout: per image [R][Cc] -> [Cc][R] transpose through a padded smem tile
+// ------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R,
+                                 int Cc, int rescale) {
+  __shared__ float tile[32][33];
+  const long long img = (long long)blockIdx.z * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = src[img + (long long)r * Cc + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) {
+      float v = tile[threadIdx.x][i];
+      if (rescale) v = fminf(fmaxf((v + 1.0f) * 127.5f, 0.0f), 255.0f);
+      dst[img + (long long)c * R + r] = v;
+    }
+  }
+}
+
+cudaError_t launch_transpose(const float* src, float* dst, int N, int R, int Cc, int rescale,
+                             cudaStream_t s) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, N), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(src, dst, R, Cc, rescale);
+  return cudaGetLastError();
+}
+
+__global__ void transpose_ld_kernel(const float* __restrict__ src, float* __restrict__ dst, int R,
+                                    int Cc, int ld_out) {
+  __shared__ float tile[32][33];
+  const float* sb = src + (long long)blockIdx.z * R * Cc;
+  float* db = dst + (long long)blockIdx.z * Cc * ld_out;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = sb[(long long)r * Cc + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) db[(long long)c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void oihw_to_ohwi_kernel(const float* __restrict__ src, float* __restrict__ dst, int O,
+                                    int I, int KK) {
+  const long long total = (long long)O * I * KK;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % I);
+    long long t = i / I;
+    int tap = (int)(t % KK);
+    long long o = t / KK;
+    dst[i] = src[(o * I + ci) * KK + tap];
+  }
+}
+
+__global__ void concat_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b,
+                              int Cb, float* __restrict__ out, long long pixels) {
+  const int C = Ca + Cb;
+  const long long total = pixels * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / C;
+    int c = (int)(i - p * C);
+    out[i] = c < Ca ? a[p * Ca + c] : b[p * Cb + (c - Ca)];
+  }
+}
+
+__global__ void upsample2x_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H,
+                                  int W, int C4) {
+  const long long total = (long long)N * 4 * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int wo = (int)(t % (2 * W));
+    t /= (2 * W);
+    int ho = (int)(t % (2 * H));
+    int n = (int)(t / (2 * H));
+    y[i] = x[(((long long)n * H + (ho >> 1)) * W + (wo >> 1)) * C4 + c];
+  }
+}
+
+__global__ void upsample2x_planar_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
+                                         int H, int W) {
+  const long long total = (long long)C * 4 * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int wo = (int)(i % (2 * W));
+    long long t = i / (2 * W);
+    int ho = (int)(t % (2 * H));
+    long long c = t / (2 * H);
+    y[i] = x[(c * H + (ho >> 1)) * W + (wo >> 1)];
+  }
+}
+
+__global__ void im2col3x3_kernel(const float4* __restrict__ x, float4* __restrict__ col, int N, int H,
+                                 int W, int C4, int stride, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * 9 * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    long long t = i / C4;
+    int tap = (int)(t % 9);
+    t /= 9;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    int hi = ho * stride + tap / 3 - 1, wi = wo * stride + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      v = x[(((long long)n * H + hi) * W + wi) * C4 + c];
+    col[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm / LayerNorm statistics
+// ------------------------------------------------------------------------------------------
+// Fast path: C % 4 == 0 and C/4 <= 1024. Thread owns one channel quad and walks pixels.
+__global__ void group_stats_vec_kernel(const float4* __restrict__ x, long long pixels, int C4, int G,
+                                       int cpg, double* __restrict__ accum) {
+  extern __shared__ float sm[];  // [2*C]
+  const int C = C4 * 4;
+  float* sm_s = sm;
+  float* sm_q = sm + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int lanes = blockDim.x / C4;
+  const int u = threadIdx.x % C4, pl = threadIdx.x / C4;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (pl < lanes) {
+    const float4* base = x + (long long)n * pixels * C4;
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < pixels;
+         p += (long long)gridDim.x * lanes) {
+      float4 v = base[p * C4 + u];
+      s[0] += v.x; q[0] += v.x * v.x;
+      s[1] += v.y; q[1] += v.y * v.y;
+      s[2] += v.z; q[2] += v.z * v.z;
+      s[3] += v.w; q[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sm_s[u * 4 + j], s[j]);
+      atomicAdd(&sm_q[u * 4 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      ds += (double)sm_s[c];
+      dq += (double)sm_q[c];
+    }
+    atomicAdd(&accum[((long long)n * G + g) * 2], ds);
+    atomicAdd(&accum[((long long)n * G + g) * 2 + 1], dq);
+  }
+}
+
+// General path: one block per (n, g).
+__global__ void group_stats_general_kernel(const float* __restrict__ x, long long pixels, int C,
+                                           int G, int cpg, double* __restrict__ accum) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const float* base = x + (long long)n * pixels * C + (long long)g * cpg;
+  double s = 0.0, q = 0.0;
+  const long long total = pixels * cpg;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    long long p = i / cpg;
+    int c = (int)(i - p * cpg);
+    float v = base[p * C + c];
+    s += v;
+    q += (double)v * v;
+  }
+  __shared__ double rs[32], rq[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffff, s, o);
+    q += __shfl_xor_sync(0xffffffff, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    rs[threadIdx.x >> 5] = s;
+    rq[threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0, tq = 0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) {
+      ts += rs[i];
+      tq += rq[i];
+    }
+    accum[((long long)n * G + g) * 2] = ts;
+    accum[((long long)n * G + g) * 2 + 1] = tq;
+  }
+}
+
+__global__ void group_stats_finalize_kernel(const double* __restrict__ accum, int NG, double count,
+                                            float eps, float2* __restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  double mean = accum[2 * i] / count;
+  double var = accum[2 * i + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
+  double inv = 1.0 / (sqrt(var) + (double)eps);
+  stats[i] = make_float2((float)mean, (float)inv);
+}
+
+template <int VEC>
+__global__ void norm_apply_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  float gamma_scalar, float* __restrict__ y, int N, int H, int W,
+                                  int C, int G, int cpg, int silu, int up, int round) {
+  const int CV = C / VEC;
+  const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long t = i / CV;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    int hi = up ? (ho >> 1) : ho, wi = up ? (wo >> 1) : wo;
+    const float* src = x + ((((long long)n * H + hi) * W + wi) * C + (long long)cv * VEC);
+    float v[VEC];
+    if (VEC == 4) {
+      float4 t4 = *reinterpret_cast<const float4*>(src);
+      v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+    } else {
+      v[0] = src[0];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      int c = cv * VEC + j;
+      float2 st = stats[n * G + c / cpg];
+      float o = (v[j] - st.x) * st.y * gamma_scalar;
+      if (gamma) o *= gamma[c];
+      if (beta) o += beta[c];
+      if (silu) o = silu_f(o);
+      if (round) o = rna_tf32(o);
+      v[j] = o;
+    }
+    float* dst = y + i * VEC;
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else
+      dst[0] = v[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------------
+__global__ void fill_uniform_kernel(float* __restrict__ p, long long n, uint64_t seed, float lo,
+                                    float hi) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + (uint64_t)i + 0x632BE59BD9B4E019ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // [0,1)
+    p[i] = lo + (hi - lo) * u;
+  }
+}
+
+__global__ void unary_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int op,
+                             float scalar) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (op == UNARY_SILU) v = v / (1.0f + expf(-v));
+    else if (op == UNARY_GELU) v = gelu_f(v);
+    else if (op == UNARY_SCALE) v = v * scalar;
+    y[i] = v;
+  }
+}
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                           float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = a[i] + b[i];
+}
+__global__ void add_channel_vec_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                       float* __restrict__ y, long long total, int C) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] + v[i % C];
+}
+
+// ------------------------------------------------------------------------------------------
+// direct convolution: thread per (pixel, cout), cout fastest
+// ------------------------------------------------------------------------------------------
+__global__ void conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int N,
+                                   int H, int W, int Cin, int Cout, int k, int pad, int stride,
+                                   int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    long long t = i / Cout;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    float acc = bias ? bias[co] : 0.f;
+    const float* wrow = w + (long long)co * k * k * Cin;
+    for (int ky = 0; ky < k; ++ky) {
+      int hi = ho * stride + ky - pad;
+      if (hi < 0 || hi >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        int wi = wo * stride + kx - pad;
+        if (wi < 0 || wi >= W) continue;
+        const float* xp = x + (((long long)n * H + hi) * W + wi) * Cin;
+        const float* wp = wrow + (ky * k + kx) * Cin;
+        for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xp[ci], wp[ci], acc);
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMV: one warp per output element (row r, column n)
+// ------------------------------------------------------------------------------------------
+__global__ void gemv_kernel(const float* __restrict__ x, int K, const float* __restrict__ Wt,
+                            const float* __restrict__ bias, const float* __restrict__ bias2,
+                            float* __restrict__ y, int N, int silu_in, int silu_out) {
+  const int warps = blockDim.x >> 5;
+  const int n = blockIdx.x * warps + (threadIdx.x >> 5);
+  const int r = blockIdx.y;
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)r * K;
+  const float* wr = Wt + (long long)n * K;
+  float acc = 0.f;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 a = *reinterpret_cast<const float4*>(xr + k);
+      float4 b = *reinterpret_cast<const float4*>(wr + k);
+      if (silu_in) {
+        a.x = a.x / (1.0f + expf(-a.x));
+        a.y = a.y / (1.0f + expf(-a.y));
+        a.z = a.z / (1.0f + expf(-a.z));
+        a.w = a.w / (1.0f + expf(-a.w));
+      }
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      float a = xr[k];
+      if (silu_in) a = a / (1.0f + expf(-a));
+      acc = fmaf(a, wr[k], acc);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+  if (lane == 0) {
+    if (bias) acc += bias[n];
+    if (bias2) acc += bias2[n];
+    if (silu_out) acc = acc / (1.0f + expf(-acc));
+    y[(long long)r * N + n] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax (unfused attention path)
+// ------------------------------------------------------------------------------------------
+// axis 0: per column j, over rows.  block (32, 8): 32 columns, 8 row lanes.
+__global__ void softmax_colstats_kernel(const float* __restrict__ S, int R, int Cc, int ld,
+                                        float scale, float2* __restrict__ st) {
+  __shared__ float sm_m[8][33], sm_l[8][33];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const float* base = S + (long long)b * R * ld;
+  float m = -FLT_MAX, l = 0.f;
+  if (j < Cc) {
+    for (int i = threadIdx.y; i < R; i += 8) {
+      float v = base[(long long)i * ld + j] * scale;
+      if (v > m) {
+        l = l * expf(m - v) + 1.0f;
+        m = v;
+      } else {
+        l += expf(v - m);
+      }
+    }
+  }
+  sm_m[threadIdx.y][threadIdx.x] = m;
+  sm_l[threadIdx.y][threadIdx.x] = l;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < Cc) {
+    float M = sm_m[0][threadIdx.x];
+    for (int t = 1; t < 8; ++t) M = fmaxf(M, sm_m[t][threadIdx.x]);
+    float L = 0.f;
+    for (int t = 0; t < 8; ++t) L += sm_l[t][threadIdx.x] * expf(sm_m[t][threadIdx.x] - M);
+    st[(long long)b * Cc + j] = make_float2(M, 1.0f / L);
+  }
+}
+__global__ void softmax_colapply_kernel(float* __restrict__ S, int R, int Cc, int ld, float scale,
+                                        const float2* __restrict__ st, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(i % Cc);
+    long long t = i / Cc;  // b * R + r
+    long long b = t / R;
+    float2 s = st[b * Cc + j];
+    float* p = S + t * ld + j;
+    *p = expf(*p * scale - s.x) * s.y;
+  }
+}
+// axis 1: block per row
+__global__ void softmax_row_kernel(float* __restrict__ S, int Cc, int ld, float scale) {
+  float* row = S + (long long)blockIdx.x * ld;
+  __shared__ float red[32];
+  float m = -FLT_MAX;
+  for (int j = threadIdx.x; j < Cc; j += blockDim.x) m = fmaxf(m, row[j] * scale);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float l = 0.f;
+  for (int j = threadIdx.x; j < Cc; j += blockDim.x) l += expf(row[j] * scale - m);
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffff, l, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) l += red[i];
+  const float inv = 1.0f / l;
+  for (int j = threadIdx.x; j < Cc; j += blockDim.x) row[j] = expf(row[j] * scale - m) * inv;
+}
+
+__global__ void ddpm_step_kernel(const float* __restrict__ x, const float* __restrict__ ec,
+                                 const float* __restrict__ eu, float cfg_scale,
+                                 const float* __restrict__ noise, float sqrt_ab, float sqrt_1mab,
+                                 float c0, float c1, float sigma, float* __restrict__ out,
+                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float e = ec[i];
+    if (eu) {
+      float u = eu[i];
+      e = (e - u) * cfg_scale + u;  // pipeline.mojo:117-119
+    }
+    float xi = x[i];
+    float x0 = (xi - e * sqrt_1mab) / sqrt_ab;  // sampler.mojo:88-90
+    float o = x0 * c0 + xi * c1;                // sampler.mojo:91-99
+    if (noise) o += noise[i] * sigma;           // sampler.mojo:101-108
+    out[i] = o;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, cudaStream_t s) {
+  return launch_transpose(src, dst, N, C, HW, 0, s);
+}
+cudaError_t launch_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, cudaStream_t s) {
+  return launch_transpose(src, dst, N, HW, C, 0, s);
+}
+cudaError_t launch_rescale_to_nchw(const float* src, float* dst, int N, int C, int HW, int rescale,
+                                   cudaStream_t s) {
+  return launch_transpose(src, dst, N, HW, C, rescale, s);
+}
+cudaError_t launch_transpose_ld(const float* src, float* dst, int B, int R, int Cc, int ld_out,
+                                cudaStream_t s) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, B), block(32, 8);
+  transpose_ld_kernel<<<grid, block, 0, s>>>(src, dst, R, Cc, ld_out);
+  return cudaGetLastError();
+}
+cudaError_t launch_oihw_to_ohwi(const float* src, float* dst, int O, int I, int KK, cudaStream_t s) {
+  long long total = (long long)O * I * KK;
+  oihw_to_ohwi_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, O, I, KK);
+  return cudaGetLastError();
+}
+cudaError_t launch_concat_channels(const float* a, int Ca, const float* b, int Cb, float* out,
+                                   long long pixels, cudaStream_t s) {
+  long long total = pixels * (Ca + Cb);
+  concat_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, Ca, b, Cb, out, pixels);
+  return cudaGetLastError();
+}
+cudaError_t launch_upsample2x(const float* x, float* y, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 4) return cudaErrorInvalidValue;
+  long long total = (long long)N * 4 * H * W * (C / 4);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x),
+                                                         reinterpret_cast<float4*>(y), N, H, W, C / 4);
+  return cudaGetLastError();
+}
+cudaError_t launch_upsample2x_planar(const float* x, float* y, int C, int H, int W, cudaStream_t s) {
+  long long total = (long long)C * 4 * H * W;
+  upsample2x_planar_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, y, C, H, W);
+  return cudaGetLastError();
+}
+cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, int C, int stride,
+                             int Ho, int Wo, cudaStream_t s) {
+  if (C % 4) return cudaErrorInvalidValue;
+  long long total = (long long)N * Ho * Wo * 9 * (C / 4);
+  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x),
+                                                        reinterpret_cast<float4*>(col), N, H, W,
+                                                        C / 4, stride, Ho, Wo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, int G, float eps,
+                               double* accum, float2* stats, cudaStream_t s) {
+  if (G <= 0 || C % G) return cudaErrorInvalidValue;
+  const int cpg = C / G;
+  const int NG = N * G;
+  if (C % 4 == 0 && C / 4 <= 1024 && 2 * C * sizeof(float) <= 48 * 1024) {
+    cudaError_t e = cudaMemsetAsync(accum, 0, sizeof(double) * 2 * NG, s);
+    if (e != cudaSuccess) return e;
+    const int C4 = C / 4;
+    int lanes = 512 / C4;
+    if (lanes < 1) lanes = 1;
+    const int threads = ((C4 * lanes + 31) / 32) * 32;
+    long long want = (pixels + lanes - 1) / lanes;          // blocks if 1 pixel step each
+    long long bx = want / 8;                                // >= 8 pixels per thread
+    long long cap = (long long)(kSMs * 4 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, N);
+    group_stats_vec_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(
+        reinterpret_cast<const float4*>(x), pixels, C4, G, cpg, accum);
+  } else {
+    dim3 grid(G, N);
+    group_stats_general_kernel<<<grid, 256, 0, s>>>(x, pixels, C, G, cpg, accum);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  group_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, s>>>(accum, NG, (double)pixels * cpg, eps,
+                                                               stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* gamma,
+                              const float* beta, float gamma_scalar, float* y, int N, int H, int W,
+                              int C, int G, int silu, int upsample2x, int round_tf32,
+                              cudaStream_t s) {
+  if (G <= 0 || C % G) return cudaErrorInvalidValue;
+  const int cpg = C / G;
+  const long long outpix = (long long)N * H * W * (upsample2x ? 4 : 1);
+  if (C % 4 == 0) {
+    long long total = outpix * (C / 4);
+    norm_apply_kernel<4><<<grid_for(total, 256), 256, 0, s>>>(x, stats, gamma, beta, gamma_scalar, y,
+                                                              N, H, W, C, G, cpg, silu, upsample2x,
+                                                              round_tf32);
+  } else {
+    long long total = outpix * C;
+    norm_apply_kernel<1><<<grid_for(total, 256), 256, 0, s>>>(x, stats, gamma, beta, gamma_scalar, y,
+                                                              N, H, W, C, G, cpg, silu, upsample2x,
+                                                              round_tf32);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_uniform(float* p, long long n, uint64_t seed, float lo, float hi, cudaStream_t s) {
+  fill_uniform_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, seed, lo, hi);
+  return cudaGetLastError();
+}
+cudaError_t launch_unary(const float* x, float* y, long long n, int op, float scalar, cudaStream_t s) {
+  unary_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, y, n, op, scalar);
+  return cudaGetLastError();
+}
+cudaError_t launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t s) {
+  add_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, y, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_add_channel_vec(const float* x, const float* v, float* y, long long pixels, int C,
+                                   cudaStream_t s) {
+  add_channel_vec_kernel<<<grid_for(pixels * C, 256), 256, 0, s>>>(x, v, y, pixels * C, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias, float* out, int N,
+                               int H, int W, int Cin, int Cout, int k, int pad, int stride, int Ho,
+                               int Wo, cudaStream_t s) {
+  long long total = (long long)N * Ho * Wo * Cout;
+  conv_direct_kernel<<<grid_for(total, 128, 16), 128, 0, s>>>(x, w, bias, out, N, H, W, Cin, Cout, k,
+                                                              pad, stride, Ho, Wo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const float* bias,
+                        const float* bias2, float* y, int N, int silu_in, int silu_out,
+                        cudaStream_t s) {
+  const int warps = 8;
+  dim3 grid((N + warps - 1) / warps, rows);
+  gemv_kernel<<<grid, warps * 32, 0, s>>>(x, K, Wt, bias, bias2, y, N, silu_in, silu_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, float scale,
+                           float* col_scratch, cudaStream_t s) {
+  if (axis == 0) {
+    dim3 grid((Cc + 31) / 32, B), block(32, 8);
+    float2* st = reinterpret_cast<float2*>(col_scratch);
+    softmax_colstats_kernel<<<grid, block, 0, s>>>(S, R, Cc, ld, scale, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    long long total = (long long)B * R * Cc;
+    softmax_colapply_kernel<<<grid_for(total, 256), 256, 0, s>>>(S, R, Cc, ld, scale, st, total);
+  } else {
+    softmax_row_kernel<<<B * R, 256, 0, s>>>(S, Cc, ld, scale);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ddpm_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
+                             const float* noise, float sqrt_ab, float sqrt_1mab, float c0, float c1,
+                             float sigma, float* out, long long n, cudaStream_t s) {
+  ddpm_step_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, eps_c, eps_u, cfg_scale, noise, sqrt_ab,
+                                                    sqrt_1mab, c0, c1, sigma, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace tsd

@@ -1,0 +1,81 @@
+// K5..K9: HBM-bound kernels around the tensor-core GEMMs: GroupNorm/LayerNorm statistics
+// and apply(+SiLU)(+nearest 2x upsample), layout changes (reference CHW <-> device NHWC),
+// channel concat, stride-2 im2col, direct convolutions for degenerate channel counts,
+// M=1 GEMV (time embedding), softmax for the unfused attention path, the DDPM sampler step.
+// All activations are fp32, NHWC (= token-major [pixels][channels]).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tsd {
+
+// ---- layout -----------------------------------------------------------------------------
+cudaError_t launch_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, cudaStream_t s);
+// per batch entry: src [R][Cc] -> dst [Cc][ld_out] (ld_out >= R; padding columns untouched)
+cudaError_t launch_transpose_ld(const float* src, float* dst, int B, int R, int Cc, int ld_out,
+                                cudaStream_t s);
+// conv weights: reference OIHW (Matrix_Array [out][in][k][k], helpers/utils.mojo:1718) ->
+// K-major [O][kh*kw][I] rows for the implicit-GEMM B operand
+cudaError_t launch_oihw_to_ohwi(const float* src, float* dst, int O, int I, int KK, cudaStream_t s);
+cudaError_t launch_concat_channels(const float* a, int Ca, const float* b, int Cb, float* out,
+                                   long long pixels, cudaStream_t s);
+// copies the first `Cout` channels of a [pixels][Cin] tensor (Q9: truncated concat)
+cudaError_t launch_upsample2x(const float* x, float* y, int N, int H, int W, int C, cudaStream_t s);
+// channel-major (C,H,W) -> (C,2H,2W), any C
+cudaError_t launch_upsample2x_planar(const float* x, float* y, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, int C, int stride,
+                             int Ho, int Wo, cudaStream_t s);
+
+// ---- normalisation ------------------------------------------------------------------------
+// stats[n][g] = (mean, 1/(std+eps)) with the reference's biased std and eps added to std
+// (helpers/utils.mojo:1360-1380, 1868-1870).  `accum` is a [N*G*2] double scratch.
+cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, int G, float eps,
+                               double* accum, float2* stats, cudaStream_t s);
+// y = (x - mean) * inv [* gamma[c] + beta[c]] ; optional SiLU ; optional TF32 rounding ;
+// optional nearest 2x upsample on write (x is [N,H,W,C], y is [N,2H,2W,C]).
+cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* gamma,
+                              const float* beta, float gamma_scalar, float* y, int N, int H, int W,
+                              int C, int G, int silu, int upsample2x, int round_tf32,
+                              cudaStream_t s);
+
+// deterministic U(lo,hi) fill (synthetic weights / probes): counter-based splitmix64 hash
+cudaError_t launch_fill_uniform(float* p, long long n, uint64_t seed, float lo, float hi, cudaStream_t s);
+
+// ---- simple elementwise --------------------------------------------------------------------
+enum UnaryOp { UNARY_SILU = 0, UNARY_GELU = 1, UNARY_SCALE = 2, UNARY_COPY = 3 };
+cudaError_t launch_unary(const float* x, float* y, long long n, int op, float scalar, cudaStream_t s);
+cudaError_t launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t s);
+// y[p][c] = x[p][c] + v[c]
+cudaError_t launch_add_channel_vec(const float* x, const float* v, float* y, long long pixels, int C,
+                                   cudaStream_t s);
+
+// ---- direct convolution (CUDA cores) for shapes the tensor-core path does not take ---------
+// x [N,H,W,Cin] ; w [Cout][k*k][Cin] ; out [N,Ho,Wo,Cout]
+cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias, float* out, int N,
+                               int H, int W, int Cin, int Cout, int k, int pad, int stride, int Ho,
+                               int Wo, cudaStream_t s);
+
+// ---- GEMV: y[r][n] = sum_k act(x[r][k]) * Wt[n][k] + bias[n] + bias2[n] ---------------------
+cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const float* bias,
+                        const float* bias2, float* y, int N, int silu_in, int silu_out,
+                        cudaStream_t s);
+
+// ---- softmax over a [B][R][Cc] score tensor (row stride ld) -------------------------------
+// axis 0: normalise each column over rows (reference Softmax(dim=2) behaviour, Q3)
+// axis 1: normalise each row over columns (standard attention)
+cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, float scale,
+                           float* col_scratch, cudaStream_t s);
+
+// ---- DDPM step (+ optional CFG combine), sampler.mojo:75-109, pipeline.mojo:117-119 --------
+// eps = cfg ? u + cfg_scale * (c - u) : c ; x0 = (x - sqrt(1-ab_t) eps)/sqrt(ab_t)
+// out = c0 * x0 + c1 * x + sigma * noise
+cudaError_t launch_ddpm_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
+                             const float* noise, float sqrt_ab, float sqrt_1mab, float c0, float c1,
+                             float sigma, float* out, long long n, cudaStream_t s);
+
+// img = clamp((v + 1) * 127.5, 0, 255), NHWC -> NCHW  (pipeline.mojo:127, utils.mojo:577-597)
+cudaError_t launch_rescale_to_nchw(const float* src, float* dst, int N, int C, int HW, int rescale,
+                                   cudaStream_t s);
+
+}  // namespace tsd

@@ -1,0 +1,75 @@
+// K1/K2: TF32 GEMM / implicit-GEMM convolution on tcgen05 tensor cores.
+//
+//   D[b][m][n] = epilogue( sum_{tap,k} A[b][pixel(m) + shift(tap)][k] * B[b][n][tap*Cin + k] )
+//
+// * A is a 4-D fp32 tensor (K innermost, then W, H, batch) - an NHWC activation, or a plain
+//   [M,K] matrix viewed as W=M,H=1.  One CTA owns a 128-row tile = a (bh x bw) pixel box; the
+//   TMA producer issues one box load per (tap, 32-channel chunk) with the tap's (dy,dx) shift
+//   added to the box coordinates; out-of-bounds elements are zero-filled by TMA, which *is*
+//   the convolution's zero padding (reference Conv2D.forward pads first, helpers/utils.mojo:1749).
+// * B is a K-major [N][taps*Cin] weight matrix (reference OIHW re-laid as O,(kh,kw),I).
+// * Both operands land in shared memory in the canonical K-major SWIZZLE_128B layout
+//   (rows of 32 fp32 = 128 B) and feed tcgen05.mma.kind::tf32 (M=128, N=BN, K=8 per instruction)
+//   issued by one thread; the accumulator lives in TMEM and is read back by 4 epilogue warps.
+// * Epilogue options: column bias, row bias, residual add, alpha scale, GEGLU
+//   (out * gelu(gate), diffusion.mojo:138-141), column-block routing (QKV split), TF32 rounding,
+//   or raw split-K partials (reduced by splitk_reduce_kernel, which then applies bias/residual).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tsd {
+
+constexpr int GEMM_BM = 128;       // rows per CTA tile (TMEM lanes)
+constexpr int GEMM_BK = 32;        // fp32 elements per K chunk = one 128 B swizzle row
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int GEMM_MAX_STAGES = 8;
+
+struct GemmKParams {
+  // output-pixel tiling (plain GEMM: H = 1, W = M, bw = 128, bh = 1)
+  int H, W, bw, bh, tiles_w, tiles_h;
+  int m_per_batch;  // img_n * H * W : rows of D per batch entry
+  // K loop
+  int taps, cin, chunks_per_tap, total_iters, splits, iters_per_split;
+  int a_box_bytes;
+  // N tiling
+  int BN, n_valid, geglu, n_half;
+  int num_stages, tmem_cols;
+  // output
+  float* D;
+  long long d_batch_stride;
+  int ldd;
+  int split_n;             // column routing: col n -> (n / split_n) * split_stride + n % split_n
+  long long split_stride;
+  const float* bias;       // [n] or nullptr
+  const float* row_bias;   // [m] or nullptr
+  const float* residual;   // [b][m][ldr] or nullptr
+  long long r_batch_stride;
+  int ldr;
+  float alpha;
+  int round_tf32;
+  float* partial;          // split-K workspace [split][b][m][n_pad] or nullptr
+  int n_pad;
+};
+
+struct SplitKReduceParams {
+  const float* partial;
+  int splits;
+  long long split_stride;  // elements between consecutive splits
+  int m, n_pad, n_valid;
+  float* D;
+  int ldd;
+  const float* bias;
+  const float* residual;
+  int ldr;
+  int round_tf32;
+};
+
+cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                             dim3 grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t stream);
+size_t gemm_smem_bytes(int BN, int num_stages);
+int gemm_pick_stages(int BN);
+
+}  // namespace tsd

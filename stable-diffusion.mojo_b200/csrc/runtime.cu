@@ -1,0 +1,533 @@
+// Context, arena, TMA descriptor encoding and the op layer (see runtime.h).
+#include "runtime.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "attention_tcgen05.cuh"
+#include "elementwise.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace tsd {
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+int Ctx::fail(int code, const std::string& msg) {
+  last_error = msg;
+  return code;
+}
+int Ctx::check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return TSD_OK;
+  last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return TSD_ERR_CUDA;
+}
+
+Arena::~Arena() {
+  if (base_) cudaFree(base_);
+}
+int Arena::reserve(size_t bytes) {
+  if (bytes <= cap_) return TSD_OK;
+  if (base_) cudaFree(base_);
+  base_ = nullptr;
+  cap_ = off_ = 0;
+  if (cudaMalloc(&base_, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return TSD_ERR_OOM;
+  }
+  cap_ = bytes;
+  return TSD_OK;
+}
+void* Arena::alloc(size_t bytes) {
+  size_t start = (off_ + 1023) & ~size_t(1023);
+  if (start + bytes > cap_) return nullptr;
+  off_ = start + bytes;
+  if (off_ > high_) high_ = off_;
+  return base_ + start;
+}
+
+int ctx_create(int device, Ctx** out, std::string* err) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    *err = "no CUDA device visible: tsd_b200 has no CPU fallback";
+    return TSD_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    *err = "device index out of range";
+    return TSD_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    *err = "cudaGetDeviceProperties failed";
+    return TSD_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    *err = std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); kernels are sm_100a only";
+    return TSD_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    *err = "cudaSetDevice failed";
+    return TSD_ERR_CUDA;
+  }
+  Ctx* c = new Ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    *err = "cudaStreamCreate failed";
+    delete c;
+    return TSD_ERR_CUDA;
+  }
+  c->own_stream = true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    *err = "cuTensorMapEncodeTiled not available from the driver";
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return TSD_ERR_CUDA;
+  }
+  c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  *out = c;
+  return TSD_OK;
+}
+
+void ctx_destroy(Ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->timer) {
+    for (auto e : c->timer->pool) cudaEventDestroy(e);
+    delete c->timer;
+  }
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+cudaEvent_t KernelTimer::get() {
+  if (next == pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pool.push_back(e);
+  }
+  return pool[next++];
+}
+TimedScope::TimedScope(Ctx* ctx, int family, double flops) : c(ctx) {
+  if (!c->timer) return;
+  KernelTimer::Rec r;
+  r.family = family;
+  r.flops = flops;
+  r.a = c->timer->get();
+  r.b = c->timer->get();
+  cudaEventRecord(r.a, c->stream);
+  idx = (int)c->timer->recs.size();
+  c->timer->recs.push_back(r);
+}
+TimedScope::~TimedScope() {
+  if (idx >= 0) cudaEventRecord(c->timer->recs[idx].b, c->stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptors
+// ------------------------------------------------------------------------------------------
+// fp32 tensor, dims innermost-first, strides in elements (stride of dim0 is 1), 128 B swizzle.
+static int make_tmap(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_elems, const uint32_t* box) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_elems[i] * sizeof(float);
+      if (gstr[i - 1] % 16 != 0) return c->fail(TSD_ERR_INVALID, "TMA: stride not a multiple of 16 bytes");
+    }
+    if (box[i] == 0 || box[i] > 256) return c->fail(TSD_ERR_INVALID, "TMA: box dim out of range");
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return c->fail(TSD_ERR_INVALID, "TMA: base address not 16-byte aligned");
+  CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                         const_cast<float*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+             box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return c->fail(TSD_ERR_CUDA, buf);
+  }
+  return TSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM / conv configuration
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct TileCfg {
+  int BN = 0, splits = 1;
+};
+
+// Cycle model used only to rank (BN, splits) candidates: MMA issue rate vs. operand feed from
+// L2 vs. fixed per-tile cost, times the number of waves over the SMs.
+TileCfg choose_tiles(int sm, long long m_tiles, int N, int total_iters, int batch, bool geglu,
+                     bool allow_split, long long m_rows) {
+  const int n_pad = (N + 15) / 16 * 16;
+  TileCfg best;
+  double best_cost = 1e300;
+  for (int BN = 16; BN <= 256; BN += 16) {
+    if (n_pad % BN) continue;
+    if (geglu && (BN % 32 || (N / 2) % (BN / 2))) continue;
+    const long long n_tiles = n_pad / BN;
+    static const int split_cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    for (int splits : split_cand) {
+      if (splits > 1 && (!allow_split || total_iters / splits < 4)) break;
+      const long long ctas = m_tiles * n_tiles * batch * splits;
+      const double active = (double)std::min<long long>(ctas, sm);
+      const double feed_bw = std::min(96.0, 6300.0 / active);  // B/cycle/SM from L2
+      const double iter_cyc = std::max(2.0 * BN, (16384.0 + 128.0 * BN) / feed_bw);
+      const int ips = (total_iters + splits - 1) / splits;
+      const double tile_cyc = ips * iter_cyc + 3500.0 + 24.0 * BN;
+      const double waves = std::ceil((double)ctas / sm);
+      double cost = waves * tile_cyc;
+      if (splits > 1) cost += 4000.0 + (double)(splits + 1) * m_rows * n_pad * 4.0 / 4000.0;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.BN = BN;
+        best.splits = splits;
+      }
+    }
+  }
+  return best;
+}
+
+struct ASpec {
+  const float* base;
+  int K;            // inner extent (channels)
+  int W, H, imgs;   // pixel grid (plain GEMM: W = M, H = 1)
+  long long ld_w, ld_h, ld_img;
+  int batch;
+  long long ld_batch;
+  int taps;
+};
+
+}  // namespace
+
+static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
+                    int b_rows, GemmKParams p, int force_bn, int force_splits, double flops) {
+  if (A.K % 4) return c->fail(TSD_ERR_INVALID, "gemm: K must be a multiple of 4");
+  if (A.batch > 1 && A.imgs > 1) return c->fail(TSD_ERR_INVALID, "gemm: batch and images are exclusive");
+  // pixel box of 128 rows
+  int bw = std::min(A.W, 128);
+  while (128 % bw) --bw;  // largest divisor of 128 not above W
+  int bh = std::min(128 / bw, A.H);
+  p.H = A.H;
+  p.W = A.W;
+  p.bw = bw;
+  p.bh = bh;
+  p.tiles_w = (A.W + bw - 1) / bw;
+  p.tiles_h = (A.H + bh - 1) / bh;
+  p.m_per_batch = A.imgs * A.H * A.W;
+  p.taps = A.taps;
+  p.cin = A.K;
+  p.chunks_per_tap = (A.K + GEMM_BK - 1) / GEMM_BK;
+  p.total_iters = p.taps * p.chunks_per_tap;
+  p.a_box_bytes = bw * bh * GEMM_BK * 4;
+  const long long m_tiles = (long long)A.imgs * p.tiles_h * p.tiles_w;
+  const int nbatch = A.batch;
+  const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
+                           p.alpha == 1.0f;
+  TileCfg cfg = choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
+                             (long long)p.m_per_batch);
+  if (force_bn > 0) cfg.BN = force_bn;
+  if (force_splits > 0 && allow_split) cfg.splits = std::min(force_splits, p.total_iters);
+  if (cfg.BN < 16 || cfg.BN > 256 || cfg.BN % 16) return c->fail(TSD_ERR_INVALID, "gemm: bad BN");
+  if (p.geglu && (cfg.BN % 32 || (N / 2) % (cfg.BN / 2)))
+    return c->fail(TSD_ERR_INVALID, "gemm: GEGLU needs BN/2 | N/2");
+  p.BN = cfg.BN;
+  p.splits = cfg.splits;
+  p.iters_per_split = (p.total_iters + p.splits - 1) / p.splits;
+  p.splits = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;  // no empty split
+  p.num_stages = gemm_pick_stages(p.BN);
+  int tc = 32;
+  while (tc < p.BN) tc <<= 1;
+  p.tmem_cols = tc;
+  p.n_pad = (N + 15) / 16 * 16;
+  const int out_cols_per_tile = p.geglu ? p.BN / 2 : p.BN;
+  const int n_out = p.geglu ? N / 2 : N;
+  const int n_tiles = (((p.geglu ? n_out : p.n_pad)) + out_cols_per_tile - 1) / out_cols_per_tile;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)A.K, (uint64_t)A.W, (uint64_t)A.H,
+                        (uint64_t)(A.batch > 1 ? A.batch : A.imgs)};
+    uint64_t str[4] = {1, (uint64_t)A.ld_w, (uint64_t)A.ld_h,
+                       (uint64_t)(A.batch > 1 ? A.ld_batch : A.ld_img)};
+    if (dims[3] == 1) str[3] = (uint64_t)A.ld_h * A.H;  // unused but must be a valid stride
+    if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
+    if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
+    uint32_t box[4] = {(uint32_t)GEMM_BK, (uint32_t)bw, (uint32_t)bh, 1};
+    int rc = make_tmap(c, &tmA, A.base, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const int ktot = A.taps * A.K;
+    uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
+    uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
+    uint32_t box[3] = {(uint32_t)GEMM_BK, (uint32_t)(p.geglu ? p.BN / 2 : p.BN), 1};
+    int rc = make_tmap(c, &tmB, B, 3, dims, str, box);
+    if (rc) return rc;
+  }
+
+  SplitKReduceParams rp{};
+  size_t mark = c->arena.mark();
+  if (p.splits > 1) {
+    const size_t elems = (size_t)p.splits * p.m_per_batch * p.n_pad;
+    float* ws = c->arena.alloc_n<float>(elems);
+    if (!ws) return c->fail(TSD_ERR_OOM, "gemm: arena exhausted (split-K workspace)");
+    rp.partial = ws;
+    rp.splits = p.splits;
+    rp.split_stride = (long long)p.m_per_batch * p.n_pad;
+    rp.m = p.m_per_batch;
+    rp.n_pad = p.n_pad;
+    rp.n_valid = p.n_valid;
+    rp.D = p.D;
+    rp.ldd = p.ldd;
+    rp.bias = p.bias;
+    rp.residual = p.residual;
+    rp.ldr = p.ldr;
+    rp.round_tf32 = p.round_tf32;
+    p.partial = ws;
+  } else {
+    p.partial = nullptr;
+  }
+
+  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)(nbatch * p.splits));
+  if (m_tiles > 65535 || grid.z > 65535) return c->fail(TSD_ERR_INVALID, "gemm: grid too large");
+  {
+    TimedScope ts(c, FAM_GEMM, flops);
+    int rc = c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages), c->stream),
+                      "gemm_tf32_kernel launch");
+    if (rc) return rc;
+    c->launches++;
+    if (p.splits > 1) {
+      rc = c->check(launch_splitk_reduce(rp, c->stream), "splitk_reduce launch");
+      if (rc) return rc;
+      c->launches++;
+    }
+  }
+  c->arena.release_to(mark);  // stream-ordered: the next op may reuse the partial buffer
+  return TSD_OK;
+}
+
+int op_gemm(Ctx* c, const GemmArgs& a) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.batch <= 0) return c->fail(TSD_ERR_INVALID, "gemm: empty problem");
+  ASpec A{};
+  A.base = a.A;
+  A.K = a.K;
+  A.W = a.M;
+  A.H = 1;
+  A.imgs = 1;
+  A.ld_w = a.lda;
+  A.ld_h = a.lda * a.M;
+  A.ld_img = A.ld_h;
+  A.batch = a.batch;
+  A.ld_batch = a.a_bs;
+  A.taps = 1;
+  GemmKParams p{};
+  p.D = a.D;
+  p.ldd = (int)a.ldd;
+  p.d_batch_stride = a.d_bs;
+  p.bias = a.bias;
+  p.row_bias = a.row_bias;
+  p.residual = a.residual;
+  p.ldr = (int)a.ldr;
+  p.r_batch_stride = a.r_bs;
+  p.alpha = a.alpha;
+  p.geglu = a.geglu;
+  p.n_half = a.N / 2;
+  p.n_valid = a.geglu ? a.N / 2 : a.N;
+  p.split_n = a.split_n > 0 ? a.split_n : (1 << 30);
+  p.split_stride = a.split_stride;
+  p.round_tf32 = a.round_tf32;
+  if ((a.ldd % 4) || (a.residual && (a.ldr % 4)))
+    return c->fail(TSD_ERR_INVALID, "gemm: ldd/ldr must be multiples of 4");
+  const double flops = 2.0 * a.M * (double)a.N * a.K * a.batch;
+  return run_gemm(c, A, a.B, a.N, a.ldb, a.b_bs, a.N, p, a.force_bn, a.force_splits, flops);
+}
+
+int op_conv2d(Ctx* c, const ConvArgs& a) {
+  const int Ho = conv_out_dim(a.H, a.k, a.pad, a.stride), Wo = conv_out_dim(a.W, a.k, a.pad, a.stride);
+  if (Ho <= 0 || Wo <= 0 || a.Cin <= 0 || a.Cout <= 0) return c->fail(TSD_ERR_INVALID, "conv2d: empty output");
+  const int ktot = a.k * a.k * a.Cin;
+  // rows of w past Cout are out of bounds for the B tensor map and read as zeros
+  const bool tensor_ok = a.Cin >= 32 && a.Cin % 4 == 0 && (a.Cout % 4 == 0 || a.Cout < 16);
+  const double flops = 2.0 * a.N * Ho * (double)Wo * a.Cout * ktot;
+  GemmKParams p{};
+  p.D = a.out;
+  p.ldd = a.Cout;
+  p.bias = a.bias;
+  p.residual = a.residual;
+  p.ldr = a.Cout;
+  p.alpha = 1.0f;
+  p.n_valid = a.Cout;
+  p.split_n = 1 << 30;
+  p.round_tf32 = a.round_tf32;
+  if (tensor_ok && ((a.k == 3 && a.pad == 1) || (a.k == 1 && a.pad == 0)) && a.stride == 1) {
+    ASpec A{};
+    A.base = a.x;
+    A.K = a.Cin;
+    A.W = a.W;
+    A.H = a.H;
+    A.imgs = a.N;
+    A.ld_w = a.Cin;
+    A.ld_h = (long long)a.W * a.Cin;
+    A.ld_img = (long long)a.H * a.W * a.Cin;
+    A.batch = 1;
+    A.taps = a.k * a.k;
+    if (a.k == 1) {  // a 1x1 conv is a plain GEMM over all pixels
+      A.W = a.N * a.H * a.W;
+      A.H = 1;
+      A.imgs = 1;
+      A.ld_h = (long long)A.W * a.Cin;
+      A.ld_img = A.ld_h;
+    }
+    return run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops);
+  }
+  if (tensor_ok && a.k == 3 && a.pad == 1 && a.stride > 1) {
+    // stride-2 downsample convs (diffusion.mojo:180,183): explicit im2col then GEMM
+    const size_t mark = c->arena.mark();
+    const long long M = (long long)a.N * Ho * Wo;
+    float* col = c->arena.alloc_n<float>((size_t)M * ktot);
+    if (!col) return c->fail(TSD_ERR_OOM, "conv2d: arena exhausted (im2col)");
+    {
+      TimedScope ts(c, FAM_OTHER, 0);
+      int rc = c->check(launch_im2col3x3(a.x, col, a.N, a.H, a.W, a.Cin, a.stride, Ho, Wo, c->stream),
+                        "im2col launch");
+      if (rc) return rc;
+      c->launches++;
+    }
+    ASpec A{};
+    A.base = col;
+    A.K = ktot;
+    A.W = (int)M;
+    A.H = 1;
+    A.imgs = 1;
+    A.ld_w = ktot;
+    A.ld_h = M * ktot;
+    A.ld_img = A.ld_h;
+    A.batch = 1;
+    A.taps = 1;
+    int rc = run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops);
+    c->arena.release_to(mark);
+    return rc;
+  }
+  // degenerate channel counts (Cin = 4 input convs) and any other geometry: CUDA-core direct conv
+  {
+    TimedScope ts(c, FAM_OTHER, flops);
+    int rc = c->check(launch_conv_direct(a.x, a.w, a.bias, a.out, a.N, a.H, a.W, a.Cin, a.Cout, a.k,
+                                         a.pad, a.stride, Ho, Wo, c->stream),
+                      "conv_direct launch");
+    if (rc) return rc;
+    c->launches++;
+    if (a.residual) {
+      rc = c->check(launch_add(a.out, a.residual, a.out, (long long)a.N * Ho * Wo * a.Cout, c->stream),
+                    "add launch");
+      if (rc) return rc;
+      c->launches++;
+    }
+  }
+  return TSD_OK;
+}
+
+int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,
+                  const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
+                  int round_tf32) {
+  if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
+  const size_t mark = c->arena.mark();
+  double* accum = c->arena.alloc_n<double>((size_t)2 * N * G);
+  float2* stats = c->arena.alloc_n<float2>((size_t)N * G);
+  if (!accum || !stats) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+  TimedScope ts(c, FAM_NORM, 0);
+  int rc = c->check(launch_group_stats(x, N, (long long)H * W, C, G, eps, accum, stats, c->stream),
+                    "group_stats launch");
+  if (rc) return rc;
+  rc = c->check(launch_norm_apply(x, stats, gamma, beta, gamma_scalar, y, N, H, W, C, G, silu, upsample,
+                                  round_tf32, c->stream),
+                "norm_apply launch");
+  if (rc) return rc;
+  c->launches += 3;
+  c->arena.release_to(mark);
+  return TSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------
+int op_attention_unfused(Ctx* c, const AttnArgs& a) {
+  if (a.causal) return c->fail(TSD_ERR_INVALID, "attention: causal mask is CLIP-only (out of scope)");
+  const int C = a.heads * a.d;
+  const int ldS = (a.Tk + 3) / 4 * 4;
+  const float scale = 1.0f / sqrtf((float)a.d);
+  const size_t mark = c->arena.mark();
+  const int BH = a.heads;  // one batch element at a time (merged O layout has two-level strides)
+  float* S = c->arena.alloc_n<float>((size_t)BH * a.Tq * ldS);
+  float* Vt = c->arena.alloc_n<float>((size_t)BH * a.d * ldS);
+  float* cst = c->arena.alloc_n<float>((size_t)BH * a.Tk * 2);
+  if (!S || !Vt || !cst) return c->fail(TSD_ERR_OOM, "attention(unfused): arena exhausted (score tensor)");
+  for (int b = 0; b < a.batch; ++b) {
+    const float* Q = a.Q + (long long)b * a.heads * a.Tq * a.d;
+    const float* K = a.K + (long long)b * a.heads * a.Tk * a.d;
+    const float* V = a.V + (long long)b * a.heads * a.Tk * a.d;
+    GemmArgs g;
+    g.A = Q; g.M = a.Tq; g.K = a.d; g.lda = a.d; g.a_bs = (long long)a.Tq * a.d;
+    g.B = K; g.N = a.Tk; g.ldb = a.d; g.b_bs = (long long)a.Tk * a.d;
+    g.batch = BH;
+    g.D = S; g.ldd = ldS; g.d_bs = (long long)a.Tq * ldS;
+    g.alpha = scale;
+    int rc = TSD_OK;
+    if (ldS != a.Tk) {  // pad columns feed the P.V GEMM as K: they must be exact zeros
+      rc = c->check(cudaMemsetAsync(S, 0, sizeof(float) * (size_t)BH * a.Tq * ldS, c->stream), "memset");
+      if (rc) return rc;
+    }
+    rc = op_gemm(c, g);
+    if (rc) return rc;
+    {
+      TimedScope ts(c, FAM_ATTN, 0);
+      rc = c->check(launch_softmax(S, BH, a.Tq, a.Tk, ldS, a.softmax_axis, 1.0f, cst, c->stream),
+                    "softmax launch");
+      if (rc) return rc;
+      c->launches += 2;
+      rc = c->check(cudaMemsetAsync(Vt, 0, sizeof(float) * (size_t)BH * a.d * ldS, c->stream), "memset");
+      if (rc) return rc;
+      rc = c->check(launch_transpose_ld(V, Vt, BH, a.Tk, a.d, ldS, c->stream), "transpose launch");
+      if (rc) return rc;
+      c->launches++;
+    }
+    GemmArgs h;
+    h.A = S; h.M = a.Tq; h.K = ldS; h.lda = ldS; h.a_bs = (long long)a.Tq * ldS;
+    h.B = Vt; h.N = a.d; h.ldb = ldS; h.b_bs = (long long)a.d * ldS;
+    h.batch = BH;
+    h.D = a.O + (long long)b * a.Tq * C; h.ldd = C; h.d_bs = a.d;
+    rc = op_gemm(c, h);
+    if (rc) return rc;
+  }
+  c->arena.release_to(mark);
+  return TSD_OK;
+}
+
+int op_attention(Ctx* c, const AttnArgs& a) {
+  if (a.Tq <= 0 || a.Tk <= 0 || a.d <= 0) return c->fail(TSD_ERR_INVALID, "attention: empty problem");
+  if (c->fused_attention && attention_fused_supported(a.d, a.causal)) return attention_fused(c, a);
+  return op_attention_unfused(c, a);
+}
+
+}  // namespace tsd

@@ -1,0 +1,157 @@
+// Device runtime under the C ABI: context (device, stream, workspace arena, TMA descriptor
+// encoder), and the op layer the model graphs are composed from.  All pointers handled here
+// are device pointers; activations are fp32 NHWC.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tsd_b200.h"  // status codes
+
+namespace tsd {
+
+struct Status {
+  int code = 0;  // 0 = OK (C ABI status)
+  std::string msg;
+  bool ok() const { return code == 0; }
+};
+
+
+// Bump allocator over one cudaMalloc'd block; reset() at the top of every forward so the same
+// call sequence yields the same addresses (CUDA-graph friendly, no allocation in the hot loop).
+class Arena {
+ public:
+  ~Arena();
+  int reserve(size_t bytes);
+  void reset() { off_ = 0; }
+  void* alloc(size_t bytes);  // 1024 B aligned; nullptr on exhaustion
+  template <class T>
+  T* alloc_n(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  size_t capacity() const { return cap_; }
+  size_t used() const { return off_; }
+  size_t high_water() const { return high_; }
+  size_t mark() const { return off_; }
+  void release_to(size_t m) { off_ = m; }
+
+ private:
+  uint8_t* base_ = nullptr;
+  size_t cap_ = 0, off_ = 0, high_ = 0;
+};
+
+using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct KernelTimer;  // optional per-launch CUDA-event timing (bench roofline leg)
+
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  PFN_encodeTiled encode = nullptr;
+  Arena arena;
+  std::string last_error;
+  int sm_count = 148;
+  int softmax_axis = 0;     // 0 = query axis (reference Softmax(dim=2), Q3) ; 1 = key axis
+  int fused_attention = 1;  // 1 = tcgen05 fused kernel ; 0 = GEMM + softmax + GEMM
+  int layernorm_mode = 0;   // 0 = global statistics (reference, Q5) ; 1 = per token
+  int force_bn = 0, force_splits = 0;  // test/tuning overrides for the GEMM tile heuristic
+  KernelTimer* timer = nullptr;
+  long long launches = 0;   // kernels launched through this context (bench "gpu_launches")
+
+  int fail(int code, const std::string& msg);
+  int check(cudaError_t e, const char* what);
+};
+
+int ctx_create(int device, Ctx** out, std::string* err);
+void ctx_destroy(Ctx* ctx);
+
+// ---- per-launch timing (used by bench.py to attribute device time to kernel families) ----
+struct KernelTimer {
+  struct Rec {
+    int family;
+    double flops;
+    cudaEvent_t a, b;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t next = 0;
+  cudaEvent_t get();
+};
+enum KernelFamily { FAM_GEMM = 0, FAM_ATTN = 1, FAM_NORM = 2, FAM_OTHER = 3, FAM_COUNT = 4 };
+struct TimedScope {
+  Ctx* c;
+  int idx = -1;
+  TimedScope(Ctx* ctx, int family, double flops);
+  ~TimedScope();
+};
+
+// ---------------------------------------------------------------------------------------
+// op layer
+// ---------------------------------------------------------------------------------------
+struct GemmArgs {
+  // A: [batch][M][K] row-major, row stride lda (elements), batch stride a_bs
+  const float* A = nullptr;
+  int M = 0, K = 0;
+  long long lda = 0, a_bs = 0;
+  // B: [batch][N][K] row-major (K-major "weight" layout), row stride ldb
+  const float* B = nullptr;
+  int N = 0;
+  long long ldb = 0, b_bs = 0;
+  int batch = 1;
+  // D: [batch][M][ldd]
+  float* D = nullptr;
+  long long ldd = 0, d_bs = 0;
+  const float* bias = nullptr;      // [N]
+  const float* row_bias = nullptr;  // [M]
+  const float* residual = nullptr;  // [batch][M][ldr]
+  long long ldr = 0, r_bs = 0;
+  float alpha = 1.0f;
+  int geglu = 0;                    // N counts both halves; D gets N/2 columns
+  int split_n = 0;                  // >0: column n goes to D + (n/split_n)*split_stride + n%split_n
+  long long split_stride = 0;
+  int round_tf32 = 0;
+  int force_bn = 0, force_splits = 0;  // tuning / tests
+};
+int op_gemm(Ctx* c, const GemmArgs& a);
+
+struct ConvArgs {
+  const float* x = nullptr;  // [N][H][W][Cin]
+  int N = 1, H = 0, W = 0, Cin = 0, Cout = 0;
+  int k = 3, pad = 1, stride = 1;
+  const float* w = nullptr;     // [Cout][k*k*Cin]  (O,(kh,kw),I)
+  const float* bias = nullptr;  // [Cout]
+  const float* residual = nullptr;  // [N][Ho][Wo][Cout]
+  float* out = nullptr;             // [N][Ho][Wo][Cout]
+  int round_tf32 = 0;
+  int force_bn = 0, force_splits = 0;
+};
+int op_conv2d(Ctx* c, const ConvArgs& a);
+inline int conv_out_dim(int in, int k, int pad, int stride) { return (in + 2 * pad - k) / stride + 1; }
+
+// GroupNorm(+SiLU)(+2x nearest upsample). stats scratch comes from the arena.
+int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,
+                  const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
+                  int round_tf32);
+
+struct AttnArgs {
+  // per (batch b, head h): Q [Tq][d], K [Tk][d], V [Tk][d], contiguous blocks
+  // (reference raw-reshape head split, attention.mojo:29-44: head h = flat block h of the
+  // [T][C] projection).  Batch stride = heads * T * d.
+  const float* Q = nullptr;
+  const float* K = nullptr;
+  const float* V = nullptr;
+  int batch = 1, heads = 1, Tq = 0, Tk = 0, d = 0;
+  float* O = nullptr;  // merged [batch][Tq][heads*d]: O[t][h*d + j]  (attention.mojo:61-62)
+  int softmax_axis = 0;
+  int causal = 0;
+};
+int op_attention(Ctx* c, const AttnArgs& a);
+int op_attention_unfused(Ctx* c, const AttnArgs& a);
+
+}  // namespace tsd

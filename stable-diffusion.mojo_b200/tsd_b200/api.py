@@ -1,0 +1,210 @@
+"""numpy-facing wrapper over the C ABI: one method per entry point of include/tsd_b200.h.
+
+Arrays go in and come out in the reference's layouts (Matrix (dim0,dim1,dim2) row-major:
+images (C,H,W), sequences (1,T,C); conv kernels OIHW; linear weights [out][in]).
+Status codes become TsdError; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import TsdError
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """tsd_ctx: one device, one stream, one workspace (tsd_init / tsd_shutdown)."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        rc = self.L.tsd_init(device, C.byref(h))
+        if rc != 0:
+            raise TsdError(rc, self.L.tsd_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tsd_shutdown(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise TsdError(rc, self.L.tsd_last_error(self.h).decode())
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.L.tsd_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int32()
+        self._ck(self.L.tsd_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        self._ck(self.L.tsd_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.L.tsd_launch_count(self.h))
+
+    # -- ops ----------------------------------------------------------------------------------
+    def conv2d(self, x, weight, bias=None, pad=0, stride=1):
+        x = _f32(x)
+        squeeze = x.ndim == 3
+        if squeeze:
+            x = x[None]
+        weight = _f32(weight)
+        n, cin, h, w = x.shape
+        cout, cin2, k, k2 = weight.shape
+        if cin2 != cin or k != k2:
+            raise TsdError(1, "conv2d: weight shape does not match input channels")
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        out = np.empty((n, cout, max(ho, 0), max(wo, 0)), np.float32)
+        b = None if bias is None else _f32(bias)
+        self._ck(self.L.tsd_conv2d(self.h, _p(x), n, cin, h, w, _p(weight), _p(b), cout, k, pad, stride,
+                                   _p(out)))
+        return out[0] if squeeze else out
+
+    def linear(self, x, weight, bias=None):
+        x = _f32(x)
+        weight = _f32(weight)
+        shp = x.shape
+        in_f = shp[-1]
+        rows = int(np.prod(shp[:-1]))
+        out_f = weight.shape[0]
+        if weight.shape[1] != in_f:
+            raise TsdError(1, "linear: invalid input dimensions")
+        out = np.empty(shp[:-1] + (out_f,), np.float32)
+        b = None if bias is None else _f32(bias)
+        self._ck(self.L.tsd_linear(self.h, _p(x), 1, rows, in_f, _p(weight), _p(b), out_f, _p(out)))
+        return out
+
+    def matmul(self, a, b):
+        a, b = _f32(a), _f32(b)
+        c, m, k = a.shape
+        c2, k2, n = b.shape
+        if c != c2 or k != k2:
+            raise TsdError(1, "matmul: non-matching dimensions")
+        out = np.empty((c, m, n), np.float32)
+        self._ck(self.L.tsd_matmul(self.h, _p(a), _p(b), c, m, k, n, _p(out)))
+        return out
+
+    def groupnorm(self, x, groups, eps=1e-5, gamma=None, beta=None):
+        x = _f32(x)
+        squeeze = x.ndim == 3
+        if squeeze:
+            x = x[None]
+        n, c, h, w = x.shape
+        out = np.empty_like(x)
+        g = None if gamma is None else _f32(gamma)
+        b = None if beta is None else _f32(beta)
+        self._ck(self.L.tsd_groupnorm(self.h, _p(x), n, c, h, w, groups, eps, _p(g), _p(b), _p(out)))
+        return out[0] if squeeze else out
+
+    def layernorm(self, x):
+        x = _f32(x)  # (C, T, 1)
+        c, t = x.shape[0], x.shape[1]
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_layernorm(self.h, _p(x), c, t, _p(out)))
+        return out
+
+    def silu(self, x):
+        x = _f32(x)
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_silu(self.h, _p(x), x.size, _p(out)))
+        return out
+
+    def gelu(self, x):
+        x = _f32(x)
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_gelu(self.h, _p(x), x.size, _p(out)))
+        return out
+
+    def upsample2x(self, x):
+        x = _f32(x)
+        c, h, w = x.shape
+        out = np.empty((c, 2 * h, 2 * w), np.float32)
+        self._ck(self.L.tsd_upsample2x(self.h, _p(x), c, h, w, _p(out)))
+        return out
+
+    def softmax(self, x, dim=2):
+        x = _f32(x)
+        c, r, cc = x.shape
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_softmax(self.h, _p(x), c, r, cc, dim, _p(out)))
+        return out
+
+    def attention_core(self, q, k, v):
+        q, k, v = _f32(q), _f32(k), _f32(v)
+        h, tq, d = q.shape
+        tk = k.shape[1]
+        out = np.empty((tq, h * d), np.float32)
+        self._ck(self.L.tsd_attention_core(self.h, _p(q), _p(k), _p(v), h, tq, tk, d, _p(out)))
+        return out
+
+    def self_attention(self, x, n_heads, w_in, b_in, w_out, b_out):
+        x = _f32(x)
+        t, c = x.shape[-2], x.shape[-1]
+        w_in, w_out = _f32(w_in), _f32(w_out)
+        b_in = None if b_in is None else _f32(b_in)
+        b_out = None if b_out is None else _f32(b_out)
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_self_attention(self.h, _p(x), t, c, n_heads, _p(w_in), _p(b_in), _p(w_out),
+                                           _p(b_out), _p(out)))
+        return out
+
+    def cross_attention(self, x, context, n_heads, wq, bq, wk, bk, wv, bv, wo, bo):
+        x, context = _f32(x), _f32(context)
+        t, c = x.shape[-2], x.shape[-1]
+        tk, dc = context.shape[-2], context.shape[-1]
+        arrs = [None if a is None else _f32(a) for a in (wq, bq, wk, bk, wv, bv, wo, bo)]
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_cross_attention(self.h, _p(x), t, c, _p(context), tk, dc, n_heads,
+                                            *[_p(a) for a in arrs], _p(out)))
+        return out
+
+    def sampler_step(self, latents, eps_cond, eps_uncond, cfg_scale, noise, sqrt_ab, sqrt_1mab, c0, c1,
+                     sigma):
+        latents, eps_cond = _f32(latents), _f32(eps_cond)
+        eu = None if eps_uncond is None else _f32(eps_uncond)
+        nz = None if noise is None else _f32(noise)
+        out = np.empty_like(latents)
+        self._ck(self.L.tsd_sampler_step(self.h, _p(latents), _p(eps_cond), _p(eu), cfg_scale, _p(nz),
+                                         sqrt_ab, sqrt_1mab, c0, c1, sigma, latents.size, _p(out)))
+        return out
+
+    # -- tuning probes --------------------------------------------------------------------------
+    def bench_gemm(self, m, n, k, batch=1, geglu=0, force_bn=0, force_splits=0, iters=20) -> float:
+        ms = C.c_double()
+        self._ck(self.L.tsd_bench_gemm(self.h, m, n, k, batch, geglu, force_bn, force_splits, iters,
+                                       C.byref(ms)))
+        return ms.value
+
+    def bench_conv(self, n, h, w, cin, cout, k=3, stride=1, force_bn=0, force_splits=0, iters=20) -> float:
+        ms = C.c_double()
+        self._ck(self.L.tsd_bench_conv(self.h, n, h, w, cin, cout, k, stride, force_bn, force_splits,
+                                       iters, C.byref(ms)))
+        return ms.value
