@@ -172,6 +172,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int out_cols = p.geglu ? (p.BN >> 1) : p.BN;
       const int n0 = nt * out_cols;
       const float rb = (p.row_bias != nullptr && row_ok) ? p.row_bias[gm] : 0.0f;
+      const float* cbias = p.bias ? p.bias + (long long)img * p.bias_img_stride : nullptr;
       float* drow = p.D + (long long)batch * p.d_batch_stride + gm * p.ldd;
       const float* rrow =
           p.residual ? p.residual + (long long)batch * p.r_batch_stride + gm * p.ldr : nullptr;
@@ -187,9 +188,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 16; ++j) {
             const int n = n0 + c + j;
             float a = __uint_as_float(v[j]), b = __uint_as_float(g[j]);
-            if (p.bias != nullptr && n < p.n_valid) {
-              a += p.bias[n];
-              b += p.bias[p.n_half + n];
+            if (cbias != nullptr && n < p.n_valid) {
+              a += cbias[n];
+              b += cbias[p.n_half + n];
             }
             f[j] = a * gelu_tanh(b);
           }
@@ -199,7 +200,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 16; ++j) {
             const int n = n0 + c + j;
             float a = __uint_as_float(v[j]) * p.alpha + rb;
-            if (p.bias != nullptr && n < p.n_valid) a += p.bias[n];
+            if (cbias != nullptr && n < p.n_valid) a += cbias[n];
             f[j] = a;
           }
         }
@@ -269,7 +270,7 @@ __global__ void splitk_reduce_kernel(const SplitKReduceParams p) {
     for (int j = 0; j < 4; ++j) {
       if (n + j < p.n_valid) {
         float a = f[j];
-        if (p.bias) a += p.bias[n + j];
+        if (p.bias) a += p.bias[(long long)(row / p.rows_per_img) * p.bias_img_stride + n + j];
         if (p.residual) a += p.residual[(long long)row * p.ldr + n + j];
         if (p.round_tf32) a = round_tf32(a);
         f[j] = a;

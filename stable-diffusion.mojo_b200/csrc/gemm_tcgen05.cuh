@@ -43,6 +43,7 @@ struct GemmKParams {
   int split_n;             // column routing: col n -> (n / split_n) * split_stride + n % split_n
   long long split_stride;
   const float* bias;       // [n] or nullptr
+  int bias_img_stride;     // conv: bias row of image i starts at bias + i * bias_img_stride
   const float* row_bias;   // [m] or nullptr
   const float* residual;   // [b][m][ldr] or nullptr
   long long r_batch_stride;
@@ -61,6 +62,7 @@ struct SplitKReduceParams {
   float* D;
   int ldd;
   const float* bias;
+  int bias_img_stride, rows_per_img;
   const float* residual;
   int ldr;
   int round_tf32;

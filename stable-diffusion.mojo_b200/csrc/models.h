@@ -1,0 +1,155 @@
+// Device-side model graphs composed from the op layer (runtime.h):
+//   Diffusion  = Time_Embedding + UNet + UNet_Output_Layer   (reference diffusion.mojo:5-318)
+//   Decoder    = VAE decoder                                  (reference vae.mojo:5-67, 162-250)
+// plus the denoising loop (reference pipeline.mojo:86-122, sampler.mojo:75-109).
+//
+// Parameters are enumerated in the reference's struct-declaration order (depth first, each
+// layer as weight then bias) and accepted in the reference's layouts (conv OIHW, linear
+// [out][in]); on the device conv kernels are re-laid as [O][kh*kw][I] and every GEMM weight is
+// rounded to TF32 once at load time (the tensor core would otherwise truncate it on every read).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "runtime.h"
+
+struct tsd_ctx;
+
+namespace tsd {
+
+enum ParamKind { P_CONV_W = 0, P_LIN_W = 1, P_VEC = 2 };
+
+struct Param {
+  std::string name;
+  int kind = P_VEC;
+  int O = 0, I = 0, KK = 1;  // conv: (O, I, k*k) ; linear: (O, I) ; vector: (O)
+  long long numel = 0;
+  long long offset = 0;      // float offset in the reference-order blob
+  float init_scale = 0.f;    // synthetic init: U(-s, s)
+  float* dev = nullptr;
+};
+
+struct ParamStore {
+  Ctx* c = nullptr;
+  std::vector<Param> params;
+  long long total = 0;
+  float* block = nullptr;  // one cudaMalloc for all parameters
+  bool loaded = false;
+
+  int add(const std::string& name, int kind, int O, int I, int KK, float init_scale);
+  // conv (weight, bias) -> index of the weight; bias is index + 1
+  int add_conv(const std::string& name, int cin, int cout, int k);
+  // linear (weight[, bias]) -> index of the weight
+  int add_linear(const std::string& name, int in_f, int out_f, bool bias);
+  int allocate();
+  int load(const float* blob, long long n_floats);
+  int init_random(uint64_t seed);
+  int get(int i, float* host_out);
+  const float* w(int i) const { return params[i].dev; }
+  void free_all();
+};
+
+struct Act {
+  float* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  long long numel() const { return (long long)N * H * W * C; }
+  long long pixels() const { return (long long)N * H * W; }
+};
+
+struct ResBlockW {
+  int cin = 0, cout = 0;
+  int conv1 = -1, lin_t = -1, conv2 = -1, skip = -1;  // param indices of the weights
+  int groups = 32;
+};
+struct AttnBlockW {
+  int heads = 8, C = 0;
+  int conv_in = -1, in_proj = -1, out_proj = -1, q = -1, k = -1, v = -1, o = -1, geglu1 = -1, geglu2 = -1,
+      conv_out = -1;
+};
+
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  int n = 0, n_ctx = 0, n_time = 0;
+  int epoch = -1;
+  const void* arena_base = nullptr;
+  long long nodes = 0;  // kernels per replay (bench gpu_launches accounting)
+};
+
+struct Diffusion {
+  tsd_ctx* h = nullptr;
+  Ctx* c = nullptr;
+  tsd_diffusion_config cfg{};
+  ParamStore ps;
+  int te1 = -1, te2 = -1, conv_in = -1, final_conv = -1, down1 = -1, down2 = -1;
+  ResBlockW res[9];
+  AttnBlockW attn[9];
+  // persistent device buffers (fixed addresses -> CUDA-graph friendly)
+  float* x_in = nullptr;      // [max_batch][4][H][W]  reference layout staging
+  float* out_nchw = nullptr;  // [max_batch][4][H][W]
+  float* ctx_in = nullptr;    // [max_batch][77][768]
+  float* time_in = nullptr;   // [max_batch][320]
+  float* kctx[9] = {};        // [n_ctx][77][C] per attention block
+  float* vctx[9] = {};
+  float* tbias[9] = {};       // [max_batch][Cout] : Linear(SiLU(t_emb)) + linear bias + conv1 bias
+  float* temb = nullptr;      // [max_batch][1280]
+  float* x_nhwc = nullptr;    // [max_batch][H][W][4]
+  float* eps_nhwc = nullptr;  // [max_batch][H][W][4]
+  GraphSlot graph;
+  struct LoopCache {
+    GraphSlot slot;
+    int cfg = 0, has_noise = 0;
+    float scale = 0.f;
+    const void* top = nullptr;
+  } loop_cache;
+  std::vector<size_t> ws_cache;
+  int ws_epoch = -1;
+  bool ctx_ready = false;
+  int ctx_n = 0;
+
+  int create();
+  void destroy();
+  size_t workspace_bytes(int n) const;
+  int prepare_context(int n_ctx);                 // ctx_in -> kctx/vctx
+  int prepare_time(int n_time, const float* time_dev /*[n_time][320]*/, float* const* tb_out,
+                   int rows_stride);              // time embedding MLP + 9 ResBlock time linears
+  int unet(int n, int n_ctx, int n_time);         // x_nhwc -> eps_nhwc (uses kctx/vctx/tbias)
+  int forward_dev(const float* x, const float* context, int n_ctx, const float* time, int n_time, int n,
+                  float* out, bool host_ptrs);
+  int run_unet_graph(int n, int n_ctx, int n_time);
+};
+
+struct Decoder {
+  tsd_ctx* h = nullptr;
+  Ctx* c = nullptr;
+  int latent_h = 0, latent_w = 0, max_batch = 1;
+  ParamStore ps;
+  int l1 = -1, l2 = -1, l10 = -1, l15 = -1, l20 = -1, l26 = -1, attn_in = -1, attn_out = -1;
+  ResBlockW res[13];  // l3, l5..l8, l11..l13, l16..l18, l21..l23
+  float* z_in = nullptr;     // [max_batch][4][h][w]
+  float* img_out = nullptr;  // [max_batch][3][8h][8w]
+  float* ping = nullptr;
+  float* pong = nullptr;
+  size_t pp_elems = 0;
+  GraphSlot graph;
+
+  int create();
+  void destroy();
+  size_t workspace_bytes(int n) const;
+  int decode(int n, int rescale);  // z_in -> img_out
+  int forward(const float* z, int n, int rescale, float* img, bool host_ptrs);
+};
+
+int generate_latents(Diffusion& m, const tsd_loop_params& lp, const float* latents_in, const float* context,
+                     int n_ctx, int n, float* latents_out);
+int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, const float* tbias,
+              int tbias_stride, float eps, float* out);
+
+}  // namespace tsd
+
+struct tsd_diffusion {
+  tsd::Diffusion m;
+};
+struct tsd_decoder {
+  tsd::Decoder m;
+};

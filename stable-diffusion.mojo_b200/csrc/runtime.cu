@@ -30,6 +30,7 @@ Arena::~Arena() {
 }
 int Arena::reserve(size_t bytes) {
   if (bytes <= cap_) return TSD_OK;
+  ++gen_;
   if (base_) cudaFree(base_);
   base_ = nullptr;
   cap_ = off_ = 0;
@@ -42,6 +43,11 @@ int Arena::reserve(size_t bytes) {
 }
 void* Arena::alloc(size_t bytes) {
   size_t start = (off_ + 1023) & ~size_t(1023);
+  if (virtual_) {
+    off_ = start + bytes;
+    if (off_ > high_) high_ = off_;
+    return reinterpret_cast<uint8_t*>(uintptr_t(1) << 40) + start;
+  }
   if (start + bytes > cap_) return nullptr;
   off_ = start + bytes;
   if (off_ > high_) high_ = off_;
@@ -266,7 +272,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   const int n_tiles = (((p.geglu ? n_out : p.n_pad)) + out_cols_per_tile - 1) / out_cols_per_tile;
 
   CUtensorMap tmA, tmB;
-  {
+  if (!c->dry_run) {
     uint64_t dims[4] = {(uint64_t)A.K, (uint64_t)A.W, (uint64_t)A.H,
                         (uint64_t)(A.batch > 1 ? A.batch : A.imgs)};
     uint64_t str[4] = {1, (uint64_t)A.ld_w, (uint64_t)A.ld_h,
@@ -278,7 +284,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     int rc = make_tmap(c, &tmA, A.base, 4, dims, str, box);
     if (rc) return rc;
   }
-  {
+  if (!c->dry_run) {
     const int ktot = A.taps * A.K;
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
     uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
@@ -302,6 +308,8 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     rp.D = p.D;
     rp.ldd = p.ldd;
     rp.bias = p.bias;
+    rp.bias_img_stride = p.bias_img_stride;
+    rp.rows_per_img = A.H * A.W;
     rp.residual = p.residual;
     rp.ldr = p.ldr;
     rp.round_tf32 = p.round_tf32;
@@ -312,7 +320,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
 
   dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)(nbatch * p.splits));
   if (m_tiles > 65535 || grid.z > 65535) return c->fail(TSD_ERR_INVALID, "gemm: grid too large");
-  {
+  if (!c->dry_run) {
     TimedScope ts(c, FAM_GEMM, flops);
     int rc = c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages), c->stream),
                       "gemm_tf32_kernel launch");
@@ -375,6 +383,7 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
   p.D = a.out;
   p.ldd = a.Cout;
   p.bias = a.bias;
+  p.bias_img_stride = a.bias_img_stride;
   p.residual = a.residual;
   p.ldr = a.Cout;
   p.alpha = 1.0f;
@@ -408,7 +417,7 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
     const long long M = (long long)a.N * Ho * Wo;
     float* col = c->arena.alloc_n<float>((size_t)M * ktot);
     if (!col) return c->fail(TSD_ERR_OOM, "conv2d: arena exhausted (im2col)");
-    {
+    if (!c->dry_run) {
       TimedScope ts(c, FAM_OTHER, 0);
       int rc = c->check(launch_im2col3x3(a.x, col, a.N, a.H, a.W, a.Cin, a.stride, Ho, Wo, c->stream),
                         "im2col launch");
@@ -431,7 +440,7 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
     return rc;
   }
   // degenerate channel counts (Cin = 4 input convs) and any other geometry: CUDA-core direct conv
-  {
+  if (!c->dry_run) {
     TimedScope ts(c, FAM_OTHER, flops);
     int rc = c->check(launch_conv_direct(a.x, a.w, a.bias, a.out, a.N, a.H, a.W, a.Cin, a.Cout, a.k,
                                          a.pad, a.stride, Ho, Wo, c->stream),
@@ -456,6 +465,10 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
   double* accum = c->arena.alloc_n<double>((size_t)2 * N * G);
   float2* stats = c->arena.alloc_n<float2>((size_t)N * G);
   if (!accum || !stats) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+  if (c->dry_run) {
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
   TimedScope ts(c, FAM_NORM, 0);
   int rc = c->check(launch_group_stats(x, N, (long long)H * W, C, G, eps, accum, stats, c->stream),
                     "group_stats launch");
@@ -485,8 +498,8 @@ int op_attention_unfused(Ctx* c, const AttnArgs& a) {
   if (!S || !Vt || !cst) return c->fail(TSD_ERR_OOM, "attention(unfused): arena exhausted (score tensor)");
   for (int b = 0; b < a.batch; ++b) {
     const float* Q = a.Q + (long long)b * a.heads * a.Tq * a.d;
-    const float* K = a.K + (long long)b * a.heads * a.Tk * a.d;
-    const float* V = a.V + (long long)b * a.heads * a.Tk * a.d;
+    const float* K = a.K + (long long)b * a.kv_batch_stride;
+    const float* V = a.V + (long long)b * a.kv_batch_stride;
     GemmArgs g;
     g.A = Q; g.M = a.Tq; g.K = a.d; g.lda = a.d; g.a_bs = (long long)a.Tq * a.d;
     g.B = K; g.N = a.Tk; g.ldb = a.d; g.b_bs = (long long)a.Tk * a.d;
@@ -494,13 +507,13 @@ int op_attention_unfused(Ctx* c, const AttnArgs& a) {
     g.D = S; g.ldd = ldS; g.d_bs = (long long)a.Tq * ldS;
     g.alpha = scale;
     int rc = TSD_OK;
-    if (ldS != a.Tk) {  // pad columns feed the P.V GEMM as K: they must be exact zeros
+    if (ldS != a.Tk && !c->dry_run) {  // pad columns feed the P.V GEMM as K: they must be exact zeros
       rc = c->check(cudaMemsetAsync(S, 0, sizeof(float) * (size_t)BH * a.Tq * ldS, c->stream), "memset");
       if (rc) return rc;
     }
     rc = op_gemm(c, g);
     if (rc) return rc;
-    {
+    if (!c->dry_run) {
       TimedScope ts(c, FAM_ATTN, 0);
       rc = c->check(launch_softmax(S, BH, a.Tq, a.Tk, ldS, a.softmax_axis, 1.0f, cst, c->stream),
                     "softmax launch");
@@ -524,7 +537,9 @@ int op_attention_unfused(Ctx* c, const AttnArgs& a) {
   return TSD_OK;
 }
 
-int op_attention(Ctx* c, const AttnArgs& a) {
+int op_attention(Ctx* c, const AttnArgs& a_in) {
+  AttnArgs a = a_in;
+  if (a.kv_batch_stride < 0) a.kv_batch_stride = (long long)a.heads * a.Tk * a.d;
   if (a.Tq <= 0 || a.Tk <= 0 || a.d <= 0) return c->fail(TSD_ERR_INVALID, "attention: empty problem");
   if (c->fused_attention && attention_fused_supported(a.d, a.causal)) return attention_fused(c, a);
   return op_attention_unfused(c, a);

@@ -36,10 +36,18 @@ class Arena {
   size_t high_water() const { return high_; }
   size_t mark() const { return off_; }
   void release_to(size_t m) { off_ = m; }
+  // planning mode: allocations succeed against an unbounded fake address range and only the
+  // high-water mark is recorded; nothing may dereference the returned pointers
+  void set_virtual(bool v) { virtual_ = v; off_ = 0; high_ = 0; }
+  bool is_virtual() const { return virtual_; }
+  const void* base() const { return base_; }
+  int generation() const { return gen_; }
 
  private:
   uint8_t* base_ = nullptr;
   size_t cap_ = 0, off_ = 0, high_ = 0;
+  bool virtual_ = false;
+  int gen_ = 0;
 };
 
 using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -63,6 +71,7 @@ struct Ctx {
   int force_bn = 0, force_splits = 0;  // test/tuning overrides for the GEMM tile heuristic
   KernelTimer* timer = nullptr;
   long long launches = 0;   // kernels launched through this context (bench "gpu_launches")
+  bool dry_run = false;     // planning pass: ops allocate workspace but launch nothing
 
   int fail(int code, const std::string& msg);
   int check(cudaError_t e, const char* what);
@@ -125,7 +134,8 @@ struct ConvArgs {
   int N = 1, H = 0, W = 0, Cin = 0, Cout = 0;
   int k = 3, pad = 1, stride = 1;
   const float* w = nullptr;     // [Cout][k*k*Cin]  (O,(kh,kw),I)
-  const float* bias = nullptr;  // [Cout]
+  const float* bias = nullptr;  // [Cout] (image i uses bias + i * bias_img_stride)
+  int bias_img_stride = 0;
   const float* residual = nullptr;  // [N][Ho][Wo][Cout]
   float* out = nullptr;             // [N][Ho][Wo][Cout]
   int round_tf32 = 0;
@@ -150,6 +160,7 @@ struct AttnArgs {
   float* O = nullptr;  // merged [batch][Tq][heads*d]: O[t][h*d + j]  (attention.mojo:61-62)
   int softmax_axis = 0;
   int causal = 0;
+  long long kv_batch_stride = -1;  // elements between batch entries of K/V; -1 = heads*Tk*d, 0 = shared
 };
 int op_attention(Ctx* c, const AttnArgs& a);
 int op_attention_unfused(Ctx* c, const AttnArgs& a);

@@ -208,3 +208,130 @@ class Context:
         self._ck(self.L.tsd_bench_conv(self.h, n, h, w, cin, cout, k, stride, force_bn, force_splits,
                                        iters, C.byref(ms)))
         return ms.value
+
+
+class _Model:
+    """Shared plumbing of the two model handles (parameter blob I/O)."""
+    _prefix = ""
+
+    def _fn(self, name):
+        return getattr(self.ctx.L, f"tsd_{self._prefix}_{name}")
+
+    def num_params(self) -> int:
+        return int(self._fn("num_params")(self.m))
+
+    def param_table(self):
+        """[(name, offset, numel)] in blob order (reference struct-declaration order)."""
+        out = []
+        for i in range(self._fn("param_count")(self.m)):
+            off, n = C.c_int64(), C.c_int64()
+            name = self._fn("param_name")(self.m, i, C.byref(off), C.byref(n))
+            out.append((name.decode(), off.value, n.value))
+        return out
+
+    def load_weights(self, blob):
+        blob = _f32(blob).reshape(-1)
+        self.ctx._ck(self._fn("load_weights")(self.m, _p(blob), blob.size))
+
+    def init_random(self, seed: int):
+        self.ctx._ck(self._fn("init_random")(self.m, C.c_uint64(seed)))
+
+    def get_param(self, i: int) -> np.ndarray:
+        _, _, n = self.param_table()[i]
+        out = np.empty(n, np.float32)
+        self.ctx._ck(self._fn("get_param")(self.m, i, _p(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "m", None) and getattr(self.ctx, "h", None):
+            self._fn("destroy")(self.m)
+        self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Diffusion(_Model):
+    """tsd_diffusion: Diffusion (diffusion.mojo:294-318) = Time_Embedding + UNet + output layer."""
+    _prefix = "diffusion"
+
+    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1, context_len=77, context_dim=768,
+                 mojo_alias_time=False):
+        self.ctx = ctx
+        self.cfg = _lib.DiffusionConfig(latent_h, latent_w, max_batch, context_len, context_dim,
+                                        int(mojo_alias_time))
+        m = C.c_void_p()
+        ctx._ck(ctx.L.tsd_diffusion_create(ctx.h, C.byref(self.cfg), C.byref(m)))
+        self.m = m
+
+    def forward(self, x, context, time):
+        """Diffusion.forward(x, context, time): x (n,4,H,W) or (4,H,W); context (n_ctx,77,768) or
+        (77,768); time (n_time,320) or (320,) -> same shape as x."""
+        x = _f32(x)
+        squeeze = x.ndim == 3
+        if squeeze:
+            x = x[None]
+        context = _f32(context)
+        if context.ndim == 2:
+            context = context[None]
+        time = _f32(time).reshape(-1, 320)
+        out = np.empty_like(x)
+        self.ctx._ck(self.ctx.L.tsd_diffusion_forward(self.m, _p(x), _p(context), context.shape[0], _p(time),
+                                                      time.shape[0], x.shape[0], _p(out)))
+        return out[0] if squeeze else out
+
+    def profile(self, x_dev, ctx_dev, n_ctx, time_dev, n_time, n, out_dev):
+        """Eager forward on device pointers with per-launch CUDA events; returns per-family
+        (ms, flops, launches) for families gemm/conv, attention, norm, other."""
+        ms = (C.c_double * 4)()
+        fl = (C.c_double * 4)()
+        ln = (C.c_int64 * 4)()
+        self.ctx._ck(self.ctx.L.tsd_diffusion_profile(self.m, x_dev, ctx_dev, n_ctx, time_dev, n_time, n, out_dev,
+                                                      ms, fl, ln))
+        fam = ("gemm", "attention", "norm", "other")
+        return {f: dict(ms=ms[i], flops=fl[i], launches=ln[i]) for i, f in enumerate(fam)}
+
+    def generate_latents(self, latents, context, timesteps, time_emb, coef, noise=None, cfg=False,
+                         cfg_scale=7.5):
+        """Whole denoising loop (pipeline.mojo:86-122) on the device.  latents (n,4,H,W);
+        context rows: cond first, then (cfg) uncond; coef (steps,5); noise (steps,n,4,H,W)."""
+        latents = _f32(latents)
+        n = latents.shape[0]
+        context = _f32(context)
+        timesteps = np.ascontiguousarray(timesteps, np.int32)
+        time_emb = _f32(time_emb)
+        coef = _f32(coef)
+        nz = None if noise is None else _f32(noise)
+        lp = _lib.LoopParams(len(timesteps), int(cfg), float(cfg_scale),
+                             timesteps.ctypes.data_as(_lib.c_i32_p), time_emb.ctypes.data_as(_lib.c_float_p),
+                             coef.ctypes.data_as(_lib.c_float_p),
+                             None if nz is None else nz.ctypes.data_as(_lib.c_float_p))
+        out = np.empty_like(latents)
+        self.ctx._ck(self.ctx.L.tsd_generate_latents(self.m, C.byref(lp), _p(latents), _p(context),
+                                                     context.shape[0], n, _p(out)))
+        return out
+
+
+class Decoder(_Model):
+    """tsd_decoder: VAE Decoder (vae.mojo:162-250)."""
+    _prefix = "decoder"
+
+    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1):
+        self.ctx = ctx
+        self.shape = (latent_h, latent_w)
+        m = C.c_void_p()
+        ctx._ck(ctx.L.tsd_decoder_create(ctx.h, latent_h, latent_w, max_batch, C.byref(m)))
+        self.m = m
+
+    def forward(self, z, rescale=False):
+        z = _f32(z)
+        squeeze = z.ndim == 3
+        if squeeze:
+            z = z[None]
+        n, _, h, w = z.shape
+        img = np.empty((n, 3, 8 * h, 8 * w), np.float32)
+        self.ctx._ck(self.ctx.L.tsd_decoder_forward(self.m, _p(z), n, int(rescale), _p(img)))
+        return img[0] if squeeze else img

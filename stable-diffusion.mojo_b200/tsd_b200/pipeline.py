@@ -1,0 +1,67 @@
+"""pipeline.generate (reference pipeline.mojo:13-128) over the C ABI.
+
+The prompt -> CLIP context stage is outside the hot path (CLIP/tokenizer are
+"next"), so `generate` takes the 77x768 context(s) the reference computes at pipeline.mojo:41-53.
+Everything from there on - the denoising loop, CFG, sampler steps, the VAE decode and the final
+rescale/clamp - runs on the device."""
+from __future__ import annotations
+
+import numpy as np
+
+from .api import Context, Decoder, Diffusion
+from .sampler import DDPMSampler, get_time_embedding
+
+
+class Pipeline:
+    def __init__(self, ctx: Context, image_size: int = 512, max_images: int = 1, cfg: bool = True, seed: int = 0,
+                 weights=None):
+        if image_size % 32:
+            raise ValueError("image_size must be a multiple of 32 (latent side a multiple of 4)")
+        self.ctx = ctx
+        self.image_size = image_size
+        self.side = image_size // 8
+        self.cfg = cfg
+        self.max_images = max_images
+        self.diffusion = Diffusion(ctx, self.side, self.side, max_batch=max_images * (2 if cfg else 1))
+        self.decoder = Decoder(ctx, self.side, self.side, max_batch=max_images)
+        if weights is None:
+            self.diffusion.init_random(seed)
+            self.decoder.init_random(seed + 1)
+        else:
+            self.diffusion.load_weights(weights[0])
+            self.decoder.load_weights(weights[1])
+
+    def schedule(self, inference_steps: int, time_as_written: bool = False):
+        s = DDPMSampler()
+        s.set_inference_timesteps(inference_steps)
+        temb = np.stack([get_time_embedding(float(t), time_as_written) for t in s.timesteps])
+        return s.timesteps.astype(np.int32), temb.astype(np.float32), s.coefficient_table()
+
+    def generate(self, context, uncond_context=None, cfg_scale: float = 7.5, inference_steps: int = 20,
+                 seed_val: int = 0, latents=None, noise=None, decode: bool = True, rescale: bool = True):
+        """Returns (images (n,3,S,S) in [0,255], latents (n,4,S/8,S/8)).  context (n|1,77,768);
+        with CFG pass uncond_context of the same shape.  latents/noise default to seeded N(0,1)."""
+        context = np.asarray(context, np.float32)
+        if context.ndim == 2:
+            context = context[None]
+        n = self.max_images if latents is None else np.asarray(latents).shape[0]
+        rng = np.random.default_rng(seed_val)
+        if latents is None:
+            latents = rng.standard_normal((n, 4, self.side, self.side), dtype=np.float32)
+        if noise is None:
+            noise = rng.standard_normal((inference_steps, n, 4, self.side, self.side), dtype=np.float32)
+        use_cfg = uncond_context is not None
+        if use_cfg and not self.cfg:
+            raise ValueError("pipeline was created with cfg=False")
+        ctx_rows = context
+        if use_cfg:
+            u = np.asarray(uncond_context, np.float32)
+            if u.ndim == 2:
+                u = u[None]
+            ctx_rows = np.concatenate([context, u], axis=0)
+        ts, temb, coef = self.schedule(inference_steps)
+        lat = self.diffusion.generate_latents(latents, ctx_rows, ts, temb, coef, noise, cfg=use_cfg,
+                                              cfg_scale=cfg_scale)
+        if not decode:
+            return None, lat
+        return self.decoder.forward(lat, rescale=rescale), lat

@@ -1,0 +1,138 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/tsd_b200.h declares, fails
+loudly without a GPU (no fallback), and the host-side logic (sampler scalars, schedule, sharding,
+gloo collectives with world_size 2) is right."""
+import ctypes as C
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import tsd_oracle as O
+from conftest import ROOT
+from tsd_b200 import _lib, dist, sampler
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 40 and "tsd_diffusion_forward" in syms and "tsd_generate_latents" in syms
+    L = _lib.lib()
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, f"declared in include/tsd_b200.h but not exported: {missing}"
+
+
+def test_library_has_blackwell_sass():
+    """The shipped .so must contain tcgen05 / TMA machine code (UTC*MMA, UTMALDG), not a fallback."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCQMMA" in sass or "UTCMMA" in sass or "UTC" in sass
+    assert "UTMALDG" in sass
+    assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.tsd_init(0, C.byref(h))
+    assert rc == 3  # TSD_ERR_NO_DEVICE
+    assert b"no CPU fallback" in L.tsd_last_error(None)
+    from tsd_b200.api import Context
+    with pytest.raises(_lib.TsdError):
+        Context(0)
+
+
+def test_null_handles_are_rejected():
+    L = _lib.lib()
+    assert L.tsd_shutdown(None) == 1
+    assert L.tsd_conv2d(None, None, 1, 1, 1, 1, None, None, 1, 1, 0, 1, None) == 1
+    assert L.tsd_diffusion_num_params(None) == 0
+    assert L.tsd_launch_count(None) == 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "stable-diffusion.mojo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "tsd_oracle" not in text and "ref_loops" not in text, f"{f} references the oracle"
+
+
+def test_host_sampler_matches_oracle():
+    for steps in (1, 20, 50):
+        a = sampler.DDPMSampler()
+        a.set_inference_timesteps(steps)
+        b = O.DDPMSampler()
+        b.set_inference_timesteps(steps)
+        assert np.array_equal(a.timesteps, b.timesteps)
+        ref = np.stack([b.coefficients(int(t)) for t in b.timesteps])
+        assert np.allclose(a.coefficient_table(), ref, rtol=1e-6)
+    assert np.array_equal(sampler.get_time_embedding(999), O.get_time_embedding(999))
+    assert np.array_equal(sampler.get_time_embedding(500, True), O.get_time_embedding(500, True))
+    s = sampler.DDPMSampler()
+    s.set_inference_timesteps(10)
+    s.set_strength(0.8)
+    assert len(s.timesteps) == 8 and s.start_step == 2
+
+
+def test_shard_indices_partition():
+    for gb in (0, 1, 7, 8, 9, 16):
+        for world in (1, 2, 4, 8):
+            parts = [dist.shard_indices(gb, r, world) for r in range(world)]
+            flat = sorted(i for p in parts for i in p)
+            assert flat == list(range(gb))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        dist.shard_indices(4, 2, 2)
+    # inputs depend on the sample index only -> invariant to the rank count
+    a = dist.sample_inputs(1234, 5, 8, 3)
+    b = dist.sample_inputs(1234, 5, 8, 3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert not np.array_equal(a[0], dist.sample_inputs(1234, 6, 8, 3)[0])
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join({root!r}, "stable-diffusion.mojo_b200"))
+from tsd_b200 import dist
+rank, world, _ = dist.init_process_group("gloo")
+ctx = np.arange(2 * 77 * 768, dtype=np.float32).reshape(2, 77, 768) if rank == 0 else None
+got = dist.broadcast_context(ctx, (2, 77, 768))
+assert got.shape == (2, 77, 768) and got[1, 76, 767] == 2 * 77 * 768 - 1
+gb = 5
+mine = dist.shard_indices(gb, rank, world)
+local = np.stack([np.full((4, 2, 2), i, np.float32) for i in mine]) if mine else np.zeros((0, 4, 2, 2), np.float32)
+full = dist.gather_samples(local, gb)
+if rank == 0:
+    assert full.shape == (gb, 4, 2, 2) and all(full[i, 0, 0, 0] == i for i in range(gb))
+else:
+    assert full is None
+assert dist.max_over_ranks(float(rank + 1)) == float(world)
+dist.barrier()
+print("RANK_OK", rank)
+"""
+
+
+def test_gloo_world2_broadcast_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"RANK_OK {r}" in o, o

@@ -1,0 +1,252 @@
+"""GPU parity, model level, through the C ABI: Diffusion.forward, the denoising loop with CFG,
+Decoder.forward - against the fp64 oracle at sizes it finishes in seconds, against the committed
+full-size goldens (BASELINE config 2 shapes), and through size-independent properties.
+Tolerance for TF32 model-level outputs: max|a-b|/max|b| <= 2e-2; measured
+values are printed."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+import tsd_oracle as O
+from conftest import GOLDEN, relerr
+from tsd_b200.api import Decoder, Diffusion
+from tsd_b200._lib import TsdError
+from tsd_b200.pipeline import Pipeline
+from tsd_b200 import sampler as host_sampler
+
+pytestmark = pytest.mark.gpu
+
+TOL_MODEL = 2e-2
+UNET_SEED, DEC_SEED = 1234, 1235
+
+
+@pytest.fixture(scope="module")
+def diff8(ctx):
+    m = Diffusion(ctx, 8, 8, max_batch=4)
+    m.init_random(UNET_SEED)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def diff64(ctx):
+    m = Diffusion(ctx, 64, 64, max_batch=2)
+    m.init_random(UNET_SEED)
+    yield m
+    m.close()
+
+
+def test_param_inventory_and_synthetic_weights(diff8, unet_weights):
+    assert diff8.num_params() == 299_742_724
+    table = diff8.param_table()
+    specs = synth.diffusion_specs()
+    assert [t[0] for t in table] == [s[0] for s in specs]
+    assert [t[2] for t in table] == [int(np.prod(s[1])) for s in specs]
+    # device-generated tensors equal the CPU twin (TF32-rounded for GEMM weights, exact for vectors)
+    for name in ("time_embed.layer1.weight", "unet.layer2.layer2.weight", "unet.layer3.layer8.bias",
+                 "unet.layer5.layer6.weight", "final.layer2.weight"):
+        i = [t[0] for t in table].index(name)
+        got = diff8.get_param(i).reshape(specs[i][1])
+        want = unet_weights[name]
+        if name.endswith(".weight"):
+            want = synth.round_tf32(want)
+        assert np.array_equal(got, want), name
+
+
+def test_unet8_matches_oracle_golden(diff8, golden_small):
+    g = golden_small
+    y = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    e = relerr(y, g["unet8_y"])
+    print(f"unet 8x8 latent rel_linf vs fp64 oracle: {e:.2e}")
+    assert e < TOL_MODEL
+    y2 = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])   # CUDA-graph replay == first (eager) pass
+    assert np.array_equal(y, y2)
+
+
+def test_unet8_switches(ctx, diff8, golden_small):
+    g = golden_small
+    ctx.set_option("softmax_axis", 1)
+    ctx.set_option("layernorm_mode", 1)
+    try:
+        y = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    finally:
+        ctx.set_option("softmax_axis", 0)
+        ctx.set_option("layernorm_mode", 0)
+    assert relerr(y, g["unet8_y_intended"]) < TOL_MODEL
+    m = Diffusion(ctx, 8, 8, max_batch=1, mojo_alias_time=True)
+    m.init_random(UNET_SEED)
+    assert relerr(m.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"]), g["unet8_y_alias"]) < TOL_MODEL
+    m.close()
+
+
+def test_unet_batch_semantics(diff8, golden_small):
+    g = golden_small
+    rng = np.random.default_rng(3)
+    x2 = np.stack([g["unet8_x"], rng.standard_normal((4, 8, 8), dtype=np.float32)])
+    c2 = np.stack([g["unet8_ctx"], rng.standard_normal((77, 768), dtype=np.float32)])
+    t2 = np.stack([g["unet8_t"], O.get_time_embedding(500)])
+    y = diff8.forward(x2, c2, t2)
+    assert relerr(y[0], g["unet8_y"]) < TOL_MODEL                        # images are independent
+    y1 = diff8.forward(x2[1], c2[1], t2[1])
+    assert relerr(y[1], y1) < 1e-5
+    ys = diff8.forward(np.stack([x2[0], x2[0]]), c2[0], t2[0])          # shared context/time rows
+    assert np.array_equal(ys[0], ys[1])
+
+
+def test_unet_eager_equals_graph(ctx, diff8, golden_small):
+    g = golden_small
+    y_graph = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    ctx.set_option("cuda_graph", 0)
+    try:
+        y_eager = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    finally:
+        ctx.set_option("cuda_graph", 1)
+    assert np.array_equal(y_graph, y_eager)
+
+
+def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
+    g = golden_small
+    ctx.set_option("fused_attention", 0)
+    try:
+        y = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    finally:
+        ctx.set_option("fused_attention", 1)
+    assert relerr(y, g["unet8_y"]) < TOL_MODEL
+
+
+def test_load_weights_blob_path(ctx, golden_small):
+    """tsd_diffusion_load_weights with a dense random blob (non-zero conv biases), 16x16 latent,
+    oracle evaluated on the same blob."""
+    specs = synth.diffusion_specs()
+    blob = synth.random_blob(specs, 77)
+    m = Diffusion(ctx, 16, 16, max_batch=1)
+    with pytest.raises(TsdError):
+        m.forward(np.zeros((4, 16, 16), np.float32), golden_small["unet8_ctx"], golden_small["unet8_t"])  # no weights yet
+    with pytest.raises(TsdError):
+        m.load_weights(blob[:-1])
+    m.load_weights(blob)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((4, 16, 16), dtype=np.float32)
+    cx = rng.standard_normal((77, 768), dtype=np.float32)
+    t = O.get_time_embedding(321)
+    y = m.forward(x, cx, t)
+    ref = O.diffusion_forward(O.Ops("np", np.float64), synth.BlobWeights(specs, blob), x, cx, t)
+    e = relerr(y, ref)
+    print(f"unet 16x16 latent (blob weights) rel_linf: {e:.2e}")
+    assert e < TOL_MODEL
+    m.close()
+
+
+def test_shape_validation(ctx):
+    with pytest.raises(TsdError):
+        Diffusion(ctx, 6, 8)          # latent side must be a multiple of 4 (Q8 round trip)
+    with pytest.raises(TsdError):
+        Diffusion(ctx, 8, 8, max_batch=0)
+
+
+def test_unet64_full_size_golden(diff64):
+    """BASELINE config 2 shape: 64x64x4 latent, 77x768 context, one UNet step."""
+    g = np.load(os.path.join(GOLDEN, "unet64.npz"))
+    y = diff64.forward(g["x"], g["ctx"], g["t"])
+    e = relerr(y, g["y"])
+    print(f"unet 64x64 latent rel_linf vs fp64 oracle golden: {e:.2e}")
+    assert e < TOL_MODEL
+    # properties at full size: batch invariance and determinism
+    y2 = diff64.forward(np.stack([g["x"], g["x"]]), g["ctx"], g["t"])
+    assert np.array_equal(y2[0], y2[1])
+    assert relerr(y2[0], y) < 1e-5
+
+
+def test_loop_with_cfg_matches_oracle(diff8, golden_small):
+    g = golden_small
+    ts, temb, coef = _schedule(3)
+    ctx_rows = np.stack([g["unet8_ctx"], g["loop8_uctx"]])
+    lat = diff8.generate_latents(g["unet8_x"][None], ctx_rows, ts, temb, coef, g["loop8_noise"][:, None], cfg=True,
+                                 cfg_scale=7.5)
+    e = relerr(lat[0], g["loop8_lat"])
+    print(f"3-step CFG loop rel_linf: {e:.2e}")
+    assert e < 5e-2   # three UNet evaluations x CFG scale 7.5 amplify the TF32 error
+    lat2 = diff8.generate_latents(g["unet8_x"][None], ctx_rows, ts, temb, coef, g["loop8_noise"][:, None], cfg=True,
+                                  cfg_scale=7.5)
+    assert np.array_equal(lat, lat2)   # graph replay is deterministic
+
+
+def _schedule(steps):
+    s = host_sampler.DDPMSampler()
+    s.set_inference_timesteps(steps)
+    temb = np.stack([host_sampler.get_time_embedding(float(t)) for t in s.timesteps])
+    return s.timesteps.astype(np.int32), temb, s.coefficient_table()
+
+
+def test_loop_properties(diff8, golden_small):
+    g = golden_small
+    ts, temb, coef = _schedule(2)
+    x = np.stack([g["unet8_x"], g["unet8_x"][::-1].copy()])
+    noise = np.random.default_rng(5).standard_normal((2, 2, 4, 8, 8), dtype=np.float32)
+    cx = g["unet8_ctx"][None]
+    both = diff8.generate_latents(x, cx, ts, temb, coef, noise)
+    one = diff8.generate_latents(x[1:], cx, ts, temb, coef, noise[:, 1:])
+    assert relerr(both[1], one[0]) < 1e-5                 # sharding invariance: a sample does not depend on its batch
+    # CFG with identical cond/uncond contexts is the plain path
+    same = diff8.generate_latents(x[:1], np.stack([cx[0], cx[0]]), ts, temb, coef, noise[:, :1], cfg=True, cfg_scale=3.0)
+    assert relerr(same[0], both[0]) < 1e-4
+    # the loop equals step-by-step Diffusion.forward + tsd_sampler_step
+    lat = x[:1].copy()
+    for i, t in enumerate(ts):
+        eps = diffusion_step(diff8, lat, cx, temb[i])
+        lat = diff8.ctx.sampler_step(lat, eps, None, 1.0, noise[i, :1] if t > 0 else None, *[float(v) for v in coef[i]])
+    assert relerr(lat[0], both[0]) < 1e-4
+
+
+def diffusion_step(m, lat, cx, temb):
+    return m.forward(lat, cx, temb)
+
+
+@pytest.fixture(scope="module")
+def dec8(ctx):
+    m = Decoder(ctx, 8, 8, max_batch=2)
+    m.init_random(DEC_SEED)
+    yield m
+    m.close()
+
+
+def test_decoder8_matches_oracle_golden(dec8, golden_small):
+    g = golden_small
+    assert dec8.num_params() == 49_467_159
+    y = dec8.forward(g["dec8_z"])
+    e = relerr(y, g["dec8_y"])
+    print(f"decoder 8x8 latent rel_linf vs fp64 oracle: {e:.2e}")
+    assert y.shape == (3, 64, 64) and e < TOL_MODEL
+    img = dec8.forward(g["dec8_z"], rescale=True)
+    assert img.min() >= 0 and img.max() <= 255
+    assert np.abs(img - O.rescale_image(g["dec8_y"])).max() < 255 * TOL_MODEL
+    y2 = dec8.forward(np.stack([g["dec8_z"], g["dec8_z"] * 0.5]))
+    assert relerr(y2[0], y) < 1e-5
+
+
+def test_decoder64_full_size_golden(ctx):
+    g = np.load(os.path.join(GOLDEN, "decoder64.npz"))
+    m = Decoder(ctx, 64, 64, max_batch=1)
+    m.init_random(DEC_SEED)
+    y = m.forward(g["z"])
+    assert y.shape == (3, 512, 512)
+    e = relerr(y[:, 3::8, 5::8], g["y_sub"])
+    print(f"decoder 64x64 latent rel_linf vs fp64 oracle golden (subsample): {e:.2e}")
+    assert e < TOL_MODEL
+    assert np.allclose(y.mean(axis=(1, 2)), g["y_mean"], atol=TOL_MODEL * float(g["y_absmax"]))
+    assert np.allclose(y.std(axis=(1, 2)), g["y_std"], rtol=TOL_MODEL)
+    m.close()
+
+
+def test_pipeline_generate_small(ctx):
+    p = Pipeline(ctx, image_size=64, max_images=2, cfg=True, seed=5)
+    rng = np.random.default_rng(6)
+    c = rng.standard_normal((1, 77, 768), dtype=np.float32)
+    u = rng.standard_normal((1, 77, 768), dtype=np.float32)
+    img, lat = p.generate(c, u, cfg_scale=7.5, inference_steps=2, seed_val=9)
+    assert img.shape == (2, 3, 64, 64) and lat.shape == (2, 4, 8, 8)
+    assert np.isfinite(img).all() and img.min() >= 0 and img.max() <= 255
+    img2, lat2 = p.generate(c, u, cfg_scale=7.5, inference_steps=2, seed_val=9)
+    assert np.array_equal(lat, lat2) and np.array_equal(img, img2)

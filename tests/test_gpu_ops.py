@@ -1,0 +1,179 @@
+"""GPU parity, op level: every op-granular entry point of include/tsd_b200.h called through the
+C ABI (host buffers in the reference's layouts) against the fp64 oracle on the same seeded
+inputs.  Tolerances (max|a-b|/max|b|):
+  TF32 tensor-core ops (conv, linear, matmul, attention): 5e-3   (10-bit mantissa products,
+       fp32 accumulate; measured ~6e-4 .. 2e-3)
+  CUDA-core fp32 ops (norms, activations, softmax, sampler, degenerate-channel convs): 2e-5
+  pure data movement (upsample): exact."""
+import numpy as np
+import pytest
+
+import tsd_oracle as O
+from conftest import relerr
+from tsd_b200._lib import TsdError
+
+pytestmark = pytest.mark.gpu
+
+TOL_TF32 = 5e-3
+TOL_FP32 = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    return O.Ops("np", np.float64)
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout,k,pad,stride", [
+    (1, 32, 16, 16, 32, 3, 1, 1),      # smallest tensor-core conv
+    (2, 64, 16, 16, 96, 3, 1, 1),      # batch of images
+    (1, 320, 32, 32, 320, 3, 1, 1),    # UNet layer-2 shape at a 32x32 latent
+    (1, 320, 16, 16, 640, 3, 1, 1),    # channel growth
+    (1, 320, 32, 32, 320, 3, 1, 2),    # stride-2 downsample (diffusion.mojo:180)
+    (1, 4, 32, 32, 320, 3, 1, 1),      # conv_in: Cin=4 -> CUDA-core direct conv
+    (1, 320, 32, 32, 4, 3, 1, 1),      # output layer: Cout=4
+    (1, 128, 24, 40, 3, 3, 1, 1),      # VAE l26: Cout=3, ragged W
+    (1, 320, 16, 16, 320, 1, 0, 1),    # 1x1 conv
+    (1, 96, 12, 20, 48, 3, 1, 1),      # ragged tile edges (W not a divisor of 128)
+    (1, 4, 8, 8, 4, 1, 0, 1),          # VAE l1
+    (3, 36, 5, 7, 20, 3, 1, 1),        # odd everything
+])
+def test_conv2d(ctx, ops, n, cin, h, w, cout, k, pad, stride):
+    rng = np.random.default_rng(cin * 1000 + cout + h)
+    x = rng.standard_normal((n, cin, h, w), dtype=np.float32)
+    wt = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32)
+    b = rng.standard_normal(cout, dtype=np.float32)
+    y = ctx.conv2d(x, wt, b, pad=pad, stride=stride)
+    ref = np.stack([ops.conv2d(x[i], wt, b, pad, stride) for i in range(n)])
+    assert y.shape == ref.shape
+    tol = TOL_FP32 if cin < 32 else TOL_TF32
+    assert relerr(y, ref) < tol
+
+
+def test_conv2d_no_bias_and_errors(ctx, ops):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((64, 8, 8), dtype=np.float32)
+    wt = (rng.standard_normal((64, 64, 3, 3)) / 24).astype(np.float32)
+    assert relerr(ctx.conv2d(x, wt, None, pad=1), ops.conv2d(x, wt, None, 1)) < TOL_TF32
+    with pytest.raises(TsdError):   # kernel larger than the padded input -> status, never a crash
+        ctx.conv2d(x[:, :2, :2], wt, None, pad=0)
+    with pytest.raises(TsdError):
+        ctx.conv2d(x, wt[:, :32], None, pad=1)
+
+
+@pytest.mark.parametrize("rows,fin,fout,bias", [
+    (128, 32, 16, True), (256, 320, 320, True), (200, 320, 960, False), (1024, 640, 5120, True),
+    (77, 768, 320, False), (333, 40, 48, True), (1, 320, 1280, True), (3, 1280, 640, True), (50, 30, 18, True),
+])
+def test_linear(ctx, ops, rows, fin, fout, bias):
+    rng = np.random.default_rng(rows + fin)
+    x = rng.standard_normal((1, rows, fin), dtype=np.float32)
+    w = (rng.standard_normal((fout, fin)) / np.sqrt(fin)).astype(np.float32)
+    b = rng.standard_normal(fout, dtype=np.float32) if bias else None
+    y = ctx.linear(x, w, b)
+    ref = ops.linear(x[0], w, b)[None]
+    tol = TOL_FP32 if (rows <= 4 or fin % 4 or fout % 4) else TOL_TF32   # M<=4 / ragged: CUDA-core GEMV
+    assert relerr(y, ref) < tol
+    with pytest.raises(TsdError):
+        ctx.linear(x, w[:, :-1], b)
+
+
+@pytest.mark.parametrize("c,m,k,n", [(8, 256, 40, 256), (8, 512, 80, 77), (2, 130, 36, 50), (1, 64, 512, 512)])
+def test_matmul(ctx, ops, c, m, k, n):
+    rng = np.random.default_rng(m + n)
+    a = rng.standard_normal((c, m, k), dtype=np.float32)
+    b = rng.standard_normal((c, k, n), dtype=np.float32)
+    assert relerr(ctx.matmul(a, b), ops.matmul(a, b)) < TOL_TF32
+    with pytest.raises(TsdError):
+        ctx.matmul(a, b[:, :-1])
+
+
+@pytest.mark.parametrize("c,h,w,g,eps", [(320, 16, 16, 32, 1e-5), (64, 8, 8, 16, 1e-5), (320, 8, 8, 320, 1e-5),
+                                         (30, 5, 7, 3, 1e-6), (1920, 16, 16, 32, 1e-5), (128, 64, 64, 32, 1e-5)])
+def test_groupnorm(ctx, ops, c, h, w, g, eps):
+    rng = np.random.default_rng(c + g)
+    x = (rng.standard_normal((c, h, w)) * 2 + 0.5).astype(np.float32)
+    assert relerr(ctx.groupnorm(x, g, eps), ops.group_norm(x, g, eps)) < TOL_FP32
+    with pytest.raises(TsdError):   # reference: "does not evenly divide" -> null Matrix (utils.mojo:1851-1853)
+        ctx.groupnorm(x, g + 1 if c % (g + 1) else 7, eps)
+
+
+def test_layernorm_both_modes(ctx, ops):
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((320, 256, 1)) * 1.5 - 0.3).astype(np.float32)   # reference (C,T,1) layout
+    want = ops.layer_norm(x[:, :, 0].T).T[:, :, None]
+    assert relerr(ctx.layernorm(x), want) < TOL_FP32
+    ctx.set_option("layernorm_mode", 1)
+    try:
+        tok = O.Ops("np", np.float64, O.Switches(layernorm="token")).layer_norm(x[:, :, 0].T).T[:, :, None]
+        assert relerr(ctx.layernorm(x), tok) < TOL_FP32
+    finally:
+        ctx.set_option("layernorm_mode", 0)
+
+
+def test_activations_and_upsample(ctx, ops):
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal(100003) * 3).astype(np.float32)
+    assert relerr(ctx.silu(x), ops.silu(x)) < TOL_FP32
+    assert relerr(ctx.gelu(x), ops.gelu(x)) < TOL_FP32
+    for c in (12, 5):
+        img = rng.standard_normal((c, 5, 7)).astype(np.float32)
+        assert np.array_equal(ctx.upsample2x(img), ops.upsample2x(img))
+
+
+def test_softmax_dims(ctx, ops):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((3, 50, 77)).astype(np.float32)
+    assert relerr(ctx.softmax(x, 2), ops.softmax(x, 2)) < TOL_FP32
+    assert relerr(ctx.softmax(x, 1), ops.softmax(x, 1)) < TOL_FP32
+    with pytest.raises(TsdError):   # reference: "Invalid dimension for softmax" (utils.mojo:446-448)
+        ctx.softmax(x, 3)
+
+
+@pytest.mark.parametrize("axis", ["query", "key"])
+@pytest.mark.parametrize("h,tq,tk,d", [(8, 256, 256, 40), (8, 128, 77, 80), (2, 64, 64, 160), (1, 256, 256, 512),
+                                       (8, 1024, 1024, 80), (8, 200, 77, 40)])
+def test_attention_core(ctx, h, tq, tk, d, axis):
+    rng = np.random.default_rng(h * tq + d)
+    q = rng.standard_normal((h, tq, d), dtype=np.float32)
+    k = rng.standard_normal((h, tk, d), dtype=np.float32)
+    v = rng.standard_normal((h, tk, d), dtype=np.float32)
+    ops = O.Ops("np", np.float64, O.Switches(softmax_axis=axis))
+    ctx.set_option("softmax_axis", 0 if axis == "query" else 1)
+    try:
+        got = ctx.attention_core(q, k, v)
+    finally:
+        ctx.set_option("softmax_axis", 0)
+    assert relerr(got, ops.attention_core(q, k, v)) < TOL_TF32
+
+
+def test_self_and_cross_attention(ctx, ops):
+    rng = np.random.default_rng(8)
+    t, c, hd = 256, 320, 8
+    x = rng.standard_normal((1, t, c), dtype=np.float32)
+    mk = lambda o, i: (rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32)  # noqa: E731
+    w_in, w_out, b_out = mk(3 * c, c), mk(c, c), rng.standard_normal(c, dtype=np.float32)
+    got = ctx.self_attention(x, hd, w_in, None, w_out, b_out)
+    assert relerr(got[0], ops.self_attention(x[0], hd, w_in, None, w_out, b_out)) < TOL_TF32
+    b_in = rng.standard_normal(3 * c, dtype=np.float32)   # VAE flavour: in_proj bias on
+    got = ctx.self_attention(x, 1, w_in, b_in, w_out, b_out)
+    assert relerr(got[0], ops.self_attention(x[0], 1, w_in, b_in, w_out, b_out)) < TOL_TF32
+    cx = rng.standard_normal((1, 77, 768), dtype=np.float32)
+    wq, wk, wv, wo = mk(c, c), mk(c, 768), mk(c, 768), mk(c, c)
+    got = ctx.cross_attention(x, cx, hd, wq, None, wk, None, wv, None, wo, b_out)
+    assert relerr(got[0], ops.cross_attention(x[0], cx[0], hd, wq, None, wk, None, wv, None, wo, b_out)) < TOL_TF32
+
+
+def test_sampler_step(ctx):
+    rng = np.random.default_rng(9)
+    n = 4 * 64 * 64
+    lat, ec, eu, nz = (rng.standard_normal(n).astype(np.float32) for _ in range(4))
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(20)
+    for t in (950, 500, 0):
+        co = sm.coefficients(t)
+        eps = O.cfg_combine(ec.astype(np.float64), eu, 7.5)
+        want = sm.step(t, lat.astype(np.float64), eps, nz)
+        got = ctx.sampler_step(lat, ec, eu, 7.5, nz if t > 0 else None, *[float(v) for v in co])
+        assert relerr(got, want) < TOL_FP32
+    got = ctx.sampler_step(lat, ec, None, 1.0, None, *[float(v) for v in sm.coefficients(500)])
+    assert relerr(got, sm.step(500, lat.astype(np.float64), ec.astype(np.float64), None)) < TOL_FP32

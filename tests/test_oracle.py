@@ -1,0 +1,208 @@
+"""CPU tests of the oracle itself: the two evaluators agree, the 'intended' switches match an
+independent implementation (torch.nn.functional), and the committed goldens are reproduced.
+PARITY UNPINNED by the reference (it has no tests): these are the pins this repo adds."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+import tsd_oracle as O
+from conftest import GOLDEN, relerr
+
+
+@pytest.fixture(scope="module")
+def ops64():
+    return O.Ops("np", np.float64)
+
+
+@pytest.fixture(scope="module")
+def opsc(oracle_lib):
+    return O.Ops("c32")
+
+
+def test_param_inventory_counts():
+    # 299.74 M (UNet + time embed + final) and 49.47 M (decoder)
+    assert synth.num_params(synth.diffusion_specs()) == 299_742_724
+    assert synth.num_params(synth.decoder_specs()) == 49_467_159
+
+
+def test_synth_generator_pinned(golden_small):
+    got = synth.synth_tensor(1234, 3, 64, np.float32(0.5))
+    assert np.array_equal(got, golden_small["synth_probe"])
+    assert np.abs(got).max() < 0.5
+    t = synth.synth_tensor(5, 0, 1 << 16, np.float32(1.0))
+    assert abs(t.mean()) < 0.02 and abs(t.std() - 1 / np.sqrt(3)) < 0.01
+
+
+def test_round_tf32():
+    x = np.array([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -1.0 - 2 ** -11, 3.14159265], np.float32)
+    r = synth.round_tf32(x)
+    assert r[0] == 1.0 and r[1] == np.float32(1.0 + 2 ** -10) and r[2] == np.float32(1.0 + 2 ** -10)
+    assert r[3] == np.float32(-1.0 - 2 ** -10)
+    assert abs(r[4] - x[4]) <= 2 ** -10
+
+
+@pytest.mark.parametrize("stride,pad,k", [(1, 1, 3), (2, 1, 3), (1, 0, 1)])
+def test_conv_vs_torch(ops64, opsc, stride, pad, k):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 9, 8))
+    w = rng.standard_normal((7, 5, k, k))
+    b = rng.standard_normal(7)
+    ref = F.conv2d(torch.from_numpy(x)[None], torch.from_numpy(w), torch.from_numpy(b), stride=stride, padding=pad)[0].numpy()
+    assert relerr(ops64.conv2d(x, w, b, pad, stride), ref) < 1e-12
+    assert relerr(opsc.conv2d(x, w, b, pad, stride), ref) < 1e-5
+
+
+def test_conv_reads_only_in_channels(ops64):
+    # Q9: a conv built for 4 input channels applied to a 6-channel tensor reads the first 4
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((6, 5, 5))
+    w = rng.standard_normal((3, 4, 3, 3))
+    assert np.array_equal(ops64.conv2d(x, w, None, 1), ops64.conv2d(x[:4], w, None, 1))
+
+
+def test_groupnorm_formula(ops64, opsc):
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((12, 4, 5)) * 3 + 1
+    # independent: torch group_norm divides by sqrt(var+eps); with eps=0 both agree exactly
+    ref0 = F.group_norm(torch.from_numpy(x)[None], 3, eps=0.0)[0].numpy()
+    assert relerr(ops64.group_norm(x, 3, 0.0), ref0) < 1e-12
+    # reference formula: eps is added to the std (utils.mojo:1868-1870)
+    g = x.reshape(3, -1)
+    want = ((g - g.mean(1, keepdims=True)) / (g.std(1, keepdims=True) + 1e-5)).reshape(x.shape)
+    assert relerr(ops64.group_norm(x, 3, 1e-5), want) < 1e-13
+    assert relerr(opsc.group_norm(x, 3, 1e-5), want) < 1e-5
+    with pytest.raises(ValueError):
+        ops64.group_norm(x, 5)
+
+
+def test_layernorm_modes(ops64):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((10, 6)) * 2 + 0.5   # (T,C)
+    glob = ops64.layer_norm(x)
+    assert relerr(glob, (x - x.mean()) / (x.std() + 1e-5)) < 1e-13          # Q5: one mean/std for the tensor
+    tok = O.Ops("np", np.float64, O.Switches(layernorm="token")).layer_norm(x)
+    ref = F.layer_norm(torch.from_numpy(x), (6,), eps=0.0).numpy()
+    assert relerr(tok, ref) < 1e-4
+
+
+def test_activations_vs_torch(ops64, opsc):
+    x = np.linspace(-6, 6, 1001)
+    assert relerr(ops64.silu(x), F.silu(torch.from_numpy(x)).numpy()) < 1e-13
+    assert relerr(ops64.gelu(x), F.gelu(torch.from_numpy(x), approximate="tanh").numpy()) < 1e-13
+    assert relerr(opsc.silu(x), ops64.silu(x)) < 1e-6
+    assert relerr(opsc.gelu(x), ops64.gelu(x)) < 1e-6
+    u = ops64.upsample2x(np.arange(12.0).reshape(1, 3, 4))
+    assert np.array_equal(u, F.interpolate(torch.arange(12.0).reshape(1, 1, 3, 4), scale_factor=2, mode="nearest")[0].numpy())
+
+
+def test_softmax_axes(ops64, opsc):
+    rng = np.random.default_rng(4)
+    s = rng.standard_normal((3, 6, 5))
+    d2 = ops64.softmax(s, 2)
+    assert np.allclose(d2.sum(axis=1), 1.0)       # Q3: dim=2 normalises every column over the rows
+    assert np.allclose(ops64.softmax(s, 1).sum(axis=2), 1.0)
+    assert relerr(ops64.softmax(s, 1), torch.softmax(torch.from_numpy(s), dim=2).numpy()) < 1e-13
+    assert relerr(opsc.softmax(s, 2), d2) < 1e-6   # no max-subtraction in the C loops (utils.mojo:413)
+    with pytest.raises(ValueError):
+        ops64.softmax(s, 3)
+
+
+def test_attention_key_axis_vs_sdpa():
+    rng = np.random.default_rng(5)
+    h, t, d, c = 4, 9, 8, 32
+    x = rng.standard_normal((t, c))
+    w_in = rng.standard_normal((3 * c, c)) / np.sqrt(c)
+    w_out = rng.standard_normal((c, c)) / np.sqrt(c)
+    b_out = rng.standard_normal(c)
+    ops = O.Ops("np", np.float64, O.Switches(softmax_axis="key"))
+    got = ops.self_attention(x, h, w_in, None, w_out, b_out)
+    # independent restatement with the raw-reshape head split (Q4) done by torch views
+    qkv = torch.from_numpy(x) @ torch.from_numpy(w_in).T
+    q, k, v = (qkv[:, i * c:(i + 1) * c].contiguous().view(h, t, d) for i in range(3))
+    o = F.scaled_dot_product_attention(q[None], k[None], v[None])[0]          # (h,t,d)
+    o = o.transpose(0, 1).reshape(t, c)
+    ref = (o @ torch.from_numpy(w_out).T + torch.from_numpy(b_out)).numpy()
+    assert relerr(got, ref) < 1e-12
+
+
+def test_attention_query_axis_definition(ops64, opsc):
+    rng = np.random.default_rng(6)
+    q = rng.standard_normal((2, 7, 4))
+    k = rng.standard_normal((2, 5, 4))
+    v = rng.standard_normal((2, 5, 4))
+    s = np.einsum("hid,hjd->hij", q, k) / 2.0
+    p = np.exp(s) / np.exp(s).sum(axis=1, keepdims=True)      # normalised over the query index
+    want = np.einsum("hij,hjd->ihd", p, v).reshape(7, 8)
+    assert relerr(ops64.attention_core(q, k, v), want) < 1e-13
+    assert relerr(opsc.attention_core(q, k, v), want) < 1e-5
+
+
+def test_sampler_against_closed_form():
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(20)
+    assert list(sm.timesteps[:3]) == [950, 900, 850] and sm.timesteps[-1] == 0
+    ab = sm.alphas_cumprod
+    t, p = 500, 450
+    s_ab, s_1mab, c0, c1, sigma = sm.coefficients(t)
+    # posterior mean/variance of q(x_{p} | x_t, x_0) (Ho et al. eq. 7) with alpha_t = ab_t/ab_p
+    a_t = ab[t] / ab[p]
+    assert np.isclose(c0, np.sqrt(ab[p]) * (1 - a_t) / (1 - ab[t]))
+    assert np.isclose(c1, np.sqrt(a_t) * (1 - ab[p]) / (1 - ab[t]))
+    assert np.isclose(sigma ** 2, (1 - ab[p]) / (1 - ab[t]) * (1 - a_t))
+    assert sm.coefficients(0)[4] == 0.0 and np.isclose(sm.coefficients(0)[2], 1.0)   # t=0: x_prev = x0_hat
+    x = np.ones((4, 2, 2))
+    assert np.allclose(sm.step(0, x, np.zeros_like(x)), x / sm.coefficients(0)[0])
+
+
+def test_time_embedding_variants():
+    e = O.get_time_embedding(999)
+    assert e.shape == (320,) and np.isclose(e[0], np.cos(999.0), atol=1e-6) and np.isclose(e[160], np.sin(999.0), atol=1e-6)
+    w = O.get_time_embedding(999, as_written=True)   # Q12: freqs ~ 0 except index 0 -> [1]*160 + [0]*160
+    assert np.allclose(w[1:159], 1.0) and np.allclose(w[161:319], 0.0)
+
+
+def test_goldens_small_reproduced(golden_small, ops64, opsc):
+    g = golden_small
+    assert relerr(ops64.conv2d(g["conv_x"], g["conv_w"], g["conv_b"], 1), g["conv_y"]) < 1e-13
+    assert relerr(ops64.conv2d(g["conv_x"], g["conv_w"], g["conv_b"], 1, 2), g["conv_y_s2"]) < 1e-13
+    assert relerr(opsc.conv2d(g["conv_x"], g["conv_w"], g["conv_b"], 1), g["conv_y"]) < 1e-5
+    assert relerr(ops64.group_norm(g["conv_x"], 3), g["gn_y"]) < 1e-13
+    assert relerr(ops64.softmax(g["sm_x"], 2), g["sm_dim2"]) < 1e-13
+    assert relerr(ops64.attention_core(g["at_q"], g["at_k"], g["at_v"]), g["at_query"]) < 1e-13
+    assert relerr(opsc.attention_core(g["at_q"], g["at_k"], g["at_v"]), g["at_query"]) < 1e-5
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(20)
+    assert np.array_equal(sm.timesteps, g["sched_t"])
+    assert np.allclose(np.stack([sm.coefficients(int(t)) for t in sm.timesteps]), g["sched_coef"], rtol=1e-12)
+
+
+def test_unet8_c_loops_match_fp64_golden(golden_small, opsc, unet_weights):
+    """The reference's fp32 scalar loop order (C) against the fp64 golden: plumbing config 1
+    (one DDPM step forward, random weights) at an 8x8 latent."""
+    g = golden_small
+    y = O.diffusion_forward(opsc, unet_weights, g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    assert y.shape == (4, 8, 8)
+    assert relerr(y, g["unet8_y"]) < 1e-4
+    # the semantic switches change the answer (they are not no-ops)
+    assert relerr(g["unet8_y_intended"], g["unet8_y"]) > 1e-3
+    assert relerr(g["unet8_y_alias"], g["unet8_y"]) > 1e-4
+
+
+def test_decoder8_c_loops_match_fp64_golden(golden_small, opsc, decoder_weights):
+    g = golden_small
+    y = O.decoder_forward(opsc, decoder_weights, g["dec8_z"])
+    assert y.shape == (3, 64, 64)
+    assert relerr(y, g["dec8_y"]) < 1e-4
+    img = O.rescale_image(y)
+    assert img.min() >= 0 and img.max() <= 255
+
+
+def test_full_size_goldens_present():
+    for name in ("unet64.npz", "decoder64.npz"):
+        assert os.path.exists(os.path.join(GOLDEN, name)), f"run tools/make_golden.py {name[:-4]}"
+    u = np.load(os.path.join(GOLDEN, "unet64.npz"))
+    assert u["y"].shape == (4, 64, 64) and np.isfinite(u["y"]).all()

@@ -1,0 +1,101 @@
+"""Generates tests/golden/*.npz with the fp64 oracle (oracle/tsd_oracle.py, backend "np").
+
+PARITY UNPINNED: the reference has no golden vectors and cannot run here; these files pin the
+repo's own restatement so that (a) the oracle cannot drift silently and (b) the GPU path is
+checked at the full BASELINE sizes, where running the oracle inside a test would take minutes.
+
+  python tools/make_golden.py small      # seconds-to-a-minute cases (ops, 8x8 UNet, 8x8 decoder, loop)
+  python tools/make_golden.py unet64     # one UNet step at the 64x64 latent of BASELINE config 2
+  python tools/make_golden.py decoder64  # one VAE decode 64x64x4 -> 512x512x3 (stored subsampled)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import synth  # noqa: E402
+import tsd_oracle as O  # noqa: E402
+
+G = os.path.join(ROOT, "tests", "golden")
+UNET_SEED, DEC_SEED = 1234, 1235
+
+
+def inputs(seed, side, n_ctx=1):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((4, side, side), dtype=np.float32)
+    ctx = rng.standard_normal((n_ctx, 77, 768), dtype=np.float32)
+    return x, ctx
+
+
+def small():
+    ops = O.Ops("np", np.float64)
+    rng = np.random.default_rng(7)
+    out = {}
+    # op level known answers
+    x = rng.standard_normal((6, 5, 7), dtype=np.float32)
+    w = rng.standard_normal((4, 6, 3, 3), dtype=np.float32) * 0.2
+    b = rng.standard_normal(4, dtype=np.float32)
+    out.update(conv_x=x, conv_w=w, conv_b=b, conv_y=ops.conv2d(x, w, b, pad=1), conv_y_s2=ops.conv2d(x, w, b, pad=1, stride=2))
+    out.update(gn_y=ops.group_norm(x, 3, 1e-5), silu_y=ops.silu(x), gelu_y=ops.gelu(x), up_y=ops.upsample2x(x))
+    s = rng.standard_normal((2, 5, 7), dtype=np.float32)
+    out.update(sm_x=s, sm_dim2=ops.softmax(s, 2), sm_dim1=ops.softmax(s, 1))
+    q = rng.standard_normal((2, 6, 4), dtype=np.float32)
+    k = rng.standard_normal((2, 5, 4), dtype=np.float32)
+    v = rng.standard_normal((2, 5, 4), dtype=np.float32)
+    out.update(at_q=q, at_k=k, at_v=v, at_query=ops.attention_core(q, k, v),
+               at_key=O.Ops("np", np.float64, O.Switches(softmax_axis="key")).attention_core(q, k, v))
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(20)
+    out.update(sched_t=sm.timesteps, sched_coef=np.stack([sm.coefficients(int(t)) for t in sm.timesteps]),
+               temb_999=O.get_time_embedding(999), temb_999_as_written=O.get_time_embedding(999, True))
+    out["synth_probe"] = synth.synth_tensor(UNET_SEED, 3, 64, np.float32(0.5))
+    # UNet step, 8x8 latent, default (reference-faithful) switches and the intended ones
+    W = synth.SynthWeights(synth.diffusion_specs(), UNET_SEED)
+    x8, ctx = inputs(11, 8)
+    t = O.get_time_embedding(999)
+    out.update(unet8_x=x8, unet8_ctx=ctx[0], unet8_t=t)
+    out["unet8_y"] = O.diffusion_forward(ops, W, x8, ctx[0], t)
+    out["unet8_y_intended"] = O.diffusion_forward(
+        O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token")), W, x8, ctx[0], t)
+    out["unet8_y_alias"] = O.diffusion_forward(O.Ops("np", np.float64, O.Switches(mojo_alias_time=True)), W, x8, ctx[0], t)
+    # 3-step loop with CFG at 8x8
+    rng2 = np.random.default_rng(12)
+    noise = rng2.standard_normal((3, 4, 8, 8), dtype=np.float32)
+    uctx = rng2.standard_normal((77, 768), dtype=np.float32)
+    out.update(loop8_noise=noise, loop8_uctx=uctx)
+    out["loop8_lat"] = O.generate_latents(ops, W, x8, ctx[0], 3, noise, cfg_context=uctx, cfg_scale=7.5)
+    # decoder at 8x8 latent
+    Wd = synth.SynthWeights(synth.decoder_specs(), DEC_SEED)
+    z = (np.random.default_rng(13).standard_normal((4, 8, 8)) * 0.18215).astype(np.float32)
+    out.update(dec8_z=z, dec8_y=O.decoder_forward(ops, Wd, z))
+    np.savez_compressed(os.path.join(G, "small.npz"), **{k: np.asarray(v) for k, v in out.items()})
+
+
+def unet64():
+    ops = O.Ops("np", np.float64)
+    W = synth.SynthWeights(synth.diffusion_specs(), UNET_SEED)
+    x, ctx = inputs(21, 64)
+    t = O.get_time_embedding(999)
+    t0 = time.time()
+    y = O.diffusion_forward(ops, W, x, ctx[0], t)
+    print("unet64 oracle seconds", time.time() - t0, flush=True)
+    np.savez_compressed(os.path.join(G, "unet64.npz"), x=x, ctx=ctx[0], t=t, y=y.astype(np.float64))
+
+
+def decoder64():
+    ops = O.Ops("np", np.float64)
+    Wd = synth.SynthWeights(synth.decoder_specs(), DEC_SEED)
+    z = (np.random.default_rng(31).standard_normal((4, 64, 64)) * 0.18215).astype(np.float32)
+    t0 = time.time()
+    y = O.decoder_forward(ops, Wd, z)
+    print("decoder64 oracle seconds", time.time() - t0, flush=True)
+    # full image is 3 MB: keep a strided subsample plus global moments
+    np.savez_compressed(os.path.join(G, "decoder64.npz"), z=z, y_sub=y[:, 3::8, 5::8].astype(np.float64),
+                        y_mean=y.mean(axis=(1, 2)), y_std=y.std(axis=(1, 2)), y_absmax=np.abs(y).max())
+
+
+if __name__ == "__main__":
+    {"small": small, "unet64": unet64, "decoder64": decoder64}[sys.argv[1]]()
