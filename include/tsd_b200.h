@@ -63,6 +63,10 @@ int32_t tsd_set_option(tsd_ctx* ctx, const char* name, int32_t value);
 int32_t tsd_get_option(tsd_ctx* ctx, const char* name, int32_t* value);
 /* number of kernels launched through ctx since creation (bench "gpu_launches") */
 int64_t tsd_launch_count(const tsd_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream: start records, stop records + waits and returns
+ * the device milliseconds in between (bench.py times the `_dev` entry points with it). */
+int32_t tsd_timer_start(tsd_ctx* ctx);
+int32_t tsd_timer_stop(tsd_ctx* ctx, double* ms);
 
 /* ---- op level (host buffers, reference layouts) ---------------------------------------- */
 /* Conv2D.forward, helpers/utils.mojo:1738-1811.  x (cin,h,w); weight OIHW (cout,cin,k,k);
@@ -113,6 +117,12 @@ int32_t tsd_attention_core(tsd_ctx* ctx, const float* q, const float* k, const f
 int32_t tsd_sampler_step(tsd_ctx* ctx, const float* latents, const float* eps_cond,
                          const float* eps_uncond, float cfg_scale, const float* noise, float sqrt_ab,
                          float sqrt_1mab, float c0, float c1, float sigma, int64_t n, float* out);
+
+/* same, device pointers, asynchronous on the context's stream (out may alias latents) */
+int32_t tsd_sampler_step_dev(tsd_ctx* ctx, const float* latents, const float* eps_cond,
+                             const float* eps_uncond, float cfg_scale, const float* noise,
+                             float sqrt_ab, float sqrt_1mab, float c0, float c1, float sigma, int64_t n,
+                             float* out);
 
 /* ---- Diffusion (time embedding MLP + UNet + output layer), diffusion.mojo:294-318 --------- */
 typedef struct tsd_diffusion_config {

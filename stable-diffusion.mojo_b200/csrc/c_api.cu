@@ -88,6 +88,8 @@ int32_t tsd_init(int32_t device, tsd_ctx** out) {
 
 int32_t tsd_shutdown(tsd_ctx* h) {
   if (!h) return TSD_ERR_INVALID;
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   ctx_destroy(h->c);
   delete h;
   return TSD_OK;
@@ -131,6 +133,34 @@ int32_t tsd_get_option(tsd_ctx* h, const char* name, int32_t* value) {
   return TSD_OK;
 }
 int64_t tsd_launch_count(const tsd_ctx* h) { return h ? h->c->launches : 0; }
+
+// CUDA-event stopwatch on the context's own stream (the stream every kernel of this library is
+// launched on; an event recorded on another stream would not see them).
+int32_t tsd_timer_start(tsd_ctx* h) {
+  if (!h) return TSD_ERR_INVALID;
+  std::lock_guard<std::mutex> g(h->mu);
+  cudaSetDevice(h->c->device);
+  if (!h->ev0) {
+    int rc = h->c->check(cudaEventCreate(&h->ev0), "event create");
+    if (rc) return rc;
+    rc = h->c->check(cudaEventCreate(&h->ev1), "event create");
+    if (rc) return rc;
+  }
+  return h->c->check(cudaEventRecord(h->ev0, h->c->stream), "event record");
+}
+int32_t tsd_timer_stop(tsd_ctx* h, double* ms) {
+  if (!h || !ms || !h->ev0) return TSD_ERR_INVALID;
+  std::lock_guard<std::mutex> g(h->mu);
+  cudaSetDevice(h->c->device);
+  int rc = h->c->check(cudaEventRecord(h->ev1, h->c->stream), "event record");
+  if (rc) return rc;
+  rc = h->c->check(cudaEventSynchronize(h->ev1), "event synchronize");
+  if (rc) return rc;
+  float t = 0.f;
+  rc = h->c->check(cudaEventElapsedTime(&t, h->ev0, h->ev1), "event elapsed");
+  *ms = t;
+  return rc;
+}
 
 // ---------------------------------------------------------------------------------------
 // op level
@@ -487,6 +517,20 @@ int32_t tsd_sampler_step(tsd_ctx* h, const float* latents, const float* eps_cond
     hc.download(out, od, n);
   }
   return hc.finish();
+}
+
+int32_t tsd_sampler_step_dev(tsd_ctx* h, const float* latents, const float* eps_cond,
+                             const float* eps_uncond, float cfg_scale, const float* noise, float sqrt_ab,
+                             float sqrt_1mab, float c0, float c1, float sigma, int64_t n, float* out) {
+  if (!h || !latents || !eps_cond || !out || n <= 0) return TSD_ERR_INVALID;
+  std::lock_guard<std::mutex> g(h->mu);
+  Ctx* c = h->c;
+  cudaSetDevice(c->device);
+  int rc = c->check(launch_ddpm_step(latents, eps_cond, eps_uncond, cfg_scale, noise, sqrt_ab, sqrt_1mab,
+                                     c0, c1, sigma, out, n, c->stream),
+                    "ddpm_step");
+  if (!rc) c->launches++;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@ struct tsd_ctx {
   tsd::Ctx* c = nullptr;
   std::mutex mu;
   int use_graph = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // tsd_timer_start / tsd_timer_stop
   int option_epoch = 0;  // bumped by tsd_set_option: captured graphs are stale afterwards
 };
 

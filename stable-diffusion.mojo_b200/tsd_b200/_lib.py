@@ -98,6 +98,8 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_set_option", i32, vp, C.c_char_p, i32)
     sig("tsd_get_option", i32, vp, C.c_char_p, c_i32_p)
     sig("tsd_launch_count", i64, vp)
+    sig("tsd_timer_start", i32, vp)
+    sig("tsd_timer_stop", i32, vp, c_double_p)
     sig("tsd_conv2d", i32, vp, fp, i32, i32, i32, i32, fp, fp, i32, i32, i32, i32, fp)
     sig("tsd_linear", i32, vp, fp, i32, i32, i32, fp, fp, i32, fp)
     sig("tsd_matmul", i32, vp, fp, fp, i32, i32, i32, i32, fp)
@@ -112,6 +114,7 @@ def _declare(L: C.CDLL) -> None:
         fp, fp)
     sig("tsd_attention_core", i32, vp, fp, fp, fp, i32, i32, i32, i32, fp)
     sig("tsd_sampler_step", i32, vp, fp, fp, fp, f32, fp, f32, f32, f32, f32, f32, i64, fp)
+    sig("tsd_sampler_step_dev", i32, vp, fp, fp, fp, f32, fp, f32, f32, f32, f32, f32, i64, fp)
     sig("tsd_diffusion_create", i32, vp, C.POINTER(DiffusionConfig), C.POINTER(vp))
     sig("tsd_diffusion_destroy", i32, vp)
     sig("tsd_diffusion_num_params", i64, vp)

@@ -70,6 +70,15 @@ class Context:
     def launch_count(self) -> int:
         return int(self.L.tsd_launch_count(self.h))
 
+    def timer_start(self):
+        self._ck(self.L.tsd_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        """Device milliseconds since timer_start (CUDA events on the context's stream)."""
+        ms = C.c_double()
+        self._ck(self.L.tsd_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     # -- ops ----------------------------------------------------------------------------------
     def conv2d(self, x, weight, bias=None, pad=0, stride=1):
         x = _f32(x)
@@ -196,6 +205,11 @@ class Context:
                                          sqrt_ab, sqrt_1mab, c0, c1, sigma, latents.size, _p(out)))
         return out
 
+    def sampler_step_dev(self, latents_dev, eps_dev, eps_uncond_dev, cfg_scale, noise_dev, coef, n, out_dev):
+        """tsd_sampler_step_dev on raw device addresses (ints); coef = the 5 schedule scalars."""
+        self._ck(self.L.tsd_sampler_step_dev(self.h, latents_dev, eps_dev, eps_uncond_dev, cfg_scale, noise_dev,
+                                             *[float(v) for v in coef], n, out_dev))
+
     # -- tuning probes --------------------------------------------------------------------------
     def bench_gemm(self, m, n, k, batch=1, geglu=0, force_bn=0, force_splits=0, iters=20) -> float:
         ms = C.c_double()
@@ -283,6 +297,12 @@ class Diffusion(_Model):
                                                       time.shape[0], x.shape[0], _p(out)))
         return out[0] if squeeze else out
 
+    def forward_dev(self, x_dev, ctx_dev, n_ctx, time_dev, n_time, n, out_dev):
+        """tsd_diffusion_forward_dev on raw device addresses (ints), asynchronous on the context's
+        stream.  ctx_dev = None reuses the context (and its hoisted K/V projections) of the last call."""
+        self.ctx._ck(self.ctx.L.tsd_diffusion_forward_dev(self.m, x_dev, ctx_dev, n_ctx, time_dev, n_time, n,
+                                                          out_dev))
+
     def profile(self, x_dev, ctx_dev, n_ctx, time_dev, n_time, n, out_dev):
         """Eager forward on device pointers with per-launch CUDA events; returns per-family
         (ms, flops, launches) for families gemm/conv, attention, norm, other."""
@@ -335,3 +355,6 @@ class Decoder(_Model):
         img = np.empty((n, 3, 8 * h, 8 * w), np.float32)
         self.ctx._ck(self.ctx.L.tsd_decoder_forward(self.m, _p(z), n, int(rescale), _p(img)))
         return img[0] if squeeze else img
+
+    def forward_dev(self, z_dev, n, rescale, img_dev):
+        self.ctx._ck(self.ctx.L.tsd_decoder_forward_dev(self.m, z_dev, n, int(rescale), img_dev))
