@@ -1,5 +1,541 @@
+// K3/K4: fused attention core on tcgen05 tensor cores - see attention_tcgen05.cuh.
+//
+// Reference semantics (helpers/attention.mojo:46-62, 105-115): per head S = Q K^T / sqrt(d),
+// Softmax(dim=2) (which normalises every COLUMN of S over the query axis, utils.mojo:435-445,
+// SURVEY Q3; "softmax_axis = 1" selects the standard key-axis form), O = P V, merged heads.
+//
+// Both softmax axes are served by the same two launches of one kernel:
+//   STATS  rows of X against all rows of Y: per X-row r the log2-domain max m_r of
+//          c * <x_r, y_j> and l_r = sum_j exp2(c * <x_r, y_j> - m_r)   (c = log2(e)/sqrt(d));
+//          query axis: X = K, Y = Q (one statistic per key column); key axis: X = Q, Y = K.
+//          The Y loop can be split over grid.z; partial (m, l) pairs are merged by the consumer.
+//   APPLY  per 128-query tile: S = Q K_t^T in TMEM, P = exp2(c * S - mu) with mu = m + log2(l)
+//          per key column (query axis) or per query row (key axis), written back over S in TMEM
+//          (tcgen05.st) and fed straight to the second MMA as the TMEM A operand:
+//          O += P V_t, V staged by TMA in its natural [key][d] layout and read MN-major.
+//          S / P never touch shared or global memory; no running-max correction of O is needed
+//          because mu is known before the pass starts.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..5 softmax /
+// epilogue (one thread per S row, TMEM lane quadrant = warp & 3).
 #include "attention_tcgen05.cuh"
+
+#include <cmath>
+
+#include "ptx_sm100.cuh"
+
 namespace tsd {
-bool attention_fused_supported(int d, int causal) { (void)d; (void)causal; return false; }
-int attention_fused(Ctx* c, const AttnArgs& a) { (void)a; return c->fail(TSD_ERR_STATE, "fused attention not built"); }
+
+int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_elems, const uint32_t* box);
+
+namespace {
+
+constexpr int ATT_BM = 128;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_BOX_ROW_BYTES = 128;  // 32 fp32 = one SWIZZLE_128B row
+enum { ATT_STATS = 0, ATT_APPLY = 1 };
+
+struct AttnKParams {
+  int mode;
+  int Tx, Ty;      // rows of the stationary operand (owned by CTAs) / of the streamed operand
+  int d, nbox;     // head dim, number of 32-float boxes covering it
+  int dpad;        // N of the P.V MMA: d rounded up to 16
+  int BN;          // streamed rows per tile (multiple of 16, <= 128)
+  int sY, sV;      // ring depths (1 or 2)
+  int heads;
+  int x_shared, y_shared, v_shared;  // tensor-map batch coordinate = head only (operand shared by the batch)
+  int tiles_per_split, total_tiles;
+  int tmem_cols;
+  float c;                // softmax scale * log2(e)
+  float2* part_out;       // STATS: [split][bh][Tx]
+  const float2* part_in;  // APPLY: [mu_splits][bh][Tmu]
+  int mu_splits, mu_per_row, Tmu;
+  long long part_stride;  // elements between splits = bh_count * T
+  float* O;               // APPLY: merged output [b][Tx][heads*d]
+  int ldo;
+  int round_out;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t rna_tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// merge `splits` partial (max, sum) pairs of one row/column into mu = max + log2(sum)
+__device__ __forceinline__ float merge_partials(const float2* __restrict__ part, long long stride, int splits,
+                                                long long idx) {
+  float2 v = part[idx];
+  float M = v.x, L = v.y;
+  for (int s = 1; s < splits; ++s) {
+    v = part[idx + (long long)s * stride];
+    const float Mn = fmaxf(M, v.x);
+    L = L * ex2(M - Mn) + v.y * ex2(v.x - Mn);
+    M = Mn;
+  }
+  return M + lg2(L);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+            const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t x_full, y_full[2], y_empty[2], v_full[2], v_empty[2];
+  __shared__ __align__(8) uint64_t s_full[2], s_free[2], p_full[2], o_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float mu_s[2][ATT_BM];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t dyn0 = smem_u32(smem_dyn);
+  const uint32_t xs = (dyn0 + 1023u) & ~1023u;
+  const uint32_t x_bytes = (uint32_t)p.nbox * ATT_BM * ATT_BOX_ROW_BYTES;
+  const uint32_t ybox = (uint32_t)p.BN * ATT_BOX_ROW_BYTES;
+  const uint32_t ystage = (uint32_t)p.nbox * ybox;
+  const uint32_t ys = xs + x_bytes;
+  const uint32_t vs = ys + (uint32_t)p.sY * ystage;
+
+  const int xt = blockIdx.x, bh = blockIdx.y, split = blockIdx.z;
+  const int h = bh % p.heads;
+  const int x0 = xt * ATT_BM;
+  const int it0 = split * p.tiles_per_split;
+  int n_it = p.total_tiles - it0;
+  if (n_it > p.tiles_per_split) n_it = p.tiles_per_split;
+  const bool apply = p.mode == ATT_APPLY;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&x_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&y_full[s], 1);
+      mbar_init(&y_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], ATT_BM);
+      mbar_init(&p_full[s], ATT_BM);
+    }
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmY);
+    if (apply) prefetch_tensormap(&tmV);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256u;  // S0: cols [0,128), S1: [128,256), O: [256, 256+dpad)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&x_full, x_bytes);
+      for (int bx = 0; bx < p.nbox; ++bx)
+        tma_load_3d_s(xs + bx * (ATT_BM * ATT_BOX_ROW_BYTES), &tmX, &x_full, bx * 32, x0,
+                    p.x_shared ? h : bh);
+      for (int it = 0; it < n_it; ++it) {
+        const int yrow = (it0 + it) * p.BN;
+        {
+          const int st = it % p.sY;
+          const uint32_t ph = (uint32_t)(it / p.sY) & 1u;
+          mbar_wait(&y_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&y_full[st], ystage);
+          for (int bx = 0; bx < p.nbox; ++bx)
+            tma_load_3d_s(ys + st * ystage + bx * ybox, &tmY, &y_full[st], bx * 32, yrow,
+                        p.y_shared ? h : bh);
+        }
+        if (apply) {
+          const int st = it % p.sV;
+          const uint32_t ph = (uint32_t)(it / p.sV) & 1u;
+          mbar_wait(&v_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&v_full[st], ystage);
+          for (int bx = 0; bx < p.nbox; ++bx)
+            tma_load_3d_s(vs + st * ystage + bx * ybox, &tmV, &v_full[st], bx * 32, yrow,
+                        p.v_shared ? h : bh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc(UMMA_FMT_TF32, ATT_BM, (uint32_t)p.BN, 0, 0);
+      const uint32_t idesc_o = umma_idesc(UMMA_FMT_TF32, ATT_BM, (uint32_t)p.dpad, 0, 1);  // B (= V) MN-major
+      const int ksteps = p.d >> 3;
+      const int pv_steps = p.BN >> 3;
+      auto issue_pv = [&](int j) {
+        const int bj = j & 1;
+        const int st = j % p.sV;
+        mbar_wait(&p_full[bj], (uint32_t)(j >> 1) & 1u);
+        mbar_wait(&v_full[st], (uint32_t)(j / p.sV) & 1u);
+        tc_fence_after_sync();
+        const uint32_t vb = vs + st * ystage;
+        for (int ks = 0; ks < pv_steps; ++ks) {
+          // V tile: [BN keys][32 floats] boxes, 8-key groups of 1024 B; N atoms (boxes) are ybox apart
+          const uint64_t bdesc = umma_smem_desc(vb + ks * 1024, ybox, 1024, UMMA_SWIZZLE_128B);
+          umma_tf32_ts(tmem_o, tmem_base + (uint32_t)(bj * 128 + ks * 8), bdesc, idesc_o,
+                       (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+      };
+      mbar_wait(&x_full, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int b = it & 1;
+        const int st = it % p.sY;
+        mbar_wait(&y_full[st], (uint32_t)(it / p.sY) & 1u);
+        if (!apply && it >= 2) mbar_wait(&s_free[b], (uint32_t)((it >> 1) - 1) & 1u);
+        tc_fence_after_sync();
+        const uint32_t yb = ys + st * ystage;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks & 3) * 32u;
+          const uint64_t adesc =
+              umma_smem_desc(xs + (ks >> 2) * (ATT_BM * ATT_BOX_ROW_BYTES) + off, 16, 1024, UMMA_SWIZZLE_128B);
+          const uint64_t bdesc = umma_smem_desc(yb + (ks >> 2) * ybox + off, 16, 1024, UMMA_SWIZZLE_128B);
+          umma_tf32(tmem_base + (uint32_t)(b * 128), adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&y_empty[st]);
+        umma_commit(&s_full[b]);
+        if (apply && it >= 1) issue_pv(it - 1);
+      }
+      if (apply) {
+        issue_pv(n_it - 1);
+        umma_commit(&o_full);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // S row == TMEM lane owned by this thread
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool row_ok = x0 + row < p.Tx;
+    const float c = p.c;
+
+    if (!apply) {
+      float m = -INFINITY, l = 0.f;
+      for (int it = 0; it < n_it; ++it) {
+        const int b = it & 1;
+        const int ycol0 = (it0 + it) * p.BN;
+        int nvalid = p.Ty - ycol0;
+        if (nvalid > p.BN) nvalid = p.BN;
+        mbar_wait(&s_full[b], (uint32_t)(it >> 1) & 1u);
+        tc_fence_after_sync();
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t v[32];
+          const bool full = c0 + 32 <= p.BN;
+          if (full) {
+            tmem_ld32(lane_base + (uint32_t)(b * 128 + c0), v);
+          } else {
+            uint32_t t16[16];
+            tmem_ld16(lane_base + (uint32_t)(b * 128 + c0), t16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = t16[j];
+#pragma unroll
+            for (int j = 16; j < 32; ++j) v[j] = 0;
+          }
+          tmem_ld_wait();
+          if (c0 + 32 >= p.BN) {  // last chunk read: the S buffer may be overwritten
+            tc_fence_before_sync();
+            mbar_arrive(&s_free[b]);
+          }
+          float x[32];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x[j] = (c0 + j < nvalid) ? __uint_as_float(v[j]) * c : -INFINITY;
+            cm = fmaxf(cm, x[j]);
+          }
+          if (cm > m) {
+            l *= ex2(m - cm);
+            m = cm;
+          }
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += ex2(x[j] - m);
+          l += acc;
+        }
+      }
+      if (row_ok) p.part_out[(long long)split * p.part_stride + (long long)bh * p.Tx + x0 + row] = make_float2(m, l);
+    } else {
+      float mu_row = 0.f;
+      if (p.mu_per_row && row_ok)
+        mu_row = merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + x0 + row);
+      float2 pre = make_float2(0.f, 1.f);
+      const bool fast_mu = !p.mu_per_row && p.mu_splits == 1;
+      if (fast_mu && row < p.BN && it0 * p.BN + row < p.Ty) pre = p.part_in[(long long)bh * p.Tmu + it0 * p.BN + row];
+      for (int it = 0; it < n_it; ++it) {
+        const int b = it & 1;
+        const int ycol0 = (it0 + it) * p.BN;
+        int nvalid = p.Ty - ycol0;
+        if (nvalid > p.BN) nvalid = p.BN;
+        if (!p.mu_per_row) {
+          if (row < p.BN) {
+            const int col = ycol0 + row;
+            float mu = INFINITY;  // masked key column: exp2(-inf) = 0
+            if (col < p.Ty)
+              mu = fast_mu ? pre.x + lg2(pre.y)
+                           : merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + col);
+            mu_s[b][row] = mu;
+          }
+          named_bar_sync(1, ATT_BM);
+          if (fast_mu && it + 1 < n_it && row < p.BN && ycol0 + p.BN + row < p.Ty)
+            pre = p.part_in[(long long)bh * p.Tmu + ycol0 + p.BN + row];
+        }
+        mbar_wait(&s_full[b], (uint32_t)(it >> 1) & 1u);
+        tc_fence_after_sync();
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          const uint32_t taddr = lane_base + (uint32_t)(b * 128 + c0);
+          const bool full = c0 + 32 <= p.BN;
+          uint32_t v[32];
+          if (full) {
+            tmem_ld32(taddr, v);
+          } else {
+            uint32_t t16[16];
+            tmem_ld16(taddr, t16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = t16[j];
+#pragma unroll
+            for (int j = 16; j < 32; ++j) v[j] = 0;
+          }
+          tmem_ld_wait();
+          if (!p.mu_per_row) {
+            const float4* mup = reinterpret_cast<const float4*>(&mu_s[b][c0]);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (!full && j4 >= 4) break;
+              const float4 m4 = mup[j4];
+              v[4 * j4 + 0] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 0]), c, -m4.x)));
+              v[4 * j4 + 1] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 1]), c, -m4.y)));
+              v[4 * j4 + 2] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 2]), c, -m4.z)));
+              v[4 * j4 + 3] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w)));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = ex2(fmaf(__uint_as_float(v[j]), c, -mu_row));
+              v[j] = (c0 + j < nvalid) ? rna_tf32_bits(e) : 0u;
+            }
+          }
+          if (full) {
+            tmem_st32(taddr, v);
+          } else {
+            uint32_t t16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) t16[j] = v[j];
+            tmem_st16(taddr, t16);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&p_full[b]);
+      }
+      // ---- epilogue: O (TMEM) -> merged [b][t][h*d + j]  (attention.mojo:61-62) ----
+      mbar_wait(&o_full, 0);
+      tc_fence_after_sync();
+      const int bidx = bh / p.heads;
+      float* orow = p.O + ((long long)bidx * p.Tx + x0 + row) * p.ldo + (long long)h * p.d;
+      for (int c0 = 0; c0 < p.dpad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (c0 + 4 * j4 < p.d) {
+              float4 o;
+              if (p.round_out) {
+                o = make_float4(__uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4]))),
+                                __uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4 + 1]))),
+                                __uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4 + 2]))),
+                                __uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4 + 3]))));
+              } else {
+                o = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+              }
+              *reinterpret_cast<float4*>(orow + c0 + 4 * j4) = o;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+struct AttnPlan {
+  int nbox, dpad, BN, sY, sV;
+  size_t smem;
+};
+
+// tile of the streamed operand and ring depths that fit the 227 KiB shared-memory budget
+AttnPlan plan_for(int d, int Ty, bool with_v) {
+  AttnPlan pl{};
+  pl.nbox = (d + 31) / 32;
+  pl.dpad = (d + 15) / 16 * 16;
+  int BN = pl.nbox <= 2 ? 128 : 64;
+  if (Ty < BN) BN = (Ty + 15) / 16 * 16;
+  pl.BN = BN;
+  const size_t xb = (size_t)pl.nbox * ATT_BM * ATT_BOX_ROW_BYTES;
+  const size_t yb = (size_t)pl.nbox * BN * ATT_BOX_ROW_BYTES;
+  const size_t budget = 212 * 1024;
+  pl.sY = 2;
+  pl.sV = with_v ? 2 : 0;
+  if (xb + (pl.sY + pl.sV) * yb > budget && with_v) pl.sV = 1;
+  if (xb + (pl.sY + pl.sV) * yb > budget) pl.sY = 1;
+  pl.smem = xb + (size_t)(pl.sY + pl.sV) * yb + 1024;
+  return pl;
+}
+
+int tmap3(Ctx* c, CUtensorMap* tm, const float* base, int d, int T, long long nb, int box_rows) {
+  uint64_t dims[3] = {(uint64_t)d, (uint64_t)T, (uint64_t)nb};
+  uint64_t str[3] = {1, (uint64_t)d, (uint64_t)T * d};
+  uint32_t box[3] = {32, (uint32_t)box_rows, 1};
+  return make_tmap_f32(c, tm, base, 3, dims, str, box);
+}
+
+cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV,
+                        const AttnKParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+  static int max_dyn = -1;
+  if (max_dyn < 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, attn_kernel);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    const int lim = optin - (int)fa.sharedSizeBytes;
+    e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return e;
+    max_dyn = lim;
+  }
+  if ((long long)smem > max_dyn) return cudaErrorInvalidConfiguration;
+  attn_kernel<<<grid, ATT_THREADS, smem, stream>>>(tmX, tmY, tmV, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool attention_fused_supported(int d, int causal) { return !causal && d >= 8 && d % 8 == 0 && d <= 160; }
+
+int attention_fused(Ctx* c, const AttnArgs& a) {
+  if (!attention_fused_supported(a.d, a.causal)) return c->fail(TSD_ERR_INVALID, "attention(fused): unsupported head dim");
+  const long long kv_full = (long long)a.heads * a.Tk * a.d;
+  if (a.kv_batch_stride != 0 && a.kv_batch_stride != kv_full)
+    return c->fail(TSD_ERR_INVALID, "attention(fused): K/V batch stride must be 0 (shared) or heads*Tk*d");
+  const int kv_shared = (a.kv_batch_stride == 0 && a.batch > 1) ? 1 : 0;
+  const int BH = a.batch * a.heads;
+  const long long kv_nb = kv_shared ? a.heads : BH;
+  const float cs = 1.4426950408889634f / sqrtf((float)a.d);
+  const bool query_axis = a.softmax_axis == 0;
+
+  // ---- pass 1: statistics --------------------------------------------------------------------
+  // query axis: one (max, sum) per key column over all queries  -> X = K, Y = Q
+  // key axis:   one (max, sum) per query row over all keys       -> X = Q, Y = K
+  const int Tx = query_axis ? a.Tk : a.Tq, Ty = query_axis ? a.Tq : a.Tk;
+  const AttnPlan sp = plan_for(a.d, Ty, false);
+  const int x_tiles = (Tx + ATT_BM - 1) / ATT_BM;
+  const int y_tiles = (Ty + sp.BN - 1) / sp.BN;
+  int splits = 1;
+  {
+    // fill the machine when the stationary side is short (cross-attention: 77 keys = 1 tile)
+    const long long ctas = (long long)x_tiles * BH;
+    if (ctas < c->sm_count) {
+      splits = (int)((c->sm_count + ctas - 1) / ctas);
+      if (splits > y_tiles) splits = y_tiles;
+      if (splits > 32) splits = 32;
+      if (splits < 1) splits = 1;
+    }
+  }
+  int tps = (y_tiles + splits - 1) / splits;
+  splits = (y_tiles + tps - 1) / tps;
+
+  const size_t mark = c->arena.mark();
+  float2* part = c->arena.alloc_n<float2>((size_t)splits * BH * Tx);
+  if (!part) return c->fail(TSD_ERR_OOM, "attention(fused): arena exhausted (softmax statistics)");
+  if (c->dry_run) {
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
+  const double core_flops = 4.0 * BH * (double)a.Tq * a.Tk * a.d;
+  {
+    TimedScope ts(c, FAM_ATTN, core_flops);
+    CUtensorMap tmX, tmY;
+    const float* X = query_axis ? a.K : a.Q;
+    const float* Y = query_axis ? a.Q : a.K;
+    const long long x_nb = query_axis ? kv_nb : BH, y_nb = query_axis ? BH : kv_nb;
+    int rc = tmap3(c, &tmX, X, a.d, Tx, x_nb, ATT_BM);
+    if (rc) return rc;
+    rc = tmap3(c, &tmY, Y, a.d, Ty, y_nb, sp.BN);
+    if (rc) return rc;
+    AttnKParams p{};
+    p.mode = ATT_STATS;
+    p.Tx = Tx; p.Ty = Ty; p.d = a.d; p.nbox = sp.nbox; p.dpad = sp.dpad; p.BN = sp.BN;
+    p.sY = sp.sY; p.sV = 1; p.heads = a.heads;
+    p.x_shared = query_axis ? kv_shared : 0;
+    p.y_shared = query_axis ? 0 : kv_shared;
+    p.tiles_per_split = tps; p.total_tiles = y_tiles;
+    p.tmem_cols = 256;
+    p.c = cs;
+    p.part_out = part;
+    p.part_stride = (long long)BH * Tx;
+    rc = c->check(launch_attn(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream),
+                  "attn_kernel (stats) launch");
+    if (rc) return rc;
+    c->launches++;
+
+    // ---- pass 2: P = exp2(c S - mu), O = P V ----------------------------------------------------
+    const AttnPlan ap = plan_for(a.d, a.Tk, true);
+    CUtensorMap tmQ, tmK, tmV;
+    rc = tmap3(c, &tmQ, a.Q, a.d, a.Tq, BH, ATT_BM);
+    if (rc) return rc;
+    rc = tmap3(c, &tmK, a.K, a.d, a.Tk, kv_nb, ap.BN);
+    if (rc) return rc;
+    rc = tmap3(c, &tmV, a.V, a.d, a.Tk, kv_nb, ap.BN);
+    if (rc) return rc;
+    AttnKParams q{};
+    q.mode = ATT_APPLY;
+    q.Tx = a.Tq; q.Ty = a.Tk; q.d = a.d; q.nbox = ap.nbox; q.dpad = ap.dpad; q.BN = ap.BN;
+    q.sY = ap.sY; q.sV = ap.sV; q.heads = a.heads;
+    q.x_shared = 0; q.y_shared = kv_shared; q.v_shared = kv_shared;
+    q.total_tiles = (a.Tk + ap.BN - 1) / ap.BN;
+    q.tiles_per_split = q.total_tiles;
+    q.tmem_cols = 512;
+    q.c = cs;
+    q.part_in = part;
+    q.mu_splits = splits;
+    q.mu_per_row = query_axis ? 0 : 1;
+    q.Tmu = Tx;
+    q.part_stride = (long long)BH * Tx;
+    q.O = a.O;
+    q.ldo = a.heads * a.d;
+    q.round_out = 1;
+    rc = c->check(launch_attn(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream),
+                  "attn_kernel (apply) launch");
+    if (rc) return rc;
+    c->launches++;
+  }
+  c->arena.release_to(mark);  // stream-ordered reuse
+  return TSD_OK;
+}
+
 }  // namespace tsd

@@ -7,6 +7,7 @@
 
 #include "../../include/tsd_b200.h"
 #include "c_api_internal.h"
+#include "attention_tcgen05.cuh"
 #include "elementwise.cuh"
 #include "runtime.h"
 
@@ -391,7 +392,7 @@ int32_t tsd_attention_core(tsd_ctx* h, const float* q, const float* k, const flo
   if (d % 4) return h->c->fail(TSD_ERR_INVALID, "attention: head dim must be a multiple of 4");
   const size_t nq = (size_t)heads * tq * d, nk = (size_t)heads * tk * d;
   size_t need = (2 * nq + 2 * nk) * 4 + (32u << 20);
-  if (!h->c->fused_attention) need += ((size_t)heads * tq * (tk + 4) + (size_t)heads * d * (tk + 4)) * 4;
+  if (!h->c->fused_attention || !attention_fused_supported(d, 0)) need += ((size_t)heads * tq * (tk + 4) + (size_t)heads * d * (tk + 4)) * 4;
   HostCall hc(h, need);
   float* qd = hc.upload(q, nq);
   float* kd = hc.upload(k, nk);
@@ -415,7 +416,7 @@ int32_t tsd_self_attention(tsd_ctx* h, const float* x, int32_t t, int32_t cch, i
     return h->c->fail(TSD_ERR_INVALID, "self_attention: unsupported shape");
   const size_t nx = (size_t)t * cch;
   size_t need = (6 * nx + 4 * (size_t)cch * cch + 4 * cch) * 4 + (32u << 20);
-  if (!h->c->fused_attention) need += ((size_t)n_heads * t * (t + 4) * 2) * 4;
+  if (!h->c->fused_attention || !attention_fused_supported(cch / n_heads, 0)) need += ((size_t)n_heads * t * (t + 4) * 2) * 4;
   HostCall hc(h, need);
   float* xd = hc.upload(x, nx);
   float* wi = hc.upload(w_in, (size_t)3 * cch * cch);
@@ -458,7 +459,7 @@ int32_t tsd_cross_attention(tsd_ctx* h, const float* x, int32_t t, int32_t cch, 
   const size_t nx = (size_t)t * cch, nc = (size_t)tk * dc, nkv = (size_t)tk * cch;
   size_t need = (5 * nx + nc + 2 * nkv + 2 * (size_t)cch * cch + 2 * (size_t)cch * dc + 4 * cch) * 4 +
                 (32u << 20);
-  if (!h->c->fused_attention) need += ((size_t)n_heads * t * (tk + 4) * 2) * 4;
+  if (!h->c->fused_attention || !attention_fused_supported(cch / n_heads, 0)) need += ((size_t)n_heads * t * (tk + 4) * 2) * 4;
   HostCall hc(h, need);
   float* xd = hc.upload(x, nx);
   float* cd = hc.upload(context, nc);

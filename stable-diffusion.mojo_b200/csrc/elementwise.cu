@@ -152,44 +152,95 @@ __global__ void im2col3x3_kernel(const float4* __restrict__ x, float4* __restric
 // ------------------------------------------------------------------------------------------
 // GroupNorm / LayerNorm statistics
 // ------------------------------------------------------------------------------------------
-// Fast path: C % 4 == 0 and C/4 <= 1024. Thread owns one channel quad and walks pixels.
-__global__ void group_stats_vec_kernel(const float4* __restrict__ x, long long pixels, int C4, int G,
-                                       int cpg, double* __restrict__ accum) {
-  extern __shared__ float sm[];  // [2*C]
+// Fast path (C % 4 == 0, C/4 <= 768): deterministic two-level reduction, no float atomics.
+// grid (nb, N): block b of image n owns a slab of pixels and all channels.  A thread owns up to
+// three fixed channel quads (coalesced float4 loads along C) and walks the slab's pixels; the
+// per-channel sums are combined through shared memory in a fixed order, folded to per-group
+// (sum, sum of squares) in double and written to partial[n][b][g].  The last block to finish
+// (atomic ticket) reduces the partials in block order and writes (mean, 1/(std+eps)), so the
+// result is bit-reproducible run to run (CUDA-graph replay == eager).
+constexpr int GS_THREADS = 256;
+constexpr int GS_MAXQ = 3;
+__global__ void __launch_bounds__(GS_THREADS)
+group_stats_vec_kernel(const float4* __restrict__ x, long long pixels, int C4, int G, int cpg, int slab,
+                       double2* __restrict__ partial, unsigned int* __restrict__ ticket, double count, float eps,
+                       float2* __restrict__ stats) {
+  extern __shared__ float sm[];  // [ppl][2][C]
+  __shared__ bool last_block;
   const int C = C4 * 4;
-  float* sm_s = sm;
-  float* sm_q = sm + C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  const int n = blockIdx.y;
-  const int lanes = blockDim.x / C4;
-  const int u = threadIdx.x % C4, pl = threadIdx.x / C4;
-  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  if (pl < lanes) {
+  const int n = blockIdx.y, nb = gridDim.x;
+  const int TU = C4 < GS_THREADS ? C4 : GS_THREADS;  // threads across the channel-quad axis
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  const int u = threadIdx.x % TU, pl = threadIdx.x / TU;
+  float s[GS_MAXQ][4], q[GS_MAXQ][4];
+#pragma unroll
+  for (int i = 0; i < GS_MAXQ; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = q[i][j] = 0.f;
+  long long p0 = (long long)blockIdx.x * slab, p1 = p0 + slab;
+  if (p1 > pixels) p1 = pixels;
+  if (pl < ppl) {
     const float4* base = x + (long long)n * pixels * C4;
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < pixels;
-         p += (long long)gridDim.x * lanes) {
-      float4 v = base[p * C4 + u];
-      s[0] += v.x; q[0] += v.x * v.x;
-      s[1] += v.y; q[1] += v.y * v.y;
-      s[2] += v.z; q[2] += v.z * v.z;
-      s[3] += v.w; q[3] += v.w * v.w;
+    for (long long p = p0 + pl; p < p1; p += ppl) {
+#pragma unroll
+      for (int i = 0; i < GS_MAXQ; ++i) {
+        const int qd = u + i * TU;
+        if (qd < C4) {
+          const float4 v = base[p * C4 + qd];
+          s[i][0] += v.x; q[i][0] += v.x * v.x;
+          s[i][1] += v.y; q[i][1] += v.y * v.y;
+          s[i][2] += v.z; q[i][2] += v.z * v.z;
+          s[i][3] += v.w; q[i][3] += v.w * v.w;
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(&sm_s[u * 4 + j], s[j]);
-      atomicAdd(&sm_q[u * 4 + j], q[j]);
+    for (int i = 0; i < GS_MAXQ; ++i) {
+      const int qd = u + i * TU;
+      if (qd < C4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sm[(pl * 2 + 0) * C + qd * 4 + j] = s[i][j];
+          sm[(pl * 2 + 1) * C + qd * 4 + j] = q[i][j];
+        }
+      }
     }
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double ds = 0.0, dq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      ds += (double)sm_s[c];
-      dq += (double)sm_q[c];
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+      for (int l = 0; l < ppl; ++l) {
+        ds += (double)sm[(l * 2 + 0) * C + c];
+        dq += (double)sm[(l * 2 + 1) * C + c];
+      }
+    partial[((long long)n * nb + blockIdx.x) * G + g] = make_double2(ds, dq);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last_block = (t == total - 1);
+    if (last_block) *ticket = 0u;  // self-resetting: launches on one stream are serialised
+  }
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  const int NG = gridDim.y * G;
+  for (int i = threadIdx.x; i < NG; i += blockDim.x) {
+    const int nn = i / G, g = i - nn * G;
+    double ds = 0.0, dq = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      const double2 v = partial[((long long)nn * nb + b) * G + g];
+      ds += v.x;
+      dq += v.y;
     }
-    atomicAdd(&accum[((long long)n * G + g) * 2], ds);
-    atomicAdd(&accum[((long long)n * G + g) * 2 + 1], dq);
+    const double mean = ds / count;
+    double var = dq / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
+    stats[i] = make_float2((float)mean, (float)(1.0 / (sqrt(var) + (double)eps)));
   }
 }
 
@@ -544,34 +595,53 @@ cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, in
   return cudaGetLastError();
 }
 
+int group_stats_blocks(int N, long long pixels, int C) {
+  // slabs of >= 8 pixels per pixel lane, about two waves of blocks over the SMs, <= 128 per image
+  const int C4 = C / 4;
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  long long nb = pixels / (8LL * ppl);
+  long long cap = (2LL * kSMs + N - 1) / N;
+  if (cap > 128) cap = 128;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+size_t group_stats_scratch_bytes(int N, long long pixels, int C, int G) {
+  if (C % 4 == 0 && C / 4 <= GS_THREADS * GS_MAXQ)
+    return sizeof(double2) * (size_t)N * group_stats_blocks(N, pixels, C) * G;
+  return sizeof(double) * 2 * (size_t)N * G;
+}
+
 cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, int G, float eps,
-                               double* accum, float2* stats, cudaStream_t s) {
+                               void* scratch, unsigned int* ticket, float2* stats, cudaStream_t s) {
   if (G <= 0 || C % G) return cudaErrorInvalidValue;
   const int cpg = C / G;
   const int NG = N * G;
-  if (C % 4 == 0 && C / 4 <= 1024 && 2 * C * sizeof(float) <= 48 * 1024) {
-    cudaError_t e = cudaMemsetAsync(accum, 0, sizeof(double) * 2 * NG, s);
-    if (e != cudaSuccess) return e;
+  if (C % 4 == 0 && C / 4 <= GS_THREADS * GS_MAXQ) {
     const int C4 = C / 4;
-    int lanes = 512 / C4;
-    if (lanes < 1) lanes = 1;
-    const int threads = ((C4 * lanes + 31) / 32) * 32;
-    long long want = (pixels + lanes - 1) / lanes;          // blocks if 1 pixel step each
-    long long bx = want / 8;                                // >= 8 pixels per thread
-    long long cap = (long long)(kSMs * 4 + N - 1) / N;
-    if (bx > cap) bx = cap;
-    if (bx < 1) bx = 1;
-    dim3 grid((unsigned)bx, N);
-    group_stats_vec_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(
-        reinterpret_cast<const float4*>(x), pixels, C4, G, cpg, accum);
-  } else {
-    dim3 grid(G, N);
-    group_stats_general_kernel<<<grid, 256, 0, s>>>(x, pixels, C, G, cpg, accum);
+    const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+    const int nb = group_stats_blocks(N, pixels, C);
+    const int slab = (int)((pixels + nb - 1) / nb);
+    const size_t smem = (size_t)ppl * 2 * C * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(group_stats_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    dim3 grid((unsigned)nb, N);
+    group_stats_vec_kernel<<<grid, GS_THREADS, smem, s>>>(reinterpret_cast<const float4*>(x), pixels, C4, G, cpg, slab,
+                                                          reinterpret_cast<double2*>(scratch), ticket,
+                                                          (double)pixels * cpg, eps, stats);
+    return cudaGetLastError();
   }
+  dim3 grid(G, N);
+  double* accum = reinterpret_cast<double*>(scratch);
+  group_stats_general_kernel<<<grid, 256, 0, s>>>(x, pixels, C, G, cpg, accum);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  group_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, s>>>(accum, NG, (double)pixels * cpg, eps,
-                                                               stats);
+  group_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, s>>>(accum, NG, (double)pixels * cpg, eps, stats);
   return cudaGetLastError();
 }
 

@@ -29,9 +29,12 @@ cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, in
 
 // ---- normalisation ------------------------------------------------------------------------
 // stats[n][g] = (mean, 1/(std+eps)) with the reference's biased std and eps added to std
-// (helpers/utils.mojo:1360-1380, 1868-1870).  `accum` is a [N*G*2] double scratch.
+// (helpers/utils.mojo:1360-1380, 1868-1870).  `scratch` holds group_stats_scratch_bytes() bytes;
+// `ticket` is a zero-initialised device counter owned by the context (self-resetting).
+// Deterministic: no floating-point atomics, fixed reduction order.
+size_t group_stats_scratch_bytes(int N, long long pixels, int C, int G);
 cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, int G, float eps,
-                               double* accum, float2* stats, cudaStream_t s);
+                               void* scratch, unsigned int* ticket, float2* stats, cudaStream_t s);
 // y = (x - mean) * inv [* gamma[c] + beta[c]] ; optional SiLU ; optional TF32 rounding ;
 // optional nearest 2x upsample on write (x is [N,H,W,C], y is [N,2H,2W,C]).
 cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* gamma,

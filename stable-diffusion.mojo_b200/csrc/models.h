@@ -125,7 +125,7 @@ struct Decoder {
   int latent_h = 0, latent_w = 0, max_batch = 1;
   ParamStore ps;
   int l1 = -1, l2 = -1, l10 = -1, l15 = -1, l20 = -1, l26 = -1, attn_in = -1, attn_out = -1;
-  ResBlockW res[13];  // l3, l5..l8, l11..l13, l16..l18, l21..l23
+  ResBlockW res[14];  // l3, l5..l8, l11..l13, l16..l18, l21..l23
   float* z_in = nullptr;     // [max_batch][4][h][w]
   float* img_out = nullptr;  // [max_batch][3][8h][8w]
   float* ping = nullptr;

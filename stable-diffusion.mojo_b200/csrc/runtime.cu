@@ -98,6 +98,12 @@ int ctx_create(int device, Ctx** out, std::string* err) {
     return TSD_ERR_CUDA;
   }
   c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  if (cudaMalloc(&c->ticket, 256) != cudaSuccess || cudaMemset(c->ticket, 0, 256) != cudaSuccess) {
+    *err = "ticket allocation failed";
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return TSD_ERR_OOM;
+  }
   *out = c;
   return TSD_OK;
 }
@@ -110,6 +116,7 @@ void ctx_destroy(Ctx* c) {
     for (auto e : c->timer->pool) cudaEventDestroy(e);
     delete c->timer;
   }
+  if (c->ticket) cudaFree(c->ticket);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -141,7 +148,7 @@ TimedScope::~TimedScope() {
 // TMA descriptors
 // ------------------------------------------------------------------------------------------
 // fp32 tensor, dims innermost-first, strides in elements (stride of dim0 is 1), 128 B swizzle.
-static int make_tmap(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
+int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_elems, const uint32_t* box) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
@@ -281,7 +288,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
     if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
     uint32_t box[4] = {(uint32_t)GEMM_BK, (uint32_t)bw, (uint32_t)bh, 1};
-    int rc = make_tmap(c, &tmA, A.base, 4, dims, str, box);
+    int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box);
     if (rc) return rc;
   }
   if (!c->dry_run) {
@@ -289,7 +296,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
     uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
     uint32_t box[3] = {(uint32_t)GEMM_BK, (uint32_t)(p.geglu ? p.BN / 2 : p.BN), 1};
-    int rc = make_tmap(c, &tmB, B, 3, dims, str, box);
+    int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box);
     if (rc) return rc;
   }
 
@@ -462,7 +469,7 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
                   int round_tf32) {
   if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
   const size_t mark = c->arena.mark();
-  double* accum = c->arena.alloc_n<double>((size_t)2 * N * G);
+  void* accum = c->arena.alloc(group_stats_scratch_bytes(N, (long long)H * W, C, G));
   float2* stats = c->arena.alloc_n<float2>((size_t)N * G);
   if (!accum || !stats) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
   if (c->dry_run) {
@@ -470,14 +477,14 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
     return TSD_OK;
   }
   TimedScope ts(c, FAM_NORM, 0);
-  int rc = c->check(launch_group_stats(x, N, (long long)H * W, C, G, eps, accum, stats, c->stream),
+  int rc = c->check(launch_group_stats(x, N, (long long)H * W, C, G, eps, accum, c->ticket, stats, c->stream),
                     "group_stats launch");
   if (rc) return rc;
   rc = c->check(launch_norm_apply(x, stats, gamma, beta, gamma_scalar, y, N, H, W, C, G, silu, upsample,
                                   round_tf32, c->stream),
                 "norm_apply launch");
   if (rc) return rc;
-  c->launches += 3;
+  c->launches += 2;
   c->arena.release_to(mark);
   return TSD_OK;
 }

@@ -69,6 +69,7 @@ struct Ctx {
   int fused_attention = 1;  // 1 = tcgen05 fused kernel ; 0 = GEMM + softmax + GEMM
   int layernorm_mode = 0;   // 0 = global statistics (reference, Q5) ; 1 = per token
   int force_bn = 0, force_splits = 0;  // test/tuning overrides for the GEMM tile heuristic
+  unsigned int* ticket = nullptr;  // zero-initialised device counter for last-block reductions
   KernelTimer* timer = nullptr;
   long long launches = 0;   // kernels launched through this context (bench "gpu_launches")
   bool dry_run = false;     // planning pass: ops allocate workspace but launch nothing
