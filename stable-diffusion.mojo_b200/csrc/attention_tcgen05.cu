@@ -20,13 +20,14 @@
 #include "attention_tcgen05.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 #include "ptx_sm100.cuh"
 
 namespace tsd {
 
 int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_elems, const uint32_t* box);
+                  const uint64_t* strides_elems, const uint32_t* box, int swizzle_atom_32b);
 
 namespace {
 
@@ -54,6 +55,7 @@ struct AttnKParams {
   float* O;               // APPLY: merged output [b][Tx][heads*d]
   int ldo;
   int round_out;
+  int debug;  // TSD_ATTN_DEBUG: 1 = P := 1, 2 = P := S (bring-up probes)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -185,8 +187,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         tc_fence_after_sync();
         const uint32_t vb = vs + st * ystage;
         for (int ks = 0; ks < pv_steps; ++ks) {
-          // V tile: [BN keys][32 floats] boxes, 8-key groups of 1024 B; N atoms (boxes) are ybox apart
-          const uint64_t bdesc = umma_smem_desc(vb + ks * 1024, ybox, 1024, UMMA_SWIZZLE_128B);
+          // V tile: [BN keys][32 floats] boxes read MN-major.  For 32-bit MN-major operands the only
+          // legal layout is SWIZZLE_128B with 32 B atoms: 4-key groups of 512 B (SBO), N atoms
+          // (boxes of 32 floats) ybox apart (LBO); one K = 8 step spans two groups.
+          const uint64_t bdesc = umma_smem_desc(vb + ks * 1024, ybox, 512, UMMA_SWIZZLE_128B_BASE32B);
           umma_tf32_ts(tmem_o, tmem_base + (uint32_t)(bj * 128 + ks * 8), bdesc, idesc_o,
                        (j > 0 || ks > 0) ? 1u : 0u);
         }
@@ -311,7 +315,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             for (int j = 16; j < 32; ++j) v[j] = 0;
           }
           tmem_ld_wait();
-          if (!p.mu_per_row) {
+          if (p.debug) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = p.debug == 1 ? 1.0f : __uint_as_float(v[j]);
+              v[j] = (c0 + j < nvalid) ? rna_tf32_bits(e) : 0u;
+            }
+          } else if (!p.mu_per_row) {
             const float4* mup = reinterpret_cast<const float4*>(&mu_s[b][c0]);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -405,11 +415,11 @@ AttnPlan plan_for(int d, int Ty, bool with_v) {
   return pl;
 }
 
-int tmap3(Ctx* c, CUtensorMap* tm, const float* base, int d, int T, long long nb, int box_rows) {
+int tmap3(Ctx* c, CUtensorMap* tm, const float* base, int d, int T, long long nb, int box_rows, int atom32 = 0) {
   uint64_t dims[3] = {(uint64_t)d, (uint64_t)T, (uint64_t)nb};
   uint64_t str[3] = {1, (uint64_t)d, (uint64_t)T * d};
   uint32_t box[3] = {32, (uint32_t)box_rows, 1};
-  return make_tmap_f32(c, tm, base, 3, dims, str, box);
+  return make_tmap_f32(c, tm, base, 3, dims, str, box, atom32);
 }
 
 cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV,
@@ -458,7 +468,8 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
   int splits = 1;
   {
     // fill the machine when the stationary side is short (cross-attention: 77 keys = 1 tile)
-    const long long ctas = (long long)x_tiles * BH;
+    // (a function of the per-image shape only: results do not depend on the batch size)
+    const long long ctas = (long long)x_tiles * a.heads;
     if (ctas < c->sm_count) {
       splits = (int)((c->sm_count + ctas - 1) / ctas);
       if (splits > y_tiles) splits = y_tiles;
@@ -510,7 +521,7 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
     if (rc) return rc;
     rc = tmap3(c, &tmK, a.K, a.d, a.Tk, kv_nb, ap.BN);
     if (rc) return rc;
-    rc = tmap3(c, &tmV, a.V, a.d, a.Tk, kv_nb, ap.BN);
+    rc = tmap3(c, &tmV, a.V, a.d, a.Tk, kv_nb, ap.BN, 1);  // MN-major tf32 operand: 128B swizzle, 32B atoms
     if (rc) return rc;
     AttnKParams q{};
     q.mode = ATT_APPLY;
@@ -529,6 +540,16 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
     q.O = a.O;
     q.ldo = a.heads * a.d;
     q.round_out = 1;
+    {
+      const char* dbg = getenv("TSD_ATTN_DEBUG");
+      q.debug = dbg ? atoi(dbg) : 0;
+      if (q.debug == 3) {  // return the statistics instead of the output
+        size_t nb = sizeof(float2) * (size_t)splits * BH * Tx, cap = sizeof(float) * (size_t)a.batch * a.Tq * a.heads * a.d;
+        cudaMemcpyAsync(a.O, part, nb < cap ? nb : cap, cudaMemcpyDeviceToDevice, c->stream);
+        c->arena.release_to(mark);
+        return TSD_OK;
+      }
+    }
     rc = c->check(launch_attn(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream),
                   "attn_kernel (apply) launch");
     if (rc) return rc;

@@ -5,6 +5,7 @@
 
 #include "../../include/tsd_b200.h"
 #include "c_api_internal.h"
+#include "elementwise.cuh"
 #include "models.h"
 
 using namespace tsd;
@@ -96,6 +97,13 @@ int32_t tsd_diffusion_profile(tsd_diffusion* d, const float* x_dev, const float*
   Guard g(d->m.h);
   Ctx* c = d->m.c;
   KernelTimer timer;
+  // one untimed eager pass (sizes the workspace, sets kernel attributes), then block the stream for
+  // 20 ms so the whole timed pass is enqueued before the GPU starts it: the per-launch events then
+  // measure device time, not host launch gaps
+  int rc0 = d->m.forward_dev(x_dev, context_dev, n_ctx, time_dev, n_time, n, out_dev, false);
+  if (rc0) return rc0;
+  cudaStreamSynchronize(c->stream);
+  launch_spin(20 * 1000 * 1000LL, c->stream);
   c->timer = &timer;
   int rc = d->m.forward_dev(x_dev, context_dev, n_ctx, time_dev, n_time, n, out_dev, false);
   int rc2 = c->check(cudaStreamSynchronize(c->stream), "profile sync");

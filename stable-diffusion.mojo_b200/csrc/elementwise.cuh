@@ -70,6 +70,9 @@ cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const 
 cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, float scale,
                            float* col_scratch, cudaStream_t s);
 
+// keeps the stream busy for `ns` nanoseconds (profiling aid)
+cudaError_t launch_spin(long long ns, cudaStream_t s);
+
 // ---- DDPM step (+ optional CFG combine), sampler.mojo:75-109, pipeline.mojo:117-119 --------
 // eps = cfg ? u + cfg_scale * (c - u) : c ; x0 = (x - sqrt(1-ab_t) eps)/sqrt(ab_t)
 // out = c0 * x0 + c1 * x + sigma * noise

@@ -226,7 +226,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //   [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset >> 4     [46,48) version (1 on sm_100)
 //   [49,52) base offset (0: tiles are 1024 B aligned)   [61,64) swizzle mode
-enum : uint64_t { UMMA_SWIZZLE_NONE = 0, UMMA_SWIZZLE_128B = 2, UMMA_SWIZZLE_64B = 4, UMMA_SWIZZLE_32B = 6 };
+enum : uint64_t { UMMA_SWIZZLE_NONE = 0, UMMA_SWIZZLE_128B_BASE32B = 1, UMMA_SWIZZLE_128B = 2, UMMA_SWIZZLE_64B = 4, UMMA_SWIZZLE_32B = 6 };
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes, uint64_t swizzle) {

@@ -149,7 +149,7 @@ TimedScope::~TimedScope() {
 // ------------------------------------------------------------------------------------------
 // fp32 tensor, dims innermost-first, strides in elements (stride of dim0 is 1), 128 B swizzle.
 int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_elems, const uint32_t* box) {
+                  const uint64_t* strides_elems, const uint32_t* box, int swizzle_atom_32b) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
@@ -166,7 +166,8 @@ int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const ui
     return c->fail(TSD_ERR_INVALID, "TMA: base address not 16-byte aligned");
   CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                          const_cast<float*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         swizzle_atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -288,7 +289,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
     if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
     uint32_t box[4] = {(uint32_t)GEMM_BK, (uint32_t)bw, (uint32_t)bh, 1};
-    int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box);
+    int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box, 0);
     if (rc) return rc;
   }
   if (!c->dry_run) {
@@ -296,7 +297,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
     uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
     uint32_t box[3] = {(uint32_t)GEMM_BK, (uint32_t)(p.geglu ? p.BN / 2 : p.BN), 1};
-    int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box);
+    int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box, 0);
     if (rc) return rc;
   }
 
