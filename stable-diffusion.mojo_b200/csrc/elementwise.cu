@@ -207,14 +207,33 @@ group_stats_vec_kernel(const float4* __restrict__ x, long long pixels, int C4, i
     }
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double ds = 0.0, dq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
-      for (int l = 0; l < ppl; ++l) {
-        ds += (double)sm[(l * 2 + 0) * C + c];
-        dq += (double)sm[(l * 2 + 1) * C + c];
+  // per-channel totals over the pixel lanes (fixed order), kept in plane 0 of the staging buffer
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = sm[c], b = sm[C + c];
+    for (int l = 1; l < ppl; ++l) {
+      a += sm[(l * 2 + 0) * C + c];
+      b += sm[(l * 2 + 1) * C + c];
+    }
+    sm[c] = a;
+    sm[C + c] = b;
+  }
+  __syncthreads();
+  // one warp per group: lanes stride over the group's channels, then a fixed xor-shuffle tree
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < G; g += nwarps) {
+      double ds = 0.0, dq = 0.0;
+      for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+        ds += (double)sm[c];
+        dq += (double)sm[C + c];
       }
-    partial[((long long)n * nb + blockIdx.x) * G + g] = make_double2(ds, dq);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      if (lane == 0) partial[((long long)n * nb + blockIdx.x) * G + g] = make_double2(ds, dq);
+    }
   }
   __threadfence();
   __syncthreads();

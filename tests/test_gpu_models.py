@@ -202,7 +202,7 @@ def test_loop_properties(diff8, golden_small):
     for i, t in enumerate(ts):
         eps = diffusion_step(diff8, lat, cx, temb[i])
         lat = diff8.ctx.sampler_step(lat, eps, None, 1.0, noise[i, :1] if t > 0 else None, *[float(v) for v in coef[i]])
-    assert relerr(lat[0], both[0]) < 1e-4
+    assert relerr(lat[0], both[0]) < TOL_BATCH          # `both` was evaluated as a batch of 2
 
 
 def diffusion_step(m, lat, cx, temb):
