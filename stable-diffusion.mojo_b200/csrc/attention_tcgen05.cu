@@ -15,8 +15,8 @@
 //          O += P V_t, V staged by TMA in its natural [key][d] layout and read MN-major.
 //          S / P never touch shared or global memory; no running-max correction of O is needed
 //          because mu is known before the pass starts.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..5 softmax /
-// epilogue (one thread per S row, TMEM lane quadrant = warp & 3).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..9 softmax /
+// epilogue (two threads per S row, each a column half; TMEM lane quadrant = warp & 3).
 #include "attention_tcgen05.cuh"
 
 #include <cmath>
@@ -32,7 +32,8 @@ int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const ui
 namespace {
 
 constexpr int ATT_BM = 128;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_SM_THREADS = 256;               // 8 softmax warps
+constexpr int ATT_THREADS = 64 + ATT_SM_THREADS;  // + TMA producer warp + MMA issuer warp
 constexpr int ATT_BOX_ROW_BYTES = 128;  // 32 fp32 = one SWIZZLE_128B row
 enum { ATT_STATS = 0, ATT_APPLY = 1 };
 
@@ -124,8 +125,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_free[s], ATT_BM);
-      mbar_init(&p_full[s], ATT_BM);
+      mbar_init(&s_free[s], ATT_SM_THREADS);
+      mbar_init(&p_full[s], ATT_SM_THREADS);
     }
     mbar_init(&o_full, 1);
     fence_barrier_init();
@@ -221,12 +222,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===================== softmax / epilogue (warps 2..5) =====================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;  // S row == TMEM lane owned by this thread
+    // ===================== softmax / epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31): both own the
+    // same 32 S rows, each a contiguous half of the tile's columns, so that every SM scheduler has
+    // two softmax warps to interleave (one alone is issue/latency bound).
+    const int sw = warp - 2;        // 0..7
+    const int q = warp & 3;         // lane quadrant
+    const int half = sw >> 2;       // column half
+    const int row = q * 32 + lane;  // S row == TMEM lane
+    const int st = sw * 32 + lane;  // 0..255 among the softmax threads
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool row_ok = x0 + row < p.Tx;
     const float c = p.c;
+    const int h0 = ((p.BN >> 4) + 1) >> 1;  // 16-column chunks owned by half 0
+    const int cb = half ? h0 * 16 : 0, ce = half ? p.BN : h0 * 16;
 
     if (!apply) {
       float m = -INFINITY, l = 0.f;
@@ -237,10 +246,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         if (nvalid > p.BN) nvalid = p.BN;
         mbar_wait(&s_full[b], (uint32_t)(it >> 1) & 1u);
         tc_fence_after_sync();
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
           uint32_t v[32];
-          const bool full = c0 + 32 <= p.BN;
-          if (full) {
+          if (c0 + 32 <= ce) {
             tmem_ld32(lane_base + (uint32_t)(b * 128 + c0), v);
           } else {
             uint32_t t16[16];
@@ -248,61 +256,77 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = t16[j];
 #pragma unroll
-            for (int j = 16; j < 32; ++j) v[j] = 0;
+            for (int j = 16; j < 32; ++j) v[j] = 0xff800000u;  // -inf
           }
           tmem_ld_wait();
-          if (c0 + 32 >= p.BN) {  // last chunk read: the S buffer may be overwritten
-            tc_fence_before_sync();
-            mbar_arrive(&s_free[b]);
-          }
-          float x[32];
-          float cm = -INFINITY;
+          if (c0 >= nvalid) continue;  // whole chunk past the last valid column
+          if (c0 + 32 > nvalid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] = (c0 + j < nvalid) ? __uint_as_float(v[j]) * c : -INFINITY;
-            cm = fmaxf(cm, x[j]);
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j >= nvalid) v[j] = 0xff800000u;
           }
+          float cm = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+          cm *= c;
           if (cm > m) {
             l *= ex2(m - cm);
             m = cm;
           }
-          float acc = 0.f;
+          float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc += ex2(x[j] - m);
-          l += acc;
+          for (int j = 0; j < 32; j += 2) {
+            a0 += ex2(fmaf(__uint_as_float(v[j]), c, -m));
+            a1 += ex2(fmaf(__uint_as_float(v[j + 1]), c, -m));
+          }
+          l += a0 + a1;
         }
+        tc_fence_before_sync();
+        mbar_arrive(&s_free[b]);  // this thread's reads of S[b] are complete
       }
-      if (row_ok) p.part_out[(long long)split * p.part_stride + (long long)bh * p.Tx + x0 + row] = make_float2(m, l);
+      // merge the two column halves of each row (half 1 -> shared -> half 0), then store
+      float2* comb = reinterpret_cast<float2*>(&mu_s[0][0]);  // 128 float2 = the whole mu_s array
+      if (half == 1) comb[row] = make_float2(m, l);
+      named_bar_sync(1, ATT_SM_THREADS);
+      if (half == 0 && row_ok) {
+        const float2 o = comb[row];
+        const float M = fmaxf(m, o.x);
+        const float L = l * ex2(m - M) + o.y * ex2(o.x - M);
+        p.part_out[(long long)split * p.part_stride + (long long)bh * p.Tx + x0 + row] = make_float2(M, L);
+      }
     } else {
+      // P is written with a 2^-11 relative boost so that the tensor core's truncation of the fp32
+      // bit pattern to TF32 acts as round-to-nearest (unbiased), at no instruction cost
+      const float rnd = 7.0436e-4f;  // log2(1 + 2^-11)
       float mu_row = 0.f;
       if (p.mu_per_row && row_ok)
-        mu_row = merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + x0 + row);
+        mu_row = merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + x0 + row) - rnd;
       float2 pre = make_float2(0.f, 1.f);
       const bool fast_mu = !p.mu_per_row && p.mu_splits == 1;
-      if (fast_mu && row < p.BN && it0 * p.BN + row < p.Ty) pre = p.part_in[(long long)bh * p.Tmu + it0 * p.BN + row];
+      if (fast_mu && st < p.BN && it0 * p.BN + st < p.Ty) pre = p.part_in[(long long)bh * p.Tmu + it0 * p.BN + st];
       for (int it = 0; it < n_it; ++it) {
         const int b = it & 1;
         const int ycol0 = (it0 + it) * p.BN;
         int nvalid = p.Ty - ycol0;
         if (nvalid > p.BN) nvalid = p.BN;
         if (!p.mu_per_row) {
-          if (row < p.BN) {
-            const int col = ycol0 + row;
+          if (st < p.BN) {
+            const int col = ycol0 + st;
             float mu = INFINITY;  // masked key column: exp2(-inf) = 0
             if (col < p.Ty)
-              mu = fast_mu ? pre.x + lg2(pre.y)
-                           : merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + col);
-            mu_s[b][row] = mu;
+              mu = (fast_mu ? pre.x + lg2(pre.y)
+                            : merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + col)) - rnd;
+            mu_s[b][st] = mu;
           }
-          named_bar_sync(1, ATT_BM);
-          if (fast_mu && it + 1 < n_it && row < p.BN && ycol0 + p.BN + row < p.Ty)
-            pre = p.part_in[(long long)bh * p.Tmu + ycol0 + p.BN + row];
+          named_bar_sync(1, ATT_SM_THREADS);
+          if (fast_mu && it + 1 < n_it && st < p.BN && ycol0 + p.BN + st < p.Ty)
+            pre = p.part_in[(long long)bh * p.Tmu + ycol0 + p.BN + st];
         }
         mbar_wait(&s_full[b], (uint32_t)(it >> 1) & 1u);
         tc_fence_after_sync();
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
           const uint32_t taddr = lane_base + (uint32_t)(b * 128 + c0);
-          const bool full = c0 + 32 <= p.BN;
+          const bool full = c0 + 32 <= ce;
           uint32_t v[32];
           if (full) {
             tmem_ld32(taddr, v);
@@ -327,16 +351,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             for (int j4 = 0; j4 < 8; ++j4) {
               if (!full && j4 >= 4) break;
               const float4 m4 = mup[j4];
-              v[4 * j4 + 0] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 0]), c, -m4.x)));
-              v[4 * j4 + 1] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 1]), c, -m4.y)));
-              v[4 * j4 + 2] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 2]), c, -m4.z)));
-              v[4 * j4 + 3] = rna_tf32_bits(ex2(fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w)));
+              v[4 * j4 + 0] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 0]), c, -m4.x)));
+              v[4 * j4 + 1] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 1]), c, -m4.y)));
+              v[4 * j4 + 2] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 2]), c, -m4.z)));
+              v[4 * j4 + 3] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w)));
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float e = ex2(fmaf(__uint_as_float(v[j]), c, -mu_row));
-              v[j] = (c0 + j < nvalid) ? rna_tf32_bits(e) : 0u;
+              v[j] = (c0 + j < nvalid) ? __float_as_uint(e) : 0u;
             }
           }
           if (full) {
@@ -357,7 +381,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       tc_fence_after_sync();
       const int bidx = bh / p.heads;
       float* orow = p.O + ((long long)bidx * p.Tx + x0 + row) * p.ldo + (long long)h * p.d;
-      for (int c0 = 0; c0 < p.dpad; c0 += 16) {
+      const int e0 = (((p.dpad >> 4) + 1) >> 1) * 16;
+      const int ob = half ? e0 : 0, oe = half ? p.dpad : e0;
+      for (int c0 = ob; c0 < oe; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
         tmem_ld_wait();

@@ -275,6 +275,189 @@ group_stats_vec_kernel(const float4* __restrict__ x, long long pixels, int C4, i
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused GroupNorm / LayerNorm: statistics + normalise (+SiLU, +TF32 rounding) in ONE launch.
+// The grid is at most one block per SM (all blocks co-resident), so a generation-counter grid
+// barrier separates the two phases:
+//   phase 1  every work item (image n, slab of pixels) -> per-group (sum, sum^2) partials in double
+//            (same deterministic thread/channel ownership as group_stats_vec_kernel)
+//   barrier  last arriver resets the arrival counter and bumps the generation (CUDA-graph safe)
+//   phase 2  every block reduces the partials of its image in a fixed order (redundantly, from L2)
+//            and normalises its own slabs, which it has just read (L2 / L1 hits).
+// The slab partition depends on the image shape only, never on the batch.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GS_THREADS)
+norm_fused_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long pixels, int C4, int G, int cpg,
+                  int slabs, int slab, int items, double2* __restrict__ partial, unsigned int* __restrict__ bar,
+                  double count, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float gamma_scalar, int silu, int round) {
+  extern __shared__ float sm[];  // [ppl][2][C] staging, then [G] float2 statistics
+  const int C = C4 * 4;
+  const int TU = C4 < GS_THREADS ? C4 : GS_THREADS;
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  const int u = threadIdx.x % TU, pl = threadIdx.x / TU;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  // ---- phase 1 ----
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int n = item / slabs, sl = item - n * slabs;
+    float s[GS_MAXQ][4], q[GS_MAXQ][4];
+#pragma unroll
+    for (int i = 0; i < GS_MAXQ; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = q[i][j] = 0.f;
+    long long p0 = (long long)sl * slab, p1 = p0 + slab;
+    if (p1 > pixels) p1 = pixels;
+    if (pl < ppl) {
+      const float4* base = x + (long long)n * pixels * C4;
+#pragma unroll 4
+      for (long long p = p0 + pl; p < p1; p += ppl) {
+#pragma unroll
+        for (int i = 0; i < GS_MAXQ; ++i) {
+          const int qd = u + i * TU;
+          if (qd < C4) {
+            const float4 v = base[p * C4 + qd];
+            s[i][0] += v.x; q[i][0] += v.x * v.x;
+            s[i][1] += v.y; q[i][1] += v.y * v.y;
+            s[i][2] += v.z; q[i][2] += v.z * v.z;
+            s[i][3] += v.w; q[i][3] += v.w * v.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < GS_MAXQ; ++i) {
+        const int qd = u + i * TU;
+        if (qd < C4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sm[(pl * 2 + 0) * C + qd * 4 + j] = s[i][j];
+            sm[(pl * 2 + 1) * C + qd * 4 + j] = q[i][j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = sm[c], b = sm[C + c];
+      for (int l = 1; l < ppl; ++l) {
+        a += sm[(l * 2 + 0) * C + c];
+        b += sm[(l * 2 + 1) * C + c];
+      }
+      sm[c] = a;
+      sm[C + c] = b;
+    }
+    __syncthreads();
+    for (int g = warp; g < G; g += nwarps) {
+      double ds = 0.0, dq = 0.0;
+      for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+        ds += (double)sm[c];
+        dq += (double)sm[C + c];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      if (lane == 0) partial[(long long)item * G + g] = make_double2(ds, dq);
+    }
+    __syncthreads();
+  }
+
+  // ---- grid barrier (all blocks are resident: gridDim.x <= number of SMs) ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = bar + 1;
+    const unsigned int g0 = *gen;
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      *bar = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g0) __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+
+  // ---- phase 2 ----
+  float2* st = reinterpret_cast<float2*>(sm);  // [G]
+  int cur_n = -1;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int n = item / slabs, sl = item - n * slabs;
+    if (n != cur_n) {
+      __syncthreads();
+      // 8 lanes per group: lane j sums slabs j, j+8, ... in order; fixed xor-shuffle tree
+      for (int e0 = 0; e0 < G; e0 += GS_THREADS / 8) {
+        const int g = e0 + (threadIdx.x >> 3), j = threadIdx.x & 7;
+        double ds = 0.0, dq = 0.0;
+        if (g < G) {
+#pragma unroll 4
+          for (int b = j; b < slabs; b += 8) {
+            const double2 v = __ldcg(&partial[((long long)n * slabs + b) * G + g]);
+            ds += v.x;
+            dq += v.y;
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          ds += __shfl_xor_sync(0xffffffffu, ds, o);
+          dq += __shfl_xor_sync(0xffffffffu, dq, o);
+        }
+        if (g < G && j == 0) {
+          const double mean = ds / count;
+          double var = dq / count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
+          st[g] = make_float2((float)mean, (float)(1.0 / (sqrt(var) + (double)eps)));
+        }
+      }
+      __syncthreads();
+      cur_n = n;
+    }
+    if (pl < ppl) {
+      float mu[GS_MAXQ][4], sc[GS_MAXQ][4], sh[GS_MAXQ][4];
+#pragma unroll
+      for (int i = 0; i < GS_MAXQ; ++i) {
+        const int qd = u + i * TU;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mu[i][j] = 0.f; sc[i][j] = 0.f; sh[i][j] = 0.f;
+          if (qd < C4) {
+            const int c = qd * 4 + j;
+            const float2 t = st[c / cpg];
+            mu[i][j] = t.x;
+            sc[i][j] = t.y * gamma_scalar * (gamma ? gamma[c] : 1.0f);
+            sh[i][j] = beta ? beta[c] : 0.0f;
+          }
+        }
+      }
+      long long p0 = (long long)sl * slab, p1 = p0 + slab;
+      if (p1 > pixels) p1 = pixels;
+      const float4* base = x + (long long)n * pixels * C4;
+      float4* obase = y + (long long)n * pixels * C4;
+#pragma unroll 2
+      for (long long p = p0 + pl; p < p1; p += ppl) {
+#pragma unroll
+        for (int i = 0; i < GS_MAXQ; ++i) {
+          const int qd = u + i * TU;
+          if (qd < C4) {
+            const float4 v = base[p * C4 + qd];
+            float o[4] = {(v.x - mu[i][0]) * sc[i][0] + sh[i][0], (v.y - mu[i][1]) * sc[i][1] + sh[i][1],
+                          (v.z - mu[i][2]) * sc[i][2] + sh[i][2], (v.w - mu[i][3]) * sc[i][3] + sh[i][3]};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (silu) o[j] = silu_f(o[j]);
+              if (round) o[j] = rna_tf32(o[j]);
+            }
+            obase[p * C4 + qd] = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // General path: one block per (n, g).
 __global__ void group_stats_general_kernel(const float* __restrict__ x, long long pixels, int C,
                                            int G, int cpg, double* __restrict__ accum) {
@@ -436,6 +619,51 @@ __global__ void conv_direct_kernel(const float* __restrict__ x, const float* __r
       }
     }
     out[i] = acc;
+  }
+}
+
+// Small-K direct convolution (k*k*Cin <= 64: the 4-channel input convs, diffusion.mojo:177,
+// vae.mojo:195): a block stages the zero-padded input patches of 32 output pixels in shared
+// memory; thread t owns output channel t (and t + 256, ...), keeps its k*k*Cin weights in
+// registers and walks the pixels: patch reads are shared-memory broadcasts, output writes are
+// coalesced along Cout.
+constexpr int CS_PIX = 32, CS_MAXK = 64, CS_THREADS = 256;
+__global__ void __launch_bounds__(CS_THREADS)
+conv_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out, int N, int H, int W, int Cin, int Cout, int k, int pad, int stride,
+                   int Ho, int Wo) {
+  __shared__ float patch[CS_PIX][CS_MAXK];
+  const int K = k * k * Cin;
+  const long long total_px = (long long)N * Ho * Wo;
+  const long long px0 = (long long)blockIdx.x * CS_PIX;
+  for (int i = threadIdx.x; i < CS_PIX * K; i += blockDim.x) {
+    const int pp = i / K, kk = i - pp * K;
+    const long long px = px0 + pp;
+    float v = 0.f;
+    if (px < total_px) {
+      const int ci = kk % Cin, tap = kk / Cin;
+      const int wo = (int)(px % Wo);
+      long long t = px / Wo;
+      const int ho = (int)(t % Ho), n = (int)(t / Ho);
+      const int hi = ho * stride + tap / k - pad, wi = wo * stride + tap % k - pad;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((long long)n * H + hi) * W + wi) * Cin + ci];
+    }
+    patch[pp][kk] = v;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float wr[CS_MAXK];
+#pragma unroll
+    for (int kk = 0; kk < CS_MAXK; ++kk) wr[kk] = kk < K ? w[(long long)co * K + kk] : 0.f;
+    const float b = bias ? bias[co] : 0.f;
+    for (int pp = 0; pp < CS_PIX; ++pp) {
+      if (px0 + pp >= total_px) break;
+      float acc = b;
+#pragma unroll
+      for (int kk = 0; kk < CS_MAXK; ++kk)
+        if (kk < K) acc = fmaf(patch[pp][kk], wr[kk], acc);
+      out[(px0 + pp) * Cout + co] = acc;
+    }
   }
 }
 
@@ -689,6 +917,47 @@ cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, i
   return cudaGetLastError();
 }
 
+bool norm_fused_supported(int C) { return C % 4 == 0 && C / 4 <= GS_THREADS * GS_MAXQ; }
+
+static int norm_fused_slabs(long long pixels, int C) {
+  const int C4 = C / 4;
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  long long s = pixels / (4LL * ppl);
+  if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+size_t norm_fused_scratch_bytes(int N, long long pixels, int C, int G) {
+  return sizeof(double2) * (size_t)N * norm_fused_slabs(pixels, C) * G;
+}
+
+cudaError_t launch_norm_fused(const float* x, float* y, int N, long long pixels, int C, int G, float eps,
+                              const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
+                              void* scratch, unsigned int* barrier_words, int sm_count, cudaStream_t s) {
+  if (G <= 0 || C % G || !norm_fused_supported(C)) return cudaErrorInvalidValue;
+  const int C4 = C / 4, cpg = C / G;
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  const int slabs = norm_fused_slabs(pixels, C);
+  const int slab = (int)((pixels + slabs - 1) / slabs);
+  const int items = N * slabs;
+  int grid = items < sm_count ? items : sm_count;
+  size_t smem = (size_t)ppl * 2 * C * sizeof(float);
+  if (smem < (size_t)G * sizeof(float2)) smem = (size_t)G * sizeof(float2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(norm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  norm_fused_kernel<<<grid, GS_THREADS, smem, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
+                                                   pixels, C4, G, cpg, slabs, slab, items,
+                                                   reinterpret_cast<double2*>(scratch), barrier_words,
+                                                   (double)pixels * cpg, eps, gamma, beta, gamma_scalar, silu,
+                                                   round_tf32);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* gamma,
                               const float* beta, float gamma_scalar, float* y, int N, int H, int W,
                               int C, int G, int silu, int upsample2x, int round_tf32,
@@ -731,6 +1000,12 @@ cudaError_t launch_add_channel_vec(const float* x, const float* v, float* y, lon
 cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias, float* out, int N,
                                int H, int W, int Cin, int Cout, int k, int pad, int stride, int Ho,
                                int Wo, cudaStream_t s) {
+  if (k * k * Cin <= CS_MAXK && Cout >= 32) {
+    const long long total_px = (long long)N * Ho * Wo;
+    conv_smallk_kernel<<<(unsigned)((total_px + CS_PIX - 1) / CS_PIX), CS_THREADS, 0, s>>>(x, w, bias, out, N, H, W, Cin,
+                                                                                          Cout, k, pad, stride, Ho, Wo);
+    return cudaGetLastError();
+  }
   long long total = (long long)N * Ho * Wo * Cout;
   conv_direct_kernel<<<grid_for(total, 128, 16), 128, 0, s>>>(x, w, bias, out, N, H, W, Cin, Cout, k,
                                                               pad, stride, Ho, Wo);

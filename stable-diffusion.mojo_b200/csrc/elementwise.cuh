@@ -42,6 +42,15 @@ cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* 
                               int C, int G, int silu, int upsample2x, int round_tf32,
                               cudaStream_t s);
 
+// One-launch GroupNorm/LayerNorm (+SiLU, +TF32 rounding): statistics, grid barrier, normalise.
+// Needs C % 4 == 0 and C <= 3072; grid <= sm_count blocks (all resident).  `barrier_words` = two
+// zero-initialised device words owned by the context.
+bool norm_fused_supported(int C);
+size_t norm_fused_scratch_bytes(int N, long long pixels, int C, int G);
+cudaError_t launch_norm_fused(const float* x, float* y, int N, long long pixels, int C, int G, float eps,
+                              const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
+                              void* scratch, unsigned int* barrier_words, int sm_count, cudaStream_t s);
+
 // deterministic U(lo,hi) fill (synthetic weights / probes): counter-based splitmix64 hash
 cudaError_t launch_fill_uniform(float* p, long long n, uint64_t seed, float lo, float hi, cudaStream_t s);
 

@@ -470,6 +470,21 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
                   int round_tf32) {
   if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
   const size_t mark = c->arena.mark();
+  if (!upsample && norm_fused_supported(C)) {
+    // one launch: statistics + grid barrier + normalise
+    void* scratch = c->arena.alloc(norm_fused_scratch_bytes(N, (long long)H * W, C, G));
+    if (!scratch) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+    if (!c->dry_run) {
+      TimedScope ts(c, FAM_NORM, 0);
+      int rc = c->check(launch_norm_fused(x, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
+                                          round_tf32, scratch, c->ticket + 4, c->sm_count, c->stream),
+                        "norm_fused launch");
+      if (rc) return rc;
+      c->launches += 1;
+    }
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
   void* accum = c->arena.alloc(group_stats_scratch_bytes(N, (long long)H * W, C, G));
   float2* stats = c->arena.alloc_n<float2>((size_t)N * G);
   if (!accum || !stats) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
