@@ -115,6 +115,9 @@ static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "cuda_graph")) return &h->use_graph;
   if (!strcmp(name, "force_bn")) return &h->c->force_bn;
   if (!strcmp(name, "force_splits")) return &h->c->force_splits;
+  if (!strcmp(name, "force_stages")) return &h->c->force_stages;
+  if (!strcmp(name, "gemm_debug")) return &h->c->gemm_debug;
+  if (!strcmp(name, "gemm_cg")) return &h->c->gemm_cg;
   return nullptr;
 }
 int32_t tsd_set_option(tsd_ctx* h, const char* name, int32_t value) {
@@ -564,6 +567,7 @@ int32_t tsd_bench_gemm(tsd_ctx* h, int32_t m, int32_t n, int32_t k, int32_t batc
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   for (int i = 0; i < 3 && !hc.rc; ++i) hc.run(op_gemm(c, g));
+  launch_spin((long long)iters * 12000, c->stream);  // queue the launches behind a spin: events see device time
   cudaEventRecord(e0, c->stream);
   for (int i = 0; i < iters && !hc.rc; ++i) hc.run(op_gemm(c, g));
   cudaEventRecord(e1, c->stream);
@@ -600,6 +604,7 @@ int32_t tsd_bench_conv(tsd_ctx* h, int32_t n, int32_t H, int32_t W, int32_t cin,
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   for (int i = 0; i < 3 && !hc.rc; ++i) hc.run(op_conv2d(c, a));
+  launch_spin((long long)iters * 12000, c->stream);
   cudaEventRecord(e0, c->stream);
   for (int i = 0; i < iters && !hc.rc; ++i) hc.run(op_conv2d(c, a));
   cudaEventRecord(e1, c->stream);

@@ -13,7 +13,9 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   // reference Gelu.forward, helpers/utils.mojo:1908-1919 (tanh form)
   const float k = 0.7978845608028654f;  // sqrt(2/pi)
   float u = k * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  float t;
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(t) : "f"(u));  // MUFU.TANH, rel. error 2^-11 (TF32 level)
+  return 0.5f * x * (1.0f + t);
 }
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -24,6 +26,117 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 }  // namespace
 
+// ---- raw shared-address forms of the PTX wrappers (addresses precomputed outside the loops) ----
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_timeout_trap() {
+  printf("tsd: gemm mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
+// bounded wait: a protocol bug surfaces as a trapped kernel, never as a hung GPU
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity))
+    if (++spins > (1u << 26)) mbar_timeout_trap();
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_a_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_b_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// all MMAs issued so far arrive on `bar` when complete; CG == 2: on the same barrier of both CTAs
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// Role loops are single-thread instruction streams: every dependent SASS instruction costs ~4-6
+// cycles and an mbarrier try_wait ~90, so (measured, profiles/r01_gemm_lab_notes.md) the first
+// version spent ~500 cycles per 32-wide K step on bookkeeping while the MMAs of the step need
+// 2*BN cycles.  Hence: K steps of 64 (two 128 B swizzle atoms per operand row, 8 MMAs per
+// barrier round trip), incremental index math, shared addresses and descriptors precomputed.
+//
+// CG == 2: CTA pairs (cluster 2x1x1 over the M tiles).  Each CTA loads its own 128 A rows and
+// HALF of the B rows; the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both
+// CTAs' shared memory and writes both CTAs' TMEM - the B operand crosses L2->SM once per pair.
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
@@ -32,33 +145,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ long long tr[8];  // lab trace (debug bit 3)
+  if (threadIdx.x == 0) tr[0] = clock64();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
 
   // 1024 B aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t a_bytes = GEMM_BM * GEMM_BK * 4;      // 16 KiB
-  const uint32_t b_bytes = (uint32_t)p.BN * GEMM_BK * 4;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int b_rows = p.BN / CG;                        // B rows staged by this CTA
+  const uint32_t a_atom = GEMM_BM * 128;               // 128 rows x 32 fp32
+  const uint32_t b_atom = (uint32_t)b_rows * 128;
+  const uint32_t stage_bytes = 2 * (a_atom + b_atom);  // K step of 64 = two atoms per operand
 
   // tile coordinates
-  const int nt = blockIdx.x;
-  int mt = blockIdx.y;
+  const int nt = blockIdx.y;
+  int mt = blockIdx.x;  // M tiles along x: a CTA pair is two consecutive M tiles (cluster 2x1x1)
   const int batch = blockIdx.z / p.splits;
   const int split = blockIdx.z - batch * p.splits;
   const int tw = mt % p.tiles_w;
   mt /= p.tiles_w;
   const int th = mt % p.tiles_h;
-  const int img = mt / p.tiles_h;
+  const int img = mt / p.tiles_h;  // >= p.imgs for the phantom tile that pads an odd tile count to a pair
   const int w0 = tw * p.bw, h0 = th * p.bh;
 
   const int it_begin = split * p.iters_per_split;
   int it_end = it_begin + p.iters_per_split;
   if (it_end > p.total_iters) it_end = p.total_iters;
+  const int n_iters = it_end - it_begin;
+  const int num_stages = p.num_stages;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), accum_a = smem_u32(&accum_bar);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.num_stages; ++s) {
+    for (int s = 0; s < num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -68,182 +188,313 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tensormap(&tmB);
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (CG == 1) {
+      tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+      tmem_relinquish();
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
   }
   tc_fence_before_sync();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before anything arrives on them
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
+  if (threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      const int cin = p.cin, debug = p.debug;
+      const bool geglu = p.geglu != 0;
+      const uint32_t a_tx = (debug & 2) ? 0u : 2u * (uint32_t)p.a_box_bytes;
+      const uint32_t b_tx = (debug & 4) ? 0u : 2u * b_atom;
+      const uint32_t tx = (uint32_t)CG * (a_tx + b_tx);  // CG == 2: the leader's barrier counts both CTAs' bytes
+      const int c3 = img + batch;
+      // first B row of this CTA's (first) box, and of the second (gate) box for single-CTA GEGLU
+      int brow0, brow1 = 0;
       const int half_rows = p.BN >> 1;
-      const uint32_t tx = (uint32_t)p.a_box_bytes + b_bytes;
+      if (geglu) {
+        if (CG == 1) {
+          brow0 = nt * half_rows;
+          brow1 = p.n_half + nt * half_rows;
+        } else {
+          brow0 = (rank == 0 ? 0 : p.n_half) + nt * half_rows;  // leader: value rows, peer: gate rows
+        }
+      } else {
+        brow0 = nt * p.BN + (int)rank * b_rows;
+      }
+      const bool two_b = geglu && CG == 1;
+      // (tap, channel chunk) of the first iteration; afterwards advanced incrementally
+      int tap = it_begin / p.chunks_per_tap;
+      int kc = (it_begin - tap * p.chunks_per_tap) * GEMM_BK;
+      int dy = 0, dx = 0;
+      if (p.taps == 9) {
+        dy = tap / 3 - 1;
+        dx = tap - (tap / 3) * 3 - 1;
+      }
+      int kb = tap * cin + kc;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = it_begin; it < it_end; ++it) {
-        const int tap = it / p.chunks_per_tap;
-        const int kc = (it - tap * p.chunks_per_tap) * GEMM_BK;
-        int dy = 0, dx = 0;
-        if (p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap - (tap / 3) * 3 - 1;
+      uint32_t sa = smem_base;
+      uint32_t fb = full0, eb = empty0;
+      const uint32_t fb_mask = (CG == 2) ? 0xFEFFFFFFu : 0xFFFFFFFFu;  // CG == 2: signal the leader's barrier
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait_a(eb, phase ^ 1u);
+        if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, tx);
+        const uint32_t fbs = fb & fb_mask;
+        if (!(debug & 2)) {
+          tma_a_4d<CG>(sa, &tmA, fbs, kc, w0 + dx, h0 + dy, c3);
+          tma_a_4d<CG>(sa + a_atom, &tmA, fbs, kc + 32, w0 + dx, h0 + dy, c3);
         }
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sa = smem_dyn + (smem_base - smem_u32(smem_dyn)) + stage * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], tx);
-        tma_load_4d(sa, &tmA, &full_bar[stage], kc, w0 + dx, h0 + dy, img + batch);
-        const int kb = tap * p.cin + kc;
-        if (!p.geglu) {
-          tma_load_3d(sb, &tmB, &full_bar[stage], kb, nt * p.BN, batch);
-        } else {
-          tma_load_3d(sb, &tmB, &full_bar[stage], kb, nt * half_rows, batch);
-          tma_load_3d(sb + half_rows * GEMM_BK * 4, &tmB, &full_bar[stage], kb,
-                      p.n_half + nt * half_rows, batch);
+        if (!(debug & 4)) {
+          const uint32_t sb = sa + 2 * a_atom;
+          if (!two_b) {
+            tma_b_3d<CG>(sb, &tmB, fbs, kb, brow0, batch);
+            tma_b_3d<CG>(sb + b_atom, &tmB, fbs, kb + 32, brow0, batch);
+          } else {
+            const uint32_t hb = (uint32_t)half_rows * 128;
+            tma_b_3d<CG>(sb, &tmB, fbs, kb, brow0, batch);
+            tma_b_3d<CG>(sb + hb, &tmB, fbs, kb, brow1, batch);
+            tma_b_3d<CG>(sb + b_atom, &tmB, fbs, kb + 32, brow0, batch);
+            tma_b_3d<CG>(sb + b_atom + hb, &tmB, fbs, kb + 32, brow1, batch);
+          }
         }
-        if (++stage == p.num_stages) {
+        kc += GEMM_BK;
+        kb += GEMM_BK;
+        if (kc >= cin) {
+          kc = 0;
+          ++tap;
+          kb = tap * cin;
+          if (++dx > 1) {
+            dx = -1;
+            ++dy;
+          }
+        }
+        sa += stage_bytes;
+        fb += 8;
+        eb += 8;
+        if (++stage == num_stages) {
           stage = 0;
           phase ^= 1u;
+          sa = smem_base;
+          fb = full0;
+          eb = empty0;
         }
       }
+      tr[2] = clock64();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, GEMM_BM, (uint32_t)p.BN, 0, 0);
+    // ===================== MMA issuer (leader CTA only when paired) =====================
+    if ((CG == 1 || rank == 0) && elect_one()) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, GEMM_BM * CG, (uint32_t)p.BN, 0, 0);
+      const int chunks = p.chunks_per_tap;
+      // K = 8 MMAs with real data in a tap's last chunk (all 8 when cin is a multiple of 64)
+      int nk_last = (p.cin - (chunks - 1) * GEMM_BK + 7) >> 3;
+      if (p.debug & 1) nk_last = 0;
+      const int nk_full = (p.debug & 1) ? 0 : GEMM_BK / 8;
+      int chunk = it_begin % chunks;
+      const uint64_t adesc0 = umma_smem_desc(smem_base, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint64_t bdesc0 = umma_smem_desc(smem_base + 2 * a_atom, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint32_t stage_step = stage_bytes >> 4, a_step = a_atom >> 4, b_step = b_atom >> 4;
       int stage = 0;
-      uint32_t phase = 0;
-      for (int it = it_begin; it < it_end; ++it) {
-        const int tap = it / p.chunks_per_tap;
-        const int kc = (it - tap * p.chunks_per_tap) * GEMM_BK;
-        int nk = (p.cin - kc + 7) >> 3;  // K=8 MMAs with real data in this chunk
-        if (nk > GEMM_BK / 8) nk = GEMM_BK / 8;
-        mbar_wait(&full_bar[stage], phase);
+      uint32_t phase = 0, soff = 0, acc = 0;
+      uint32_t fb = full0, eb = empty0;
+      for (int it = 0; it < n_iters; ++it) {
+        const int nk = (chunk == chunks - 1) ? nk_last : nk_full;
+        if (++chunk == chunks) chunk = 0;
+        mbar_wait_a(fb, phase);
         tc_fence_after_sync();
-        const uint32_t sa = smem_base + stage * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
-        for (int kk = 0; kk < nk; ++kk) {
-          const uint64_t adesc = umma_smem_desc(sa + kk * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          const uint64_t bdesc = umma_smem_desc(sb + kk * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          umma_tf32(tmem_d, adesc, bdesc, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
+        const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
+        if (nk == GEMM_BK / 8) {
+#pragma unroll
+          for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
+            umma_tf32_cg<CG>(tmem_d, ad + (kk >> 2) * a_step + 2u * (kk & 3), bd + (kk >> 2) * b_step + 2u * (kk & 3),
+                             idesc, acc);
+            acc = 1u;
+          }
+        } else {
+          for (int kk = 0; kk < nk; ++kk) {
+            umma_tf32_cg<CG>(tmem_d, ad + (kk >> 2) * a_step + 2u * (kk & 3), bd + (kk >> 2) * b_step + 2u * (kk & 3),
+                             idesc, acc);
+            acc = 1u;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-        if (++stage == p.num_stages) {
+        umma_commit_cg<CG>(eb);  // smem slot reusable (in both CTAs) once these MMAs retire
+        soff += stage_step;
+        fb += 8;
+        eb += 8;
+        if (++stage == num_stages) {
           stage = 0;
           phase ^= 1u;
+          soff = 0;
+          fb = full0;
+          eb = empty0;
         }
       }
-      umma_commit(&accum_bar);  // accumulator complete
+      umma_commit_cg<CG>(accum_a);  // accumulator complete
+      tr[3] = clock64();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const int r = q * 32 + lane;
-    const int lh = r / p.bw, lw = r - lh * p.bw;
-    const int h = h0 + lh, w = w0 + lw;
-    const bool row_ok = (lh < p.bh) && (h < p.H) && (w < p.W);
-    const long long gm = ((long long)img * p.H + h) * p.W + w;
-
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after_sync();
-
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM -> registers (thread = output row) -> per-warp shared staging tile -> coalesced global
+    // stores (8 lanes x 16 B cover 128 B of one row; a warp instruction writes 4 full rows).
+    // Two warps per TMEM lane quadrant, interleaved over the 32-column chunks.  The staging tiles
+    // reuse the operand ring: every MMA has retired once accum_bar completes.
+    const int ew = warp - 2;   // 0..7
+    const int q = warp & 3;    // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;  // which of the two warps of the quadrant
+    constexpr int ST = 36;     // staging row stride in floats (conflict-free float4 rows)
+    float* stg = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn))) + ew * (32 * ST);
     const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
-    if (p.partial != nullptr) {
-      // raw split-K partials
-      float* dst = p.partial +
-                   (((long long)split * gridDim.z / p.splits + batch) * p.m_per_batch + gm) * p.n_pad +
-                   (long long)nt * p.BN;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + c, v);
-        tmem_ld_wait();
-        if (row_ok && nt * p.BN + c < p.n_pad) {
-          float4* o = reinterpret_cast<float4*>(dst + c);
+    const bool partial = p.partial != nullptr;
+    const bool geglu = p.geglu && !partial;
+    const int out_cols = geglu ? (p.BN >> 1) : p.BN;
+    const int n0 = nt * out_cols;
+    const int n_valid = p.n_valid;
+    const int n_lim = partial ? p.n_pad : n_valid;
+    const bool img_ok = img < p.imgs;
+
+    // the row this lane owns while in the thread = row layout (row bias / alpha / GEGLU)
+    float rb = 0.0f;
+    if (p.row_bias != nullptr && !partial) {
+      const int r_own = q * 32 + lane;
+      const int lh = r_own / p.bw, lw = r_own - lh * p.bw;
+      const int h = h0 + lh, w = w0 + lw;
+      if (img_ok && lh < p.bh && h < p.H && w < p.W) rb = p.row_bias[((long long)img * p.H + h) * p.W + w];
+    }
+    const float* cbias = (p.bias && !partial) ? p.bias + (long long)img * p.bias_img_stride : nullptr;
+    const float alpha = partial ? 1.0f : p.alpha;
+    const bool plain = (alpha == 1.0f) && (p.row_bias == nullptr || partial);
+
+    // the 8 rows this lane stores (row = q*32 + i*4 + lane/8), 4 consecutive columns at lane%8*4
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    float* dbase;
+    long long ldd;
+    if (partial) {
+      dbase = p.partial + ((long long)split * (gridDim.z / p.splits) + batch) * p.m_per_batch * p.n_pad;
+      ldd = p.n_pad;
+    } else {
+      dbase = p.D + (long long)batch * p.d_batch_stride;
+      ldd = p.ldd;
+    }
+    const float* rbase = (p.residual && !partial) ? p.residual + (long long)batch * p.r_batch_stride : nullptr;
+    float* drow[8];
+    const float* rrow[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    for (int i = 0; i < 8; ++i) {
+      const int r = q * 32 + i * 4 + sub;
+      const int lh = r / p.bw, lw = r - lh * p.bw;
+      const int h = h0 + lh, w = w0 + lw;
+      const bool ok = img_ok && (lh < p.bh) && (h < p.H) && (w < p.W);
+      const long long g = ((long long)img * p.H + h) * p.W + w;
+      drow[i] = ok ? dbase + g * ldd : nullptr;
+      rrow[i] = rbase ? rbase + g * p.ldr : nullptr;
+    }
+    const bool routed = !partial && p.split_n < (1 << 30);
+    const bool vec_ok = partial || (((n_valid | p.ldd | p.split_n) & 3) == 0 && (p.split_stride & 3) == 0 &&
+                                    (rbase == nullptr || (p.ldr & 3) == 0) &&
+                                    (cbias == nullptr || (((p.bias_img_stride & 3) == 0) &&
+                                                          (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
+    const bool round_out = p.round_tf32 && !partial;
+
+    mbar_wait_a(accum_a, 0);
+    tc_fence_after_sync();
+    if (threadIdx.x == 64) tr[4] = clock64();
+
+    for (int c = half * 32; c < out_cols; c += 64) {
+      uint32_t v[32];
+      tmem_ld32(trow + c, v);
+      if (geglu) {
+        uint32_t g[32];
+        tmem_ld32(trow + out_cols + c, g);
+        float bo[32], bg[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c + j;
+          const bool okb = cbias != nullptr && n < n_valid && c + j < out_cols;
+          bo[j] = okb ? __ldg(cbias + n) : 0.0f;
+          bg[j] = okb ? __ldg(cbias + p.n_half + n) : 0.0f;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = __float_as_uint((__uint_as_float(v[j]) + bo[j]) * gelu_tanh(__uint_as_float(g[j]) + bg[j]));
+      } else {
+        tmem_ld_wait();
+        if (!plain) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), alpha, rb));
         }
       }
-    } else {
-      const int out_cols = p.geglu ? (p.BN >> 1) : p.BN;
-      const int n0 = nt * out_cols;
-      const float rb = (p.row_bias != nullptr && row_ok) ? p.row_bias[gm] : 0.0f;
-      const float* cbias = p.bias ? p.bias + (long long)img * p.bias_img_stride : nullptr;
-      float* drow = p.D + (long long)batch * p.d_batch_stride + gm * p.ldd;
-      const float* rrow =
-          p.residual ? p.residual + (long long)batch * p.r_batch_stride + gm * p.ldr : nullptr;
-      for (int c = 0; c < out_cols; c += 16) {
-        uint32_t v[16];
-        float f[16];
-        tmem_ld16(trow + c, v);
-        if (p.geglu) {
-          uint32_t g[16];
-          tmem_ld16(trow + out_cols + c, g);
-          tmem_ld_wait();
+      uint4* srow = reinterpret_cast<uint4*>(stg + lane * ST);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c + j;
-            float a = __uint_as_float(v[j]), b = __uint_as_float(g[j]);
-            if (cbias != nullptr && n < p.n_valid) {
-              a += cbias[n];
-              b += cbias[p.n_half + n];
+      for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const int n = n0 + c + c4;  // first of this lane's 4 columns
+      if (c + c4 < out_cols && n < n_lim) {
+        long long col;
+        if (partial) col = (long long)nt * p.BN + c + c4;
+        else if (routed) col = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
+        else col = n;
+        if (vec_ok) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cbias != nullptr && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(cbias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (drow[i] == nullptr) continue;
+            float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
+            t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+            if (rbase != nullptr) {
+              const float4 rr = *reinterpret_cast<const float4*>(rrow[i] + n);
+              t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
             }
-            f[j] = a * gelu_tanh(b);
+            if (round_out) {
+              t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
+            }
+            *reinterpret_cast<float4*>(drow[i] + col) = t;
           }
         } else {
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c + j;
-            float a = __uint_as_float(v[j]) * p.alpha + rb;
-            if (cbias != nullptr && n < p.n_valid) a += cbias[n];
-            f[j] = a;
-          }
-        }
-        const int n = n0 + c;
-        if (!row_ok || n >= p.n_valid) continue;
-        const long long col = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
-        if (n + 16 <= p.n_valid) {
-          if (rrow != nullptr) {
-            const float4* rr = reinterpret_cast<const float4*>(rrow + n);
+          for (int i = 0; i < 8; ++i) {
+            if (drow[i] == nullptr) continue;
+            const float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
+            const float e[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float4 t = rr[j];
-              f[4 * j] += t.x;
-              f[4 * j + 1] += t.y;
-              f[4 * j + 2] += t.z;
-              f[4 * j + 3] += t.w;
+              const int nn = n + j;
+              if (nn >= n_valid) break;
+              float a = e[j];
+              if (cbias != nullptr && !geglu) a += cbias[nn];
+              if (rbase != nullptr) a += rrow[i][nn];
+              if (round_out) a = round_tf32(a);
+              drow[i][(long long)(nn / p.split_n) * p.split_stride + (nn % p.split_n)] = a;
             }
-          }
-          if (p.round_tf32) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = round_tf32(f[j]);
-          }
-          float4* o = reinterpret_cast<float4*>(drow + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 16 && n + j < p.n_valid; ++j) {
-            float a = f[j];
-            if (rrow != nullptr) a += rrow[n + j];
-            if (p.round_tf32) a = round_tf32(a);
-            drow[col + j] = a;
           }
         }
       }
+      __syncwarp();
     }
+    if (threadIdx.x == 64) tr[5] = clock64();
     tc_fence_before_sync();
   }
 
   __syncthreads();
+  if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    printf("gemm trace: setup %lld producer_done %lld mma_issued %lld accum_ready %lld epilogue_done %lld end %lld (clk since entry)\n",
+           tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], clock64() - tr[0]);
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may release TMEM / exit while the pair is in flight
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+    if constexpr (CG == 1) {
+      tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    }
   }
 }
 
@@ -285,38 +536,61 @@ __global__ void splitk_reduce_kernel(const SplitKReduceParams p) {
   }
 }
 
-size_t gemm_smem_bytes(int BN, int num_stages) {
-  return (size_t)num_stages * (GEMM_BM * GEMM_BK * 4 + (size_t)BN * GEMM_BK * 4) + 1024;
+static size_t gemm_stage_bytes(int BN, int cg) { return 2 * ((size_t)GEMM_BM * 128 + (size_t)(BN / cg) * 128); }
+
+size_t gemm_smem_bytes(int BN, int num_stages, int cg) {
+  size_t ring = (size_t)num_stages * gemm_stage_bytes(BN, cg);
+  const size_t staging = 8 * 32 * 36 * 4;  // epilogue staging tiles live in the (then idle) ring
+  if (ring < staging) ring = staging;
+  return ring + 1024;
 }
 
-int gemm_pick_stages(int BN) {
-  const size_t budget = 200 * 1024;
-  int s = (int)((budget - 1024) / (GEMM_BM * GEMM_BK * 4 + (size_t)BN * GEMM_BK * 4));
+int gemm_pick_stages(int BN, int cg) {
+  const size_t budget = 224 * 1024;  // 227 KiB opt-in minus static shared memory
+  int s = (int)((budget - 1024) / gemm_stage_bytes(BN, cg));
   if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
   if (s < 2) s = 2;
   return s;
 }
 
-cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
-                             dim3 grid, size_t smem_bytes, cudaStream_t stream) {
+template <int CG>
+static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
+                                  size_t smem_bytes, cudaStream_t stream) {
   // static + dynamic shared memory must fit the 227 KiB opt-in limit together
   static int max_dyn = -1;
   if (max_dyn < 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tf32_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tf32_kernel<CG>);
     if (e != cudaSuccess) return e;
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     const int lim = optin - (int)fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    e = cudaFuncSetAttribute(gemm_tf32_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
     max_dyn = lim;
   }
   if ((long long)smem_bytes > max_dyn) return cudaErrorInvalidConfiguration;
-  gemm_tf32_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<CG>, tmA, tmB, p);
+}
+
+cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                             dim3 grid, size_t smem_bytes, cudaStream_t stream) {
+  if (p.cg == 2) return launch_gemm_cg<2>(tmA, tmB, p, grid, smem_bytes, stream);
+  return launch_gemm_cg<1>(tmA, tmB, p, grid, smem_bytes, stream);
 }
 
 cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t stream) {

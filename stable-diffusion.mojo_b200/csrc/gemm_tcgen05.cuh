@@ -22,9 +22,9 @@
 namespace tsd {
 
 constexpr int GEMM_BM = 128;       // rows per CTA tile (TMEM lanes)
-constexpr int GEMM_BK = 32;        // fp32 elements per K chunk = one 128 B swizzle row
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
-constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_BK = 64;        // fp32 elements per K step = two 128 B swizzle atoms per operand row
+constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue
+constexpr int GEMM_MAX_STAGES = 6;
 
 struct GemmKParams {
   // output-pixel tiling (plain GEMM: H = 1, W = M, bw = 128, bh = 1)
@@ -52,6 +52,9 @@ struct GemmKParams {
   int round_tf32;
   float* partial;          // split-K workspace [split][b][m][n_pad] or nullptr
   int n_pad;
+  int debug;               // lab only (Ctx::gemm_debug)
+  int cg;                  // 1, or 2 = CTA pairs over consecutive M tiles (cluster 2x1x1, grid.x even)
+  int imgs;                // images (rows of tiles past the last image are phantom: loaded as zeros, never stored)
 };
 
 struct SplitKReduceParams {
@@ -71,7 +74,7 @@ struct SplitKReduceParams {
 cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                              dim3 grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t stream);
-size_t gemm_smem_bytes(int BN, int num_stages);
-int gemm_pick_stages(int BN);
+size_t gemm_smem_bytes(int BN, int num_stages, int cg);
+int gemm_pick_stages(int BN, int cg);
 
 }  // namespace tsd

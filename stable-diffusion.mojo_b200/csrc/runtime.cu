@@ -187,36 +187,44 @@ int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const ui
 namespace {
 
 struct TileCfg {
-  int BN = 0, splits = 1;
+  int BN = 0, splits = 1, cg = 1;
 };
 
-// Cycle model used only to rank (BN, splits) candidates: MMA issue rate vs. operand feed from
-// L2 vs. fixed per-tile cost, times the number of waves over the SMs.
+// Cycle model used only to rank (BN, splits, pairing) candidates.  Per 64-wide K step a CTA needs
+// 4*BN tensor cycles, ~450 cycles of barrier round trips in the single-thread role loops, and
+// its operand bytes from L2 (~6300 B/clk chip-wide, shared by the active SMs).
 TileCfg choose_tiles(int sm, long long m_tiles, int N, int total_iters, int batch, bool geglu,
-                     bool allow_split, long long m_rows) {
+                     bool allow_split, long long m_rows, int force_cg) {
   const int n_pad = (N + 15) / 16 * 16;
   TileCfg best;
   double best_cost = 1e300;
-  for (int BN = 16; BN <= 256; BN += 16) {
-    if (n_pad % BN) continue;
-    if (geglu && (BN % 32 || (N / 2) % (BN / 2))) continue;
-    const long long n_tiles = n_pad / BN;
-    static const int split_cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
-    for (int splits : split_cand) {
-      if (splits > 1 && (!allow_split || total_iters / splits < 4)) break;
-      const long long ctas = m_tiles * n_tiles * batch * splits;
-      const double active = (double)std::min<long long>(ctas, sm);
-      const double feed_bw = std::min(96.0, 6300.0 / active);  // B/cycle/SM from L2
-      const double iter_cyc = std::max(2.0 * BN, (16384.0 + 128.0 * BN) / feed_bw);
-      const int ips = (total_iters + splits - 1) / splits;
-      const double tile_cyc = ips * iter_cyc + 3500.0 + 24.0 * BN;
-      const double waves = std::ceil((double)ctas / sm);
-      double cost = waves * tile_cyc;
-      if (splits > 1) cost += 4000.0 + (double)(splits + 1) * m_rows * n_pad * 4.0 / 4000.0;
-      if (cost < best_cost) {
-        best_cost = cost;
-        best.BN = BN;
-        best.splits = splits;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (force_cg && cg != force_cg) continue;
+    if (cg == 2 && m_tiles < 2) continue;
+    const long long mt = cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles;
+    for (int BN = 16; BN <= 256; BN += 16) {
+      if (n_pad % BN) continue;
+      if (geglu && (BN % 32 || (N / 2) % (BN / 2))) continue;
+      const long long n_tiles = n_pad / BN;
+      static const int split_cand[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+      for (int splits : split_cand) {
+        if (splits > 1 && (!allow_split || total_iters / splits < 2)) break;
+        const long long ctas = mt * n_tiles * batch * splits;
+        const double active = (double)std::min<long long>(ctas, sm);
+        const double feed_bw = std::min(80.0, 6300.0 / active);  // B/cycle/SM from L2
+        const double bytes = 2.0 * (16384.0 + 128.0 * BN / cg);
+        const double iter_cyc = std::max(std::max(4.0 * BN, 450.0), bytes / feed_bw);
+        const int ips = (total_iters + splits - 1) / splits;
+        const double tile_cyc = ips * iter_cyc + 3000.0 + 25.0 * BN;
+        const double waves = std::ceil((double)ctas / sm);
+        double cost = waves * tile_cyc;
+        if (splits > 1) cost += 5000.0 + (double)(splits + 1) * m_rows * n_pad * 4.0 / 3000.0;
+        if (cost < best_cost) {
+          best_cost = cost;
+          best.BN = BN;
+          best.splits = splits;
+          best.cg = cg;
+        }
       }
     }
   }
@@ -254,14 +262,17 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   p.cin = A.K;
   p.chunks_per_tap = (A.K + GEMM_BK - 1) / GEMM_BK;
   p.total_iters = p.taps * p.chunks_per_tap;
-  p.a_box_bytes = bw * bh * GEMM_BK * 4;
+  p.a_box_bytes = bw * bh * 32 * 4;  // one 32-float atom; a K step loads two
   const long long m_tiles = (long long)A.imgs * p.tiles_h * p.tiles_w;
   const int nbatch = A.batch;
   const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
                            p.alpha == 1.0f;
   TileCfg cfg = choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
-                             (long long)p.m_per_batch);
+                             (long long)p.m_per_batch, c->gemm_cg);
   if (force_bn > 0) cfg.BN = force_bn;
+  if (cfg.BN <= 0) return c->fail(TSD_ERR_INVALID, "gemm: no tile configuration");
+  p.cg = cfg.cg;
+  p.imgs = A.imgs;
   if (force_splits > 0 && allow_split) cfg.splits = std::min(force_splits, p.total_iters);
   if (cfg.BN < 16 || cfg.BN > 256 || cfg.BN % 16) return c->fail(TSD_ERR_INVALID, "gemm: bad BN");
   if (p.geglu && (cfg.BN % 32 || (N / 2) % (cfg.BN / 2)))
@@ -270,9 +281,13 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   p.splits = cfg.splits;
   p.iters_per_split = (p.total_iters + p.splits - 1) / p.splits;
   p.splits = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;  // no empty split
-  p.num_stages = gemm_pick_stages(p.BN);
+  p.num_stages = gemm_pick_stages(p.BN, p.cg);
+  if (c->force_stages > 0 && c->force_stages < p.num_stages) p.num_stages = c->force_stages;
+  p.debug = c->gemm_debug;
+  // the epilogue reads TMEM in 32-column chunks: keep the last (partial) chunk inside the allocation
+  const int tmem_need = p.geglu ? p.BN + 16 : p.BN + ((p.BN & 31) ? 16 : 0);
   int tc = 32;
-  while (tc < p.BN) tc <<= 1;
+  while (tc < tmem_need) tc <<= 1;
   p.tmem_cols = tc;
   p.n_pad = (N + 15) / 16 * 16;
   const int out_cols_per_tile = p.geglu ? p.BN / 2 : p.BN;
@@ -288,7 +303,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     if (dims[3] == 1) str[3] = (uint64_t)A.ld_h * A.H;  // unused but must be a valid stride
     if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
     if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
-    uint32_t box[4] = {(uint32_t)GEMM_BK, (uint32_t)bw, (uint32_t)bh, 1};
+    uint32_t box[4] = {32u, (uint32_t)bw, (uint32_t)bh, 1};
     int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box, 0);
     if (rc) return rc;
   }
@@ -296,7 +311,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     const int ktot = A.taps * A.K;
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
     uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
-    uint32_t box[3] = {(uint32_t)GEMM_BK, (uint32_t)(p.geglu ? p.BN / 2 : p.BN), 1};
+    uint32_t box[3] = {32u, (uint32_t)((p.geglu || p.cg == 2) ? p.BN / 2 : p.BN), 1};
     int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box, 0);
     if (rc) return rc;
   }
@@ -326,11 +341,12 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     p.partial = nullptr;
   }
 
-  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)(nbatch * p.splits));
-  if (m_tiles > 65535 || grid.z > 65535) return c->fail(TSD_ERR_INVALID, "gemm: grid too large");
+  const long long m_tiles_grid = p.cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles;  // pairs: phantom tile pads odd counts
+  dim3 grid((unsigned)m_tiles_grid, (unsigned)n_tiles, (unsigned)(nbatch * p.splits));
+  if (n_tiles > 65535 || grid.z > 65535) return c->fail(TSD_ERR_INVALID, "gemm: grid too large");
   if (!c->dry_run) {
     TimedScope ts(c, FAM_GEMM, flops);
-    int rc = c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages), c->stream),
+    int rc = c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg), c->stream),
                       "gemm_tf32_kernel launch");
     if (rc) return rc;
     c->launches++;

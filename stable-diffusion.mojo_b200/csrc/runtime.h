@@ -69,6 +69,9 @@ struct Ctx {
   int fused_attention = 1;  // 1 = tcgen05 fused kernel ; 0 = GEMM + softmax + GEMM
   int layernorm_mode = 0;   // 0 = global statistics (reference, Q5) ; 1 = per token
   int force_bn = 0, force_splits = 0;  // test/tuning overrides for the GEMM tile heuristic
+  int force_stages = 0;     // tuning: operand ring depth override
+  int gemm_cg = 0;          // tuning: 0 = model decides, 1 = single CTAs, 2 = CTA pairs (cta_group::2)
+  int gemm_debug = 0;       // lab only: bit0 skip MMAs, bit1 skip A loads, bit2 skip B loads (results invalid)
   unsigned int* ticket = nullptr;  // zero-initialised device counter for last-block reductions
   KernelTimer* timer = nullptr;
   long long launches = 0;   // kernels launched through this context (bench "gpu_launches")

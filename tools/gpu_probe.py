@@ -79,6 +79,7 @@ def gemm():
     import torch
     from tsd_b200.api import Context
     ctx = Context(0)
+    ctx.set_option("gemm_cg", int(os.environ.get("GEMM_CG", "0")))
     rng = np.random.default_rng(0)
     ok = True
     cases = [  # (rows, in, out, bias, force_bn, force_splits)
@@ -128,6 +129,7 @@ def conv():
     import torch.nn.functional as F
     from tsd_b200.api import Context
     ctx = Context(0)
+    ctx.set_option("gemm_cg", int(os.environ.get("GEMM_CG", "0")))
     rng = np.random.default_rng(1)
     ok = True
     cases = [  # n, cin, h, w, cout, k, pad, stride, bn, splits
