@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "pdl.cuh"
 #include "ptx_sm100.cuh"
 
 namespace tsd {
@@ -142,6 +143,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();               // Q/K/V and the statistics come from predecessor kernels
+  pdl_launch_dependents();  // resources are held: the next kernel may start its prologue
   const uint32_t tmem_o = tmem_base + 256u;  // S0: cols [0,128), S1: [128,256), O: [256, 256+dpad)
 
   if (warp == 0) {
@@ -465,8 +468,7 @@ cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CU
     max_dyn = lim;
   }
   if ((long long)smem > max_dyn) return cudaErrorInvalidConfiguration;
-  attn_kernel<<<grid, ATT_THREADS, smem, stream>>>(tmX, tmY, tmV, p);
-  return cudaGetLastError();
+  return launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);
 }
 
 }  // namespace

@@ -1,12 +1,14 @@
 // extern "C" surface (include/tsd_b200.h): context + op-level entry points.
 // Model-level entry points (Diffusion / Decoder / loop) live in c_api_models.cu.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 
 #include "../../include/tsd_b200.h"
 #include "c_api_internal.h"
+#include "pdl.cuh"
 #include "attention_tcgen05.cuh"
 #include "elementwise.cuh"
 #include "runtime.h"
@@ -84,6 +86,12 @@ int32_t tsd_init(int32_t device, tsd_ctx** out) {
   tsd_ctx* h = new tsd_ctx();
   h->c = c;
   *out = h;
+  // tuning / A-B switches from the environment: TSD_OPT_<option name>=<int>  (same names as tsd_set_option)
+  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "pdl", "gemm_cg", "force_bn", "force_splits", "fused_attention"};
+  for (const char* name : kEnvOpts) {
+    const std::string key = std::string("TSD_OPT_") + name;
+    if (const char* v = getenv(key.c_str())) tsd_set_option(h, name, atoi(v));
+  }
   return TSD_OK;
 }
 
@@ -118,6 +126,10 @@ static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "force_stages")) return &h->c->force_stages;
   if (!strcmp(name, "gemm_debug")) return &h->c->gemm_debug;
   if (!strcmp(name, "gemm_cg")) return &h->c->gemm_cg;
+  if (!strcmp(name, "producer_stats")) return &h->c->producer_stats;
+  if (!strcmp(name, "norm_v2")) return &h->c->norm_v2;
+  if (!strcmp(name, "pdl")) return &tsd::pdl_enabled();
+  if (!strcmp(name, "bench_stats_groups")) return &h->c->bench_stats_groups;
   return nullptr;
 }
 int32_t tsd_set_option(tsd_ctx* h, const char* name, int32_t value) {
@@ -563,6 +575,13 @@ int32_t tsd_bench_gemm(tsd_ctx* h, int32_t m, int32_t n, int32_t k, int32_t batc
   g.B = B; g.N = n; g.ldb = k; g.b_bs = (long long)n * k; g.batch = batch;
   g.D = D; g.ldd = geglu ? n / 2 : n; g.d_bs = (long long)m * g.ldd; g.bias = bias; g.geglu = geglu;
   g.force_bn = force_bn; g.force_splits = force_splits;
+  NormHint bench_nh;
+  if (c->bench_stats_groups > 0) {
+    bench_nh.G = c->bench_stats_groups; bench_nh.eps = 1e-5f; bench_nh.imgs = 1;
+    bench_nh.scratch_elems = norm_scratch_elems(1, m, n, bench_nh.G);
+    bench_nh.scratch = reinterpret_cast<float2*>(hc.dev(2 * bench_nh.scratch_elems));
+    g.nh = &bench_nh;
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -600,6 +619,13 @@ int32_t tsd_bench_conv(tsd_ctx* h, int32_t n, int32_t H, int32_t W, int32_t cin,
   ConvArgs a;
   a.x = x; a.N = n; a.H = H; a.W = W; a.Cin = cin; a.Cout = cout; a.k = k; a.pad = pad; a.stride = stride;
   a.w = w; a.bias = bias; a.out = o; a.force_bn = force_bn; a.force_splits = force_splits;
+  NormHint bench_nh;
+  if (c->bench_stats_groups > 0) {
+    bench_nh.G = c->bench_stats_groups; bench_nh.eps = 1e-5f;
+    bench_nh.scratch_elems = norm_scratch_elems(n, (long long)Ho * Wo, cout, bench_nh.G);
+    bench_nh.scratch = reinterpret_cast<float2*>(hc.dev(2 * bench_nh.scratch_elems));
+    a.nh = &bench_nh;
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);

@@ -1,6 +1,11 @@
 // K5..K9 kernel bodies - see elementwise.cuh.
 #include "elementwise.cuh"
 
+#include "pdl.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
 #include <cfloat>
 
 namespace tsd {
@@ -33,6 +38,8 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // ------------------------------------------------------------------------------------------
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R,
                                  int Cc, int rescale) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float tile[32][33];
   const long long img = (long long)blockIdx.z * R * Cc;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -54,7 +61,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 cudaError_t launch_transpose(const float* src, float* dst, int N, int R, int Cc, int rescale,
                              cudaStream_t s) {
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, N), block(32, 8);
-  transpose_kernel<<<grid, block, 0, s>>>(src, dst, R, Cc, rescale);
+  { cudaError_t e_ = launch_pdl(transpose_kernel, dim3(grid), dim3(block), 0, s, src, dst, R, Cc, rescale); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 
@@ -90,6 +97,8 @@ __global__ void oihw_to_ohwi_kernel(const float* __restrict__ src, float* __rest
 
 __global__ void concat_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b,
                               int Cb, float* __restrict__ out, long long pixels) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = Ca + Cb;
   const long long total = pixels * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -102,6 +111,8 @@ __global__ void concat_kernel(const float* __restrict__ a, int Ca, const float* 
 
 __global__ void upsample2x_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H,
                                   int W, int C4) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = (long long)N * 4 * H * W * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -130,6 +141,8 @@ __global__ void upsample2x_planar_kernel(const float* __restrict__ x, float* __r
 
 __global__ void im2col3x3_kernel(const float4* __restrict__ x, float4* __restrict__ col, int N, int H,
                                  int W, int C4, int stride, int Ho, int Wo) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = (long long)N * Ho * Wo * 9 * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -291,6 +304,7 @@ norm_fused_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
                   int slabs, int slab, int items, double2* __restrict__ partial, unsigned int* __restrict__ bar,
                   double count, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float gamma_scalar, int silu, int round) {
+  pdl_wait();
   extern __shared__ float sm[];  // [ppl][2][C] staging, then [G] float2 statistics
   const int C = C4 * 4;
   const int TU = C4 < GS_THREADS ? C4 : GS_THREADS;
@@ -458,6 +472,305 @@ norm_fused_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused GroupNorm / LayerNorm v2: statistics + normalise (+SiLU, +TF32 rounding) in ONE launch with
+// the activation read from L2 ONCE.  One block per (image, slab of pixels); all blocks are
+// co-resident (grid <= 2 per SM), so a two-level barrier separates the phases:
+//   phase 1  load the slab into registers, per-group (sum, sum^2) -> part[item][g]
+//   level 1  blocks arrive on the counter of their sub-group (<= 16 consecutive slabs of one image);
+//            the last arriver folds the sub-group's partials -> part2[sub][g] and arrives on the root
+//   level 2  the last sub-group bumps the generation word every block is polling
+//   phase 2  fold part2 of the image (<= 19 entries per group), normalise the registers, store.
+// Contended atomics stay <= 16-19 per address; every fold has a fixed order (bit-reproducible).
+// The source is either a plain activation or the split-K partials of a GEMM (+bias, +residual): then
+// this kernel IS the split-K reduction and `raw` (optional) receives the un-normalised sum.
+// ------------------------------------------------------------------------------------------
+constexpr int NF_THREADS = 256, NF_SUB = 16;
+struct NormFused2Params {
+  const float4* x;      // plain source, or the first split's partial
+  int splits;           // 1 = plain
+  long long split_stride4;  // float4 elements between splits
+  int ldx4;             // row stride of the source in float4 (n_pad / 4 for split-K partials, C4 otherwise)
+  const float* bias;    // split-K source only: [C] per image (bias + img * bias_img_stride) or nullptr
+  int bias_img_stride;
+  const float4* residual;  // split-K source only
+  float4* raw;          // split-K source only: un-normalised result (nullptr: not needed)
+  float4* y;
+  int pixels, C4, G, cpg;
+  int slabs_per_img, slab, subs_per_img;
+  float2* part;         // [items][G]
+  float2* part2;        // [N * subs_per_img][G]
+  unsigned int* bar;    // [0] root count, [1] generation, [32 * (1 + k)] sub-group counters
+  float inv_count, eps;
+  const float* gamma;
+  const float* beta;
+  float gamma_scalar;
+  int silu, round;
+  int trace;  // lab: block 0 prints its phase timestamps
+};
+
+template <int NQ, int MAXIT, bool CACHE>
+__global__ void __launch_bounds__(NF_THREADS, 2)
+norm_fused2_kernel(const NormFused2Params p) {
+  pdl_wait();
+  extern __shared__ float nf_sm[];  // [ppl][2][C] staging; later [G] float2 statistics
+  __shared__ unsigned int flag_s;
+  __shared__ unsigned int gen_s;
+  const int C4 = p.C4, C = C4 * 4;
+  const int TU = C4 < NF_THREADS ? C4 : NF_THREADS;
+  const int ppl = C4 < NF_THREADS ? NF_THREADS / C4 : 1;
+  const int u = threadIdx.x % TU, pl = threadIdx.x / TU;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  const int n = item / p.slabs_per_img, sl = item - n * p.slabs_per_img;
+  const int p0 = sl * p.slab;
+  int p1 = p0 + p.slab;
+  if (p1 > p.pixels) p1 = p.pixels;
+  long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+  if (threadIdx.x == 0) {
+    t0 = clock64();
+    gen_s = *reinterpret_cast<volatile unsigned int*>(p.bar + 1);  // before this block arrives
+  }
+
+  auto load = [&](int px, int qd) -> float4 {
+    const long long row = (long long)n * p.pixels + px;
+    float4 a = p.x[row * p.ldx4 + qd];
+    if (p.splits > 1) {
+      for (int s = 1; s < p.splits; ++s) {
+        const float4 t = p.x[row * p.ldx4 + qd + s * p.split_stride4];
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      if (p.bias) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + (long long)n * p.bias_img_stride + qd * 4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (p.residual) {
+        const float4 t = p.residual[row * C4 + qd];
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      if (p.raw) p.raw[row * C4 + qd] = a;
+    }
+    return a;
+  };
+
+  // ---- phase 1 ----
+  float4 v[CACHE ? MAXIT : 1][NQ];
+  float s[NQ][4], q[NQ][4];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = q[i][j] = 0.f;
+  if (pl < ppl) {
+    if (CACHE) {
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        const int px = p0 + pl + it * ppl;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const int qd = u + i * TU;
+          v[it][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (px < p1 && qd < C4) v[it][i] = load(px, qd);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float4 t = v[it][i];
+          s[i][0] += t.x; q[i][0] = fmaf(t.x, t.x, q[i][0]);
+          s[i][1] += t.y; q[i][1] = fmaf(t.y, t.y, q[i][1]);
+          s[i][2] += t.z; q[i][2] = fmaf(t.z, t.z, q[i][2]);
+          s[i][3] += t.w; q[i][3] = fmaf(t.w, t.w, q[i][3]);
+        }
+    } else {
+#pragma unroll 4
+      for (int px = p0 + pl; px < p1; px += ppl) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const int qd = u + i * TU;
+          if (qd < C4) {
+            const float4 t = load(px, qd);
+            s[i][0] += t.x; q[i][0] = fmaf(t.x, t.x, q[i][0]);
+            s[i][1] += t.y; q[i][1] = fmaf(t.y, t.y, q[i][1]);
+            s[i][2] += t.z; q[i][2] = fmaf(t.z, t.z, q[i][2]);
+            s[i][3] += t.w; q[i][3] = fmaf(t.w, t.w, q[i][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int qd = u + i * TU;
+      if (qd < C4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          nf_sm[(pl * 2 + 0) * C + qd * 4 + j] = s[i][j];
+          nf_sm[(pl * 2 + 1) * C + qd * 4 + j] = q[i][j];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NF_THREADS) {  // fold the pixel lanes in a fixed order
+    float a = nf_sm[c], b = nf_sm[C + c];
+    for (int l = 1; l < ppl; ++l) {
+      a += nf_sm[(l * 2 + 0) * C + c];
+      b += nf_sm[(l * 2 + 1) * C + c];
+    }
+    nf_sm[c] = a;
+    nf_sm[C + c] = b;
+  }
+  __syncthreads();
+  for (int g = warp; g < p.G; g += NF_THREADS / 32) {  // one warp per group
+    float a = 0.f, b = 0.f;
+    for (int c = g * p.cpg + lane; c < (g + 1) * p.cpg; c += 32) {
+      a += nf_sm[c];
+      b += nf_sm[C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) p.part[(long long)item * p.G + g] = make_float2(a, b);
+  }
+
+  if (threadIdx.x == 0) t1 = clock64();
+  // ---- level 1: sub-group of <= NF_SUB consecutive slabs of this image ----
+  const int sub = sl / NF_SUB;
+  const int sub_first = sub * NF_SUB;
+  int members = p.slabs_per_img - sub_first;
+  if (members > NF_SUB) members = NF_SUB;
+  const int sub_global = n * p.subs_per_img + sub;
+  unsigned int* sub_ctr = p.bar + 32 * (1 + sub_global);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    flag_s = (atomicAdd(sub_ctr, 1u) == (unsigned int)members - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (flag_s) {
+    __threadfence();
+    const float2* src = p.part + ((long long)n * p.slabs_per_img + sub_first) * p.G;
+    for (int g = warp; g < p.G; g += NF_THREADS / 32) {
+      float2 t = make_float2(0.f, 0.f);
+      if (lane < members) t = __ldcg(src + (long long)lane * p.G + g);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {  // NF_SUB = 16 lanes
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+      }
+      if (lane == 0) p.part2[(long long)sub_global * p.G + g] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *sub_ctr = 0u;  // self-resetting: launches on one stream are serialised
+      __threadfence();
+      const unsigned int total_subs = (gridDim.x / p.slabs_per_img) * p.subs_per_img;
+      if (atomicAdd(p.bar, 1u) == total_subs - 1) {
+        *p.bar = 0u;
+        __threadfence();
+        atomicAdd(p.bar + 1, 1u);  // release every block
+      }
+    }
+  }
+  // ---- level 2: wait for the generation to move ----
+  if (threadIdx.x == 0) {
+    t2 = clock64();
+    volatile unsigned int* gen = p.bar + 1;
+    unsigned int spins = 0;
+    while (*gen == gen_s) {
+      __nanosleep(32);
+      if (++spins > (1u << 24)) {
+        printf("tsd: norm_fused2 grid barrier timed out (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
+    t3 = clock64();
+  }
+  __syncthreads();
+
+  // ---- phase 2: statistics of this image, normalise ----
+  float2* st = reinterpret_cast<float2*>(nf_sm);
+  {
+    const float2* src = p.part2 + (long long)n * p.subs_per_img * p.G;
+    for (int g = warp; g < p.G; g += NF_THREADS / 32) {
+      float2 t = make_float2(0.f, 0.f);
+      if (lane < p.subs_per_img) t = __ldcg(src + (long long)lane * p.G + g);  // subs_per_img <= 32
+      double ds = (double)t.x, dq = (double)t.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      if (lane == 0) {
+        const double mean = ds * (double)p.inv_count;
+        double var = dq * (double)p.inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
+        st[g] = make_float2((float)mean, 1.0f / (sqrtf((float)var) + p.eps));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) t4 = clock64();
+  if (pl >= ppl) return;
+  float mu[NQ][4], sc[NQ][4], sh[NQ][4];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int qd = u + i * TU;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mu[i][j] = 0.f; sc[i][j] = 0.f; sh[i][j] = 0.f;
+      if (qd < C4) {
+        const int c = qd * 4 + j;
+        const float2 t = st[c / p.cpg];
+        mu[i][j] = t.x;
+        sc[i][j] = t.y * p.gamma_scalar * (p.gamma ? p.gamma[c] : 1.0f);
+        sh[i][j] = p.beta ? p.beta[c] : 0.0f;
+      }
+    }
+  }
+  float4* obase = p.y + (long long)n * p.pixels * C4;
+  auto emit = [&](int px, int i, int qd, float4 t) {
+    float o[4] = {(t.x - mu[i][0]) * sc[i][0] + sh[i][0], (t.y - mu[i][1]) * sc[i][1] + sh[i][1],
+                  (t.z - mu[i][2]) * sc[i][2] + sh[i][2], (t.w - mu[i][3]) * sc[i][3] + sh[i][3]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p.silu) o[j] = silu_f(o[j]);
+      if (p.round) o[j] = rna_tf32(o[j]);
+    }
+    obase[(long long)px * C4 + qd] = make_float4(o[0], o[1], o[2], o[3]);
+  };
+  if (CACHE) {
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int px = p0 + pl + it * ppl;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int qd = u + i * TU;
+        if (px < p1 && qd < C4) emit(px, i, qd, v[it][i]);
+      }
+    }
+  } else {
+    const float4* src = (p.splits > 1) ? p.raw : p.x;  // re-read mode of a split-K source reads back the raw sum
+    const int ld = (p.splits > 1) ? C4 : p.ldx4;
+#pragma unroll 2
+    for (int px = p0 + pl; px < p1; px += ppl) {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int qd = u + i * TU;
+        if (qd < C4) emit(px, i, qd, src[((long long)n * p.pixels + px) * ld + qd]);
+      }
+    }
+  }
+  if (p.trace && threadIdx.x == 0 && blockIdx.x == 0)
+    printf("norm2 trace: phase1 %lld arrive..spin %lld spin %lld fold %lld apply %lld (clk) grid %d\n", t1 - t0, t2 - t1, t3 - t2,
+           t4 - t3, clock64() - t4, gridDim.x);
+}
+
 // General path: one block per (n, g).
 __global__ void group_stats_general_kernel(const float* __restrict__ x, long long pixels, int C,
                                            int G, int cpg, double* __restrict__ accum) {
@@ -510,6 +823,8 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, const float2* __r
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   float gamma_scalar, float* __restrict__ y, int N, int H, int W,
                                   int C, int G, int cpg, int silu, int up, int round) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int CV = C / VEC;
   const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
   const long long total = (long long)N * Ho * Wo * CV;
@@ -546,6 +861,65 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, const float2* __r
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     else
       dst[0] = v[0];
+  }
+}
+
+// Normalise pass for producer-side partial statistics (norm_stats.cuh): grid (slabs, N).  Every
+// block first folds the partials of its image to (mean, 1/(std+eps)) per group (a few hundred
+// float2 from L2), then a thread owns up to three fixed channel quads (coalesced float4 along C)
+// and walks the pixels of its slab, `ppl` pixels in flight per block - no index divisions.
+__global__ void __launch_bounds__(GS_THREADS)
+norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, const NormStatsReq req,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float gamma_scalar,
+                          int pixels, int C4, int slab, int silu, int round) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float2 st[512];
+  const int n = blockIdx.y;
+  norm_stats_fold(req, n, threadIdx.x, GS_THREADS, st);
+  __syncthreads();
+  const int cpg = req.cpg;
+  const int TU = C4 < GS_THREADS ? C4 : GS_THREADS;
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  const int u = threadIdx.x % TU, pl = threadIdx.x / TU;
+  if (pl >= ppl) return;
+  float mu[GS_MAXQ][4], sc[GS_MAXQ][4], sh[GS_MAXQ][4];
+#pragma unroll
+  for (int i = 0; i < GS_MAXQ; ++i) {
+    const int qd = u + i * TU;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mu[i][j] = 0.f; sc[i][j] = 0.f; sh[i][j] = 0.f;
+      if (qd < C4) {
+        const int c = qd * 4 + j;
+        const float2 t = st[c / cpg];
+        mu[i][j] = t.x;
+        sc[i][j] = t.y * gamma_scalar * (gamma ? gamma[c] : 1.0f);
+        sh[i][j] = beta ? beta[c] : 0.0f;
+      }
+    }
+  }
+  int p0 = blockIdx.x * slab, p1 = p0 + slab;
+  if (p1 > pixels) p1 = pixels;
+  const float4* base = x + (long long)n * pixels * C4;
+  float4* obase = y + (long long)n * pixels * C4;
+#pragma unroll 2
+  for (int p = p0 + pl; p < p1; p += ppl) {
+#pragma unroll
+    for (int i = 0; i < GS_MAXQ; ++i) {
+      const int qd = u + i * TU;
+      if (qd < C4) {
+        const float4 v = base[(long long)p * C4 + qd];
+        float o[4] = {(v.x - mu[i][0]) * sc[i][0] + sh[i][0], (v.y - mu[i][1]) * sc[i][1] + sh[i][1],
+                      (v.z - mu[i][2]) * sc[i][2] + sh[i][2], (v.w - mu[i][3]) * sc[i][3] + sh[i][3]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (silu) o[j] = silu_f(o[j]);
+          if (round) o[j] = rna_tf32(o[j]);
+        }
+        obase[(long long)p * C4 + qd] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
 }
 
@@ -632,6 +1006,8 @@ __global__ void __launch_bounds__(CS_THREADS)
 conv_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ out, int N, int H, int W, int Cin, int Cout, int k, int pad, int stride,
                    int Ho, int Wo) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float patch[CS_PIX][CS_MAXK];
   const int K = k * k * Cin;
   const long long total_px = (long long)N * Ho * Wo;
@@ -798,6 +1174,8 @@ __global__ void ddpm_step_kernel(const float* __restrict__ x, const float* __res
                                  const float* __restrict__ noise, float sqrt_ab, float sqrt_1mab,
                                  float c0, float c1, float sigma, float* __restrict__ out,
                                  long long n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float e = ec[i];
@@ -842,14 +1220,14 @@ cudaError_t launch_oihw_to_ohwi(const float* src, float* dst, int O, int I, int 
 cudaError_t launch_concat_channels(const float* a, int Ca, const float* b, int Cb, float* out,
                                    long long pixels, cudaStream_t s) {
   long long total = pixels * (Ca + Cb);
-  concat_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, Ca, b, Cb, out, pixels);
+  { cudaError_t e_ = launch_pdl(concat_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, a, Ca, b, Cb, out, pixels); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 cudaError_t launch_upsample2x(const float* x, float* y, int N, int H, int W, int C, cudaStream_t s) {
   if (C % 4) return cudaErrorInvalidValue;
   long long total = (long long)N * 4 * H * W * (C / 4);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x),
-                                                         reinterpret_cast<float4*>(y), N, H, W, C / 4);
+  { cudaError_t e_ = launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, reinterpret_cast<const float4*>(x),
+                                                         reinterpret_cast<float4*>(y), N, H, W, C / 4); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 cudaError_t launch_upsample2x_planar(const float* x, float* y, int C, int H, int W, cudaStream_t s) {
@@ -861,9 +1239,9 @@ cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, in
                              int Ho, int Wo, cudaStream_t s) {
   if (C % 4) return cudaErrorInvalidValue;
   long long total = (long long)N * Ho * Wo * 9 * (C / 4);
-  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x),
+  { cudaError_t e_ = launch_pdl(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, reinterpret_cast<const float4*>(x),
                                                         reinterpret_cast<float4*>(col), N, H, W,
-                                                        C / 4, stride, Ho, Wo);
+                                                        C / 4, stride, Ho, Wo); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 
@@ -950,11 +1328,127 @@ cudaError_t launch_norm_fused(const float* x, float* y, int N, long long pixels,
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  norm_fused_kernel<<<grid, GS_THREADS, smem, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
+  { cudaError_t e_ = launch_pdl(norm_fused_kernel, dim3(grid), dim3(GS_THREADS), smem, s, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
                                                    pixels, C4, G, cpg, slabs, slab, items,
                                                    reinterpret_cast<double2*>(scratch), barrier_words,
                                                    (double)pixels * cpg, eps, gamma, beta, gamma_scalar, silu,
-                                                   round_tf32);
+                                                   round_tf32); if (e_ != cudaSuccess) return e_; }
+  return cudaGetLastError();
+}
+
+
+// ---- fused norm v2 ----
+struct NormFused2Plan {
+  int ppl, slab, slabs_per_img, subs_per_img, nq, iters;
+  bool cache;
+};
+static NormFused2Plan norm_fused2_plan(int N, long long pixels, int C, int sm_count) {
+  NormFused2Plan pl{};
+  const int C4 = C / 4;
+  pl.ppl = C4 < NF_THREADS ? NF_THREADS / C4 : 1;
+  pl.nq = (C4 + NF_THREADS - 1) / NF_THREADS;
+  int max_blocks = 2 * sm_count;
+  int spi = max_blocks / N;
+  if (spi < 1) spi = 1;
+  const long long groups = (pixels + pl.ppl - 1) / pl.ppl;  // pixel groups in flight per block pass
+  if (spi > groups) spi = (int)groups;
+  long long slab = (pixels + spi - 1) / spi;
+  slab = (slab + pl.ppl - 1) / pl.ppl * pl.ppl;
+  pl.slab = (int)slab;
+  pl.slabs_per_img = (int)((pixels + slab - 1) / slab);
+  pl.subs_per_img = (pl.slabs_per_img + NF_SUB - 1) / NF_SUB;
+  pl.iters = (int)(slab / pl.ppl);
+  const int maxit = pl.nq == 1 ? 16 : (pl.nq == 2 ? 8 : 5);
+  pl.cache = pl.iters <= maxit;
+  return pl;
+}
+bool norm_fused2_supported(int N, long long pixels, int C, int G, int sm_count) {
+  if (C % 4 || C / 4 > 3 * NF_THREADS || G <= 0 || C % G || pixels >= (1 << 30)) return false;
+  if (N > 2 * sm_count) return false;
+  const NormFused2Plan pl = norm_fused2_plan(N, pixels, C, sm_count);
+  return pl.subs_per_img <= 32 && (long long)N * pl.subs_per_img + 1 <= kNormBarrierCounters;
+}
+size_t norm_fused2_scratch_bytes(int N, long long pixels, int C, int G, int sm_count) {
+  const NormFused2Plan pl = norm_fused2_plan(N, pixels, C, sm_count);
+  return sizeof(float2) * (size_t)N * G * ((size_t)pl.slabs_per_img + pl.subs_per_img) + 256;
+}
+cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long long pixels, int C, int G, float eps,
+                               const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
+                               void* scratch, unsigned int* barrier_words, int sm_count, cudaStream_t s) {
+  if (!norm_fused2_supported(N, pixels, C, G, sm_count)) return cudaErrorInvalidValue;
+  const NormFused2Plan pl = norm_fused2_plan(N, pixels, C, sm_count);
+  NormFused2Params p{};
+  p.x = reinterpret_cast<const float4*>(src.x);
+  p.splits = src.splits > 1 ? src.splits : 1;
+  p.split_stride4 = src.split_stride / 4;
+  p.ldx4 = src.splits > 1 ? src.ldx / 4 : C / 4;
+  p.bias = src.bias;
+  p.bias_img_stride = src.bias_img_stride;
+  p.residual = reinterpret_cast<const float4*>(src.residual);
+  p.raw = reinterpret_cast<float4*>(src.raw);
+  p.y = reinterpret_cast<float4*>(y);
+  p.pixels = (int)pixels;
+  p.C4 = C / 4;
+  p.G = G;
+  p.cpg = C / G;
+  p.slabs_per_img = pl.slabs_per_img;
+  p.slab = pl.slab;
+  p.subs_per_img = pl.subs_per_img;
+  p.part = reinterpret_cast<float2*>(scratch);
+  p.part2 = p.part + (size_t)N * pl.slabs_per_img * G;
+  p.bar = barrier_words;
+  p.inv_count = (float)(1.0 / ((double)pixels * (C / G)));
+  p.eps = eps;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.gamma_scalar = gamma_scalar;
+  p.silu = silu;
+  p.round = round_tf32;
+  {
+    static int tr = -1;
+    if (tr < 0) { const char* v = getenv("TSD_NORM_TRACE"); tr = v ? atoi(v) : 0; }
+    p.trace = tr;
+  }
+  bool cache = pl.cache;
+  if (p.splits > 1 && !cache && p.raw == nullptr) return cudaErrorInvalidValue;  // re-read mode needs the raw sum
+  const int grid = N * pl.slabs_per_img;
+  size_t smem = (size_t)pl.ppl * 2 * C * sizeof(float);
+  if (smem < (size_t)G * sizeof(float2)) smem = (size_t)G * sizeof(float2);
+#define NF2_LAUNCH(NQ, MAXIT, CACHE)                                                                        \
+  do {                                                                                                      \
+    static bool attr_set = false;                                                                           \
+    if (!attr_set) {                                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(norm_fused2_kernel<NQ, MAXIT, CACHE>,                            \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);         \
+      if (e != cudaSuccess) return e;                                                                       \
+      attr_set = true;                                                                                      \
+    }                                                                                                       \
+    { cudaError_t e_ = launch_pdl(norm_fused2_kernel<NQ, MAXIT, CACHE>, dim3(grid), dim3(NF_THREADS), smem, s, p); if (e_ != cudaSuccess) return e_; } \
+  } while (0)
+  if (pl.nq == 1) { if (cache) NF2_LAUNCH(1, 16, true); else NF2_LAUNCH(1, 16, false); }
+  else if (pl.nq == 2) { if (cache) NF2_LAUNCH(2, 8, true); else NF2_LAUNCH(2, 8, false); }
+  else { if (cache) NF2_LAUNCH(3, 5, true); else NF2_LAUNCH(3, 5, false); }
+#undef NF2_LAUNCH
+  return cudaGetLastError();
+}
+
+bool norm_apply_partial_supported(int C, int G) { return C % 4 == 0 && C / 4 <= GS_MAXQ * GS_THREADS && G <= 512; }
+
+cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsReq& req, int N, long long pixels_ll,
+                                      const float* gamma, const float* beta, float gamma_scalar, int silu,
+                                      int round_tf32, cudaStream_t s) {
+  if (!norm_apply_partial_supported(req.C, req.G) || pixels_ll >= (1 << 30)) return cudaErrorInvalidValue;
+  const int C4 = req.C / 4, pixels = (int)pixels_ll;
+  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  // ~4 blocks per SM over the whole batch; a slab is a multiple of the pixels in flight
+  int slabs = (4 * 148 + N - 1) / N;
+  int slab = (pixels + slabs - 1) / slabs;
+  slab = (slab + ppl - 1) / ppl * ppl;
+  if (slab < ppl) slab = ppl;
+  slabs = (pixels + slab - 1) / slab;
+  { cudaError_t e_ = launch_pdl(norm_apply_partial_kernel, dim3(dim3(slabs, N)), dim3(GS_THREADS), 0, s, reinterpret_cast<const float4*>(x),
+                                                                  reinterpret_cast<float4*>(y), req, gamma, beta,
+                                                                  gamma_scalar, pixels, C4, slab, silu, round_tf32); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 
@@ -967,14 +1461,14 @@ cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* 
   const long long outpix = (long long)N * H * W * (upsample2x ? 4 : 1);
   if (C % 4 == 0) {
     long long total = outpix * (C / 4);
-    norm_apply_kernel<4><<<grid_for(total, 256), 256, 0, s>>>(x, stats, gamma, beta, gamma_scalar, y,
+    { cudaError_t e_ = launch_pdl(norm_apply_kernel<4>, dim3(grid_for(total, 256)), dim3(256), 0, s, x, stats, gamma, beta, gamma_scalar, y,
                                                               N, H, W, C, G, cpg, silu, upsample2x,
-                                                              round_tf32);
+                                                              round_tf32); if (e_ != cudaSuccess) return e_; }
   } else {
     long long total = outpix * C;
-    norm_apply_kernel<1><<<grid_for(total, 256), 256, 0, s>>>(x, stats, gamma, beta, gamma_scalar, y,
+    { cudaError_t e_ = launch_pdl(norm_apply_kernel<1>, dim3(grid_for(total, 256)), dim3(256), 0, s, x, stats, gamma, beta, gamma_scalar, y,
                                                               N, H, W, C, G, cpg, silu, upsample2x,
-                                                              round_tf32);
+                                                              round_tf32); if (e_ != cudaSuccess) return e_; }
   }
   return cudaGetLastError();
 }
@@ -1002,8 +1496,8 @@ cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias
                                int Wo, cudaStream_t s) {
   if (k * k * Cin <= CS_MAXK && Cout >= 32) {
     const long long total_px = (long long)N * Ho * Wo;
-    conv_smallk_kernel<<<(unsigned)((total_px + CS_PIX - 1) / CS_PIX), CS_THREADS, 0, s>>>(x, w, bias, out, N, H, W, Cin,
-                                                                                          Cout, k, pad, stride, Ho, Wo);
+    { cudaError_t e_ = launch_pdl(conv_smallk_kernel, dim3((unsigned)((total_px + CS_PIX - 1) / CS_PIX)), dim3(CS_THREADS), 0, s, x, w, bias, out, N, H, W, Cin,
+                                                                                          Cout, k, pad, stride, Ho, Wo); if (e_ != cudaSuccess) return e_; }
     return cudaGetLastError();
   }
   long long total = (long long)N * Ho * Wo * Cout;
@@ -1045,8 +1539,8 @@ cudaError_t launch_spin(long long ns, cudaStream_t s) {
 cudaError_t launch_ddpm_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
                              const float* noise, float sqrt_ab, float sqrt_1mab, float c0, float c1,
                              float sigma, float* out, long long n, cudaStream_t s) {
-  ddpm_step_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, eps_c, eps_u, cfg_scale, noise, sqrt_ab,
-                                                    sqrt_1mab, c0, c1, sigma, out, n);
+  { cudaError_t e_ = launch_pdl(ddpm_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, s, x, eps_c, eps_u, cfg_scale, noise, sqrt_ab,
+                                                    sqrt_1mab, c0, c1, sigma, out, n); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 

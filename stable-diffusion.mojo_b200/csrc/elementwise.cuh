@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "norm_stats.cuh"
+
 namespace tsd {
 
 // ---- layout -----------------------------------------------------------------------------
@@ -37,6 +39,27 @@ cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, i
                                void* scratch, unsigned int* ticket, float2* stats, cudaStream_t s);
 // y = (x - mean) * inv [* gamma[c] + beta[c]] ; optional SiLU ; optional TF32 rounding ;
 // optional nearest 2x upsample on write (x is [N,H,W,C], y is [N,2H,2W,C]).
+// fused norm v2 (one launch, activation read once; optionally also the split-K reduction of its producer)
+constexpr int kNormBarrierCounters = 512;  // 128 B apart: root/generation line + sub-group counters
+struct NormFused2Src {
+  const float* x = nullptr;       // activation [N][pixels][C], or split-K partials [splits][N*pixels][ldx]
+  int splits = 1;
+  long long split_stride = 0;     // floats between splits
+  int ldx = 0;                    // row stride of the partials (floats)
+  const float* bias = nullptr;    // split-K source: per-image bias rows
+  int bias_img_stride = 0;
+  const float* residual = nullptr;  // split-K source: [N*pixels][C]
+  float* raw = nullptr;             // split-K source: un-normalised result [N*pixels][C] (nullptr: not needed)
+};
+bool norm_fused2_supported(int N, long long pixels, int C, int G, int sm_count);
+size_t norm_fused2_scratch_bytes(int N, long long pixels, int C, int G, int sm_count);
+cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long long pixels, int C, int G, float eps,
+                               const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
+                               void* scratch, unsigned int* barrier_words, int sm_count, cudaStream_t s);
+bool norm_apply_partial_supported(int C, int G);
+cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsReq& req, int N, long long pixels,
+                                      const float* gamma, const float* beta, float gamma_scalar, int silu,
+                                      int round_tf32, cudaStream_t s);
 cudaError_t launch_norm_apply(const float* x, const float2* stats, const float* gamma,
                               const float* beta, float gamma_scalar, float* y, int N, int H, int W,
                               int C, int G, int silu, int upsample2x, int round_tf32,

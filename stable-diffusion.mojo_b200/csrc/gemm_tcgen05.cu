@@ -3,6 +3,7 @@
 
 #include <cstdio>
 
+#include "pdl.cuh"
 #include "ptx_sm100.cuh"
 
 namespace tsd {
@@ -204,6 +205,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
   if (threadIdx.x == 0) tr[1] = clock64();
+  pdl_launch_dependents();  // resources are held: the next kernel may start its own prologue
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -242,26 +244,49 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t sa = smem_base;
       uint32_t fb = full0, eb = empty0;
       const uint32_t fb_mask = (CG == 2) ? 0xFEFFFFFFu : 0xFFFFFFFFu;  // CG == 2: signal the leader's barrier
+      auto load_b = [&](uint32_t sa_, uint32_t fbs_, int kb_) {
+        const uint32_t sb = sa_ + 2 * a_atom;
+        if (!two_b) {
+          tma_b_3d<CG>(sb, &tmB, fbs_, kb_, brow0, batch);
+          tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
+        } else {
+          const uint32_t hb = (uint32_t)half_rows * 128;
+          tma_b_3d<CG>(sb, &tmB, fbs_, kb_, brow0, batch);
+          tma_b_3d<CG>(sb + hb, &tmB, fbs_, kb_, brow1, batch);
+          tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
+          tma_b_3d<CG>(sb + b_atom + hb, &tmB, fbs_, kb_ + 32, brow1, batch);
+        }
+      };
+      // Weights do not depend on the predecessor kernel: the B halves of the first ring pass are
+      // requested BEFORE the programmatic-dependency wait, so their HBM latency overlaps its tail.
+      int pre = 0;
+      if (p.b_static && !(debug & 4)) {
+        pre = n_iters < num_stages ? n_iters : num_stages;
+        int kc2 = kc, tap2 = tap, kb2 = kb;
+        for (int it = 0; it < pre; ++it) {
+          const uint32_t fb2 = full0 + 8u * it;
+          if (CG == 1 || rank == 0) mbar_expect_tx_a(fb2, tx);
+          load_b(smem_base + it * stage_bytes, fb2 & fb_mask, kb2);
+          kc2 += GEMM_BK;
+          kb2 += GEMM_BK;
+          if (kc2 >= cin) {
+            kc2 = 0;
+            ++tap2;
+            kb2 = tap2 * cin;
+          }
+        }
+      }
+      pdl_wait();  // A (and any aliasing of the arena) belongs to the predecessor: no other global access before this
       for (int it = 0; it < n_iters; ++it) {
-        mbar_wait_a(eb, phase ^ 1u);
-        if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, tx);
         const uint32_t fbs = fb & fb_mask;
+        if (it >= pre) {
+          mbar_wait_a(eb, phase ^ 1u);
+          if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, tx);
+          if (!(debug & 4)) load_b(sa, fbs, kb);
+        }
         if (!(debug & 2)) {
           tma_a_4d<CG>(sa, &tmA, fbs, kc, w0 + dx, h0 + dy, c3);
           tma_a_4d<CG>(sa + a_atom, &tmA, fbs, kc + 32, w0 + dx, h0 + dy, c3);
-        }
-        if (!(debug & 4)) {
-          const uint32_t sb = sa + 2 * a_atom;
-          if (!two_b) {
-            tma_b_3d<CG>(sb, &tmB, fbs, kb, brow0, batch);
-            tma_b_3d<CG>(sb + b_atom, &tmB, fbs, kb + 32, brow0, batch);
-          } else {
-            const uint32_t hb = (uint32_t)half_rows * 128;
-            tma_b_3d<CG>(sb, &tmB, fbs, kb, brow0, batch);
-            tma_b_3d<CG>(sb + hb, &tmB, fbs, kb, brow1, batch);
-            tma_b_3d<CG>(sb + b_atom, &tmB, fbs, kb + 32, brow0, batch);
-            tma_b_3d<CG>(sb + b_atom + hb, &tmB, fbs, kb + 32, brow1, batch);
-          }
         }
         kc += GEMM_BK;
         kb += GEMM_BK;
@@ -344,6 +369,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // stores (8 lanes x 16 B cover 128 B of one row; a warp instruction writes 4 full rows).
     // Two warps per TMEM lane quadrant, interleaved over the 32-column chunks.  The staging tiles
     // reuse the operand ring: every MMA has retired once accum_bar completes.
+    pdl_wait();                // before the first global access of this role (row bias, residual, D)
     const int ew = warp - 2;   // 0..7
     const int q = warp & 3;    // TMEM lane quadrant this warp may read
     const int half = ew >> 2;  // which of the two warps of the quadrant
@@ -400,6 +426,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     (cbias == nullptr || (((p.bias_img_stride & 3) == 0) &&
                                                           (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
     const bool round_out = p.round_tf32 && !partial;
+    // producer-side norm statistics: per-column (sum, sum^2) of the stored values of this tile
+    const bool want_stats = p.ns.partial != nullptr;
+    float2* cs = reinterpret_cast<float2*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + 8 * 32 * ST * 4);  // [4][256]
 
     mbar_wait_a(accum_a, 0);
     tc_fence_after_sync();
@@ -435,6 +464,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
       const int n = n0 + c + c4;  // first of this lane's 4 columns
+      float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c + c4 < out_cols && n < n_lim) {
         long long col;
         if (partial) col = (long long)nt * p.BN + c + c4;
@@ -456,6 +486,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
             }
             *reinterpret_cast<float4*>(drow[i] + col) = t;
+            ss.x += t.x; ss.y += t.y; ss.z += t.z; ss.w += t.w;
+            qq.x = fmaf(t.x, t.x, qq.x); qq.y = fmaf(t.y, t.y, qq.y); qq.z = fmaf(t.z, t.z, qq.z); qq.w = fmaf(t.w, t.w, qq.w);
           }
         } else {
 #pragma unroll
@@ -476,7 +508,58 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (want_stats) {
+        // fold the 4 row groups of the warp (lanes with equal lane % 8): fixed xor tree, all lanes take part
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+          ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+          qq.x += __shfl_xor_sync(0xffffffffu, qq.x, o); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, o);
+          qq.z += __shfl_xor_sync(0xffffffffu, qq.z, o); qq.w += __shfl_xor_sync(0xffffffffu, qq.w, o);
+        }
+        if (sub == 0 && c + c4 < out_cols) {
+          float2* d = cs + q * 256 + c + c4;
+          d[0] = make_float2(ss.x, qq.x); d[1] = make_float2(ss.y, qq.y);
+          d[2] = make_float2(ss.z, qq.z); d[3] = make_float2(ss.w, qq.w);
+        }
+      }
       __syncwarp();
+    }
+    if (want_stats) {
+      // quadrant sums -> column sums -> sums of the groups overlapping this tile -> partial; the last CTA finalises
+      const int te = threadIdx.x - 64;  // 0..255 among the epilogue threads
+      named_bar_sync(2, 256);
+      {
+        float2 a = cs[te], b = cs[256 + te], c2 = cs[512 + te], d2 = cs[768 + te];
+        const bool okc = te < out_cols && n0 + te < n_valid;
+        cs[te] = okc ? make_float2((a.x + b.x) + (c2.x + d2.x), (a.y + b.y) + (c2.y + d2.y)) : make_float2(0.f, 0.f);
+      }
+      named_bar_sync(2, 256);
+      if (img_ok) {
+        const int cpg = p.ns.cpg;
+        const int g_lo = n0 / cpg;
+        int n_end = n0 + out_cols;
+        if (n_end > n_valid) n_end = n_valid;
+        const int g_hi = (n_end - 1) / cpg;
+        float2* dst = p.ns.partial + ((long long)blockIdx.x * p.ns.n_tiles + nt) * p.ns.lg;
+        for (int g = g_lo + ew; g <= g_hi; g += 8) {  // one warp per group: lanes stride over its columns in the tile
+          int c_lo = g * cpg - n0, c_hi = (g + 1) * cpg - n0;
+          if (c_lo < 0) c_lo = 0;
+          if (c_hi > n_end - n0) c_hi = n_end - n0;
+          float s = 0.f, qv = 0.f;
+          for (int cc = c_lo + lane; cc < c_hi; cc += 32) {
+            const float2 t = cs[cc];
+            s += t.x;
+            qv += t.y;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            qv += __shfl_xor_sync(0xffffffffu, qv, o);
+          }
+          if (lane == 0) dst[g - g_lo] = make_float2(s, qv);
+        }
+      }
     }
     if (threadIdx.x == 64) tr[5] = clock64();
     tc_fence_before_sync();
@@ -500,6 +583,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // Sums split-K partials and applies the (bias, residual, rounding) epilogue.
 __global__ void splitk_reduce_kernel(const SplitKReduceParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int n4 = p.n_pad >> 2;
   const long long total = (long long)p.m * n4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -540,7 +625,7 @@ static size_t gemm_stage_bytes(int BN, int cg) { return 2 * ((size_t)GEMM_BM * 1
 
 size_t gemm_smem_bytes(int BN, int num_stages, int cg) {
   size_t ring = (size_t)num_stages * gemm_stage_bytes(BN, cg);
-  const size_t staging = 8 * 32 * 36 * 4;  // epilogue staging tiles live in the (then idle) ring
+  const size_t staging = 8 * 32 * 36 * 4 + 4 * 256 * 8;  // epilogue staging tiles + column statistics live in the (then idle) ring
   if (ring < staging) ring = staging;
   return ring + 1024;
 }
@@ -577,13 +662,15 @@ static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<CG>, tmA, tmB, p);
 }
 
@@ -593,13 +680,116 @@ cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   return launch_gemm_cg<1>(tmA, tmB, p, grid, smem_bytes, stream);
 }
 
+// Slab variant with producer-side norm statistics (norm_stats.cuh): a block owns `slab_rows` rows x all
+// columns; a thread owns up to three fixed column quads, so the per-column sums of the values it
+// stores accumulate in registers with no atomics.
+constexpr int RK_THREADS = 256, RK_MAXQ = 3;
+__global__ void __launch_bounds__(RK_THREADS)
+splitk_reduce_stats_kernel(const SplitKReduceParams p) {
+  extern __shared__ float2 rk_sm[];  // [ppl][C] column sums, folded into [C]
+  pdl_wait();
+  pdl_launch_dependents();
+  const int n4 = p.n_valid >> 2, C = p.n_valid;
+  const int TU = n4 < RK_THREADS ? n4 : RK_THREADS;
+  const int ppl = n4 < RK_THREADS ? RK_THREADS / n4 : 1;
+  const int u = threadIdx.x % TU, pl = threadIdx.x / TU;
+  const int row0 = blockIdx.x * p.slab_rows;
+  float4 ss[RK_MAXQ], qq[RK_MAXQ];
+#pragma unroll
+  for (int i = 0; i < RK_MAXQ; ++i) ss[i] = qq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < ppl) {
+    for (int r = pl; r < p.slab_rows; r += ppl) {
+      const int row = row0 + r;
+      if (row >= p.m) break;
+      const float* brow = p.bias ? p.bias + (long long)(row / p.rows_per_img) * p.bias_img_stride : nullptr;
+#pragma unroll
+      for (int i = 0; i < RK_MAXQ; ++i) {
+        const int qd = u + i * TU;
+        if (qd < n4) {
+          const float* src = p.partial + (long long)row * p.n_pad + qd * 4;
+          float4 acc = *reinterpret_cast<const float4*>(src);
+          for (int sp = 1; sp < p.splits; ++sp) {
+            const float4 t = *reinterpret_cast<const float4*>(src + sp * p.split_stride);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          if (brow) {
+            const float4 b = *reinterpret_cast<const float4*>(brow + qd * 4);
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+          }
+          if (p.residual) {
+            const float4 t = *reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + qd * 4);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          if (p.round_tf32) {
+            acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
+          }
+          *reinterpret_cast<float4*>(p.D + (long long)row * p.ldd + qd * 4) = acc;
+          ss[i].x += acc.x; ss[i].y += acc.y; ss[i].z += acc.z; ss[i].w += acc.w;
+          qq[i].x = fmaf(acc.x, acc.x, qq[i].x); qq[i].y = fmaf(acc.y, acc.y, qq[i].y);
+          qq[i].z = fmaf(acc.z, acc.z, qq[i].z); qq[i].w = fmaf(acc.w, acc.w, qq[i].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RK_MAXQ; ++i) {
+      const int qd = u + i * TU;
+      if (qd < n4) {
+        float2* d = rk_sm + (long long)pl * C + qd * 4;
+        d[0] = make_float2(ss[i].x, qq[i].x); d[1] = make_float2(ss[i].y, qq[i].y);
+        d[2] = make_float2(ss[i].z, qq[i].z); d[3] = make_float2(ss[i].w, qq[i].w);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += RK_THREADS) {  // fold the row lanes in a fixed order
+    float2 a = rk_sm[c];
+    for (int l = 1; l < ppl; ++l) {
+      const float2 t = rk_sm[(long long)l * C + c];
+      a.x += t.x;
+      a.y += t.y;
+    }
+    rk_sm[c] = a;
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* dst = p.ns.partial + (long long)blockIdx.x * p.ns.lg;
+    for (int g = warp; g < p.ns.G; g += RK_THREADS / 32) {
+      float s = 0.f, qv = 0.f;
+      for (int cc = g * p.ns.cpg + lane; cc < (g + 1) * p.ns.cpg; cc += 32) {
+        const float2 t = rk_sm[cc];
+        s += t.x;
+        qv += t.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        qv += __shfl_xor_sync(0xffffffffu, qv, o);
+      }
+      if (lane == 0) dst[g] = make_float2(s, qv);
+    }
+  }
+}
+
 cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t stream) {
+  if (p.ns.partial != nullptr) {
+    const int n4 = p.n_valid >> 2;
+    const int ppl = n4 < RK_THREADS ? RK_THREADS / n4 : 1;
+    const size_t smem = (size_t)ppl * p.n_valid * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(splitk_reduce_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    const int blocks = (p.m + p.slab_rows - 1) / p.slab_rows;
+    return launch_pdl(splitk_reduce_stats_kernel, dim3(blocks), dim3(RK_THREADS), smem, stream, p);
+  }
   const long long total = (long long)p.m * (p.n_pad >> 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, p);
 }
 
 }  // namespace tsd

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "norm_stats.cuh"
+
 namespace tsd {
 
 constexpr int GEMM_BM = 128;       // rows per CTA tile (TMEM lanes)
@@ -54,6 +56,8 @@ struct GemmKParams {
   int n_pad;
   int debug;               // lab only (Ctx::gemm_debug)
   int cg;                  // 1, or 2 = CTA pairs over consecutive M tiles (cluster 2x1x1, grid.x even)
+  NormStatsReq ns;         // producer-side GroupNorm statistics of D (ns.partial == nullptr: off)
+  int b_static;            // B holds weights (never written by a predecessor kernel): may be loaded before pdl_wait
   int imgs;                // images (rows of tiles past the last image are phantom: loaded as zeros, never stored)
 };
 
@@ -69,6 +73,8 @@ struct SplitKReduceParams {
   const float* residual;
   int ldr;
   int round_tf32;
+  NormStatsReq ns;  // optional statistics of D (slab variant below when ns.partial != nullptr)
+  int slab_rows;    // rows per block of the slab variant
 };
 
 cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,

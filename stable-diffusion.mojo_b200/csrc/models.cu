@@ -283,8 +283,9 @@ static float* walloc(Ctx* c, long long n) { return c->arena.alloc_n<float>((size
 
 static int conv(Ctx* c, const ParamStore& ps, int wi, const float* x, int N, int H, int W, int cin, int cout,
                 int k, int pad, int stride, const float* bias_override, int bias_img_stride,
-                const float* residual, float* out, int round_out) {
+                const float* residual, float* out, int round_out, NormHint* nh = nullptr) {
   ConvArgs a;
+  a.nh = nh;
   a.x = x; a.N = N; a.H = H; a.W = W; a.Cin = cin; a.Cout = cout; a.k = k; a.pad = pad; a.stride = stride;
   a.w = ps.w(wi);
   a.bias = bias_override ? bias_override : ps.w(wi + 1);
@@ -298,8 +299,10 @@ static int conv(Ctx* c, const ParamStore& ps, int wi, const float* x, int N, int
 
 static int linear(Ctx* c, const float* x, long long M, int K, const float* w, const float* bias, int N,
                   float* out, long long ldd, const float* residual, int round_out, int geglu = 0,
-                  int split_n = 0, long long split_stride = 0) {
+                  int split_n = 0, long long split_stride = 0, NormHint* nh = nullptr) {
   GemmArgs g;
+  g.nh = nh;
+  g.b_static = 1;  // every Linear of the models multiplies by a parameter matrix
   g.A = x; g.M = (int)M; g.K = K; g.lda = K;
   g.B = w; g.N = N; g.ldb = K;
   g.D = out; g.ldd = ldd;
@@ -315,45 +318,62 @@ static int linear(Ctx* c, const float* x, long long M, int K, const float* w, co
 // Unet_Residual_Block.forward (diffusion.mojo:54-72) / VAE Res_Block.forward (vae.mojo:57-67).
 // tbias (optional) = Linear(SiLU(t)) + its bias + conv1 bias, one row per image.
 int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, const float* tbias,
-              int tbias_stride, float eps, float* out) {
+              int tbias_stride, float eps, float* out, NormHint* next) {
   const int N = x.N, H = x.H, W = x.W;
   const long long px = x.pixels();
   const size_t mark = c->arena.mark();
   WALLOC(h1, px * w.cin);
-  TRY(op_group_norm(c, x.p, h1, N, H, W, w.cin, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1));
+  const NormStatsReq* xs = (x.ns.G == w.groups && x.ns.eps == eps && x.C == w.cin) ? x.ns.ready() : nullptr;
+  TRY(op_group_norm(c, x.p, h1, N, H, W, w.cin, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, xs));
   WALLOC(h2, px * w.cout);
-  TRY(conv(c, ps, w.conv1, h1, N, H, W, w.cin, w.cout, 3, 1, 1, tbias, tbias_stride, nullptr, h2, 0));
+  NormHint mid;
+  mid.G = w.groups;
+  mid.eps = eps;
+  mid.scratch_elems = norm_scratch_elems(N, (long long)H * W, w.cout, w.groups);
+  mid.scratch = c->arena.alloc_n<float2>(mid.scratch_elems);
+  if (!mid.scratch) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+  TRY(conv(c, ps, w.conv1, h1, N, H, W, w.cin, w.cout, 3, 1, 1, tbias, tbias_stride, nullptr, h2, 0, &mid));
   WALLOC(h3, px * w.cout);
-  TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1));
+  TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, mid.ready()));
   const float* r = x.p;
   if (w.cin != w.cout) {
     WALLOC(rr, px * w.cout);
     TRY(conv(c, ps, w.skip, x.p, N, H, W, w.cin, w.cout, 1, 0, 1, nullptr, 0, nullptr, rr, 0));
     r = rr;
   }
-  TRY(conv(c, ps, w.conv2, h3, N, H, W, w.cout, w.cout, 3, 1, 1, nullptr, 0, r, out, 0));
+  TRY(conv(c, ps, w.conv2, h3, N, H, W, w.cout, w.cout, 3, 1, 1, nullptr, 0, r, out, 0, next));
   c->arena.release_to(mark);
   return TSD_OK;
 }
 
 // LayerNorm.forward = GroupNorm(1, C) over the whole (C,T) tensor of one image (Q5), or per token
-static int layer_norm(Ctx* c, const float* x, float* y, int N, long long T, int C) {
-  if (c->layernorm_mode == 0) return op_group_norm(c, x, y, N, (int)T, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1);
+static int layer_norm(Ctx* c, const float* x, float* y, int N, long long T, int C, const NormStatsReq* pre = nullptr) {
+  if (c->layernorm_mode == 0)
+    return op_group_norm(c, x, y, N, (int)T, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1, pre);
   return op_group_norm(c, x, y, (int)(N * T), 1, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1);
 }
 
 // Unet_Attention_Block.forward, diffusion.mojo:112-147
 static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const Act& x, const float* kctx,
-                      const float* vctx, int n_ctx, int ctx_len, float* out) {
+                      const float* vctx, int n_ctx, int ctx_len, float* out, NormHint* next = nullptr) {
   const int N = x.N, C = w.C, d = C / w.heads;
   const long long T = (long long)x.H * x.W, M = N * T;
   const size_t mark = c->arena.mark();
   WALLOC(a, M * C);
-  TRY(op_group_norm(c, x.p, a, N, x.H, x.W, C, 32, 1e-6f, nullptr, nullptr, 1.0f, 0, 0, 1));
+  const NormStatsReq* xs = (x.ns.G == 32 && x.ns.eps == 1e-6f) ? x.ns.ready() : nullptr;
+  TRY(op_group_norm(c, x.p, a, N, x.H, x.W, C, 32, 1e-6f, nullptr, nullptr, 1.0f, 0, 0, 1, xs));
+  // LayerNorm with global statistics (Q5) = one group per image: the producing GEMMs fold the sums
+  NormHint ln;
+  ln.G = c->layernorm_mode == 0 ? 1 : 0;
+  ln.eps = 1e-5f;
+  ln.imgs = N;
+  ln.scratch_elems = norm_scratch_elems(N, T, C, 1);
+  ln.scratch = c->arena.alloc_n<float2>(ln.scratch_elems);
+  if (!ln.scratch) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
   WALLOC(u, M * C);
-  TRY(linear(c, a, M, C, ps.w(w.conv_in), ps.w(w.conv_in + 1), C, u, C, nullptr, 0));
+  TRY(linear(c, a, M, C, ps.w(w.conv_in), ps.w(w.conv_in + 1), C, u, C, nullptr, 0, 0, 0, 0, &ln));
   WALLOC(v, M * C);
-  TRY(layer_norm(c, u, v, N, T, C));
+  TRY(layer_norm(c, u, v, N, T, C, ln.ready()));
   WALLOC(qkv, 3 * M * C);
   TRY(linear(c, v, M, C, ps.w(w.in_proj), nullptr, 3 * C, qkv, C, nullptr, 1, 0, C, M * C));
   WALLOC(o, M * C);
@@ -365,8 +385,8 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
     TRY(op_attention(c, at));
   }
   WALLOC(u2, M * C);
-  TRY(linear(c, o, M, C, ps.w(w.out_proj), ps.w(w.out_proj + 1), C, u2, C, u, 0));
-  TRY(layer_norm(c, u2, v, N, T, C));
+  TRY(linear(c, o, M, C, ps.w(w.out_proj), ps.w(w.out_proj + 1), C, u2, C, u, 0, 0, 0, 0, &ln));
+  TRY(layer_norm(c, u2, v, N, T, C, ln.ready()));
   float* q = qkv;
   TRY(linear(c, v, M, C, ps.w(w.q), nullptr, C, q, C, nullptr, 1));
   {
@@ -378,14 +398,15 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
     TRY(op_attention(c, at));
   }
   WALLOC(u3, M * C);
-  TRY(linear(c, o, M, C, ps.w(w.o), ps.w(w.o + 1), C, u3, C, u2, 0));
-  TRY(layer_norm(c, u3, v, N, T, C));
+  TRY(linear(c, o, M, C, ps.w(w.o), ps.w(w.o + 1), C, u3, C, u2, 0, 0, 0, 0, &ln));
+  TRY(layer_norm(c, u3, v, N, T, C, ln.ready()));
   WALLOC(g, M * 4 * C);
   // GEGLU: Linear(C -> 8C), chunk(2,2), out * gelu(gate)  (diffusion.mojo:138-141)
   TRY(linear(c, v, M, C, ps.w(w.geglu1), ps.w(w.geglu1 + 1), 8 * C, g, 4 * C, nullptr, 1, 1));
   float* u4 = u;  // u is dead after u2
   TRY(linear(c, g, M, 4 * C, ps.w(w.geglu2), ps.w(w.geglu2 + 1), C, u4, C, u3, 1));
-  TRY(linear(c, u4, M, C, ps.w(w.conv_out), ps.w(w.conv_out + 1), C, out, C, x.p, 0));
+  if (next) next->imgs = N;
+  TRY(linear(c, u4, M, C, ps.w(w.conv_out), ps.w(w.conv_out + 1), C, out, C, x.p, 0, 0, 0, 0, next));
   c->arena.release_to(mark);
   return TSD_OK;
 }
@@ -547,17 +568,34 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
     return a;
   };
 #define NEED(a) if (!(a).p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)")
+  auto hint_scratch = [&](Act& a) -> bool {  // partial-statistics buffer living as long as the activation
+    a.ns.imgs = a.N;
+    a.ns.scratch_elems = norm_scratch_elems(a.N, (long long)a.H * a.W, a.C, a.ns.G);
+    a.ns.scratch = c->arena.alloc_n<float2>(a.ns.scratch_elems);
+    return a.ns.scratch != nullptr;
+  };
   auto RES = [&](int i, const Act& in, Act& out_) -> int {
     out_ = act(res[i].cout, in.H, in.W);
     if (!out_.p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)");
     Act v = in;
     v.C = res[i].cin;
-    return res_block(c, ps, res[i], v, tbias[i], tstride * res[i].cout, 1e-5f, out_.p);
+    // every ResBlock of the UNet feeds an attention block: GroupNorm(32, eps 1e-6) (diffusion.mojo:104)
+    out_.ns.G = 32;
+    out_.ns.eps = 1e-6f;
+    if (!hint_scratch(out_)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+    return res_block(c, ps, res[i], v, tbias[i], tstride * res[i].cout, 1e-5f, out_.p, &out_.ns);
   };
   auto ATT = [&](int i, const Act& in, Act& out_) -> int {
     out_ = act(attn[i].C, in.H, in.W);
     if (!out_.p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)");
-    return attn_block(c, ps, attn[i], in, kctx[i], vctx[i], n_ctx, L, out_.p);
+    NormHint* nh = nullptr;
+    if (i == 8) {  // a23 feeds UNet_Output_Layer's GroupNorm(320 groups) (diffusion.mojo:280)
+      out_.ns.G = 320;
+      out_.ns.eps = 1e-5f;
+      if (!hint_scratch(out_)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+      nh = &out_.ns;
+    }
+    return attn_block(c, ps, attn[i], in, kctx[i], vctx[i], n_ctx, L, out_.p, nh);
   };
   auto CAT = [&](const Act& a, const Act& b, Act& out_) -> int {
     out_ = act(a.C + b.C, a.H, a.W);
@@ -581,12 +619,18 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
   TRY(ATT(0, r2, a3));  // skip2: dead input of layer20 (Q9)
   Act d4 = act(320, H / 2, W / 2);
   NEED(d4);
-  TRY(conv(c, ps, down1, a3.p, n, H, W, 320, 320, 3, 1, 2, nullptr, 0, nullptr, d4.p, 0));
+  d4.ns.G = 32;  // consumed by ResBlock 1's first GroupNorm
+  d4.ns.eps = 1e-5f;
+  if (!hint_scratch(d4)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+  TRY(conv(c, ps, down1, a3.p, n, H, W, 320, 320, 3, 1, 2, nullptr, 0, nullptr, d4.p, 0, &d4.ns));
   TRY(RES(1, d4, r5));
   TRY(ATT(1, r5, a6));  // skip4: dead input of layer15 (Q9)
   Act d7 = act(640, H / 4, W / 4);
   NEED(d7);
-  TRY(conv(c, ps, down2, a6.p, n, H / 2, W / 2, 640, 640, 3, 1, 2, nullptr, 0, nullptr, d7.p, 0));
+  d7.ns.G = 32;
+  d7.ns.eps = 1e-5f;
+  if (!hint_scratch(d7)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+  TRY(conv(c, ps, down2, a6.p, n, H / 2, W / 2, 640, 640, 3, 1, 2, nullptr, 0, nullptr, d7.p, 0, &d7.ns));
   TRY(RES(2, d7, r8));
   TRY(ATT(2, r8, a9));
   // decoders (diffusion.mojo:252-272)
@@ -612,7 +656,8 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
   // UNet_Output_Layer: GroupNorm(320 groups) -> SiLU -> conv 320->4 (diffusion.mojo:280, 287-291)
   Act f = act(320, H, W);
   NEED(f);
-  TRY(op_group_norm(c, a23.p, f.p, n, H, W, 320, 320, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1));
+  TRY(op_group_norm(c, a23.p, f.p, n, H, W, 320, 320, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1,
+                    (a23.ns.G == 320) ? a23.ns.ready() : nullptr));
   TRY(conv(c, ps, final_conv, f.p, n, H, W, 320, 4, 3, 1, 1, nullptr, 0, nullptr, eps_nhwc, 0));
 #undef NEED
   return TSD_OK;

@@ -53,6 +53,7 @@ struct ParamStore {
 struct Act {
   float* p = nullptr;
   int N = 0, H = 0, W = 0, C = 0;
+  NormHint ns;  // statistics left by the producer for the consumer's first norm (ns.stats == nullptr: none)
   long long numel() const { return (long long)N * H * W * C; }
   long long pixels() const { return (long long)N * H * W; }
 };
@@ -142,8 +143,9 @@ struct Decoder {
 
 int generate_latents(Diffusion& m, const tsd_loop_params& lp, const float* latents_in, const float* context,
                      int n_ctx, int n, float* latents_out);
+// next: in = (G, eps) of the norm that will consume `out`; out = next->stats when the last conv produced them
 int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, const float* tbias,
-              int tbias_stride, float eps, float* out);
+              int tbias_stride, float eps, float* out, NormHint* next = nullptr);
 
 }  // namespace tsd
 

@@ -98,6 +98,11 @@ int ctx_create(int device, Ctx** out, std::string* err) {
     return TSD_ERR_CUDA;
   }
   c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  if (cudaMalloc(&c->norm_bar, 128 * kNormBarrierCounters) != cudaSuccess ||
+      cudaMemset(c->norm_bar, 0, 128 * kNormBarrierCounters) != cudaSuccess) {
+    *err = "norm barrier allocation failed";
+    return TSD_ERR_OOM;
+  }
   if (cudaMalloc(&c->ticket, 256) != cudaSuccess || cudaMemset(c->ticket, 0, 256) != cudaSuccess) {
     *err = "ticket allocation failed";
     cudaStreamDestroy(c->stream);
@@ -117,6 +122,7 @@ void ctx_destroy(Ctx* c) {
     delete c->timer;
   }
   if (c->ticket) cudaFree(c->ticket);
+  if (c->norm_bar) cudaFree(c->norm_bar);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -244,7 +250,8 @@ struct ASpec {
 }  // namespace
 
 static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
-                    int b_rows, GemmKParams p, int force_bn, int force_splits, double flops) {
+                    int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh = nullptr) {
+  if (nh) nh->req = NormStatsReq();
   if (A.K % 4) return c->fail(TSD_ERR_INVALID, "gemm: K must be a multiple of 4");
   if (A.batch > 1 && A.imgs > 1) return c->fail(TSD_ERR_INVALID, "gemm: batch and images are exclusive");
   // pixel box of 128 rows
@@ -342,6 +349,56 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   }
 
   const long long m_tiles_grid = p.cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles;  // pairs: phantom tile pads odd counts
+  // producer-side norm statistics (norm_stats.cuh): only where the vector epilogue stores every element
+  if (nh && nh->G > 0 && c->producer_stats && !p.geglu && nbatch == 1 && p.split_n >= (1 << 30) &&
+      N % 4 == 0 && p.ldd % 4 == 0 && N % nh->G == 0 && (!p.residual || p.ldr % 4 == 0) &&
+      (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0))) {
+    const bool conv_mode = A.H > 1 || A.imgs > 1;
+    const int cpg = N / nh->G;
+    long long slabs_per_img = 0, rows_per_img = 0;
+    int imgs = 1;
+    if (conv_mode) {
+      imgs = A.imgs;
+      rows_per_img = (long long)A.H * A.W;
+    } else if (nh->imgs > 0 && A.W % nh->imgs == 0) {
+      imgs = nh->imgs;
+      rows_per_img = A.W / nh->imgs;
+    }
+    NormStatsReq ns;
+    if (p.splits == 1) {
+      // statistics folded into the GEMM epilogue: one slab per M tile
+      if (conv_mode) slabs_per_img = (long long)p.tiles_h * p.tiles_w;
+      else if (rows_per_img > 0 && rows_per_img % GEMM_BM == 0) slabs_per_img = rows_per_img / GEMM_BM;
+      ns.lg = (p.BN + cpg - 1) / cpg + 1;  // groups that can overlap BN consecutive columns
+      ns.BN = p.BN;
+      ns.n_tiles = n_tiles;
+    } else if (c->producer_stats >= 2 && rows_per_img > 0 && N / 4 <= 3 * 256 && (size_t)std::max(1, 256 / (N / 4)) * N * 8 <= 96 * 1024) {
+      // statistics folded into the split-K reduction: slabs of rows_per_img / 128 rows
+      int R = (int)std::max<long long>(1, rows_per_img / 128);
+      if (rows_per_img % R == 0) {
+        slabs_per_img = rows_per_img / R;
+        rp.slab_rows = R;
+        ns.lg = nh->G;
+        ns.BN = p.n_pad > N ? p.n_pad : N;
+        ns.n_tiles = 1;
+      }
+    }
+    if (slabs_per_img > 0 && nh->scratch != nullptr &&
+        (size_t)imgs * slabs_per_img * ns.n_tiles * ns.lg <= nh->scratch_elems) {
+      ns.partial = nh->scratch;
+      ns.C = N;
+      ns.G = nh->G;
+      ns.cpg = cpg;
+      ns.slabs_per_img = (int)slabs_per_img;
+      ns.imgs = imgs;
+      ns.inv_count = (float)(1.0 / ((double)rows_per_img * cpg));
+      ns.eps = nh->eps;
+      if (p.splits == 1) p.ns = ns;
+      else rp.ns = ns;
+      nh->req = ns;
+    }
+  }
+
   dim3 grid((unsigned)m_tiles_grid, (unsigned)n_tiles, (unsigned)(nbatch * p.splits));
   if (n_tiles > 65535 || grid.z > 65535) return c->fail(TSD_ERR_INVALID, "gemm: grid too large");
   if (!c->dry_run) {
@@ -390,10 +447,11 @@ int op_gemm(Ctx* c, const GemmArgs& a) {
   p.split_n = a.split_n > 0 ? a.split_n : (1 << 30);
   p.split_stride = a.split_stride;
   p.round_tf32 = a.round_tf32;
+  p.b_static = a.b_static;
   if ((a.ldd % 4) || (a.residual && (a.ldr % 4)))
     return c->fail(TSD_ERR_INVALID, "gemm: ldd/ldr must be multiples of 4");
   const double flops = 2.0 * a.M * (double)a.N * a.K * a.batch;
-  return run_gemm(c, A, a.B, a.N, a.ldb, a.b_bs, a.N, p, a.force_bn, a.force_splits, flops);
+  return run_gemm(c, A, a.B, a.N, a.ldb, a.b_bs, a.N, p, a.force_bn, a.force_splits, flops, a.nh);
 }
 
 int op_conv2d(Ctx* c, const ConvArgs& a) {
@@ -414,6 +472,7 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
   p.n_valid = a.Cout;
   p.split_n = 1 << 30;
   p.round_tf32 = a.round_tf32;
+  p.b_static = 1;  // convolution kernels are parameters
   if (tensor_ok && ((a.k == 3 && a.pad == 1) || (a.k == 1 && a.pad == 0)) && a.stride == 1) {
     ASpec A{};
     A.base = a.x;
@@ -433,8 +492,11 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
       A.ld_h = (long long)A.W * a.Cin;
       A.ld_img = A.ld_h;
     }
-    return run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops);
+    NormHint* nh = a.nh;
+    if (nh) nh->imgs = a.N;
+    return run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops, nh);
   }
+  if (a.nh) a.nh->req = NormStatsReq();
   if (tensor_ok && a.k == 3 && a.pad == 1 && a.stride > 1) {
     // stride-2 downsample convs (diffusion.mojo:180,183): explicit im2col then GEMM
     const size_t mark = c->arena.mark();
@@ -459,7 +521,8 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
     A.ld_img = A.ld_h;
     A.batch = 1;
     A.taps = 1;
-    int rc = run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops);
+    if (a.nh) a.nh->imgs = a.N;
+    int rc = run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops, a.nh);
     c->arena.release_to(mark);
     return rc;
   }
@@ -483,9 +546,39 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
 
 int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,
                   const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
-                  int round_tf32) {
+                  int round_tf32, const NormStatsReq* pre) {
   if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
+  if (pre != nullptr && pre->partial != nullptr && !upsample && pre->G == G && pre->C == C && pre->imgs == N &&
+      norm_apply_partial_supported(C, G)) {
+    // the producer left per-tile partial sums: one normalise pass that folds them per block
+    if (!c->dry_run) {
+      TimedScope ts(c, FAM_NORM, 0);
+      int rc = c->check(launch_norm_apply_partial(x, y, *pre, N, (long long)H * W, gamma, beta, gamma_scalar, silu,
+                                                  round_tf32, c->stream),
+                        "norm_apply_partial launch");
+      if (rc) return rc;
+      c->launches += 1;
+    }
+    return TSD_OK;
+  }
   const size_t mark = c->arena.mark();
+  if (!upsample && c->norm_v2 && norm_fused2_supported(N, (long long)H * W, C, G, c->sm_count)) {
+    // one launch: the slab stays in registers across a two-level grid barrier
+    void* scratch = c->arena.alloc(norm_fused2_scratch_bytes(N, (long long)H * W, C, G, c->sm_count));
+    if (!scratch) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+    if (!c->dry_run) {
+      TimedScope ts(c, FAM_NORM, 0);
+      NormFused2Src src;
+      src.x = x;
+      int rc = c->check(launch_norm_fused2(src, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
+                                           round_tf32, scratch, c->norm_bar, c->sm_count, c->stream),
+                        "norm_fused2 launch");
+      if (rc) return rc;
+      c->launches += 1;
+    }
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
   if (!upsample && norm_fused_supported(C)) {
     // one launch: statistics + grid barrier + normalise
     void* scratch = c->arena.alloc(norm_fused_scratch_bytes(N, (long long)H * W, C, G));

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/tsd_b200.h"  // status codes
+#include "norm_stats.cuh"
 
 namespace tsd {
 
@@ -57,6 +58,27 @@ using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 struct KernelTimer;  // optional per-launch CUDA-event timing (bench roofline leg)
 
+// Request to the producer of an activation: "the next consumer normalises this tensor with G groups
+// and this eps".  If the producing kernel can fold partial statistics into its epilogue
+// (norm_stats.cuh) it fills `req` (req.partial != nullptr) and the consumer runs a single
+// normalise pass; otherwise the consumer computes the statistics itself.  `scratch` is owned by
+// the caller and must stay valid until the consumer has been enqueued.
+struct NormHint {
+  int G = 0;
+  float eps = 0.f;
+  int imgs = 1;  // plain GEMM outputs: rows = imgs * rows_per_image
+  float2* scratch = nullptr;
+  size_t scratch_elems = 0;
+  NormStatsReq req;
+  const NormStatsReq* ready() const { return req.partial ? &req : nullptr; }
+};
+// upper bound of the partial entries a producer may write for an [imgs][rows_per_img][C] activation
+inline size_t norm_scratch_elems(int imgs, long long rows_per_img, int C, int G) {
+  const long long slabs = (rows_per_img + 63) / 64 + 64;  // conv tiles are pixel boxes: allow ragged edges
+  return (size_t)imgs * (size_t)slabs * (size_t)(G + C / 8 + 2);
+}
+
+
 struct Ctx {
   int device = -1;
   cudaStream_t stream = nullptr;
@@ -72,7 +94,11 @@ struct Ctx {
   int force_stages = 0;     // tuning: operand ring depth override
   int gemm_cg = 0;          // tuning: 0 = model decides, 1 = single CTAs, 2 = CTA pairs (cta_group::2)
   int gemm_debug = 0;       // lab only: bit0 skip MMAs, bit1 skip A loads, bit2 skip B loads (results invalid)
-  unsigned int* ticket = nullptr;  // zero-initialised device counter for last-block reductions
+  unsigned int* ticket = nullptr;  // zero-initialised device counters for last-block reductions
+  int bench_stats_groups = 0;      // lab: tsd_bench_conv / tsd_bench_gemm request norm statistics with this many groups
+  unsigned int* norm_bar = nullptr;  // zero-initialised barrier words of the fused norm (elementwise.cuh)
+  int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
+  int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;
   long long launches = 0;   // kernels launched through this context (bench "gpu_launches")
   bool dry_run = false;     // planning pass: ops allocate workspace but launch nothing
@@ -130,6 +156,8 @@ struct GemmArgs {
   long long split_stride = 0;
   int round_tf32 = 0;
   int force_bn = 0, force_splits = 0;  // tuning / tests
+  NormHint* nh = nullptr;              // optional: statistics of D for the next norm
+  int b_static = 0;                    // B is a weight matrix no kernel writes during the forward pass
 };
 int op_gemm(Ctx* c, const GemmArgs& a);
 
@@ -144,6 +172,7 @@ struct ConvArgs {
   float* out = nullptr;             // [N][Ho][Wo][Cout]
   int round_tf32 = 0;
   int force_bn = 0, force_splits = 0;
+  NormHint* nh = nullptr;  // optional: statistics of `out` for the next norm
 };
 int op_conv2d(Ctx* c, const ConvArgs& a);
 inline int conv_out_dim(int in, int k, int pad, int stride) { return (in + 2 * pad - k) / stride + 1; }
@@ -151,7 +180,7 @@ inline int conv_out_dim(int in, int k, int pad, int stride) { return (in + 2 * p
 // GroupNorm(+SiLU)(+2x nearest upsample). stats scratch comes from the arena.
 int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,
                   const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
-                  int round_tf32);
+                  int round_tf32, const NormStatsReq* pre = nullptr);
 
 struct AttnArgs {
   // per (batch b, head h): Q [Tq][d], K [Tk][d], V [Tk][d], contiguous blocks

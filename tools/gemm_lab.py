@@ -116,6 +116,28 @@ def trace():
     ctx.set_option("gemm_cg", 0)
 
 
+def stats():
+    """overhead of the producer-side norm statistics (epilogue / split-K reduce variants)"""
+    from tsd_b200.api import Context
+    ctx = Context(0)
+    for (kind, a, bn, sp) in (("conv", (64, 64, 320, 320), 160, 1), ("conv", (64, 64, 320, 320), 160, 2),
+                              ("conv", (32, 32, 640, 640), 128, 3), ("conv", (16, 16, 1280, 1280), 128, 6),
+                              ("gemm", (4096, 320, 320, 0), 160, 1), ("gemm", (256, 1280, 1280, 0), 64, 1)):
+        for g in (0, 32, 1):
+            ctx.set_option("bench_stats_groups", g)
+            ms, tf = run(ctx, kind, a, bn, sp, iters=20)
+            print(f"{kind} {a} bn={bn} sp={sp} stats_groups={g}: {ms * 1e3:.2f} us", flush=True)
+    ctx.set_option("bench_stats_groups", 0)
+    ctx.set_option("gemm_debug", 8)
+    for g in (0, 32):
+        ctx.set_option("bench_stats_groups", g)
+        run(ctx, "conv", (64, 64, 320, 320), 160, 1, iters=1)
+        ctx.synchronize()
+        print("^^ stats_groups", g, flush=True)
+    ctx.set_option("gemm_debug", 0)
+    ctx.set_option("bench_stats_groups", 0)
+
+
 def ncu():
     from tsd_b200.api import Context
     ctx = Context(0)
@@ -126,4 +148,4 @@ def ncu():
 
 
 if __name__ == "__main__":
-    {"feed": feed, "shapes": shapes, "ncu": ncu, "trace": trace}[sys.argv[1]]()
+    {"feed": feed, "shapes": shapes, "ncu": ncu, "trace": trace, "stats": stats}[sys.argv[1]]()
