@@ -128,6 +128,239 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+// ===================== epilogue (8 warps: kernel warps 2..9) =====================
+// TMEM -> registers (thread = output row) -> per-warp shared staging tile -> coalesced global
+// stores (8 lanes x 16 B cover 128 B of one row; a warp instruction writes 4 full rows).
+// Two warps per TMEM lane quadrant, interleaved over the 32-column chunks.  The staging tiles
+// reuse the operand ring: every MMA has retired once the accumulator barrier completes.
+// Shared by the GEMM / implicit-GEMM kernel and the halo convolution kernel.
+struct EpilogueCtx {
+  uint8_t* ring;        // 1024 B aligned start of the (idle) operand ring: staging tiles + column statistics
+  uint32_t tmem_d;      // accumulator tile(s)
+  uint32_t accum_bar;   // shared address of the accumulator-complete barrier
+  int n_iters;          // > 1: two accumulator tiles (even / odd K steps) to be added
+  int nt, img, h0, w0, batch, split;
+  long long* tr;        // lab trace slots
+};
+__device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const EpilogueCtx& ec) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* const smem_ring = ec.ring;
+  const uint32_t tmem_d = ec.tmem_d;
+  const uint32_t accum_a = ec.accum_bar;
+  const int n_iters = ec.n_iters;
+  const int nt = ec.nt, img = ec.img, h0 = ec.h0, w0 = ec.w0, batch = ec.batch, split = ec.split;
+  long long* const tr = ec.tr;
+  pdl_wait();                // before the first global access of this role (row bias, residual, D)
+  const int ew = warp - 2;   // 0..7
+  const int q = warp & 3;    // TMEM lane quadrant this warp may read
+  const int half = ew >> 2;  // which of the two warps of the quadrant
+  constexpr int ST = 36;     // staging row stride in floats (conflict-free float4 rows)
+  float* stg = reinterpret_cast<float*>(smem_ring) + ew * (32 * ST);
+  const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+  const bool partial = p.partial != nullptr;
+  const bool geglu = p.geglu && !partial;
+  const int out_cols = geglu ? (p.BN >> 1) : p.BN;
+  const int n0 = nt * out_cols;
+  const int n_valid = p.n_valid;
+  const int n_lim = partial ? p.n_pad : n_valid;
+  const bool img_ok = img < p.imgs;
+
+  // the row this lane owns while in the thread = row layout (row bias / alpha / GEGLU)
+  float rb = 0.0f;
+  if (p.row_bias != nullptr && !partial) {
+    const int r_own = q * 32 + lane;
+    const int lh = r_own / p.bw, lw = r_own - lh * p.bw;
+    const int h = h0 + lh, w = w0 + lw;
+    if (img_ok && lh < p.bh && h < p.H && w < p.W) rb = p.row_bias[((long long)img * p.H + h) * p.W + w];
+  }
+  const float* cbias = (p.bias && !partial) ? p.bias + (long long)img * p.bias_img_stride : nullptr;
+  const float alpha = partial ? 1.0f : p.alpha;
+  const bool plain = (alpha == 1.0f) && (p.row_bias == nullptr || partial);
+
+  // the 8 rows this lane stores (row = q*32 + i*4 + lane/8), 4 consecutive columns at lane%8*4
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  float* dbase;
+  long long ldd;
+  if (partial) {
+    dbase = p.partial + ((long long)split * (gridDim.z / p.splits) + batch) * p.m_per_batch * p.n_pad;
+    ldd = p.n_pad;
+  } else {
+    dbase = p.D + (long long)batch * p.d_batch_stride;
+    ldd = p.ldd;
+  }
+  const float* rbase = (p.residual && !partial) ? p.residual + (long long)batch * p.r_batch_stride : nullptr;
+  float* drow[8];
+  const float* rrow[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = q * 32 + i * 4 + sub;
+    const int lh = r / p.bw, lw = r - lh * p.bw;
+    const int h = h0 + lh, w = w0 + lw;
+    const bool ok = img_ok && (lh < p.bh) && (h < p.H) && (w < p.W);
+    const long long g = ((long long)img * p.H + h) * p.W + w;
+    drow[i] = ok ? dbase + g * ldd : nullptr;
+    rrow[i] = rbase ? rbase + g * p.ldr : nullptr;
+  }
+  const bool routed = !partial && p.split_n < (1 << 30);
+  const bool vec_ok = partial || (((n_valid | p.ldd | p.split_n) & 3) == 0 && (p.split_stride & 3) == 0 &&
+                                  (rbase == nullptr || (p.ldr & 3) == 0) &&
+                                  (cbias == nullptr || (((p.bias_img_stride & 3) == 0) &&
+                                                        (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
+  const bool round_out = p.round_tf32 && !partial;
+  // producer-side norm statistics: per-column (sum, sum^2) of the stored values of this tile
+  const bool want_stats = p.ns.partial != nullptr;
+  float2* cs = reinterpret_cast<float2*>(smem_ring + 8 * 32 * ST * 4);  // [4][256]
+
+  mbar_wait_a(accum_a, 0);
+  tc_fence_after_sync();
+  if (threadIdx.x == 64) tr[4] = clock64();
+
+  const bool two_acc = n_iters > 1;
+  const uint32_t trow1 = trow + (uint32_t)p.acc_stride;  // the odd-K-step issuer's accumulator
+  for (int c = half * 32; c < out_cols; c += 64) {
+    uint32_t v[32];
+    tmem_ld32(trow + c, v);
+    if (two_acc) {
+      uint32_t v1[32];
+      tmem_ld32(trow1 + c, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
+    }
+    if (geglu) {
+      uint32_t g[32];
+      tmem_ld32(trow + out_cols + c, g);
+      if (two_acc) {
+        uint32_t g1[32];
+        tmem_ld32(trow1 + out_cols + c, g1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(__uint_as_float(g[j]) + __uint_as_float(g1[j]));
+      }
+      float bo[32], bg[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c + j;
+        const bool okb = cbias != nullptr && n < n_valid && c + j < out_cols;
+        bo[j] = okb ? __ldg(cbias + n) : 0.0f;
+        bg[j] = okb ? __ldg(cbias + p.n_half + n) : 0.0f;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = __float_as_uint((__uint_as_float(v[j]) + bo[j]) * gelu_tanh(__uint_as_float(g[j]) + bg[j]));
+    } else {
+      tmem_ld_wait();
+      if (!plain) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), alpha, rb));
+      }
+    }
+    uint4* srow = reinterpret_cast<uint4*>(stg + lane * ST);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int n = n0 + c + c4;  // first of this lane's 4 columns
+    float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + c4 < out_cols && n < n_lim) {
+      long long col;
+      if (partial) col = (long long)nt * p.BN + c + c4;
+      else if (routed) col = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
+      else col = n;
+      if (vec_ok) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cbias != nullptr && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(cbias + n));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (drow[i] == nullptr) continue;
+          float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
+          t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+          if (rbase != nullptr) {
+            const float4 rr = *reinterpret_cast<const float4*>(rrow[i] + n);
+            t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+          }
+          if (round_out) {
+            t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
+          }
+          *reinterpret_cast<float4*>(drow[i] + col) = t;
+          ss.x += t.x; ss.y += t.y; ss.z += t.z; ss.w += t.w;
+          qq.x = fmaf(t.x, t.x, qq.x); qq.y = fmaf(t.y, t.y, qq.y); qq.z = fmaf(t.z, t.z, qq.z); qq.w = fmaf(t.w, t.w, qq.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (drow[i] == nullptr) continue;
+          const float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
+          const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int nn = n + j;
+            if (nn >= n_valid) break;
+            float a = e[j];
+            if (cbias != nullptr && !geglu) a += cbias[nn];
+            if (rbase != nullptr) a += rrow[i][nn];
+            if (round_out) a = round_tf32(a);
+            drow[i][(long long)(nn / p.split_n) * p.split_stride + (nn % p.split_n)] = a;
+          }
+        }
+      }
+    }
+    if (want_stats) {
+      // fold the 4 row groups of the warp (lanes with equal lane % 8): fixed xor tree, all lanes take part
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+        ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+        qq.x += __shfl_xor_sync(0xffffffffu, qq.x, o); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, o);
+        qq.z += __shfl_xor_sync(0xffffffffu, qq.z, o); qq.w += __shfl_xor_sync(0xffffffffu, qq.w, o);
+      }
+      if (sub == 0 && c + c4 < out_cols) {
+        float2* d = cs + q * 256 + c + c4;
+        d[0] = make_float2(ss.x, qq.x); d[1] = make_float2(ss.y, qq.y);
+        d[2] = make_float2(ss.z, qq.z); d[3] = make_float2(ss.w, qq.w);
+      }
+    }
+    __syncwarp();
+  }
+  if (want_stats) {
+    // quadrant sums -> column sums -> sums of the groups overlapping this tile -> partial; the last CTA finalises
+    const int te = threadIdx.x - 64;  // 0..255 among the epilogue threads
+    named_bar_sync(2, 256);
+    {
+      float2 a = cs[te], b = cs[256 + te], c2 = cs[512 + te], d2 = cs[768 + te];
+      const bool okc = te < out_cols && n0 + te < n_valid;
+      cs[te] = okc ? make_float2((a.x + b.x) + (c2.x + d2.x), (a.y + b.y) + (c2.y + d2.y)) : make_float2(0.f, 0.f);
+    }
+    named_bar_sync(2, 256);
+    if (img_ok) {
+      const int cpg = p.ns.cpg;
+      const int g_lo = n0 / cpg;
+      int n_end = n0 + out_cols;
+      if (n_end > n_valid) n_end = n_valid;
+      const int g_hi = (n_end - 1) / cpg;
+      float2* dst = p.ns.partial + ((long long)blockIdx.x * p.ns.n_tiles + nt) * p.ns.lg;
+      for (int g = g_lo + ew; g <= g_hi; g += 8) {  // one warp per group: lanes stride over its columns in the tile
+        int c_lo = g * cpg - n0, c_hi = (g + 1) * cpg - n0;
+        if (c_lo < 0) c_lo = 0;
+        if (c_hi > n_end - n0) c_hi = n_end - n0;
+        float s = 0.f, qv = 0.f;
+        for (int cc = c_lo + lane; cc < c_hi; cc += 32) {
+          const float2 t = cs[cc];
+          s += t.x;
+          qv += t.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          qv += __shfl_xor_sync(0xffffffffu, qv, o);
+        }
+        if (lane == 0) dst[g - g_lo] = make_float2(s, qv);
+      }
+    }
+  }
+  if (threadIdx.x == 64) tr[5] = clock64();
+}
+
 // Role loops are single-thread instruction streams: every dependent SASS instruction costs ~4-6
 // cycles and an mbarrier try_wait ~90, so (measured, profiles/r01_gemm_lab_notes.md) the first
 // version spent ~500 cycles per 32-wide K step on bookkeeping while the MMAs of the step need
@@ -158,7 +391,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int b_rows = p.BN / CG;                        // B rows staged by this CTA
   const uint32_t a_atom = GEMM_BM * 128;               // 128 rows x 32 fp32
   const uint32_t b_atom = (uint32_t)b_rows * 128;
-  const uint32_t stage_bytes = 2 * (a_atom + b_atom);  // K step of 64 = two atoms per operand
+  const int bk = p.bk;            // K step: 64 (two 128 B atoms per operand row) or 32 (one)
+  const uint32_t natoms = (uint32_t)bk >> 5;
+  const uint32_t stage_bytes = natoms * (a_atom + b_atom);
 
   // tile coordinates
   const int nt = blockIdx.y;
@@ -183,7 +418,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    mbar_init(&accum_bar, n_iters > 1 ? 2 : 1);  // one commit per MMA issuer
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -207,13 +442,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) tr[1] = clock64();
   pdl_launch_dependents();  // resources are held: the next kernel may start its own prologue
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  // Role warps: 0 / 10 = TMA producers, 1 / 11 = MMA issuers (1 also owns TMEM), 2..9 = epilogue.
+  // Both role pairs run the same loop over every other K step (parity 0 / 1): the per-step barrier
+  // round trip and the instruction issue of a single thread (~40 clk per MMA, ~65 per TMA) are what
+  // bounds small-N tiles, so they are spread over two threads.  The two issuers accumulate into two
+  // separate TMEM tiles (no ordering between them is needed); the epilogue adds them.
+  const int role_parity = warp >= 10 ? 1 : 0;
+  const int n_par = n_iters > 1 ? 2 : 1;                // issuers / producers with work
+  if ((warp == 0 || warp == 10) && role_parity < n_par) {
+    // ===================== TMA producer (K steps it = parity, parity + 2, ...) =====================
     if (elect_one()) {
       const int cin = p.cin, debug = p.debug;
       const bool geglu = p.geglu != 0;
-      const uint32_t a_tx = (debug & 2) ? 0u : 2u * (uint32_t)p.a_box_bytes;
-      const uint32_t b_tx = (debug & 4) ? 0u : 2u * b_atom;
+      const uint32_t a_tx = (debug & 2) ? 0u : natoms * (uint32_t)p.a_box_bytes;
+      const uint32_t b_tx = (debug & 4) ? 0u : natoms * b_atom;
       const uint32_t tx = (uint32_t)CG * (a_tx + b_tx);  // CG == 2: the leader's barrier counts both CTAs' bytes
       const int c3 = img + batch;
       // first B row of this CTA's (first) box, and of the second (gate) box for single-CTA GEGLU
@@ -230,338 +472,160 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         brow0 = nt * p.BN + (int)rank * b_rows;
       }
       const bool two_b = geglu && CG == 1;
-      // (tap, channel chunk) of the first iteration; afterwards advanced incrementally
-      int tap = it_begin / p.chunks_per_tap;
-      int kc = (it_begin - tap * p.chunks_per_tap) * GEMM_BK;
+      const int step = n_par;
+      // (tap, channel chunk) of this thread's first iteration; afterwards advanced incrementally
+      const int it_first = it_begin + role_parity;
+      int tap = it_first / p.chunks_per_tap;
+      int kc = (it_first - tap * p.chunks_per_tap) * bk;
       int dy = 0, dx = 0;
       if (p.taps == 9) {
         dy = tap / 3 - 1;
         dx = tap - (tap / 3) * 3 - 1;
       }
       int kb = tap * cin + kc;
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t sa = smem_base;
-      uint32_t fb = full0, eb = empty0;
+      auto advance = [&]() {
+        for (int s = 0; s < step; ++s) {
+          kc += bk;
+          kb += bk;
+          if (kc >= cin) {
+            kc = 0;
+            ++tap;
+            kb = tap * cin;
+            if (++dx > 1) {
+              dx = -1;
+              ++dy;
+            }
+          }
+        }
+      };
+      int stage = role_parity % num_stages;
+      uint32_t phase = (uint32_t)(role_parity / num_stages) & 1u;
       const uint32_t fb_mask = (CG == 2) ? 0xFEFFFFFFu : 0xFFFFFFFFu;  // CG == 2: signal the leader's barrier
       auto load_b = [&](uint32_t sa_, uint32_t fbs_, int kb_) {
-        const uint32_t sb = sa_ + 2 * a_atom;
+        const uint32_t sb = sa_ + natoms * a_atom;
         if (!two_b) {
           tma_b_3d<CG>(sb, &tmB, fbs_, kb_, brow0, batch);
-          tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
+          if (natoms == 2) tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
         } else {
           const uint32_t hb = (uint32_t)half_rows * 128;
           tma_b_3d<CG>(sb, &tmB, fbs_, kb_, brow0, batch);
           tma_b_3d<CG>(sb + hb, &tmB, fbs_, kb_, brow1, batch);
-          tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
-          tma_b_3d<CG>(sb + b_atom + hb, &tmB, fbs_, kb_ + 32, brow1, batch);
+          if (natoms == 2) {
+            tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
+            tma_b_3d<CG>(sb + b_atom + hb, &tmB, fbs_, kb_ + 32, brow1, batch);
+          }
         }
       };
       // Weights do not depend on the predecessor kernel: the B halves of the first ring pass are
       // requested BEFORE the programmatic-dependency wait, so their HBM latency overlaps its tail.
-      int pre = 0;
+      int pre_end = role_parity;  // iterations < pre_end (of this parity) already have their B tile in flight
       if (p.b_static && !(debug & 4)) {
-        pre = n_iters < num_stages ? n_iters : num_stages;
+        pre_end = n_iters < num_stages ? n_iters : num_stages;
         int kc2 = kc, tap2 = tap, kb2 = kb;
-        for (int it = 0; it < pre; ++it) {
+        for (int it = role_parity; it < pre_end; it += step) {
           const uint32_t fb2 = full0 + 8u * it;
           if (CG == 1 || rank == 0) mbar_expect_tx_a(fb2, tx);
           load_b(smem_base + it * stage_bytes, fb2 & fb_mask, kb2);
-          kc2 += GEMM_BK;
-          kb2 += GEMM_BK;
-          if (kc2 >= cin) {
-            kc2 = 0;
-            ++tap2;
-            kb2 = tap2 * cin;
+          for (int s = 0; s < step; ++s) {
+            kc2 += bk;
+            kb2 += bk;
+            if (kc2 >= cin) {
+              kc2 = 0;
+              ++tap2;
+              kb2 = tap2 * cin;
+            }
           }
         }
       }
       pdl_wait();  // A (and any aliasing of the arena) belongs to the predecessor: no other global access before this
-      for (int it = 0; it < n_iters; ++it) {
+      for (int it = role_parity; it < n_iters; it += step) {
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint32_t fb = full0 + 8u * stage, eb = empty0 + 8u * stage;
         const uint32_t fbs = fb & fb_mask;
-        if (it >= pre) {
+        if (it >= pre_end) {
           mbar_wait_a(eb, phase ^ 1u);
           if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, tx);
           if (!(debug & 4)) load_b(sa, fbs, kb);
         }
         if (!(debug & 2)) {
           tma_a_4d<CG>(sa, &tmA, fbs, kc, w0 + dx, h0 + dy, c3);
-          tma_a_4d<CG>(sa + a_atom, &tmA, fbs, kc + 32, w0 + dx, h0 + dy, c3);
+          if (natoms == 2) tma_a_4d<CG>(sa + a_atom, &tmA, fbs, kc + 32, w0 + dx, h0 + dy, c3);
         }
-        kc += GEMM_BK;
-        kb += GEMM_BK;
-        if (kc >= cin) {
-          kc = 0;
-          ++tap;
-          kb = tap * cin;
-          if (++dx > 1) {
-            dx = -1;
-            ++dy;
-          }
-        }
-        sa += stage_bytes;
-        fb += 8;
-        eb += 8;
-        if (++stage == num_stages) {
-          stage = 0;
+        advance();
+        stage += step;
+        if (stage >= num_stages) {
+          stage -= num_stages;
           phase ^= 1u;
-          sa = smem_base;
-          fb = full0;
-          eb = empty0;
         }
       }
-      tr[2] = clock64();
+      if (role_parity == 0) tr[2] = clock64();
     }
-  } else if (warp == 1) {
+  } else if ((warp == 1 || warp == 11) && role_parity < n_par) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
     if ((CG == 1 || rank == 0) && elect_one()) {
       const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, GEMM_BM * CG, (uint32_t)p.BN, 0, 0);
       const int chunks = p.chunks_per_tap;
+      const int step = n_par;
       // K = 8 MMAs with real data in a tap's last chunk (all 8 when cin is a multiple of 64)
-      int nk_last = (p.cin - (chunks - 1) * GEMM_BK + 7) >> 3;
+      int nk_last = (p.cin - (chunks - 1) * bk + 7) >> 3;
       if (p.debug & 1) nk_last = 0;
-      const int nk_full = (p.debug & 1) ? 0 : GEMM_BK / 8;
-      int chunk = it_begin % chunks;
+      const int nk_full = (p.debug & 1) ? 0 : bk / 8;
+      int chunk = (it_begin + role_parity) % chunks;
       const uint64_t adesc0 = umma_smem_desc(smem_base, 16, 1024, UMMA_SWIZZLE_128B);
-      const uint64_t bdesc0 = umma_smem_desc(smem_base + 2 * a_atom, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint64_t bdesc0 = umma_smem_desc(smem_base + natoms * a_atom, 16, 1024, UMMA_SWIZZLE_128B);
       const uint32_t stage_step = stage_bytes >> 4, a_step = a_atom >> 4, b_step = b_atom >> 4;
-      int stage = 0;
-      uint32_t phase = 0, soff = 0, acc = 0;
-      uint32_t fb = full0, eb = empty0;
-      for (int it = 0; it < n_iters; ++it) {
+      const uint32_t tmem_acc = tmem_d + (uint32_t)(role_parity * p.acc_stride);  // this issuer's accumulator tile
+      int stage = role_parity % num_stages;
+      uint32_t phase = (uint32_t)(role_parity / num_stages) & 1u;
+      uint32_t acc = 0;
+      for (int it = role_parity; it < n_iters; it += step) {
         const int nk = (chunk == chunks - 1) ? nk_last : nk_full;
-        if (++chunk == chunks) chunk = 0;
-        mbar_wait_a(fb, phase);
+        chunk += step;
+        while (chunk >= chunks) chunk -= chunks;
+        const uint32_t soff = (uint32_t)stage * stage_step;
+        mbar_wait_a(full0 + 8u * stage, phase);
         tc_fence_after_sync();
         const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
-        if (nk == GEMM_BK / 8) {
+        if (nk == 8) {
 #pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
-            umma_tf32_cg<CG>(tmem_d, ad + (kk >> 2) * a_step + 2u * (kk & 3), bd + (kk >> 2) * b_step + 2u * (kk & 3),
+          for (int kk = 0; kk < 8; ++kk) {
+            umma_tf32_cg<CG>(tmem_acc, ad + (kk >> 2) * a_step + 2u * (kk & 3), bd + (kk >> 2) * b_step + 2u * (kk & 3),
                              idesc, acc);
+            acc = 1u;
+          }
+        } else if (nk == 4) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_tf32_cg<CG>(tmem_acc, ad + 2u * kk, bd + 2u * kk, idesc, acc);
             acc = 1u;
           }
         } else {
           for (int kk = 0; kk < nk; ++kk) {
-            umma_tf32_cg<CG>(tmem_d, ad + (kk >> 2) * a_step + 2u * (kk & 3), bd + (kk >> 2) * b_step + 2u * (kk & 3),
+            umma_tf32_cg<CG>(tmem_acc, ad + (kk >> 2) * a_step + 2u * (kk & 3), bd + (kk >> 2) * b_step + 2u * (kk & 3),
                              idesc, acc);
             acc = 1u;
           }
         }
-        umma_commit_cg<CG>(eb);  // smem slot reusable (in both CTAs) once these MMAs retire
-        soff += stage_step;
-        fb += 8;
-        eb += 8;
-        if (++stage == num_stages) {
-          stage = 0;
+        umma_commit_cg<CG>(empty0 + 8u * stage);  // smem slot reusable (in both CTAs) once these MMAs retire
+        stage += step;
+        if (stage >= num_stages) {
+          stage -= num_stages;
           phase ^= 1u;
-          soff = 0;
-          fb = full0;
-          eb = empty0;
         }
       }
-      umma_commit_cg<CG>(accum_a);  // accumulator complete
-      tr[3] = clock64();
+      umma_commit_cg<CG>(accum_a);  // this issuer's accumulator complete
+      if (role_parity == 0) tr[3] = clock64();
     }
-  } else {
+  } else if (warp >= 2 && warp < 10) {
     // ===================== epilogue (warps 2..9) =====================
-    // TMEM -> registers (thread = output row) -> per-warp shared staging tile -> coalesced global
-    // stores (8 lanes x 16 B cover 128 B of one row; a warp instruction writes 4 full rows).
-    // Two warps per TMEM lane quadrant, interleaved over the 32-column chunks.  The staging tiles
-    // reuse the operand ring: every MMA has retired once accum_bar completes.
-    pdl_wait();                // before the first global access of this role (row bias, residual, D)
-    const int ew = warp - 2;   // 0..7
-    const int q = warp & 3;    // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;  // which of the two warps of the quadrant
-    constexpr int ST = 36;     // staging row stride in floats (conflict-free float4 rows)
-    float* stg = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn))) + ew * (32 * ST);
-    const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
-    const bool partial = p.partial != nullptr;
-    const bool geglu = p.geglu && !partial;
-    const int out_cols = geglu ? (p.BN >> 1) : p.BN;
-    const int n0 = nt * out_cols;
-    const int n_valid = p.n_valid;
-    const int n_lim = partial ? p.n_pad : n_valid;
-    const bool img_ok = img < p.imgs;
-
-    // the row this lane owns while in the thread = row layout (row bias / alpha / GEGLU)
-    float rb = 0.0f;
-    if (p.row_bias != nullptr && !partial) {
-      const int r_own = q * 32 + lane;
-      const int lh = r_own / p.bw, lw = r_own - lh * p.bw;
-      const int h = h0 + lh, w = w0 + lw;
-      if (img_ok && lh < p.bh && h < p.H && w < p.W) rb = p.row_bias[((long long)img * p.H + h) * p.W + w];
-    }
-    const float* cbias = (p.bias && !partial) ? p.bias + (long long)img * p.bias_img_stride : nullptr;
-    const float alpha = partial ? 1.0f : p.alpha;
-    const bool plain = (alpha == 1.0f) && (p.row_bias == nullptr || partial);
-
-    // the 8 rows this lane stores (row = q*32 + i*4 + lane/8), 4 consecutive columns at lane%8*4
-    const int sub = lane >> 3, c4 = (lane & 7) * 4;
-    float* dbase;
-    long long ldd;
-    if (partial) {
-      dbase = p.partial + ((long long)split * (gridDim.z / p.splits) + batch) * p.m_per_batch * p.n_pad;
-      ldd = p.n_pad;
-    } else {
-      dbase = p.D + (long long)batch * p.d_batch_stride;
-      ldd = p.ldd;
-    }
-    const float* rbase = (p.residual && !partial) ? p.residual + (long long)batch * p.r_batch_stride : nullptr;
-    float* drow[8];
-    const float* rrow[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = q * 32 + i * 4 + sub;
-      const int lh = r / p.bw, lw = r - lh * p.bw;
-      const int h = h0 + lh, w = w0 + lw;
-      const bool ok = img_ok && (lh < p.bh) && (h < p.H) && (w < p.W);
-      const long long g = ((long long)img * p.H + h) * p.W + w;
-      drow[i] = ok ? dbase + g * ldd : nullptr;
-      rrow[i] = rbase ? rbase + g * p.ldr : nullptr;
-    }
-    const bool routed = !partial && p.split_n < (1 << 30);
-    const bool vec_ok = partial || (((n_valid | p.ldd | p.split_n) & 3) == 0 && (p.split_stride & 3) == 0 &&
-                                    (rbase == nullptr || (p.ldr & 3) == 0) &&
-                                    (cbias == nullptr || (((p.bias_img_stride & 3) == 0) &&
-                                                          (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
-    const bool round_out = p.round_tf32 && !partial;
-    // producer-side norm statistics: per-column (sum, sum^2) of the stored values of this tile
-    const bool want_stats = p.ns.partial != nullptr;
-    float2* cs = reinterpret_cast<float2*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + 8 * 32 * ST * 4);  // [4][256]
-
-    mbar_wait_a(accum_a, 0);
-    tc_fence_after_sync();
-    if (threadIdx.x == 64) tr[4] = clock64();
-
-    for (int c = half * 32; c < out_cols; c += 64) {
-      uint32_t v[32];
-      tmem_ld32(trow + c, v);
-      if (geglu) {
-        uint32_t g[32];
-        tmem_ld32(trow + out_cols + c, g);
-        float bo[32], bg[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c + j;
-          const bool okb = cbias != nullptr && n < n_valid && c + j < out_cols;
-          bo[j] = okb ? __ldg(cbias + n) : 0.0f;
-          bg[j] = okb ? __ldg(cbias + p.n_half + n) : 0.0f;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = __float_as_uint((__uint_as_float(v[j]) + bo[j]) * gelu_tanh(__uint_as_float(g[j]) + bg[j]));
-      } else {
-        tmem_ld_wait();
-        if (!plain) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), alpha, rb));
-        }
-      }
-      uint4* srow = reinterpret_cast<uint4*>(stg + lane * ST);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      const int n = n0 + c + c4;  // first of this lane's 4 columns
-      float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c + c4 < out_cols && n < n_lim) {
-        long long col;
-        if (partial) col = (long long)nt * p.BN + c + c4;
-        else if (routed) col = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
-        else col = n;
-        if (vec_ok) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cbias != nullptr && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(cbias + n));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (drow[i] == nullptr) continue;
-            float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
-            t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
-            if (rbase != nullptr) {
-              const float4 rr = *reinterpret_cast<const float4*>(rrow[i] + n);
-              t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
-            }
-            if (round_out) {
-              t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
-            }
-            *reinterpret_cast<float4*>(drow[i] + col) = t;
-            ss.x += t.x; ss.y += t.y; ss.z += t.z; ss.w += t.w;
-            qq.x = fmaf(t.x, t.x, qq.x); qq.y = fmaf(t.y, t.y, qq.y); qq.z = fmaf(t.z, t.z, qq.z); qq.w = fmaf(t.w, t.w, qq.w);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (drow[i] == nullptr) continue;
-            const float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
-            const float e[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int nn = n + j;
-              if (nn >= n_valid) break;
-              float a = e[j];
-              if (cbias != nullptr && !geglu) a += cbias[nn];
-              if (rbase != nullptr) a += rrow[i][nn];
-              if (round_out) a = round_tf32(a);
-              drow[i][(long long)(nn / p.split_n) * p.split_stride + (nn % p.split_n)] = a;
-            }
-          }
-        }
-      }
-      if (want_stats) {
-        // fold the 4 row groups of the warp (lanes with equal lane % 8): fixed xor tree, all lanes take part
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-          ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
-          ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
-          qq.x += __shfl_xor_sync(0xffffffffu, qq.x, o); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, o);
-          qq.z += __shfl_xor_sync(0xffffffffu, qq.z, o); qq.w += __shfl_xor_sync(0xffffffffu, qq.w, o);
-        }
-        if (sub == 0 && c + c4 < out_cols) {
-          float2* d = cs + q * 256 + c + c4;
-          d[0] = make_float2(ss.x, qq.x); d[1] = make_float2(ss.y, qq.y);
-          d[2] = make_float2(ss.z, qq.z); d[3] = make_float2(ss.w, qq.w);
-        }
-      }
-      __syncwarp();
-    }
-    if (want_stats) {
-      // quadrant sums -> column sums -> sums of the groups overlapping this tile -> partial; the last CTA finalises
-      const int te = threadIdx.x - 64;  // 0..255 among the epilogue threads
-      named_bar_sync(2, 256);
-      {
-        float2 a = cs[te], b = cs[256 + te], c2 = cs[512 + te], d2 = cs[768 + te];
-        const bool okc = te < out_cols && n0 + te < n_valid;
-        cs[te] = okc ? make_float2((a.x + b.x) + (c2.x + d2.x), (a.y + b.y) + (c2.y + d2.y)) : make_float2(0.f, 0.f);
-      }
-      named_bar_sync(2, 256);
-      if (img_ok) {
-        const int cpg = p.ns.cpg;
-        const int g_lo = n0 / cpg;
-        int n_end = n0 + out_cols;
-        if (n_end > n_valid) n_end = n_valid;
-        const int g_hi = (n_end - 1) / cpg;
-        float2* dst = p.ns.partial + ((long long)blockIdx.x * p.ns.n_tiles + nt) * p.ns.lg;
-        for (int g = g_lo + ew; g <= g_hi; g += 8) {  // one warp per group: lanes stride over its columns in the tile
-          int c_lo = g * cpg - n0, c_hi = (g + 1) * cpg - n0;
-          if (c_lo < 0) c_lo = 0;
-          if (c_hi > n_end - n0) c_hi = n_end - n0;
-          float s = 0.f, qv = 0.f;
-          for (int cc = c_lo + lane; cc < c_hi; cc += 32) {
-            const float2 t = cs[cc];
-            s += t.x;
-            qv += t.y;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            qv += __shfl_xor_sync(0xffffffffu, qv, o);
-          }
-          if (lane == 0) dst[g - g_lo] = make_float2(s, qv);
-        }
-      }
-    }
-    if (threadIdx.x == 64) tr[5] = clock64();
+    EpilogueCtx ec;
+    ec.ring = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    ec.tmem_d = tmem_d;
+    ec.accum_bar = accum_a;
+    ec.n_iters = n_iters;
+    ec.nt = nt; ec.img = img; ec.h0 = h0; ec.w0 = w0; ec.batch = batch; ec.split = split;
+    ec.tr = tr;
+    gemm_epilogue(p, ec);
     tc_fence_before_sync();
   }
 
@@ -570,6 +634,219 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     printf("gemm trace: setup %lld producer_done %lld mma_issued %lld accum_ready %lld epilogue_done %lld end %lld (clk since entry)\n",
            tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], clock64() - tr[0]);
   if constexpr (CG == 2) cluster_sync_all();  // neither CTA may release TMEM / exit while the pair is in flight
+  if (warp == 1) {
+    tc_fence_after_sync();
+    if constexpr (CG == 1) {
+      tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolution with the activation halo kept in shared memory.
+//
+// The implicit GEMM above re-loads the 128-pixel A tile once per tap: 9 x 16 KiB per 32 channels,
+// and the L2 -> SM port (~76 B/clk/SM measured) - not the tensor core - bounds every tile with
+// N <= 256.  Here a CTA owns a 16 x 8 pixel box and loads its (18 x 16) x 32-channel halo ONCE per
+// channel chunk (36 KiB, TMA zero fill = padding); the nine taps are nine shifted VIEWS of that
+// tile: with a row pitch of 16 pixels the 8-pixel rows of the box sit a uniform 2 KiB apart, so a
+// tap is just another start address with stride-dimension byte offset 2048 (the hardware swizzles on
+// absolute address bits, so TMA's pattern and the shifted UMMA view agree).  A traffic drops 4x; B (weights) streams through its own ring,
+// three taps (one kernel row) per stage.  K order: channel chunk major, tap minor.
+// ------------------------------------------------------------------------------------------
+constexpr int HALO_A_BYTES = 18 * 16 * 128;  // 36 KiB per 32-channel chunk
+constexpr int HALO_SA = 2, HALO_SB_MAX = 16, HALO_TB = 3;
+
+template <int CG>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t a_full[HALO_SA], a_empty[HALO_SA];
+  __shared__ __align__(8) uint64_t b_full[HALO_SB_MAX], b_empty[HALO_SB_MAX];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ long long tr[8];
+  if (threadIdx.x == 0) tr[0] = clock64();
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int b_rows = p.BN / CG;
+  const uint32_t b_atom = (uint32_t)b_rows * 128;
+  const uint32_t b_stage = HALO_TB * b_atom;
+  const uint32_t b_ring = smem_base + HALO_SA * HALO_A_BYTES;
+  const int SB = p.num_stages;
+
+  const int nt = blockIdx.y;
+  int mt = blockIdx.x;
+  const int batch = 0;
+  const int split = blockIdx.z;
+  const int tw = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int th = mt % p.tiles_h;
+  const int img = mt / p.tiles_h;
+  const int w0 = tw * 8, h0 = th * 16;
+
+  // K range of this split, in 32-channel chunks
+  const int c_begin = split * p.iters_per_split;
+  int c_end = c_begin + p.iters_per_split;
+  if (c_end > p.total_iters) c_end = p.total_iters;
+  const int n_chunks = c_end - c_begin;
+  const uint32_t af0 = smem_u32(&a_full[0]), ae0 = smem_u32(&a_empty[0]);
+  const uint32_t bf0 = smem_u32(&b_full[0]), be0 = smem_u32(&b_empty[0]), accum_a = smem_u32(&accum_bar);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HALO_SA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    if constexpr (CG == 1) {
+      tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+      tmem_relinquish();
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
+  }
+  tc_fence_before_sync();
+  if constexpr (CG == 2) cluster_sync_all();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = tmem_slot;
+  if (threadIdx.x == 0) tr[1] = clock64();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int cin = p.cin;
+      const uint32_t a_tx = (uint32_t)CG * HALO_A_BYTES;
+      const uint32_t b_tx = (uint32_t)CG * b_stage;
+      const uint32_t mask = (CG == 2) ? 0xFEFFFFFFu : 0xFFFFFFFFu;  // pairs: signal the leader's barrier
+      const int brow0 = nt * p.BN + (int)rank * b_rows;
+      const int nb = n_chunks * 3;  // B stages of this CTA: (chunk, kernel row)
+      auto load_b = [&](int j) {
+        const int st = j % SB;
+        const int chunk = c_begin + j / 3, r = j - (j / 3) * 3;
+        const uint32_t fb = bf0 + 8u * st;
+        if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, b_tx);
+        const uint32_t dst = b_ring + st * b_stage;
+#pragma unroll
+        for (int t = 0; t < HALO_TB; ++t)
+          tma_b_3d<CG>(dst + t * b_atom, &tmB, fb & mask, (r * 3 + t) * cin + chunk * 32, brow0, 0);
+      };
+      // weights first: they do not depend on the predecessor kernel
+      int jb = 0;
+      const int pre = nb < SB ? nb : SB;
+      for (; jb < pre; ++jb) load_b(jb);
+      pdl_wait();
+      uint32_t a_phase = 0;
+      int sa = 0;
+      for (int ci = 0; ci < n_chunks; ++ci) {
+        mbar_wait_a(ae0 + 8u * sa, a_phase ^ 1u);
+        const uint32_t fa = af0 + 8u * sa;
+        if (CG == 1 || rank == 0) mbar_expect_tx_a(fa, a_tx);
+        tma_a_4d<CG>(smem_base + sa * HALO_A_BYTES, &tmA, fa & mask, (c_begin + ci) * 32, w0 - 1, h0 - 1, img);
+        if (++sa == HALO_SA) {
+          sa = 0;
+          a_phase ^= 1u;
+        }
+        // B stages of this chunk (never wait on a slot whose consumer needs an A tile not yet requested)
+        const int want = (ci + 1) * 3 < nb ? (ci + 1) * 3 : nb;
+        for (; jb < want; ++jb) {
+          if (jb >= SB) mbar_wait_a(be0 + 8u * (jb % SB), (uint32_t)(((jb / SB) & 1) ^ 1));
+          load_b(jb);
+        }
+      }
+      tr[2] = clock64();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only when paired) =====================
+    if ((CG == 1 || rank == 0) && elect_one()) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, GEMM_BM * CG, (uint32_t)p.BN, 0, 0);
+      const int nk_full = 4;
+      const int nk_last = (p.cin - (p.total_iters - 1) * 32 + 7) >> 3;  // K = 8 MMAs with data in the last chunk
+      // measured (tools/lab/halo_probe.py): the 128 B swizzle is a function of the absolute shared-memory
+      // address bits, so a tap view needs no base-offset field; debug bit 4 sets it (lab: gives wrong results)
+      const bool use_base_off = (p.debug & 16) != 0;
+      const uint64_t adesc0 = umma_smem_desc(smem_base, 16, 2048, UMMA_SWIZZLE_128B);
+      const uint64_t bdesc0 = umma_smem_desc(b_ring, 16, 1024, UMMA_SWIZZLE_128B);
+      uint32_t acc = 0;
+      int sa = 0, j = 0;
+      uint32_t a_phase = 0;
+      for (int ci = 0; ci < n_chunks; ++ci) {
+        const int nk = (c_begin + ci == p.total_iters - 1) ? nk_last : nk_full;
+        mbar_wait_a(af0 + 8u * sa, a_phase);
+        // descriptors advance by plain adds: (bytes >> 4) in the low word, no carry out of the 14-bit field
+        const uint64_t ad_chunk = adesc0 + (uint32_t)((sa * HALO_A_BYTES) >> 4) + (use_base_off ? 0u : 0u);
+        for (int r = 0; r < 3; ++r, ++j) {
+          const int st = j % SB;
+          mbar_wait_a(bf0 + 8u * st, (uint32_t)((j / SB) & 1));
+          tc_fence_after_sync();
+          const uint64_t bd_stage = bdesc0 + (uint32_t)((st * b_stage) >> 4);
+#pragma unroll
+          for (int t = 0; t < HALO_TB; ++t) {
+            uint64_t ad = ad_chunk + (uint32_t)((r * 16 + t) * 8);  // tap view: +((dy+1)*16 + (dx+1)) rows of 128 B
+            if (use_base_off) ad |= (uint64_t)(((smem_base + sa * HALO_A_BYTES + (r * 16 + t) * 128) >> 7) & 7u) << 49;
+            const uint64_t bd = bd_stage + (uint32_t)((t * b_atom) >> 4);
+            if (nk == 4) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                umma_tf32_cg<CG>(tmem_d, ad + 2u * kk, bd + 2u * kk, idesc, acc);
+                acc = 1u;
+              }
+            } else {
+              for (int kk = 0; kk < nk; ++kk) {
+                umma_tf32_cg<CG>(tmem_d, ad + 2u * kk, bd + 2u * kk, idesc, acc);
+                acc = 1u;
+              }
+            }
+          }
+          umma_commit_cg<CG>(be0 + 8u * st);
+        }
+        umma_commit_cg<CG>(ae0 + 8u * sa);
+        if (++sa == HALO_SA) {
+          sa = 0;
+          a_phase ^= 1u;
+        }
+      }
+      umma_commit_cg<CG>(accum_a);
+      tr[3] = clock64();
+    }
+  } else if (warp >= 2 && warp < 10) {
+    EpilogueCtx ec;
+    ec.ring = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    ec.tmem_d = tmem_d;
+    ec.accum_bar = accum_a;
+    ec.n_iters = 1;  // one accumulator tile
+    ec.nt = nt; ec.img = img; ec.h0 = h0; ec.w0 = w0; ec.batch = batch; ec.split = split;
+    ec.tr = tr;
+    gemm_epilogue(p, ec);
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    printf("halo trace: setup %lld producer_done %lld mma_issued %lld accum_ready %lld epilogue_done %lld end %lld (clk since entry)\n",
+           tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], clock64() - tr[0]);
+  if constexpr (CG == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after_sync();
     if constexpr (CG == 1) {
@@ -621,21 +898,30 @@ __global__ void splitk_reduce_kernel(const SplitKReduceParams p) {
   }
 }
 
-static size_t gemm_stage_bytes(int BN, int cg) { return 2 * ((size_t)GEMM_BM * 128 + (size_t)(BN / cg) * 128); }
+static size_t gemm_stage_bytes(int BN, int cg, int bk) { return (size_t)(bk / 32) * ((size_t)GEMM_BM * 128 + (size_t)(BN / cg) * 128); }
 
-size_t gemm_smem_bytes(int BN, int num_stages, int cg) {
-  size_t ring = (size_t)num_stages * gemm_stage_bytes(BN, cg);
+size_t gemm_smem_bytes(int BN, int num_stages, int cg, int bk) {
+  size_t ring = (size_t)num_stages * gemm_stage_bytes(BN, cg, bk);
   const size_t staging = 8 * 32 * 36 * 4 + 4 * 256 * 8;  // epilogue staging tiles + column statistics live in the (then idle) ring
   if (ring < staging) ring = staging;
   return ring + 1024;
 }
 
-int gemm_pick_stages(int BN, int cg) {
-  const size_t budget = 224 * 1024;  // 227 KiB opt-in minus static shared memory
-  int s = (int)((budget - 1024) / gemm_stage_bytes(BN, cg));
-  if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-  if (s < 2) s = 2;
-  return s;
+// Ring depth and K step.  The two role pairs (even / odd K steps) must own disjoint stage sets for
+// their completions to stay ordered, so the depth is even; K steps of 64 are preferred (fewer
+// barrier round trips) unless they leave fewer than 4 stages in shared memory.
+void gemm_pick_ring(int BN, int cg, int* bk, int* stages) {
+  const size_t budget = 224 * 1024 - 1024;  // 227 KiB opt-in minus static shared memory and alignment
+  for (int k : {64, 32}) {
+    int s = (int)(budget / gemm_stage_bytes(BN, cg, k));
+    if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
+    s &= ~1;
+    if (s >= 4 || k == 32) {
+      *bk = k;
+      *stages = s < 2 ? 2 : s;
+      return;
+    }
+  }
 }
 
 template <int CG>
@@ -672,6 +958,63 @@ static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<CG>, tmA, tmB, p);
+}
+
+// halo convolution: B ring depth that fits next to the two halo tiles (0: configuration unsupported)
+int halo_pick_sb(int BN, int cg) {
+  const size_t budget = 224 * 1024 - 1024;
+  const size_t b_stage = (size_t)HALO_TB * (BN / cg) * 128;
+  if ((size_t)HALO_SA * HALO_A_BYTES + 2 * b_stage > budget) return 0;
+  int sb = (int)((budget - (size_t)HALO_SA * HALO_A_BYTES) / b_stage);
+  if (sb > HALO_SB_MAX) sb = HALO_SB_MAX;
+  return sb;
+}
+size_t halo_smem_bytes(int BN, int cg, int sb) {
+  size_t ring = (size_t)HALO_SA * HALO_A_BYTES + (size_t)sb * HALO_TB * (BN / cg) * 128;
+  const size_t staging = 8 * 32 * 36 * 4 + 4 * 256 * 8;
+  if (ring < staging) ring = staging;
+  return ring + 1024;
+}
+
+template <int CG>
+static cudaError_t launch_halo_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
+                                  size_t smem_bytes, cudaStream_t stream) {
+  static int max_dyn = -1;
+  if (max_dyn < 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv3x3_halo_kernel<CG>);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    const int lim = optin - (int)fa.sharedSizeBytes;
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return e;
+    max_dyn = lim;
+  }
+  if ((long long)smem_bytes > max_dyn) return cudaErrorInvalidConfiguration;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<CG>, tmA, tmB, p);
+}
+
+cudaError_t launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
+                             size_t smem_bytes, cudaStream_t stream) {
+  if (p.cg == 2) return launch_halo_cg<2>(tmA, tmB, p, grid, smem_bytes, stream);
+  return launch_halo_cg<1>(tmA, tmB, p, grid, smem_bytes, stream);
 }
 
 cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,

@@ -24,8 +24,8 @@
 namespace tsd {
 
 constexpr int GEMM_BM = 128;       // rows per CTA tile (TMEM lanes)
-constexpr int GEMM_BK = 64;        // fp32 elements per K step = two 128 B swizzle atoms per operand row
-constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue
+constexpr int GEMM_BK = 64;        // preferred K step (fp32 elements) = two 128 B swizzle atoms per operand row; 32 when smem-bound
+constexpr int GEMM_THREADS = 384;  // warps 0/10 TMA producers, 1/11 MMA issuers (1: TMEM alloc), 2..9 epilogue
 constexpr int GEMM_MAX_STAGES = 6;
 
 struct GemmKParams {
@@ -38,6 +38,9 @@ struct GemmKParams {
   // N tiling
   int BN, n_valid, geglu, n_half;
   int num_stages, tmem_cols;
+  int bk;                  // K step of this launch: 64 or 32
+  int halo;                // 1: conv3x3_halo_kernel (total_iters / iters_per_split count 32-channel chunks; num_stages = B ring depth)
+  int acc_stride;          // TMEM columns between the two issuers' accumulator tiles
   // output
   float* D;
   long long d_batch_stride;
@@ -80,7 +83,11 @@ struct SplitKReduceParams {
 cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                              dim3 grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t stream);
-size_t gemm_smem_bytes(int BN, int num_stages, int cg);
-int gemm_pick_stages(int BN, int cg);
+int halo_pick_sb(int BN, int cg);
+size_t halo_smem_bytes(int BN, int cg, int sb);
+cudaError_t launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
+                             size_t smem_bytes, cudaStream_t stream);
+size_t gemm_smem_bytes(int BN, int num_stages, int cg, int bk);
+void gemm_pick_ring(int BN, int cg, int* bk, int* stages);
 
 }  // namespace tsd

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <vector>
 
 #include "attention_tcgen05.cuh"
 #include "elementwise.cuh"
@@ -113,6 +115,7 @@ int ctx_create(int device, Ctx** out, std::string* err) {
   return TSD_OK;
 }
 
+static void tune_cache_free(Ctx* c);
 void ctx_destroy(Ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -123,6 +126,8 @@ void ctx_destroy(Ctx* c) {
   }
   if (c->ticket) cudaFree(c->ticket);
   if (c->norm_bar) cudaFree(c->norm_bar);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  tune_cache_free(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -194,13 +199,20 @@ namespace {
 
 struct TileCfg {
   int BN = 0, splits = 1, cg = 1;
+  int halo = 0;  // 3x3 convolutions: halo-in-shared-memory kernel (splits then count 32-channel chunks)
 };
+// two accumulator tiles (even / odd K steps) of BN (+ the epilogue's read-ahead pad) columns must fit TMEM
+inline bool bn_fits_tmem(int BN, bool geglu) {
+  const int need = geglu ? BN + 16 : BN + ((BN & 31) ? 16 : 0);
+  return 2 * ((need + 31) / 32 * 32) <= 512;
+}
 
 // Cycle model used only to rank (BN, splits, pairing) candidates.  Per 64-wide K step a CTA needs
 // 4*BN tensor cycles, ~450 cycles of barrier round trips in the single-thread role loops, and
 // its operand bytes from L2 (~6300 B/clk chip-wide, shared by the active SMs).
 TileCfg choose_tiles(int sm, long long m_tiles, int N, int total_iters, int batch, bool geglu,
-                     bool allow_split, long long m_rows, int force_cg) {
+                     bool allow_split, long long m_rows, int force_cg, int halo_cin = 0, int H = 0, int W = 0,
+                     int imgs = 1) {
   const int n_pad = (N + 15) / 16 * 16;
   TileCfg best;
   double best_cost = 1e300;
@@ -209,7 +221,7 @@ TileCfg choose_tiles(int sm, long long m_tiles, int N, int total_iters, int batc
     if (cg == 2 && m_tiles < 2) continue;
     const long long mt = cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles;
     for (int BN = 16; BN <= 256; BN += 16) {
-      if (n_pad % BN) continue;
+      if (n_pad % BN || !bn_fits_tmem(BN, geglu)) continue;
       if (geglu && (BN % 32 || (N / 2) % (BN / 2))) continue;
       const long long n_tiles = n_pad / BN;
       static const int split_cand[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
@@ -230,6 +242,41 @@ TileCfg choose_tiles(int sm, long long m_tiles, int N, int total_iters, int batc
           best.BN = BN;
           best.splits = splits;
           best.cg = cg;
+          best.halo = 0;
+        }
+      }
+    }
+  }
+  if (halo_cin > 0) {
+    // halo kernel: 16 x 8 pixel boxes, K loop over 32-channel chunks (nine taps each)
+    const long long mt0 = (long long)imgs * ((H + 15) / 16) * ((W + 7) / 8);
+    const int chunks = (halo_cin + 31) / 32;
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (force_cg && cg != force_cg) continue;
+      if (cg == 2 && mt0 < 2) continue;
+      const long long mt = cg == 2 ? (mt0 + 1) / 2 * 2 : mt0;
+      for (int BN = 16; BN <= 256; BN += 16) {
+        if (n_pad % BN || halo_pick_sb(BN, cg) < 2) continue;
+        const long long n_tiles = n_pad / BN;
+        for (int splits = 1; splits <= 8; ++splits) {
+          if (splits > 1 && (!allow_split || chunks / splits < 2)) break;
+          const long long ctas = mt * n_tiles * splits;
+          const double active = (double)std::min<long long>(ctas, sm);
+          const double feed_bw = std::min(76.0, 11000.0 / active);
+          const double bytes = 36864.0 + 9.0 * 128.0 * BN / cg;
+          const double chunk_cyc = std::max(std::max(18.0 * BN, 9.0 * 4 * 40.0), bytes / feed_bw);
+          const int cps = (chunks + splits - 1) / splits;
+          const double tile_cyc = cps * chunk_cyc + 3500.0 + 25.0 * BN;
+          const double waves = std::ceil((double)ctas / sm);
+          double cost = waves * tile_cyc;
+          if (splits > 1) cost += 5000.0 + (double)(splits + 1) * m_rows * n_pad * 4.0 / 3000.0;
+          if (cost < best_cost) {
+            best_cost = cost;
+            best.BN = BN;
+            best.splits = splits;
+            best.cg = cg;
+            best.halo = 1;
+          }
         }
       }
     }
@@ -237,6 +284,9 @@ TileCfg choose_tiles(int sm, long long m_tiles, int N, int total_iters, int batc
   return best;
 }
 
+struct ASpec;
+}  // namespace
+namespace {
 struct ASpec {
   const float* base;
   int K;            // inner extent (channels)
@@ -249,8 +299,17 @@ struct ASpec {
 
 }  // namespace
 
-static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
-                    int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh = nullptr) {
+// One GEMM launch (+ split-K reduction) with the tile configuration `use` (nullptr: the cost model decides).
+// `ws_splits_plan` > 0 (planning pass): reserve split-K workspace for that many splits.
+// 3x3 / stride 1 / pad 1 convolution over an NHWC image that the halo kernel can take
+static bool conv_halo_eligible(const Ctx* c, const ASpec& A, int N, const GemmKParams& p) {
+  return c->conv_halo > 0 && A.taps == 9 && A.batch == 1 && A.K % 4 == 0 && A.W >= c->halo_min_w && A.H >= c->halo_min_h &&
+         !p.geglu && p.row_bias == nullptr && N >= 16;
+}
+
+static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
+                        int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh,
+                        const TileCfg* use, int ws_splits_plan) {
   if (nh) nh->req = NormStatsReq();
   if (A.K % 4) return c->fail(TSD_ERR_INVALID, "gemm: K must be a multiple of 4");
   if (A.batch > 1 && A.imgs > 1) return c->fail(TSD_ERR_INVALID, "gemm: batch and images are exclusive");
@@ -260,41 +319,64 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   int bh = std::min(128 / bw, A.H);
   p.H = A.H;
   p.W = A.W;
+  p.m_per_batch = A.imgs * A.H * A.W;
+  p.taps = A.taps;
+  p.cin = A.K;
+  p.chunks_per_tap = (A.K + GEMM_BK - 1) / GEMM_BK;  // provisional (K steps of 64): the ring below may pick 32
+  p.total_iters = p.taps * p.chunks_per_tap;
+  long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
+  const int nbatch = A.batch;
+  const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
+                           p.alpha == 1.0f;
+  const bool halo_ok = conv_halo_eligible(c, A, N, p);
+  TileCfg cfg = use ? *use
+                    : choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
+                                   (long long)p.m_per_batch, c->gemm_cg, halo_ok ? A.K : 0, A.H, A.W, A.imgs);
+  if (force_bn > 0) cfg.BN = force_bn;
+  if (cfg.BN <= 0) return c->fail(TSD_ERR_INVALID, "gemm: no tile configuration");
+  if (cfg.halo && !halo_ok) cfg.halo = 0;
+  if (c->conv_halo == 2 && halo_ok && halo_pick_sb(cfg.BN, cfg.cg) >= 2) cfg.halo = 1;  // lab: force
+  p.halo = cfg.halo;
+  if (p.halo) {  // 16 x 8 pixel boxes
+    bw = 8;
+    bh = 16;
+    m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
+  }
   p.bw = bw;
   p.bh = bh;
   p.tiles_w = (A.W + bw - 1) / bw;
   p.tiles_h = (A.H + bh - 1) / bh;
-  p.m_per_batch = A.imgs * A.H * A.W;
-  p.taps = A.taps;
-  p.cin = A.K;
-  p.chunks_per_tap = (A.K + GEMM_BK - 1) / GEMM_BK;
-  p.total_iters = p.taps * p.chunks_per_tap;
   p.a_box_bytes = bw * bh * 32 * 4;  // one 32-float atom; a K step loads two
-  const long long m_tiles = (long long)A.imgs * p.tiles_h * p.tiles_w;
-  const int nbatch = A.batch;
-  const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
-                           p.alpha == 1.0f;
-  TileCfg cfg = choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
-                             (long long)p.m_per_batch, c->gemm_cg);
-  if (force_bn > 0) cfg.BN = force_bn;
-  if (cfg.BN <= 0) return c->fail(TSD_ERR_INVALID, "gemm: no tile configuration");
   p.cg = cfg.cg;
+  if (p.cg == 2 && m_tiles < 2) p.cg = 1;
   p.imgs = A.imgs;
   if (force_splits > 0 && allow_split) cfg.splits = std::min(force_splits, p.total_iters);
   if (cfg.BN < 16 || cfg.BN > 256 || cfg.BN % 16) return c->fail(TSD_ERR_INVALID, "gemm: bad BN");
   if (p.geglu && (cfg.BN % 32 || (N / 2) % (cfg.BN / 2)))
     return c->fail(TSD_ERR_INVALID, "gemm: GEGLU needs BN/2 | N/2");
   p.BN = cfg.BN;
-  p.splits = cfg.splits;
+  if (p.halo) {
+    p.bk = 32;
+    p.num_stages = halo_pick_sb(p.BN, p.cg);  // B ring depth
+    if (p.num_stages < 2) return c->fail(TSD_ERR_INVALID, "conv(halo): tile does not fit shared memory");
+    p.chunks_per_tap = (A.K + 31) / 32;
+    p.total_iters = p.chunks_per_tap;  // the K loop runs over channel chunks, nine taps each
+  } else {
+    gemm_pick_ring(p.BN, p.cg, &p.bk, &p.num_stages);
+    if (c->force_stages >= 2 && c->force_stages < p.num_stages) p.num_stages = c->force_stages & ~1;
+    p.chunks_per_tap = (A.K + p.bk - 1) / p.bk;
+    p.total_iters = p.taps * p.chunks_per_tap;
+  }
+  p.splits = std::min(cfg.splits, p.total_iters);
   p.iters_per_split = (p.total_iters + p.splits - 1) / p.splits;
   p.splits = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;  // no empty split
-  p.num_stages = gemm_pick_stages(p.BN, p.cg);
-  if (c->force_stages > 0 && c->force_stages < p.num_stages) p.num_stages = c->force_stages;
   p.debug = c->gemm_debug;
   // the epilogue reads TMEM in 32-column chunks: keep the last (partial) chunk inside the allocation
   const int tmem_need = p.geglu ? p.BN + 16 : p.BN + ((p.BN & 31) ? 16 : 0);
+  p.acc_stride = (tmem_need + 31) / 32 * 32;
   int tc = 32;
-  while (tc < tmem_need) tc <<= 1;
+  while (tc < (p.halo ? 1 : 2) * p.acc_stride) tc <<= 1;  // GEMM kernel: two accumulator tiles (even / odd K steps)
+  if (tc > 512) return c->fail(TSD_ERR_INVALID, "gemm: accumulators exceed tensor memory");
   p.tmem_cols = tc;
   p.n_pad = (N + 15) / 16 * 16;
   const int out_cols_per_tile = p.geglu ? p.BN / 2 : p.BN;
@@ -310,7 +392,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     if (dims[3] == 1) str[3] = (uint64_t)A.ld_h * A.H;  // unused but must be a valid stride
     if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
     if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
-    uint32_t box[4] = {32u, (uint32_t)bw, (uint32_t)bh, 1};
+    uint32_t box[4] = {32u, (uint32_t)(p.halo ? 16 : bw), (uint32_t)(p.halo ? 18 : bh), 1};
     int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box, 0);
     if (rc) return rc;
   }
@@ -325,6 +407,12 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
 
   SplitKReduceParams rp{};
   size_t mark = c->arena.mark();
+  if (c->dry_run && ws_splits_plan > p.splits) {
+    // planning pass: the autotuner may later pick more splits than the model did
+    if (!c->arena.alloc_n<float>((size_t)ws_splits_plan * p.m_per_batch * p.n_pad))
+      return c->fail(TSD_ERR_OOM, "gemm: arena exhausted (split-K workspace plan)");
+    c->arena.release_to(mark);
+  }
   if (p.splits > 1) {
     const size_t elems = (size_t)p.splits * p.m_per_batch * p.n_pad;
     float* ws = c->arena.alloc_n<float>(elems);
@@ -403,8 +491,10 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   if (n_tiles > 65535 || grid.z > 65535) return c->fail(TSD_ERR_INVALID, "gemm: grid too large");
   if (!c->dry_run) {
     TimedScope ts(c, FAM_GEMM, flops);
-    int rc = c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg), c->stream),
-                      "gemm_tf32_kernel launch");
+    int rc = p.halo ? c->check(launch_conv_halo(tmA, tmB, p, grid, halo_smem_bytes(p.BN, p.cg, p.num_stages), c->stream),
+                               "conv3x3_halo_kernel launch")
+                    : c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg, p.bk), c->stream),
+                               "gemm_tf32_kernel launch");
     if (rc) return rc;
     c->launches++;
     if (p.splits > 1) {
@@ -415,6 +505,189 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   }
   c->arena.release_to(mark);  // stream-ordered: the next op may reuse the partial buffer
   return TSD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Tile autotuning.  The cost model ranks (BN, splits, pairing) only roughly for these small,
+// latency-dominated problems, so the first time a problem signature is executed (outside graph
+// capture) a short list of candidates is timed in place - L2 flushed before every run, because in
+// the step graph each weight matrix is read exactly once and always comes from HBM - and the
+// winner is cached per context.  Results of different candidates differ only at TF32 rounding level.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct TuneKey {
+  int v[12];
+  bool operator<(const TuneKey& o) const { return std::lexicographical_compare(v, v + 12, o.v, o.v + 12); }
+};
+constexpr int kTuneMaxSplits = 16;
+}  // namespace
+
+struct TuneCache {
+  std::map<TuneKey, TileCfg> best;
+};
+static void tune_cache_free(Ctx* c) {
+  delete c->tune;
+  c->tune = nullptr;
+}
+
+static std::vector<TileCfg> tune_candidates(int sm, long long m_tiles, int N, int total_iters, bool geglu, bool allow_split,
+                                            int force_cg, int halo_cin = 0, int H = 0, int W = 0, int imgs = 1) {
+  std::vector<TileCfg> out;
+  const int n_pad = (N + 15) / 16 * 16;
+  if (halo_cin > 0) {
+    const long long mt0 = (long long)imgs * ((H + 15) / 16) * ((W + 7) / 8);
+    const int chunks = (halo_cin + 31) / 32;
+    static const int hbn[] = {64, 80, 96, 128, 160, 192, 256};
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (force_cg && cg != force_cg) continue;
+      if (cg == 2 && mt0 < 2) continue;
+      const long long mt = cg == 2 ? (mt0 + 1) / 2 * 2 : mt0;
+      for (int BN : hbn) {
+        if (n_pad % BN || halo_pick_sb(BN, cg) < 2) continue;
+        const long long base = mt * (n_pad / BN);
+        for (int sp = 1; sp <= 8; ++sp) {
+          if (sp > 1 && (!allow_split || chunks / sp < 2)) break;
+          const long long ctas = base * sp;
+          if (sp == 1 || (ctas >= sm / 3 && ctas <= 2 * sm)) {
+            TileCfg t;
+            t.BN = BN;
+            t.splits = sp;
+            t.cg = cg;
+            t.halo = 1;
+            out.push_back(t);
+          }
+          if (ctas > 2 * sm) break;
+        }
+      }
+    }
+  }
+  static const int bn_cand[] = {32, 48, 64, 80, 96, 128, 160, 192, 256};
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (force_cg && cg != force_cg) continue;
+    if (cg == 2 && m_tiles < 2) continue;
+    const long long mt = cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles;
+    for (int BN : bn_cand) {
+      if (n_pad % BN || !bn_fits_tmem(BN, geglu)) continue;
+      if (geglu && (BN % 32 || (N / 2) % (BN / 2))) continue;
+      const long long base = mt * (n_pad / BN);
+      // no split, plus the splits that bring the CTA count near one wave
+      for (int sp = 1; sp <= kTuneMaxSplits; ++sp) {
+        if (sp > 1 && (!allow_split || total_iters / sp < 2)) break;
+        const long long ctas = base * sp;
+        const bool near_wave = ctas >= sm / 3 && ctas <= 2 * sm;
+        if (sp == 1 || (near_wave && (sp <= 4 || sp % 2 == 0))) {
+          if (sp == 1 && ctas < sm / 8 && allow_split && total_iters >= 4) continue;  // hopeless without a split
+          TileCfg t;
+          t.BN = BN;
+          t.splits = sp;
+          t.cg = cg;
+          out.push_back(t);
+        }
+        if (ctas > 2 * sm) break;
+      }
+    }
+  }
+  return out;
+}
+
+static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
+                    int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh = nullptr) {
+  const bool allow_split = !p.geglu && A.batch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) && p.alpha == 1.0f;
+  const bool tunable = c->autotune && force_bn <= 0 && force_splits <= 0 && c->gemm_debug == 0 && c->force_stages == 0;
+  if (!tunable) return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, force_bn, force_splits, flops, nh, nullptr, 0);
+  if (c->dry_run) {
+    // planning pass: reserve split-K workspace for the largest split count a candidate may use
+    int bw = std::min(A.W, 128);
+    while (128 % bw) --bw;
+    const int bh = std::min(128 / bw, A.H);
+    const long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
+    const int total_iters = A.taps * ((A.K + GEMM_BK - 1) / GEMM_BK);
+    int max_sp = 0;
+    if (allow_split)
+      for (const TileCfg& t : tune_candidates(c->sm_count, m_tiles, N, total_iters, p.geglu != 0, true, c->gemm_cg,
+                                              conv_halo_eligible(c, A, N, p) ? A.K : 0, A.H, A.W, A.imgs))
+        max_sp = std::max(max_sp, t.splits);
+    return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, nullptr, max_sp);
+  }
+  if (!c->tune) c->tune = new TuneCache();
+  TuneKey key{};
+  {
+    int bw = std::min(A.W, 128);
+    while (128 % bw) --bw;
+    int i = 0;
+    key.v[i++] = A.K; key.v[i++] = A.W; key.v[i++] = A.H; key.v[i++] = A.imgs; key.v[i++] = A.batch; key.v[i++] = A.taps;
+    key.v[i++] = N; key.v[i++] = p.geglu; key.v[i++] = allow_split ? 1 : 0; key.v[i++] = p.residual ? 1 : 0;
+    key.v[i++] = (nh && nh->G > 0 && c->producer_stats) ? nh->G : 0; key.v[i++] = c->gemm_cg * 4 + c->conv_halo;
+  }
+  auto it = c->tune->best.find(key);
+  if (it != c->tune->best.end())
+    return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, &it->second, 0);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &cap);
+  const bool in_place = p.residual != nullptr && p.residual == p.D;  // re-running would accumulate
+  if (cap != cudaStreamCaptureStatusNone || in_place || c->timer != nullptr)
+    return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, nullptr, 0);
+
+  // ---- time the candidates in place ----
+  int bw = std::min(A.W, 128);
+  while (128 % bw) --bw;
+  const int bh = std::min(128 / bw, A.H);
+  const long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
+  const int total_iters = A.taps * ((A.K + GEMM_BK - 1) / GEMM_BK);
+  const int halo_cin = conv_halo_eligible(c, A, N, p) ? A.K : 0;
+  std::vector<TileCfg> cands = tune_candidates(c->sm_count, m_tiles, N, total_iters, p.geglu != 0, allow_split, c->gemm_cg,
+                                               halo_cin, A.H, A.W, A.imgs);
+  TileCfg model = choose_tiles(c->sm_count, m_tiles, N, total_iters, A.batch, p.geglu != 0, allow_split,
+                               (long long)A.imgs * A.H * A.W, c->gemm_cg, halo_cin, A.H, A.W, A.imgs);
+  cands.push_back(model);
+  if (!c->flush_buf) {
+    if (cudaMalloc(&c->flush_buf, kFlushBytes) != cudaSuccess) {
+      cudaGetLastError();
+      c->flush_buf = nullptr;
+    }
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const long long launches0 = c->launches;
+  float best_ms = 1e30f;
+  TileCfg best = model;
+  int rc = TSD_OK;
+  for (const TileCfg& cand : cands) {
+    float ms_c = 1e30f;
+    for (int rep = 0; rep < 3 && !rc; ++rep) {
+      if (c->flush_buf && c->tune_flush) cudaMemsetAsync(c->flush_buf, rep, kFlushBytes, c->stream);
+      cudaEventRecord(e0, c->stream);
+      rc = run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, &cand, 0);
+      cudaEventRecord(e1, c->stream);
+      if (rc) break;
+      if (cudaEventSynchronize(e1) != cudaSuccess) {
+        rc = c->check(cudaGetLastError(), "gemm autotune");
+        break;
+      }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < ms_c) ms_c = ms;
+    }
+    if (rc) {  // a candidate the launcher rejects (shared memory, grid): skip it
+      rc = TSD_OK;
+      c->last_error.clear();
+      continue;
+    }
+    if (ms_c < best_ms) {
+      best_ms = ms_c;
+      best = cand;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  c->launches = launches0;  // tuning runs are not part of the product's launch count
+  c->tune->best[key] = best;
+  if (c->tune_verbose)
+    fprintf(stderr, "tsd autotune: K=%d W=%d H=%d imgs=%d taps=%d N=%d geglu=%d -> BN=%d splits=%d cg=%d halo=%d (%.1f us, %zu candidates)\n",
+            A.K, A.W, A.H, A.imgs, A.taps, N, p.geglu, best.BN, best.splits, best.cg, best.halo, best_ms * 1e3f, cands.size());
+  return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, &best, 0);
 }
 
 int op_gemm(Ctx* c, const GemmArgs& a) {

@@ -57,6 +57,8 @@ using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct KernelTimer;  // optional per-launch CUDA-event timing (bench roofline leg)
+struct TuneCache;    // per-context GEMM tile autotuning results (runtime.cu)
+constexpr size_t kFlushBytes = 192u << 20;  // > L2: written before every autotune timing run
 
 // Request to the producer of an activation: "the next consumer normalises this tensor with G groups
 // and this eps".  If the producing kernel can fold partial statistics into its epilogue
@@ -97,6 +99,13 @@ struct Ctx {
   unsigned int* ticket = nullptr;  // zero-initialised device counters for last-block reductions
   int bench_stats_groups = 0;      // lab: tsd_bench_conv / tsd_bench_gemm request norm statistics with this many groups
   unsigned int* norm_bar = nullptr;  // zero-initialised barrier words of the fused norm (elementwise.cuh)
+  TuneCache* tune = nullptr;
+  void* flush_buf = nullptr;
+  int autotune = 1;                // time tile candidates on first use of a GEMM signature (0: cost model only)
+  int conv_halo = 0;               // 3x3 convolutions: 0 never (default: measured on par with the implicit GEMM), 1 autotuner may choose, 2 whenever eligible
+  int halo_min_w = 16, halo_min_h = 18;  // lab: smallest image the halo TMA box is used on
+  int tune_verbose = 0;
+  int tune_flush = 0;              // 1: flush L2 before every autotune timing run (weights AND activations cold)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;

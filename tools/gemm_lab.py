@@ -116,6 +116,26 @@ def trace():
     ctx.set_option("gemm_cg", 0)
 
 
+def roles():
+    """which single-thread role bounds the K loop?  (dbg bit0: no MMAs, bit1: no A loads, bit2: no B loads)"""
+    from tsd_b200.api import Context
+    ctx = Context(0)
+    ctx.set_option("autotune", 0)
+    for (kind, a, bn, sp) in (("conv", (64, 64, 320, 320), 80, 1), ("conv", (64, 64, 320, 320), 160, 1),
+                              ("conv", (64, 64, 320, 320), 160, 2), ("gemm", (4096, 2560, 320, 1), 160, 1),
+                              ("gemm", (256, 1280, 5120, 0), 160, 5)):
+        for cg in (1, 2):
+            ctx.set_option("gemm_cg", cg)
+            line = []
+            for dbg in (0, 1, 6, 7):
+                ctx.set_option("gemm_debug", dbg)
+                ms, tf = run(ctx, kind, a, bn, sp, iters=20)
+                line.append(f"dbg={dbg:03b}:{ms * 1e3:6.1f}")
+            print(f"{kind} {a} bn={bn} sp={sp} cg={cg}  " + "  ".join(line), flush=True)
+    ctx.set_option("gemm_debug", 0)
+    ctx.set_option("gemm_cg", 0)
+
+
 def stats():
     """overhead of the producer-side norm statistics (epilogue / split-K reduce variants)"""
     from tsd_b200.api import Context
@@ -148,4 +168,4 @@ def ncu():
 
 
 if __name__ == "__main__":
-    {"feed": feed, "shapes": shapes, "ncu": ncu, "trace": trace, "stats": stats}[sys.argv[1]]()
+    {"feed": feed, "shapes": shapes, "ncu": ncu, "trace": trace, "stats": stats, "roles": roles}[sys.argv[1]]()
