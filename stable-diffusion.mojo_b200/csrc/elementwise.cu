@@ -22,7 +22,7 @@ inline int grid_for(long long work_items, int threads, int max_waves = 8) {
   return (int)b;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_f(float x) {
   const float k = 0.7978845608028654f;
   return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
@@ -563,18 +563,21 @@ norm_fused2_kernel(const NormFused2Params p) {
     for (int j = 0; j < 4; ++j) s[i][j] = q[i][j] = 0.f;
   if (pl < ppl) {
     if (CACHE) {
+      const int iters = (p1 - p0 - pl + ppl - 1) / ppl;  // pixels this thread owns (uniform per pixel lane)
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
+        if (it >= iters) break;  // a branch, not predication: unused iterations cost no issue slots
         const int px = p0 + pl + it * ppl;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
           const int qd = u + i * TU;
           v[it][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (px < p1 && qd < C4) v[it][i] = load(px, qd);
+          if (qd < C4) v[it][i] = load(px, qd);
         }
       }
 #pragma unroll
-      for (int it = 0; it < MAXIT; ++it)
+      for (int it = 0; it < MAXIT; ++it) {
+        if (it >= iters) break;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
           const float4 t = v[it][i];
@@ -583,6 +586,7 @@ norm_fused2_kernel(const NormFused2Params p) {
           s[i][2] += t.z; q[i][2] = fmaf(t.z, t.z, q[i][2]);
           s[i][3] += t.w; q[i][3] = fmaf(t.w, t.w, q[i][3]);
         }
+      }
     } else {
 #pragma unroll 4
       for (int px = p0 + pl; px < p1; px += ppl) {
@@ -653,15 +657,27 @@ norm_fused2_kernel(const NormFused2Params p) {
   if (flag_s) {
     __threadfence();
     const float2* src = p.part + ((long long)n * p.slabs_per_img + sub_first) * p.G;
-    for (int g = warp; g < p.G; g += NF_THREADS / 32) {
-      float2 t = make_float2(0.f, 0.f);
-      if (lane < members) t = __ldcg(src + (long long)lane * p.G + g);
+    for (int g0 = warp; g0 < p.G; g0 += 4 * (NF_THREADS / 32)) {  // 4 groups per pass: their L2 loads overlap
+      float2 t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = g0 + k * (NF_THREADS / 32);
+        t[k] = make_float2(0.f, 0.f);
+        if (g < p.G && lane < members) t[k] = __ldcg(src + (long long)lane * p.G + g);
+      }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {  // NF_SUB = 16 lanes
-        t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
-        t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[k].x += __shfl_xor_sync(0xffffffffu, t[k].x, o);
+          t[k].y += __shfl_xor_sync(0xffffffffu, t[k].y, o);
+        }
       }
-      if (lane == 0) p.part2[(long long)sub_global * p.G + g] = t;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = g0 + k * (NF_THREADS / 32);
+        if (lane == 0 && g < p.G) p.part2[(long long)sub_global * p.G + g] = t[k];
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -696,18 +712,31 @@ norm_fused2_kernel(const NormFused2Params p) {
   float2* st = reinterpret_cast<float2*>(nf_sm);
   {
     const float2* src = p.part2 + (long long)n * p.subs_per_img * p.G;
-    for (int g = warp; g < p.G; g += NF_THREADS / 32) {
-      float2 t = make_float2(0.f, 0.f);
-      if (lane < p.subs_per_img) t = __ldcg(src + (long long)lane * p.G + g);  // subs_per_img <= 32
-      double ds = (double)t.x, dq = (double)t.y;
+    for (int g0 = warp; g0 < p.G; g0 += 4 * (NF_THREADS / 32)) {  // 4 groups per pass: their L2 loads overlap
+      float2 t[4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ds += __shfl_xor_sync(0xffffffffu, ds, o);
-        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      for (int k = 0; k < 4; ++k) {
+        const int g = g0 + k * (NF_THREADS / 32);
+        t[k] = make_float2(0.f, 0.f);
+        if (g < p.G && lane < p.subs_per_img) t[k] = __ldcg(src + (long long)lane * p.G + g);  // subs_per_img <= 32
       }
-      if (lane == 0) {
-        const double mean = ds * (double)p.inv_count;
-        double var = dq * (double)p.inv_count - mean * mean;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {  // fp32 tree (fp64 issue is slow on this part); the subtraction below is fp64
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[k].x += __shfl_xor_sync(0xffffffffu, t[k].x, o);
+          t[k].y += __shfl_xor_sync(0xffffffffu, t[k].y, o);
+        }
+      }
+      // every lane holds the four totals: lane k finishes group k
+      float2 mine = t[0];
+      if (lane == 1) mine = t[1];
+      if (lane == 2) mine = t[2];
+      if (lane == 3) mine = t[3];
+      const int g = g0 + lane * (NF_THREADS / 32);
+      if (lane < 4 && g < p.G) {
+        const double mean = (double)mine.x * (double)p.inv_count;
+        double var = (double)mine.y * (double)p.inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
         // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
         st[g] = make_float2((float)mean, 1.0f / (sqrtf((float)var) + p.eps));
@@ -745,13 +774,15 @@ norm_fused2_kernel(const NormFused2Params p) {
     obase[(long long)px * C4 + qd] = make_float4(o[0], o[1], o[2], o[3]);
   };
   if (CACHE) {
+    const int iters = (p1 - p0 - pl + ppl - 1) / ppl;
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
+      if (it >= iters) break;
       const int px = p0 + pl + it * ppl;
 #pragma unroll
       for (int i = 0; i < NQ; ++i) {
         const int qd = u + i * TU;
-        if (px < p1 && qd < C4) emit(px, i, qd, v[it][i]);
+        if (qd < C4) emit(px, i, qd, v[it][i]);
       }
     }
   } else {
@@ -1001,22 +1032,23 @@ __global__ void conv_direct_kernel(const float* __restrict__ x, const float* __r
 // memory; thread t owns output channel t (and t + 256, ...), keeps its k*k*Cin weights in
 // registers and walks the pixels: patch reads are shared-memory broadcasts, output writes are
 // coalesced along Cout.
-constexpr int CS_PIX = 32, CS_MAXK = 64, CS_THREADS = 256;
-__global__ void __launch_bounds__(CS_THREADS)
+constexpr int CS_PIX = 16, CS_MAXK = 64;
+template <int KPAD>  // k*k*Cin rounded up to a multiple of 4 (36 for the 4-channel 3x3 input convs), <= CS_MAXK
+__global__ void __launch_bounds__(512)
 conv_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ out, int N, int H, int W, int Cin, int Cout, int k, int pad, int stride,
                    int Ho, int Wo) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ float patch[CS_PIX][CS_MAXK];
+  __shared__ __align__(16) float patch[CS_PIX][KPAD];
   const int K = k * k * Cin;
   const long long total_px = (long long)N * Ho * Wo;
   const long long px0 = (long long)blockIdx.x * CS_PIX;
-  for (int i = threadIdx.x; i < CS_PIX * K; i += blockDim.x) {
-    const int pp = i / K, kk = i - pp * K;
+  for (int i = threadIdx.x; i < CS_PIX * KPAD; i += blockDim.x) {
+    const int pp = i / KPAD, kk = i - pp * KPAD;
     const long long px = px0 + pp;
     float v = 0.f;
-    if (px < total_px) {
+    if (px < total_px && kk < K) {
       const int ci = kk % Cin, tap = kk / Cin;
       const int wo = (int)(px % Wo);
       long long t = px / Wo;
@@ -1028,17 +1060,27 @@ conv_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   }
   __syncthreads();
   for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-    float wr[CS_MAXK];
+    float wr[KPAD];
 #pragma unroll
-    for (int kk = 0; kk < CS_MAXK; ++kk) wr[kk] = kk < K ? w[(long long)co * K + kk] : 0.f;
+    for (int kk = 0; kk < KPAD; ++kk) wr[kk] = kk < K ? w[(long long)co * K + kk] : 0.f;
     const float b = bias ? bias[co] : 0.f;
-    for (int pp = 0; pp < CS_PIX; ++pp) {
-      if (px0 + pp >= total_px) break;
-      float acc = b;
+#pragma unroll 1
+    for (int pp = 0; pp < CS_PIX; pp += 4) {  // four pixels in flight: independent accumulation chains
+      float acc[4] = {b, b, b, b};
 #pragma unroll
-      for (int kk = 0; kk < CS_MAXK; ++kk)
-        if (kk < K) acc = fmaf(patch[pp][kk], wr[kk], acc);
-      out[(px0 + pp) * Cout + co] = acc;
+      for (int kk = 0; kk < KPAD; kk += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = *reinterpret_cast<const float4*>(&patch[pp + j][kk]);  // shared-memory broadcast
+          acc[j] = fmaf(pv.x, wr[kk], acc[j]);
+          acc[j] = fmaf(pv.y, wr[kk + 1], acc[j]);
+          acc[j] = fmaf(pv.z, wr[kk + 2], acc[j]);
+          acc[j] = fmaf(pv.w, wr[kk + 3], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (px0 + pp + j < total_px) out[(px0 + pp + j) * Cout + co] = acc[j];
     }
   }
 }
@@ -1496,9 +1538,13 @@ cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias
                                int Wo, cudaStream_t s) {
   if (k * k * Cin <= CS_MAXK && Cout >= 32) {
     const long long total_px = (long long)N * Ho * Wo;
-    { cudaError_t e_ = launch_pdl(conv_smallk_kernel, dim3((unsigned)((total_px + CS_PIX - 1) / CS_PIX)), dim3(CS_THREADS), 0, s, x, w, bias, out, N, H, W, Cin,
-                                                                                          Cout, k, pad, stride, Ho, Wo); if (e_ != cudaSuccess) return e_; }
-    return cudaGetLastError();
+    const int K = k * k * Cin;
+    int threads = (Cout + 31) / 32 * 32;
+    if (threads > 512) threads = 512;
+    const dim3 grid((unsigned)((total_px + CS_PIX - 1) / CS_PIX));
+    if (K <= 36)
+      return launch_pdl(conv_smallk_kernel<36>, grid, dim3(threads), 0, s, x, w, bias, out, N, H, W, Cin, Cout, k, pad, stride, Ho, Wo);
+    return launch_pdl(conv_smallk_kernel<CS_MAXK>, grid, dim3(threads), 0, s, x, w, bias, out, N, H, W, Cin, Cout, k, pad, stride, Ho, Wo);
   }
   long long total = (long long)N * Ho * Wo * Cout;
   conv_direct_kernel<<<grid_for(total, 128, 16), 128, 0, s>>>(x, w, bias, out, N, H, W, Cin, Cout, k,

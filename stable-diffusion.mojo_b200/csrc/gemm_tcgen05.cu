@@ -207,6 +207,17 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
                                   (cbias == nullptr || (((p.bias_img_stride & 3) == 0) &&
                                                         (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
   const bool round_out = p.round_tf32 && !partial;
+  // LayerNorm of the A operand folded into this epilogue: scale r and shift -r*mu*rowsum(W)
+  float ln_r = 1.0f, ln_rmu = 0.0f;
+  const bool ln_fold = p.ln.partial != nullptr && !partial;
+  if (ln_fold) {
+    __shared__ float2 ln_st[1];
+    const int img_ln = (int)(((long long)blockIdx.x * GEMM_BM) / p.ln_rows_per_img);
+    norm_stats_fold(p.ln, img_ln < p.ln.imgs ? img_ln : 0, threadIdx.x - 64, 256, ln_st);
+    named_bar_sync(3, 256);
+    ln_r = ln_st[0].y;
+    ln_rmu = ln_st[0].x * ln_st[0].y;
+  }
   // producer-side norm statistics: per-column (sum, sum^2) of the stored values of this tile
   const bool want_stats = p.ns.partial != nullptr;
   float2* cs = reinterpret_cast<float2*>(smem_ring + 8 * 32 * ST * 4);  // [4][256]
@@ -215,7 +226,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
   tc_fence_after_sync();
   if (threadIdx.x == 64) tr[4] = clock64();
 
-  const bool two_acc = n_iters > 1;
+  const bool two_acc = n_iters > 1 && GEMM_ROLE_PAIRS > 1;
   const uint32_t trow1 = trow + (uint32_t)p.acc_stride;  // the odd-K-step issuer's accumulator
   for (int c = half * 32; c < out_cols; c += 64) {
     uint32_t v[32];
@@ -244,11 +255,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         const bool okb = cbias != nullptr && n < n_valid && c + j < out_cols;
         bo[j] = okb ? __ldg(cbias + n) : 0.0f;
         bg[j] = okb ? __ldg(cbias + p.n_half + n) : 0.0f;
+        if (ln_fold && n < n_valid && c + j < out_cols) {
+          bo[j] -= ln_rmu * __ldg(p.wsum + n);
+          bg[j] -= ln_rmu * __ldg(p.wsum + p.n_half + n);
+        }
       }
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        v[j] = __float_as_uint((__uint_as_float(v[j]) + bo[j]) * gelu_tanh(__uint_as_float(g[j]) + bg[j]));
+        v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), ln_r, bo[j]) * gelu_tanh(fmaf(__uint_as_float(g[j]), ln_r, bg[j])));
     } else {
       tmem_ld_wait();
       if (!plain) {
@@ -270,11 +285,17 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       if (vec_ok) {
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cbias != nullptr && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(cbias + n));
+        float sc = 1.0f;
+        if (ln_fold && !geglu) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.wsum + n));
+          b4.x -= ln_rmu * w4.x; b4.y -= ln_rmu * w4.y; b4.z -= ln_rmu * w4.z; b4.w -= ln_rmu * w4.w;
+          sc = ln_r;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (drow[i] == nullptr) continue;
           float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
-          t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+          t.x = fmaf(t.x, sc, b4.x); t.y = fmaf(t.y, sc, b4.y); t.z = fmaf(t.z, sc, b4.z); t.w = fmaf(t.w, sc, b4.w);
           if (rbase != nullptr) {
             const float4 rr = *reinterpret_cast<const float4*>(rrow[i] + n);
             t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
@@ -418,7 +439,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, n_iters > 1 ? 2 : 1);  // one commit per MMA issuer
+    mbar_init(&accum_bar, (n_iters > 1 && GEMM_ROLE_PAIRS > 1) ? 2 : 1);  // one commit per MMA issuer
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -448,7 +469,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // bounds small-N tiles, so they are spread over two threads.  The two issuers accumulate into two
   // separate TMEM tiles (no ordering between them is needed); the epilogue adds them.
   const int role_parity = warp >= 10 ? 1 : 0;
-  const int n_par = n_iters > 1 ? 2 : 1;                // issuers / producers with work
+  const int n_par = (n_iters > 1 && GEMM_ROLE_PAIRS > 1) ? 2 : 1;  // issuers / producers with work
   if ((warp == 0 || warp == 10) && role_parity < n_par) {
     // ===================== TMA producer (K steps it = parity, parity + 2, ...) =====================
     if (elect_one()) {
@@ -915,8 +936,8 @@ void gemm_pick_ring(int BN, int cg, int* bk, int* stages) {
   for (int k : {64, 32}) {
     int s = (int)(budget / gemm_stage_bytes(BN, cg, k));
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    s &= ~1;
-    if (s >= 4 || k == 32) {
+    if (GEMM_ROLE_PAIRS > 1) s &= ~1;
+    if (s >= (GEMM_ROLE_PAIRS > 1 ? 4 : 2) || k == 32) {
       *bk = k;
       *stages = s < 2 ? 2 : s;
       return;

@@ -25,7 +25,12 @@ namespace tsd {
 
 constexpr int GEMM_BM = 128;       // rows per CTA tile (TMEM lanes)
 constexpr int GEMM_BK = 64;        // preferred K step (fp32 elements) = two 128 B swizzle atoms per operand row; 32 when smem-bound
-constexpr int GEMM_THREADS = 384;  // warps 0/10 TMA producers, 1/11 MMA issuers (1: TMEM alloc), 2..9 epilogue
+// Role pairs (TMA producer + MMA issuer threads) per CTA: 2 spreads the K steps over two thread pairs
+// with separate accumulators.  Measured on B200: no gain (the K loop is bound by shared-memory
+// bandwidth, not by instruction issue) and the 12-warp CTA caps registers at 168 (epilogue spills),
+// so 1 is used; the two-pair path stays for wider tiles / other precisions.
+constexpr int GEMM_ROLE_PAIRS = 1;
+constexpr int GEMM_THREADS = 320 + 64 * (GEMM_ROLE_PAIRS - 1);  // warps 0/10 TMA producers, 1/11 MMA issuers (1: TMEM alloc), 2..9 epilogue
 constexpr int GEMM_MAX_STAGES = 6;
 
 struct GemmKParams {
@@ -60,6 +65,11 @@ struct GemmKParams {
   int debug;               // lab only (Ctx::gemm_debug)
   int cg;                  // 1, or 2 = CTA pairs over consecutive M tiles (cluster 2x1x1, grid.x even)
   NormStatsReq ns;         // producer-side GroupNorm statistics of D (ns.partial == nullptr: off)
+  // LayerNorm (global statistics, one group per image) of the A operand folded into the epilogue:
+  //   W.((x - mu) r) + b  =  r (W.x) + (b - r mu rowsum(W));  ln.partial == nullptr: off
+  NormStatsReq ln;
+  const float* wsum;       // [N] row sums of the (TF32-rounded) weight matrix
+  int ln_rows_per_img;
   int b_static;            // B holds weights (never written by a predecessor kernel): may be loaded before pdl_wait
   int imgs;                // images (rows of tiles past the last image are phantom: loaded as zeros, never stored)
 };

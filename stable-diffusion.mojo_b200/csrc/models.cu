@@ -189,6 +189,10 @@ int ParamStore::allocate() {
   return TSD_OK;
 }
 void ParamStore::free_all() {
+  for (float* r : rowsum_dev)
+    if (r) cudaFree(r);
+  rowsum_dev.clear();
+  rowsum_gen.clear();
   if (block) cudaFree(block);
   block = nullptr;
 }
@@ -232,6 +236,7 @@ int ParamStore::load(const float* blob, long long n_floats) {
   if (rc) return rc;
   if (rc2) return rc2;
   loaded = true;
+  ++gen;
   return TSD_OK;
 }
 int ParamStore::init_random(uint64_t seed) {
@@ -250,6 +255,7 @@ int ParamStore::init_random(uint64_t seed) {
   }
   TRY(c->check(cudaStreamSynchronize(c->stream), "init_random sync"));
   loaded = true;
+  ++gen;
   return TSD_OK;
 }
 int ParamStore::get(int i, float* host_out) {
@@ -271,6 +277,36 @@ int ParamStore::get(int i, float* host_out) {
   int rc2 = c->check(cudaStreamSynchronize(c->stream), "get_param sync");
   if (tmp) cudaFree(tmp);
   return rc ? rc : rc2;
+}
+
+__global__ void weight_rowsum_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int I) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= O) return;
+  float s = 0.f;
+  for (int k = lane; k < I; k += 32) s += w[(long long)row * I + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+
+const float* ParamStore::rowsum(int i) {
+  if (rowsum_dev.size() != params.size()) {
+    rowsum_dev.assign(params.size(), nullptr);
+    rowsum_gen.assign(params.size(), -1);
+  }
+  const Param& p = params[i];
+  if (!rowsum_dev[i]) {
+    if (cudaMalloc(&rowsum_dev[i], sizeof(float) * (size_t)p.O) != cudaSuccess) {
+      c->fail(TSD_ERR_OOM, "rowsum allocation failed");
+      return nullptr;
+    }
+  }
+  if (rowsum_gen[i] != gen && !c->dry_run) {
+    weight_rowsum_kernel<<<(p.O + 7) / 8, 256, 0, c->stream>>>(p.dev, rowsum_dev[i], p.O, p.I * p.KK);
+    if (c->check(cudaGetLastError(), "weight_rowsum launch")) return nullptr;
+    rowsum_gen[i] = gen;
+  }
+  return rowsum_dev[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -299,9 +335,12 @@ static int conv(Ctx* c, const ParamStore& ps, int wi, const float* x, int N, int
 
 static int linear(Ctx* c, const float* x, long long M, int K, const float* w, const float* bias, int N,
                   float* out, long long ldd, const float* residual, int round_out, int geglu = 0,
-                  int split_n = 0, long long split_stride = 0, NormHint* nh = nullptr) {
+                  int split_n = 0, long long split_stride = 0, NormHint* nh = nullptr,
+                  const NormStatsReq* ln_fold = nullptr, const float* wsum = nullptr) {
   GemmArgs g;
   g.nh = nh;
+  g.ln_fold = ln_fold;
+  g.wsum = wsum;
   g.b_static = 1;  // every Linear of the models multiplies by a parameter matrix
   g.A = x; g.M = (int)M; g.K = K; g.lda = K;
   g.B = w; g.N = N; g.ldb = K;
@@ -373,9 +412,20 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   WALLOC(u, M * C);
   TRY(linear(c, a, M, C, ps.w(w.conv_in), ps.w(w.conv_in + 1), C, u, C, nullptr, 0, 0, 0, 0, &ln));
   WALLOC(v, M * C);
-  TRY(layer_norm(c, u, v, N, T, C, ln.ready()));
+  // LayerNorm folded into the consuming GEMM's epilogue when its statistics came with the producer
+  auto ln_then_linear = [&](const float* src, int wi, const float* bias, int Nout, float* dst, long long ldd, int geglu,
+                            int split_n, long long split_stride) -> int {
+    if (c->ln_fold && ln.ready() && T % 128 == 0) {
+      const float* ws = const_cast<ParamStore&>(ps).rowsum(wi);
+      if (!ws) return c->fail(TSD_ERR_OOM, "rowsum");
+      const NormStatsReq req = ln.req;  // the producer of `src` filled it; the next producer will overwrite ln
+      return linear(c, src, M, C, ps.w(wi), bias, Nout, dst, ldd, nullptr, 1, geglu, split_n, split_stride, nullptr, &req, ws);
+    }
+    TRY(layer_norm(c, src, v, N, T, C, ln.ready()));
+    return linear(c, v, M, C, ps.w(wi), bias, Nout, dst, ldd, nullptr, 1, geglu, split_n, split_stride);
+  };
   WALLOC(qkv, 3 * M * C);
-  TRY(linear(c, v, M, C, ps.w(w.in_proj), nullptr, 3 * C, qkv, C, nullptr, 1, 0, C, M * C));
+  TRY(ln_then_linear(u, w.in_proj, nullptr, 3 * C, qkv, C, 0, C, M * C));
   WALLOC(o, M * C);
   {
     AttnArgs at;
@@ -386,9 +436,8 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   }
   WALLOC(u2, M * C);
   TRY(linear(c, o, M, C, ps.w(w.out_proj), ps.w(w.out_proj + 1), C, u2, C, u, 0, 0, 0, 0, &ln));
-  TRY(layer_norm(c, u2, v, N, T, C, ln.ready()));
   float* q = qkv;
-  TRY(linear(c, v, M, C, ps.w(w.q), nullptr, C, q, C, nullptr, 1));
+  TRY(ln_then_linear(u2, w.q, nullptr, C, q, C, 0, 0, 0));
   {
     AttnArgs at;
     at.Q = q; at.K = kctx; at.V = vctx;
@@ -399,10 +448,9 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   }
   WALLOC(u3, M * C);
   TRY(linear(c, o, M, C, ps.w(w.o), ps.w(w.o + 1), C, u3, C, u2, 0, 0, 0, 0, &ln));
-  TRY(layer_norm(c, u3, v, N, T, C, ln.ready()));
   WALLOC(g, M * 4 * C);
   // GEGLU: Linear(C -> 8C), chunk(2,2), out * gelu(gate)  (diffusion.mojo:138-141)
-  TRY(linear(c, v, M, C, ps.w(w.geglu1), ps.w(w.geglu1 + 1), 8 * C, g, 4 * C, nullptr, 1, 1));
+  TRY(ln_then_linear(u3, w.geglu1, ps.w(w.geglu1 + 1), 8 * C, g, 4 * C, 1, 0, 0));
   float* u4 = u;  // u is dead after u2
   TRY(linear(c, g, M, 4 * C, ps.w(w.geglu2), ps.w(w.geglu2 + 1), C, u4, C, u3, 1));
   if (next) next->imgs = N;

@@ -47,6 +47,12 @@ struct ParamStore {
   int init_random(uint64_t seed);
   int get(int i, float* host_out);
   const float* w(int i) const { return params[i].dev; }
+  // row sums of a [O][I] weight matrix (over the values the tensor core sees), computed on first use after
+  // every (re)load; for LayerNorm folding (GemmArgs::ln_fold)
+  const float* rowsum(int i);
+  std::vector<float*> rowsum_dev;
+  std::vector<int> rowsum_gen;
+  int gen = 0;  // bumped by load / init_random
   void free_all();
 };
 

@@ -29,34 +29,49 @@ struct NormStatsReq {
 // One warp per group; lanes stride over the (slab, n-tile) entries of the group.
 __device__ __forceinline__ void norm_stats_fold(const NormStatsReq& r, int img, int tid, int nthreads, float2* st) {
   const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-  for (int g = warp; g < r.G; g += nwarps) {
-    const int nt0 = (g * r.cpg) / r.BN, nt1 = ((g + 1) * r.cpg - 1) / r.BN;  // n-tiles overlapping the group
-    const int span = nt1 - nt0 + 1;
-    const int entries = r.slabs_per_img * span;
-    const float2* base = r.partial + (long long)img * r.slabs_per_img * r.n_tiles * r.lg;
-    double ds = 0.0, dq = 0.0;
-    for (int k0 = 0; k0 < entries; k0 += 128) {
-      float2 v[4];
+  const float2* base = r.partial + (long long)img * r.slabs_per_img * r.n_tiles * r.lg;
+  for (int g0 = warp; g0 < r.G; g0 += 4 * nwarps) {  // 4 groups per pass so that their L2 loads overlap
+    float fs[4], fq[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = k0 + j * 32 + lane;
-        v[j] = make_float2(0.f, 0.f);
-        if (k < entries) {
-          const int sl = k / span, nt = nt0 + (k - sl * span);
-          v[j] = __ldcg(base + ((long long)sl * r.n_tiles + nt) * r.lg + (g - (nt * r.BN) / r.cpg));
+    for (int k = 0; k < 4; ++k) {
+      fs[k] = fq[k] = 0.f;
+      const int g = g0 + k * nwarps;
+      if (g >= r.G) continue;
+      const int nt0 = (g * r.cpg) / r.BN, nt1 = ((g + 1) * r.cpg - 1) / r.BN;  // n-tiles overlapping the group
+      const int span = nt1 - nt0 + 1;
+      const int entries = r.slabs_per_img * span;
+      for (int k0 = 0; k0 < entries; k0 += 128) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = k0 + j * 32 + lane;
+          v[j] = make_float2(0.f, 0.f);
+          if (e < entries) {
+            const int sl = e / span, nt = nt0 + (e - sl * span);
+            v[j] = __ldcg(base + ((long long)sl * r.n_tiles + nt) * r.lg + (g - (nt * r.BN) / r.cpg));
+          }
         }
+        fs[k] += (v[0].x + v[1].x) + (v[2].x + v[3].x);
+        fq[k] += (v[0].y + v[1].y) + (v[2].y + v[3].y);
       }
-      ds += ((double)v[0].x + (double)v[1].x) + ((double)v[2].x + (double)v[3].x);
-      dq += ((double)v[0].y + (double)v[1].y) + ((double)v[2].y + (double)v[3].y);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ds += __shfl_xor_sync(0xffffffffu, ds, o);
-      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    for (int o = 16; o > 0; o >>= 1) {  // fp32 trees (fp64 issue is slow on this part); the subtraction below is fp64
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        fs[k] += __shfl_xor_sync(0xffffffffu, fs[k], o);
+        fq[k] += __shfl_xor_sync(0xffffffffu, fq[k], o);
+      }
     }
-    if (lane == 0) {
-      const double mean = ds * (double)r.inv_count;
-      double var = dq * (double)r.inv_count - mean * mean;
+    // every lane holds the four totals: lane k finishes group k
+    float ms = fs[0], mq = fq[0];
+    if (lane == 1) { ms = fs[1]; mq = fq[1]; }
+    if (lane == 2) { ms = fs[2]; mq = fq[2]; }
+    if (lane == 3) { ms = fs[3]; mq = fq[3]; }
+    const int g = g0 + lane * nwarps;
+    if (lane < 4 && g < r.G) {
+      const double mean = (double)ms * (double)r.inv_count;
+      double var = (double)mq * (double)r.inv_count - mean * mean;
       if (var < 0.0) var = 0.0;
       st[g] = make_float2((float)mean, 1.0f / (sqrtf((float)var) + r.eps));
     }

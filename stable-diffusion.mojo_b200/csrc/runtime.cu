@@ -204,7 +204,7 @@ struct TileCfg {
 // two accumulator tiles (even / odd K steps) of BN (+ the epilogue's read-ahead pad) columns must fit TMEM
 inline bool bn_fits_tmem(int BN, bool geglu) {
   const int need = geglu ? BN + 16 : BN + ((BN & 31) ? 16 : 0);
-  return 2 * ((need + 31) / 32 * 32) <= 512;
+  return GEMM_ROLE_PAIRS * ((need + 31) / 32 * 32) <= 512;
 }
 
 // Cycle model used only to rank (BN, splits, pairing) candidates.  Per 64-wide K step a CTA needs
@@ -327,7 +327,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
   const int nbatch = A.batch;
   const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
-                           p.alpha == 1.0f;
+                           p.alpha == 1.0f && p.ln.partial == nullptr;
   const bool halo_ok = conv_halo_eligible(c, A, N, p);
   TileCfg cfg = use ? *use
                     : choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
@@ -363,7 +363,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     p.total_iters = p.chunks_per_tap;  // the K loop runs over channel chunks, nine taps each
   } else {
     gemm_pick_ring(p.BN, p.cg, &p.bk, &p.num_stages);
-    if (c->force_stages >= 2 && c->force_stages < p.num_stages) p.num_stages = c->force_stages & ~1;
+    if (c->force_stages >= 2 && c->force_stages < p.num_stages) p.num_stages = GEMM_ROLE_PAIRS > 1 ? (c->force_stages & ~1) : c->force_stages;
     p.chunks_per_tap = (A.K + p.bk - 1) / p.bk;
     p.total_iters = p.taps * p.chunks_per_tap;
   }
@@ -375,7 +375,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   const int tmem_need = p.geglu ? p.BN + 16 : p.BN + ((p.BN & 31) ? 16 : 0);
   p.acc_stride = (tmem_need + 31) / 32 * 32;
   int tc = 32;
-  while (tc < (p.halo ? 1 : 2) * p.acc_stride) tc <<= 1;  // GEMM kernel: two accumulator tiles (even / odd K steps)
+  while (tc < ((p.halo || GEMM_ROLE_PAIRS == 1) ? 1 : 2) * p.acc_stride) tc <<= 1;  // one accumulator tile per role pair
   if (tc > 512) return c->fail(TSD_ERR_INVALID, "gemm: accumulators exceed tensor memory");
   p.tmem_cols = tc;
   p.n_pad = (N + 15) / 16 * 16;
@@ -593,7 +593,8 @@ static std::vector<TileCfg> tune_candidates(int sm, long long m_tiles, int N, in
 
 static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
                     int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh = nullptr) {
-  const bool allow_split = !p.geglu && A.batch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) && p.alpha == 1.0f;
+  const bool allow_split = !p.geglu && A.batch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) && p.alpha == 1.0f &&
+                           p.ln.partial == nullptr;
   const bool tunable = c->autotune && force_bn <= 0 && force_splits <= 0 && c->gemm_debug == 0 && c->force_stages == 0;
   if (!tunable) return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, force_bn, force_splits, flops, nh, nullptr, 0);
   if (c->dry_run) {
@@ -721,6 +722,14 @@ int op_gemm(Ctx* c, const GemmArgs& a) {
   p.split_stride = a.split_stride;
   p.round_tf32 = a.round_tf32;
   p.b_static = a.b_static;
+  if (a.ln_fold && a.ln_fold->partial) {
+    if (!a.wsum || a.ln_fold->G != 1 || a.batch != 1 || a.alpha != 1.0f || a.row_bias || (a.N % 4) ||
+        a.ln_fold->imgs <= 0 || a.M % a.ln_fold->imgs || (a.M / a.ln_fold->imgs) % GEMM_BM)
+      return c->fail(TSD_ERR_INVALID, "gemm: LayerNorm fold needs global statistics, image rows in whole tiles and row sums");
+    p.ln = *a.ln_fold;
+    p.wsum = a.wsum;
+    p.ln_rows_per_img = a.M / a.ln_fold->imgs;
+  }
   if ((a.ldd % 4) || (a.residual && (a.ldr % 4)))
     return c->fail(TSD_ERR_INVALID, "gemm: ldd/ldr must be multiples of 4");
   const double flops = 2.0 * a.M * (double)a.N * a.K * a.batch;

@@ -106,6 +106,7 @@ struct Ctx {
   int halo_min_w = 16, halo_min_h = 18;  // lab: smallest image the halo TMA box is used on
   int tune_verbose = 0;
   int tune_flush = 0;              // 1: flush L2 before every autotune timing run (weights AND activations cold)
+  int ln_fold = 1;                 // fold global-statistics LayerNorm into the consuming GEMM epilogue (0: separate pass)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;
@@ -167,6 +168,10 @@ struct GemmArgs {
   int force_bn = 0, force_splits = 0;  // tuning / tests
   NormHint* nh = nullptr;              // optional: statistics of D for the next norm
   int b_static = 0;                    // B is a weight matrix no kernel writes during the forward pass
+  // LayerNorm (global statistics) of A folded into the epilogue: statistics of A left by ITS producer,
+  // and the row sums of B; the GEMM then reads the un-normalised A
+  const NormStatsReq* ln_fold = nullptr;
+  const float* wsum = nullptr;
 };
 int op_gemm(Ctx* c, const GemmArgs& a);
 
