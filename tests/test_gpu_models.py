@@ -121,6 +121,53 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
     assert relerr(y, g["unet8_y"]) < TOL_MODEL
 
 
+@pytest.mark.parametrize("opts", [
+    {"ln_fold": 0},                       # LayerNorm as a separate pass instead of the GEMM-epilogue fold
+    {"producer_stats": 0},                # every norm computes its own statistics (no epilogue partial sums)
+    {"producer_stats": 0, "norm_v2": 1},  # ... with the register-resident fused norm kernel
+    {"pdl": 0},                           # no programmatic dependent launch
+    {"autotune": 0},                      # cost-model tile choice only
+    {"autotune": 0, "conv_halo": 2, "halo_min_w": 8, "halo_min_h": 8},  # halo convolution kernel everywhere
+    {"gemm_cg": 1},                       # single CTAs only (no cta_group::2 pairs)
+])
+def test_unet8_execution_switches(ctx, diff8, golden_small, opts):
+    """Every execution-plan switch computes the same UNet step (to TF32 rounding level): the
+    defaults are optimisations, not semantics."""
+    g = golden_small
+    old = {k: ctx.get_option(k) for k in opts}
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        y = diff8.forward(g["unet8_x"], g["unet8_ctx"], g["unet8_t"])
+    finally:
+        for k, v in old.items():
+            ctx.set_option(k, v)
+    assert relerr(y, g["unet8_y"]) < TOL_MODEL
+
+
+def test_unet64_switches_agree_at_full_size(ctx, diff64):
+    """At the BASELINE latent size the producer-side statistics and the LayerNorm fold are active
+    (token counts are multiples of the 128-row tiles): turning them off must not change the result
+    beyond TF32 rounding level, and a batch of two must match as well."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((4, 64, 64), dtype=np.float32)
+    cx = rng.standard_normal((77, 768), dtype=np.float32)
+    t = host_sampler.get_time_embedding(500.0)
+    y_default = diff64.forward(x, cx, t)
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}):
+        old = {k: ctx.get_option(k) for k in opts}
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        try:
+            y = diff64.forward(x, cx, t)
+        finally:
+            for k, v in old.items():
+                ctx.set_option(k, v)
+        e = relerr(y, y_default)
+        print(f"unet64 {opts}: rel_linf vs default plan {e:.2e}")
+        assert e < TOL_BATCH
+
+
 def test_load_weights_blob_path(ctx, golden_small):
     """tsd_diffusion_load_weights with a dense random blob (non-zero conv biases), 16x16 latent,
     oracle evaluated on the same blob."""

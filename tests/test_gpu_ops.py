@@ -177,3 +177,82 @@ def test_sampler_step(ctx):
         assert relerr(got, want) < TOL_FP32
     got = ctx.sampler_step(lat, ec, None, 1.0, None, *[float(v) for v in sm.coefficients(500)])
     assert relerr(got, sm.step(500, lat.astype(np.float64), ec.astype(np.float64), None)) < TOL_FP32
+
+
+# ------------------------------------------------------------------------------------------------
+# execution variants of the tensor-core GEMM / convolution: every variant must meet the same
+# tolerance against the oracle (the autotuner may pick any of them)
+# ------------------------------------------------------------------------------------------------
+class _Options:
+    """set tsd options for the duration of a with-block (restored afterwards)"""
+
+    def __init__(self, ctx, **kv):
+        self.ctx, self.kv, self.old = ctx, kv, {}
+
+    def __enter__(self):
+        for k, v in self.kv.items():
+            self.old[k] = self.ctx.get_option(k)
+            self.ctx.set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            self.ctx.set_option(k, v)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("bn,splits", [(0, 0), (64, 1), (160, 1), (80, 2), (160, 3)])
+def test_conv2d_tile_variants(ctx, ops, cg, bn, splits):
+    """single CTAs vs CTA pairs (tcgen05 cta_group::2), forced tile widths and split-K factors"""
+    rng = np.random.default_rng(100 + bn + splits)
+    x = rng.standard_normal((320, 32, 32), dtype=np.float32)
+    wt = (rng.standard_normal((320, 320, 3, 3)) / np.sqrt(2880)).astype(np.float32)
+    b = rng.standard_normal(320, dtype=np.float32)
+    ref = ops.conv2d(x, wt, b, 1, 1)
+    with _Options(ctx, autotune=0, gemm_cg=cg, force_bn=bn, force_splits=splits):
+        y = ctx.conv2d(x, wt, b, pad=1)
+    assert relerr(y, ref) < TOL_TF32
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout,bn,splits,cg", [
+    (1, 32, 32, 32, 32, 0, 0, 1), (1, 320, 32, 32, 320, 160, 1, 2), (1, 320, 32, 32, 320, 80, 2, 2),
+    (2, 96, 40, 24, 48, 0, 0, 0),      # ragged edges, two images
+    (1, 36, 20, 28, 80, 0, 0, 0),      # partial channel chunk
+    (1, 64, 16, 16, 64, 0, 0, 1),      # TMA box taller than the image
+    (2, 64, 8, 8, 32, 0, 0, 1),        # box larger than the image in both directions
+])
+def test_conv2d_halo_kernel(ctx, ops, n, cin, h, w, cout, bn, splits, cg):
+    """3x3 convolution with the activation halo held in shared memory (nine taps = nine shifted
+    UMMA descriptor views of one TMA tile): zero padding, ragged tiles, CTA pairs, split-K"""
+    rng = np.random.default_rng(7 * cin + cout)
+    x = rng.standard_normal((n, cin, h, w), dtype=np.float32)
+    wt = (rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32)
+    b = rng.standard_normal(cout, dtype=np.float32)
+    ref = np.stack([ops.conv2d(x[i], wt, b, 1, 1) for i in range(n)])
+    with _Options(ctx, autotune=0, conv_halo=2, halo_min_w=8, halo_min_h=8, gemm_cg=cg, force_bn=bn, force_splits=splits):
+        y = ctx.conv2d(x, wt, b, pad=1)
+    assert relerr(y, ref) < TOL_TF32
+
+
+def test_linear_autotune_is_stable(ctx, ops):
+    """the autotuner's choice is cached per context: repeated calls are bit-identical"""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1, 1024, 640), dtype=np.float32)
+    w = (rng.standard_normal((640, 640)) / np.sqrt(640)).astype(np.float32)
+    with _Options(ctx, autotune=1):
+        y0 = ctx.linear(x, w, None)
+        y1 = ctx.linear(x, w, None)
+    assert np.array_equal(y0, y1)
+    assert relerr(y0, ops.linear(x[0], w, None)[None]) < TOL_TF32
+
+
+@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("c,h,w,g,eps", [(320, 16, 16, 32, 1e-5), (1920, 16, 16, 32, 1e-5), (320, 8, 8, 320, 1e-5),
+                                         (640, 32, 32, 1, 1e-5), (128, 64, 64, 32, 1e-6)])
+def test_groupnorm_fused_kernels(ctx, ops, v2, c, h, w, g, eps):
+    """both single-launch norm kernels (grid barrier v1, register-resident two-level barrier v2)"""
+    rng = np.random.default_rng(c + h)
+    x = (rng.standard_normal((c, h, w)) * 2 + 0.5).astype(np.float32)
+    with _Options(ctx, norm_v2=v2):
+        y = ctx.groupnorm(x, g, eps)
+    assert relerr(y, ops.group_norm(x, g, eps)) < TOL_FP32
