@@ -223,6 +223,17 @@ def tf32_peak():
         return 0.5 * 1400.0, "0.5 x 1.4 PFLOP/s bf16 sustained of fallback (B200_PROFILING.md)"
 
 
+def kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/r01_kernel_traffic.json, written by tools/ncu_summary.py from
+    the capture named there); None when the file is absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
+        return float(t["dram_bytes_per_launch"]), t.get("note")
+    except Exception:
+        return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -378,8 +389,10 @@ def run_ours(args):
         g = fam["gemm"]
         ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         step_ach = (UNET_GFLOP - CTX_KV_GFLOP) * 1e9 * (K / (ms_dev * 1e-3)) / 1e12
+        traffic, traffic_note = kernel_traffic()
         roof = {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32 implicit-GEMM conv + linear)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": peak_src, "launches_per_step": g["launches"], "flops_per_step": g["flops"],
                 "ms_per_step_in_kernel": g["ms"],
                 "whole_step": {"achieved": step_ach, "frac": step_ach / peak,

@@ -58,6 +58,19 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *                      1 = per token
  *   "fused_attention"  1 = fused tcgen05 attention kernel [default], 0 = GEMM+softmax+GEMM
  *   "cuda_graph"       1 = replay model forwards from a captured CUDA graph [default], 0 = eager
+ * Execution-plan knobs (never change semantics; results agree to TF32 rounding level):
+ *   "autotune"         1 = time tile candidates on first use of a GEMM signature [default], 0 = cost model
+ *                          (TSD_TUNE_CACHE=<file> in the environment persists the choices)
+ *   "gemm_cg"          0 = plan decides [default], 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2)
+ *   "conv_halo"        3x3 convolutions: 0 = implicit GEMM [default], 1 = autotuner may pick the
+ *                          halo-in-shared-memory kernel, 2 = whenever eligible
+ *   "producer_stats"   1 = GEMM epilogues leave GroupNorm/LayerNorm partial sums for the consumer [default]
+ *   "ln_fold"          1 = global-statistics LayerNorm folded into the consuming GEMM epilogue [default]
+ *   "norm_v2"          0/1 = which single-launch fused norm kernel serves the remaining norms
+ *   "pdl"              1 = programmatic dependent launch between the kernels of a graph [default]
+ *   "force_bn" / "force_splits" / "force_stages" / "gemm_debug" / "halo_min_w" / "halo_min_h" /
+ *   "tune_verbose" / "tune_flush" / "bench_stats_groups": tests and lab tooling only.
+ * Every option can also be preset as TSD_OPT_<name>=<int> in the environment of tsd_init().
  */
 int32_t tsd_set_option(tsd_ctx* ctx, const char* name, int32_t value);
 int32_t tsd_get_option(tsd_ctx* ctx, const char* name, int32_t* value);

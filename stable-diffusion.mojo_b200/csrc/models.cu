@@ -642,6 +642,13 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
       out_.ns.eps = 1e-5f;
       if (!hint_scratch(out_)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
       nh = &out_.ns;
+    } else if (i == 4 || i == 6) {
+      // a13 / a18 are upsampled (nearest x2) and then normalised by a ResBlock's GroupNorm(32): replicating every
+      // pixel four times leaves mean and variance unchanged, so the statistics of the source serve the upsampled tensor
+      out_.ns.G = 32;
+      out_.ns.eps = 1e-5f;
+      if (!hint_scratch(out_)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+      nh = &out_.ns;
     }
     return attn_block(c, ps, attn[i], in, kctx[i], vctx[i], n_ctx, L, out_.p, nh);
   };
@@ -655,6 +662,7 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
     out_ = act(a.C, a.H * 2, a.W * 2);
     if (!out_.p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)");
     LAUNCH(c, launch_upsample2x(a.p, out_.p, a.N, a.H, a.W, a.C, c->stream), "upsample2x");
+    out_.ns = a.ns;  // statistics are invariant under nearest-neighbour replication
     return TSD_OK;
   };
 
