@@ -67,6 +67,7 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *   "producer_stats"   1 = GEMM epilogues leave GroupNorm/LayerNorm partial sums for the consumer [default]
  *   "ln_fold"          1 = global-statistics LayerNorm folded into the consuming GEMM epilogue [default]
  *   "norm_v2"          0/1 = which single-launch fused norm kernel serves the remaining norms
+ *   "splitk_fixup"     1 = split-K partials reduced in-kernel by the last CTA of each tile, 0 = reduce kernel [default]
  *   "pdl"              1 = programmatic dependent launch between the kernels of a graph [default]
  *   "force_bn" / "force_splits" / "force_stages" / "gemm_debug" / "halo_min_w" / "halo_min_h" /
  *   "tune_verbose" / "tune_flush" / "bench_stats_groups": tests and lab tooling only.

@@ -191,6 +191,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
   const float* rbase = (p.residual && !partial) ? p.residual + (long long)batch * p.r_batch_stride : nullptr;
   float* drow[8];
   const float* rrow[8];
+  long long grow[8];  // global output row of each of this lane's 8 rows (-1: outside the image)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = q * 32 + i * 4 + sub;
@@ -198,6 +199,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
     const int h = h0 + lh, w = w0 + lw;
     const bool ok = img_ok && (lh < p.bh) && (h < p.H) && (w < p.W);
     const long long g = ((long long)img * p.H + h) * p.W + w;
+    grow[i] = ok ? g : -1;
     drow[i] = ok ? dbase + g * ldd : nullptr;
     rrow[i] = rbase ? rbase + g * p.ldr : nullptr;
   }
@@ -209,7 +211,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
   const bool round_out = p.round_tf32 && !partial;
   // LayerNorm of the A operand folded into this epilogue: scale r and shift -r*mu*rowsum(W)
   float ln_r = 1.0f, ln_rmu = 0.0f;
-  const bool ln_fold = p.ln.partial != nullptr && !partial;
+  const bool fixup = p.fixup != 0 && partial;  // split-K: the last CTA of a tile reduces and runs the real epilogue
+  const bool ln_fold = p.ln.partial != nullptr && (!partial || fixup);
   if (ln_fold) {
     __shared__ float2 ln_st[1];
     const int img_ln = (int)(((long long)blockIdx.x * GEMM_BM) / p.ln_rows_per_img);
@@ -219,7 +222,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
     ln_rmu = ln_st[0].x * ln_st[0].y;
   }
   // producer-side norm statistics: per-column (sum, sum^2) of the stored values of this tile
-  const bool want_stats = p.ns.partial != nullptr;
+  const bool want_stats = p.ns.partial != nullptr && (!partial || fixup);
+  const bool stats_pass1 = want_stats && !partial;
   float2* cs = reinterpret_cast<float2*>(smem_ring + 8 * 32 * ST * 4);  // [4][256]
 
   mbar_wait_a(accum_a, 0);
@@ -286,7 +290,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cbias != nullptr && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(cbias + n));
         float sc = 1.0f;
-        if (ln_fold && !geglu) {
+        if (ln_fold && !geglu && !partial) {
           const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.wsum + n));
           b4.x -= ln_rmu * w4.x; b4.y -= ln_rmu * w4.y; b4.z -= ln_rmu * w4.z; b4.w -= ln_rmu * w4.w;
           sc = ln_r;
@@ -326,7 +330,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         }
       }
     }
-    if (want_stats) {
+    if (stats_pass1) {
       // fold the 4 row groups of the warp (lanes with equal lane % 8): fixed xor tree, all lanes take part
 #pragma unroll
       for (int o = 8; o <= 16; o <<= 1) {
@@ -342,6 +346,75 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       }
     }
     __syncwarp();
+  }
+  if (fixup) {
+    // ---- split-K fix-up: every CTA has stored its raw partial tile; the last one to arrive for this
+    // output tile sums the partials in split order (deterministic) and runs the real epilogue ----
+    __shared__ unsigned int fix_last;
+    const int te0 = threadIdx.x - 64;
+    named_bar_sync(2, 256);
+    if (te0 == 0) {
+      __threadfence();
+      unsigned int* tk = p.tile_tickets + (blockIdx.y * gridDim.x + blockIdx.x);
+      const unsigned int old = atomicAdd(tk, 1u);
+      fix_last = (old == (unsigned int)p.splits - 1) ? 1u : 0u;
+      if (fix_last) *tk = 0u;  // self-resetting: launches on one stream are serialised
+    }
+    named_bar_sync(2, 256);
+    if (!fix_last) return;
+    __threadfence();
+    const float* cb2 = p.bias ? p.bias + (long long)img * p.bias_img_stride : nullptr;
+    const float* ws0 = p.partial;
+    const long long ws_split = (long long)p.m_per_batch * p.n_pad;  // floats between splits (batch == 1)
+    for (int c = half * 32; c < out_cols; c += 64) {
+      const int n = n0 + c + c4;
+      float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + c4 < out_cols && n < n_valid) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb2 != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(cb2 + n));
+        float sc = 1.0f;
+        if (ln_fold) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.wsum + n));
+          b4.x -= ln_rmu * w4.x; b4.y -= ln_rmu * w4.y; b4.z -= ln_rmu * w4.z; b4.w -= ln_rmu * w4.w;
+          sc = ln_r;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (grow[i] < 0) continue;
+          const float* src = ws0 + grow[i] * p.n_pad + (long long)nt * p.BN + c + c4;
+          float4 t = __ldcg(reinterpret_cast<const float4*>(src));
+          for (int s = 1; s < p.splits; ++s) {
+            const float4 u = __ldcg(reinterpret_cast<const float4*>(src + s * ws_split));
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+          }
+          t.x = fmaf(t.x, sc, b4.x); t.y = fmaf(t.y, sc, b4.y); t.z = fmaf(t.z, sc, b4.z); t.w = fmaf(t.w, sc, b4.w);
+          if (p.residual != nullptr) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + grow[i] * p.ldr + n);
+            t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+          }
+          if (p.round_tf32) {
+            t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
+          }
+          *reinterpret_cast<float4*>(p.D + grow[i] * p.ldd + n) = t;
+          ss.x += t.x; ss.y += t.y; ss.z += t.z; ss.w += t.w;
+          qq.x = fmaf(t.x, t.x, qq.x); qq.y = fmaf(t.y, t.y, qq.y); qq.z = fmaf(t.z, t.z, qq.z); qq.w = fmaf(t.w, t.w, qq.w);
+        }
+      }
+      if (want_stats) {
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+          ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+          qq.x += __shfl_xor_sync(0xffffffffu, qq.x, o); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, o);
+          qq.z += __shfl_xor_sync(0xffffffffu, qq.z, o); qq.w += __shfl_xor_sync(0xffffffffu, qq.w, o);
+        }
+        if (sub == 0 && c + c4 < out_cols) {
+          float2* d = cs + q * 256 + c + c4;
+          d[0] = make_float2(ss.x, qq.x); d[1] = make_float2(ss.y, qq.y);
+          d[2] = make_float2(ss.z, qq.z); d[3] = make_float2(ss.w, qq.w);
+        }
+      }
+    }
   }
   if (want_stats) {
     // quadrant sums -> column sums -> sums of the groups overlapping this tile -> partial; the last CTA finalises

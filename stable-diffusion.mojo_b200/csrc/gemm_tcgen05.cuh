@@ -62,6 +62,8 @@ struct GemmKParams {
   int round_tf32;
   float* partial;          // split-K workspace [split][b][m][n_pad] or nullptr
   int n_pad;
+  int fixup;               // split-K: the last CTA of every output tile reduces the partials and runs the epilogue
+  unsigned int* tile_tickets;  // [grid.x * grid.y] zero-initialised, self-resetting arrival counters (fixup)
   int debug;               // lab only (Ctx::gemm_debug)
   int cg;                  // 1, or 2 = CTA pairs over consecutive M tiles (cluster 2x1x1, grid.x even)
   NormStatsReq ns;         // producer-side GroupNorm statistics of D (ns.partial == nullptr: off)

@@ -101,6 +101,11 @@ int ctx_create(int device, Ctx** out, std::string* err) {
     return TSD_ERR_CUDA;
   }
   c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  if (cudaMalloc(&c->tile_tickets, sizeof(unsigned int) * kTileTickets) != cudaSuccess ||
+      cudaMemset(c->tile_tickets, 0, sizeof(unsigned int) * kTileTickets) != cudaSuccess) {
+    *err = "tile ticket allocation failed";
+    return TSD_ERR_OOM;
+  }
   if (cudaMalloc(&c->norm_bar, 128 * kNormBarrierCounters) != cudaSuccess ||
       cudaMemset(c->norm_bar, 0, 128 * kNormBarrierCounters) != cudaSuccess) {
     *err = "norm barrier allocation failed";
@@ -127,6 +132,7 @@ void ctx_destroy(Ctx* c) {
   }
   if (c->ticket) cudaFree(c->ticket);
   if (c->norm_bar) cudaFree(c->norm_bar);
+  if (c->tile_tickets) cudaFree(c->tile_tickets);
   if (c->flush_buf) cudaFree(c->flush_buf);
   tune_cache_free(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -328,7 +334,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
   const int nbatch = A.batch;
   const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
-                           p.alpha == 1.0f && p.ln.partial == nullptr;
+                           p.alpha == 1.0f && (p.ln.partial == nullptr || c->splitk_fixup);
   const bool halo_ok = conv_halo_eligible(c, A, N, p);
   TileCfg cfg = use ? *use
                     : choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
@@ -433,9 +439,19 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     rp.ldr = p.ldr;
     rp.round_tf32 = p.round_tf32;
     p.partial = ws;
+    // in-kernel reduction by the last CTA of every output tile (needs the vector epilogue and a ticket per tile)
+    const long long tiles = (long long)(p.cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles) * n_tiles;
+    p.fixup = (c->splitk_fixup && tiles <= kTileTickets && N % 4 == 0 && p.ldd % 4 == 0 && (!p.residual || p.ldr % 4 == 0) &&
+               (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)))
+                  ? 1
+                  : 0;
+    p.tile_tickets = c->tile_tickets;
   } else {
     p.partial = nullptr;
+    p.fixup = 0;
   }
+  if (p.ln.partial != nullptr && p.splits > 1 && !p.fixup)
+    return c->fail(TSD_ERR_INVALID, "gemm: LayerNorm fold with split-K needs the in-kernel fix-up");
 
   const long long m_tiles_grid = p.cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles;  // pairs: phantom tile pads odd counts
   // producer-side norm statistics (norm_stats.cuh): only where the vector epilogue stores every element
@@ -454,8 +470,8 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
       rows_per_img = A.W / nh->imgs;
     }
     NormStatsReq ns;
-    if (p.splits == 1) {
-      // statistics folded into the GEMM epilogue: one slab per M tile
+    if (p.splits == 1 || p.fixup) {
+      // statistics folded into the GEMM epilogue (of the last CTA per tile when split-K): one slab per M tile
       if (conv_mode) slabs_per_img = (long long)p.tiles_h * p.tiles_w;
       else if (rows_per_img > 0 && rows_per_img % GEMM_BM == 0) slabs_per_img = rows_per_img / GEMM_BM;
       ns.lg = (p.BN + cpg - 1) / cpg + 1;  // groups that can overlap BN consecutive columns
@@ -482,7 +498,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
       ns.imgs = imgs;
       ns.inv_count = (float)(1.0 / ((double)rows_per_img * cpg));
       ns.eps = nh->eps;
-      if (p.splits == 1) p.ns = ns;
+      if (p.splits == 1 || p.fixup) p.ns = ns;
       else rp.ns = ns;
       nh->req = ns;
     }
@@ -498,7 +514,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
                                "gemm_tf32_kernel launch");
     if (rc) return rc;
     c->launches++;
-    if (p.splits > 1) {
+    if (p.splits > 1 && !p.fixup) {
       rc = c->check(launch_splitk_reduce(rp, c->stream), "splitk_reduce launch");
       if (rc) return rc;
       c->launches++;
@@ -625,7 +641,7 @@ static std::vector<TileCfg> tune_candidates(int sm, long long m_tiles, int N, in
 static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
                     int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh = nullptr) {
   const bool allow_split = !p.geglu && A.batch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) && p.alpha == 1.0f &&
-                           p.ln.partial == nullptr;
+                           (p.ln.partial == nullptr || c->splitk_fixup);
   const bool tunable = c->autotune && force_bn <= 0 && force_splits <= 0 && c->gemm_debug == 0 && c->force_stages == 0;
   if (!tunable) return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, force_bn, force_splits, flops, nh, nullptr, 0);
   if (c->dry_run) {
@@ -713,7 +729,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     // A split-K candidate cannot leave norm statistics in its epilogue: the consumer then runs the
     // stand-alone fused norm (~18 us) instead of the normalise-only pass (~6 us) or, for a folded
     // LayerNorm, instead of nothing at all.  Charge that to the candidate (measured, profiles/).
-    if (nh && nh->G > 0 && c->producer_stats == 1 && cand.splits > 1)
+    if (nh && nh->G > 0 && c->producer_stats == 1 && cand.splits > 1 && !c->splitk_fixup)
       ms_c += (nh->G == 1 && c->ln_fold) ? 0.018f : 0.012f;
     if (ms_c < best_ms) {
       best_ms = ms_c;

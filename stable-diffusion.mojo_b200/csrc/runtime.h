@@ -58,6 +58,7 @@ using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 struct KernelTimer;  // optional per-launch CUDA-event timing (bench roofline leg)
 struct TuneCache;    // per-context GEMM tile autotuning results (runtime.cu)
+constexpr int kTileTickets = 1 << 16;
 constexpr size_t kFlushBytes = 192u << 20;  // > L2: written before every autotune timing run
 
 // Request to the producer of an activation: "the next consumer normalises this tensor with G groups
@@ -98,6 +99,8 @@ struct Ctx {
   int gemm_debug = 0;       // lab only: bit0 skip MMAs, bit1 skip A loads, bit2 skip B loads (results invalid)
   unsigned int* ticket = nullptr;  // zero-initialised device counters for last-block reductions
   int bench_stats_groups = 0;      // lab: tsd_bench_conv / tsd_bench_gemm request norm statistics with this many groups
+  unsigned int* tile_tickets = nullptr;  // zero-initialised per-tile arrival counters of the split-K fix-up
+  int splitk_fixup = 0;            // 1: split-K partials reduced by the last CTA of each tile (measured slower than the separate reduce kernel: serial tail)
   unsigned int* norm_bar = nullptr;  // zero-initialised barrier words of the fused norm (elementwise.cuh)
   TuneCache* tune = nullptr;
   void* flush_buf = nullptr;

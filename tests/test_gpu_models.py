@@ -129,6 +129,7 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
     {"autotune": 0},                      # cost-model tile choice only
     {"autotune": 0, "conv_halo": 2, "halo_min_w": 8, "halo_min_h": 8},  # halo convolution kernel everywhere
     {"gemm_cg": 1},                       # single CTAs only (no cta_group::2 pairs)
+    {"splitk_fixup": 1},                  # split-K reduced in-kernel by the last CTA of each tile
 ])
 def test_unet8_execution_switches(ctx, diff8, golden_small, opts):
     """Every execution-plan switch computes the same UNet step (to TF32 rounding level): the
@@ -154,7 +155,7 @@ def test_unet64_switches_agree_at_full_size(ctx, diff64):
     cx = rng.standard_normal((77, 768), dtype=np.float32)
     t = host_sampler.get_time_embedding(500.0)
     y_default = diff64.forward(x, cx, t)
-    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}):
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}):
         old = {k: ctx.get_option(k) for k in opts}
         for k, v in opts.items():
             ctx.set_option(k, v)
