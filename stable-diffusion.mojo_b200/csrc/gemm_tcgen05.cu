@@ -477,7 +477,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) tr[0] = clock64();
 
   const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
 
   // 1024 B aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)

@@ -887,7 +887,7 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
                   int round_tf32, const NormStatsReq* pre) {
   if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
   if (pre != nullptr && pre->partial != nullptr && !upsample && pre->G == G && pre->C == C && pre->imgs == N &&
-      norm_apply_partial_supported(C, G)) {
+      c->gn_partial && G <= c->gn_partial_max_groups && norm_apply_partial_supported(C, G)) {
     // the producer left per-tile partial sums: one normalise pass that folds them per block
     if (!c->dry_run) {
       TimedScope ts(c, FAM_NORM, 0);

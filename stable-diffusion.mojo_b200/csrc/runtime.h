@@ -109,6 +109,8 @@ struct Ctx {
   int halo_min_w = 16, halo_min_h = 18;  // lab: smallest image the halo TMA box is used on
   int tune_verbose = 0;
   int tune_flush = 0;              // 1: flush L2 before every autotune timing run (weights AND activations cold)
+  int gn_partial = 1;              // GroupNorm consumes producer-side partial statistics (0: always the stand-alone fused norm)
+  int gn_partial_max_groups = 64;  // ... only up to this many groups (every block folds all groups of its image)
   int ln_fold = 1;                 // fold global-statistics LayerNorm into the consuming GEMM epilogue (0: separate pass)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
