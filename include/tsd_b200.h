@@ -44,6 +44,7 @@ extern "C" {
 typedef struct tsd_ctx tsd_ctx;             /* device + stream + workspace */
 typedef struct tsd_diffusion tsd_diffusion; /* Diffusion (diffusion.mojo:294-318) */
 typedef struct tsd_decoder tsd_decoder;     /* VAE Decoder (vae.mojo:162-250) */
+typedef struct tsd_clip tsd_clip;           /* CLIP text encoder (clip.mojo:56-109) */
 
 /* ---- context ------------------------------------------------------------------------ */
 int32_t tsd_init(int32_t device, tsd_ctx** out);
@@ -189,6 +190,24 @@ int32_t tsd_decoder_get_param(const tsd_decoder* m, int32_t i, float* out);
 int32_t tsd_decoder_forward(tsd_decoder* m, const float* z, int32_t n, int32_t rescale, float* img);
 int32_t tsd_decoder_forward_dev(tsd_decoder* m, const float* z, int32_t n, int32_t rescale,
                                 float* img);
+
+/* ---- CLIP text encoder ------------------------------------------------
+ * Replaces CLIP.__init__ / CLIP.forward (clip.mojo:70-109): ClipEmbedding (token table + position),
+ * 12 ClipPlayer layers (LayerNorm, causal 12-head Self_Attention, quick-GELU MLP; clip.mojo:36-53) and
+ * the final LayerNorm.  n_vocab / n_layers <= 0 select the reference's 49408 / 12.  Parameters in
+ * struct-declaration order: embedding.token_embedding.weight [n_vocab][768], embedding.position_embedding
+ * [77][768], then per layer in_proj / out_proj / layer4 / layer5 (weight [out][in], bias).
+ * tokens: up to 77 int32 ids, zero-padded to 77 as clip.mojo:90-92 does; context: [77][768] fp32.
+ * "softmax_axis" / "layernorm_mode" apply as in the UNet; the causal mask is the standard triu(1). */
+int32_t tsd_clip_create(tsd_ctx* ctx, int32_t n_vocab, int32_t n_layers, tsd_clip** out);
+int32_t tsd_clip_destroy(tsd_clip* m);
+int64_t tsd_clip_num_params(const tsd_clip* m);
+int32_t tsd_clip_load_weights(tsd_clip* m, const float* blob, int64_t n_floats);
+int32_t tsd_clip_init_random(tsd_clip* m, uint64_t seed);
+int32_t tsd_clip_param_count(const tsd_clip* m);
+const char* tsd_clip_param_name(const tsd_clip* m, int32_t i, int64_t* offset, int64_t* numel);
+int32_t tsd_clip_forward(tsd_clip* m, const int32_t* tokens, int32_t n_tokens, float* context);
+int32_t tsd_clip_forward_dev(tsd_clip* m, const int32_t* tokens, int32_t n_tokens, float* context);
 
 /* ---- whole denoising loop on the device, pipeline.mojo:86-122 ------------------------------- */
 typedef struct tsd_loop_params {

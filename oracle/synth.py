@@ -142,6 +142,20 @@ def decoder_specs():
     return sp
 
 
+def clip_specs(n_vocab: int = 49408, n_layers: int = 12, n_embed: int = 768, n_tokens: int = 77):
+    """CLIP text encoder (clip.mojo:5-15, 23-34, 56-87) in struct-declaration order.  The embedding
+    table and the position embedding are stored flat (device kind P_VEC); LayerNorm owns no tensor."""
+    sp = [("embedding.token_embedding.weight", (n_vocab * n_embed,), np.float32(1.0)),
+          ("embedding.position_embedding", (n_tokens * n_embed,), np.float32(0.0))]
+    for l in range(1, n_layers + 1):
+        b = f"player{l}"
+        _linear(sp, b + ".layer2.in_proj", n_embed, 3 * n_embed, True)
+        _linear(sp, b + ".layer2.out_proj", n_embed, n_embed, True)
+        _linear(sp, b + ".layer4", n_embed, 4 * n_embed, True)
+        _linear(sp, b + ".layer5", 4 * n_embed, n_embed, True)
+    return sp
+
+
 def num_params(specs) -> int:
     return int(sum(int(np.prod(s)) for _, s, _ in specs))
 

@@ -203,10 +203,12 @@ class Ops:
         return e / e.sum(axis=axis, keepdims=True)
 
     # attention core, helpers/attention.mojo:46-62 / 105-115; q (h,Tq,d), k,v (h,Tk,d) -> (Tq, h*d)
-    def attention_core(self, q, k, v):
+    def attention_core(self, q, k, v, causal=False):
         h, tq, d = q.shape
         tk = k.shape[1]
         key_axis = self.sw.softmax_axis == "key"
+        if causal and self.backend == "c32":
+            raise NotImplementedError("the C restatement covers the per-step path only (no causal mask)")
         if self.backend == "c32":
             q, k, v = _f32(q), _f32(k), _f32(v)
             out = np.empty((tq, h * d), np.float32)
@@ -214,20 +216,29 @@ class Ops:
             return out
         out = np.empty((tq, h, d), self.dtype)
         for i in range(h):  # one head at a time bounds the T x T score plane
-            s = (self.arr(q[i]) @ self.arr(k[i]).T) / np.sqrt(self.dtype(d))
+            s = self.arr(q[i]) @ self.arr(k[i]).T
+            if causal:
+                # Self_Attention.forward, helpers/attention.mojo:48-56: masked_fill(triu(1), -inf) before the
+                # 1/sqrt(d) scaling; triu(1) taken as the standard strict upper triangle (class G)
+                s = np.where(np.triu(np.ones((tq, tk), bool), 1), -np.inf, s)
+            s = s / np.sqrt(self.dtype(d))
             p = self.softmax(s[None], dim=1 if key_axis else 2)[0]
             out[:, i, :] = p @ self.arr(v[i])
         return out.reshape(tq, h * d)
 
     # Self_Attention.forward, helpers/attention.mojo:26-65; x (T,C)
-    def self_attention(self, x, n_heads, w_in, b_in, w_out, b_out):
+    def self_attention(self, x, n_heads, w_in, b_in, w_out, b_out, causal=False):
         t, c = x.shape
         qkv = self.linear(x, w_in, b_in)                       # (T,3C)
         q, k, v = (np.ascontiguousarray(qkv[:, i * c:(i + 1) * c]) for i in range(3))   # chunk(2,3) :29
         d = c // n_heads
         q, k, v = (a.reshape(n_heads, t, d) for a in (q, k, v))  # raw reshape, no transpose (Q4) :30-44
-        o = self.attention_core(q, k, v)
+        o = self.attention_core(q, k, v, causal=causal)
         return self.linear(o, w_out, b_out)
+
+    def quick_gelu(self, x):  # ClipPlayer.forward, clip.mojo:49-50 (intent: x * sigmoid(1.702 x))
+        x = self.arr(x)
+        return x / (1.0 + np.exp(-1.702 * x))
 
     # Cross_Attention.forward, helpers/attention.mojo:96-118; x (T,C), context (Tk,Dc)
     def cross_attention(self, x, context, n_heads, wq, bq, wk, bk, wv, bv, wo, bo):
@@ -243,6 +254,33 @@ class Ops:
 # ---------------------------------------------------------------------------------------------
 # blocks and models
 # ---------------------------------------------------------------------------------------------
+def clip_forward(ops: Ops, W, tokens, n_embed=768, n_tokens=77, n_heads=12, n_layers=12):
+    """CLIP.forward, clip.mojo:88-109 (ClipEmbedding :17-20, ClipPlayer :36-53): token ids -> (77, 768).
+    LayerNorm here is ops.layer_norm, i.e. the reference's GroupNorm(1, C) over the whole tensor unless the
+    per-token switch is set; the softmax axis follows ops.sw (Q3); the causal mask is the standard one."""
+    tok = np.zeros(n_tokens, np.int64)          # reshaped_tokens *= 0 ; set_items(...)  :90-92
+    t_in = np.asarray(tokens).reshape(-1)
+    tok[:t_in.size] = t_in
+    table = W["embedding.token_embedding.weight"].reshape(-1, n_embed)
+    pos = W["embedding.position_embedding"].reshape(n_tokens, n_embed)
+    x = ops.arr(table[tok]) + ops.arr(pos)                                   # :17-20
+    for l in range(1, n_layers + 1):
+        b = f"player{l}"
+        residue = x
+        h = ops.layer_norm(x)                                                # :38-41
+        h = ops.self_attention(h, n_heads, W[b + ".layer2.in_proj.weight"], W[b + ".layer2.in_proj.bias"],
+                               W[b + ".layer2.out_proj.weight"], W[b + ".layer2.out_proj.bias"], causal=True)  # :42
+        x = h + residue                                                      # :43
+        residue = x
+        h = ops.layer_norm(x)                                                # :45-47
+        h = ops.linear(h, W[b + ".layer4.weight"], W[b + ".layer4.bias"])    # :48
+        h = ops.quick_gelu(h)                                                # :49-50
+        h = ops.linear(h, W[b + ".layer5.weight"], W[b + ".layer5.bias"])    # :51
+        x = h + residue                                                      # :52
+    return ops.layer_norm(x)                                                 # :106-108
+
+
+
 def time_embedding_mlp(ops: Ops, W, t):
     """Time_Embedding.forward, diffusion.mojo:17-21; t (320,) -> (1280,)"""
     h = ops.linear(ops.arr(t)[None, :], W["time_embed.layer1.weight"], W["time_embed.layer1.bias"])

@@ -197,6 +197,69 @@ int32_t tsd_decoder_forward_dev(tsd_decoder* d, const float* z, int32_t n, int32
   return d->m.forward(z, n, rescale, img, false);
 }
 
+// ---- CLIP text encoder (clip.mojo:56-109) ------------------------------------------------------
+int32_t tsd_clip_create(tsd_ctx* h, int32_t n_vocab, int32_t n_layers, tsd_clip** out) {
+  if (!h || !out) return TSD_ERR_INVALID;
+  *out = nullptr;
+  Guard g(h);
+  tsd_clip* d = new tsd_clip();
+  d->m.h = h;
+  d->m.c = h->c;
+  if (n_vocab > 0) d->m.n_vocab = n_vocab;
+  if (n_layers > 0) d->m.n_layers = n_layers;
+  int rc = d->m.create();
+  if (rc) {
+    d->m.destroy();
+    delete d;
+    return rc;
+  }
+  *out = d;
+  return TSD_OK;
+}
+int32_t tsd_clip_destroy(tsd_clip* d) {
+  if (!d) return TSD_ERR_INVALID;
+  {
+    Guard g(d->m.h);
+    d->m.destroy();
+  }
+  delete d;
+  return TSD_OK;
+}
+int64_t tsd_clip_num_params(const tsd_clip* d) { return d ? d->m.ps.total : 0; }
+int32_t tsd_clip_load_weights(tsd_clip* d, const float* blob, int64_t n_floats) {
+  if (!d || !blob) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  return d->m.ps.load(blob, n_floats);
+}
+int32_t tsd_clip_init_random(tsd_clip* d, uint64_t seed) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  return d->m.ps.init_random(seed);
+}
+int32_t tsd_clip_param_count(const tsd_clip* d) { return d ? (int32_t)d->m.ps.params.size() : 0; }
+const char* tsd_clip_param_name(const tsd_clip* d, int32_t i, int64_t* offset, int64_t* numel) {
+  if (!d || i < 0 || i >= (int32_t)d->m.ps.params.size()) return nullptr;
+  const Param& p = d->m.ps.params[i];
+  if (offset) *offset = p.offset;
+  if (numel) *numel = p.numel;
+  return p.name.c_str();
+}
+int32_t tsd_clip_forward(tsd_clip* d, const int32_t* tokens, int32_t n_tokens, float* context) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  int rc = d->m.forward(tokens, n_tokens, context, true);
+  if (rc) {
+    cudaStreamSynchronize(d->m.c->stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
+int32_t tsd_clip_forward_dev(tsd_clip* d, const int32_t* tokens, int32_t n_tokens, float* context) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  return d->m.forward(tokens, n_tokens, context, false);
+}
+
 // ---- loop -----------------------------------------------------------------------------------
 int32_t tsd_generate_latents(tsd_diffusion* d, const tsd_loop_params* lp, const float* latents_in,
                              const float* context, int32_t n_ctx, int32_t n, float* latents_out) {

@@ -978,6 +978,7 @@ __global__ void unary_kernel(const float* __restrict__ x, float* __restrict__ y,
     if (op == UNARY_SILU) v = v / (1.0f + expf(-v));
     else if (op == UNARY_GELU) v = gelu_f(v);
     else if (op == UNARY_SCALE) v = v * scalar;
+    else if (op == UNARY_QUICKGELU) v = v / (1.0f + expf(-1.702f * v));  // x * sigmoid(1.702 x), clip.mojo:49-50
     y[i] = v;
   }
 }
@@ -1134,8 +1135,10 @@ __global__ void gemv_kernel(const float* __restrict__ x, int K, const float* __r
 // softmax (unfused attention path)
 // ------------------------------------------------------------------------------------------
 // axis 0: per column j, over rows.  block (32, 8): 32 columns, 8 row lanes.
+// `causal`: entry (row i = query, column j = key) is masked (= -inf before the softmax) when j > i
+// (Self_Attention.forward with causal_mask, helpers/attention.mojo:48-56, with the standard triu(1)).
 __global__ void softmax_colstats_kernel(const float* __restrict__ S, int R, int Cc, int ld,
-                                        float scale, float2* __restrict__ st) {
+                                        float scale, float2* __restrict__ st, int causal) {
   __shared__ float sm_m[8][33], sm_l[8][33];
   const int b = blockIdx.y;
   const int j = blockIdx.x * 32 + threadIdx.x;
@@ -1143,6 +1146,7 @@ __global__ void softmax_colstats_kernel(const float* __restrict__ S, int R, int 
   float m = -FLT_MAX, l = 0.f;
   if (j < Cc) {
     for (int i = threadIdx.y; i < R; i += 8) {
+      if (causal && j > i) continue;
       float v = base[(long long)i * ld + j] * scale;
       if (v > m) {
         l = l * expf(m - v) + 1.0f;
@@ -1160,11 +1164,11 @@ __global__ void softmax_colstats_kernel(const float* __restrict__ S, int R, int 
     for (int t = 1; t < 8; ++t) M = fmaxf(M, sm_m[t][threadIdx.x]);
     float L = 0.f;
     for (int t = 0; t < 8; ++t) L += sm_l[t][threadIdx.x] * expf(sm_m[t][threadIdx.x] - M);
-    st[(long long)b * Cc + j] = make_float2(M, 1.0f / L);
+    st[(long long)b * Cc + j] = make_float2(M, L > 0.f ? 1.0f / L : 0.f);  // a fully masked column (j >= R) yields zeros
   }
 }
 __global__ void softmax_colapply_kernel(float* __restrict__ S, int R, int Cc, int ld, float scale,
-                                        const float2* __restrict__ st, long long total) {
+                                        const float2* __restrict__ st, long long total, int causal) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int j = (int)(i % Cc);
@@ -1172,12 +1176,17 @@ __global__ void softmax_colapply_kernel(float* __restrict__ S, int R, int Cc, in
     long long b = t / R;
     float2 s = st[b * Cc + j];
     float* p = S + t * ld + j;
-    *p = expf(*p * scale - s.x) * s.y;
+    const int r = (int)(t - b * R);
+    *p = (causal && j > r) ? 0.f : expf(*p * scale - s.x) * s.y;
   }
 }
 // axis 1: block per row
-__global__ void softmax_row_kernel(float* __restrict__ S, int Cc, int ld, float scale) {
+__global__ void softmax_row_kernel(float* __restrict__ S, int Cc_all, int ld, float scale, int R, int causal) {
   float* row = S + (long long)blockIdx.x * ld;
+  const int r = blockIdx.x % R;
+  const int Cc = (causal && r + 1 < Cc_all) ? r + 1 : Cc_all;  // causal: keys 0..r only
+  if (causal)
+    for (int j = Cc + threadIdx.x; j < Cc_all; j += blockDim.x) row[j] = 0.f;
   __shared__ float red[32];
   float m = -FLT_MAX;
   for (int j = threadIdx.x; j < Cc; j += blockDim.x) m = fmaxf(m, row[j] * scale);
@@ -1196,6 +1205,19 @@ __global__ void softmax_row_kernel(float* __restrict__ S, int Cc, int ld, float 
   for (int i = 0; i < (blockDim.x >> 5); ++i) l += red[i];
   const float inv = 1.0f / l;
   for (int j = threadIdx.x; j < Cc; j += blockDim.x) row[j] = expf(row[j] * scale - m) * inv;
+}
+
+// ClipEmbedding.forward (clip.mojo:17-20; Embedding.forward, helpers/utils.mojo:2032-2046):
+// out[t][:] = token_table[tokens[t]][:] + position[t][:]
+__global__ void clip_embed_kernel(const int* __restrict__ tokens, const float4* __restrict__ table,
+                                  const float4* __restrict__ pos, float4* __restrict__ out, int T, int d4) {
+  const long long total = (long long)T * d4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / d4), c = (int)(i - (long long)t * d4);
+    const float4 a = table[(long long)tokens[t] * d4 + c], b = pos[i];
+    out[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
 }
 
 // Holds the stream busy for `ns` nanoseconds so that the host can enqueue a whole step behind it
@@ -1562,18 +1584,27 @@ cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const 
 }
 
 cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, float scale,
-                           float* col_scratch, cudaStream_t s) {
+                           float* col_scratch, cudaStream_t s, int causal) {
   if (axis == 0) {
     dim3 grid((Cc + 31) / 32, B), block(32, 8);
     float2* st = reinterpret_cast<float2*>(col_scratch);
-    softmax_colstats_kernel<<<grid, block, 0, s>>>(S, R, Cc, ld, scale, st);
+    softmax_colstats_kernel<<<grid, block, 0, s>>>(S, R, Cc, ld, scale, st, causal);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     long long total = (long long)B * R * Cc;
-    softmax_colapply_kernel<<<grid_for(total, 256), 256, 0, s>>>(S, R, Cc, ld, scale, st, total);
+    softmax_colapply_kernel<<<grid_for(total, 256), 256, 0, s>>>(S, R, Cc, ld, scale, st, total, causal);
   } else {
-    softmax_row_kernel<<<B * R, 256, 0, s>>>(S, Cc, ld, scale);
+    softmax_row_kernel<<<B * R, 256, 0, s>>>(S, Cc, ld, scale, R, causal);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clip_embed(const int* tokens, const float* table, const float* pos, float* out, int T, int d,
+                              cudaStream_t s) {
+  if (d % 4) return cudaErrorInvalidValue;
+  clip_embed_kernel<<<grid_for((long long)T * (d / 4), 256), 256, 0, s>>>(tokens, reinterpret_cast<const float4*>(table),
+                                                                        reinterpret_cast<const float4*>(pos),
+                                                                        reinterpret_cast<float4*>(out), T, d / 4);
   return cudaGetLastError();
 }
 

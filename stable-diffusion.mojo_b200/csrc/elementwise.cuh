@@ -78,7 +78,7 @@ cudaError_t launch_norm_fused(const float* x, float* y, int N, long long pixels,
 cudaError_t launch_fill_uniform(float* p, long long n, uint64_t seed, float lo, float hi, cudaStream_t s);
 
 // ---- simple elementwise --------------------------------------------------------------------
-enum UnaryOp { UNARY_SILU = 0, UNARY_GELU = 1, UNARY_SCALE = 2, UNARY_COPY = 3 };
+enum UnaryOp { UNARY_SILU = 0, UNARY_GELU = 1, UNARY_SCALE = 2, UNARY_COPY = 3, UNARY_QUICKGELU = 4 };
 cudaError_t launch_unary(const float* x, float* y, long long n, int op, float scalar, cudaStream_t s);
 cudaError_t launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t s);
 // y[p][c] = x[p][c] + v[c]
@@ -100,9 +100,11 @@ cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const 
 // axis 0: normalise each column over rows (reference Softmax(dim=2) behaviour, Q3)
 // axis 1: normalise each row over columns (standard attention)
 cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, float scale,
-                           float* col_scratch, cudaStream_t s);
+                           float* col_scratch, cudaStream_t s, int causal = 0);
 
 // keeps the stream busy for `ns` nanoseconds (profiling aid)
+cudaError_t launch_clip_embed(const int* tokens, const float* table, const float* pos, float* out, int T, int d,
+                              cudaStream_t s);
 cudaError_t launch_spin(long long ns, cudaStream_t s);
 
 // ---- DDPM step (+ optional CFG combine), sampler.mojo:75-109, pipeline.mojo:117-119 --------

@@ -147,6 +147,27 @@ struct Decoder {
   int forward(const float* z, int n, int rescale, float* img, bool host_ptrs);
 };
 
+// CLIP text encoder (clip.mojo:5-109) - models_clip.cu
+struct Clip {
+  static constexpr int kMaxLayers = 24;
+  tsd_ctx* h = nullptr;
+  Ctx* c = nullptr;
+  int n_vocab = 49408, n_embed = 768, n_tokens = 77, n_heads = 12, n_layers = 12;  // clip.mojo:71-83
+  ParamStore ps;
+  int tok = -1, pos = -1;
+  struct Layer {
+    int in_proj = -1, out_proj = -1, fc1 = -1, fc2 = -1;
+  } layer[kMaxLayers];
+  int* tokens_dev = nullptr;
+  float* out_dev = nullptr;  // [n_tokens][n_embed]
+
+  int create();
+  void destroy();
+  size_t workspace_bytes() const;
+  int encode();  // tokens_dev -> out_dev
+  int forward(const int32_t* tokens, int n, float* out, bool host_ptrs);
+};
+
 int generate_latents(Diffusion& m, const tsd_loop_params& lp, const float* latents_in, const float* context,
                      int n_ctx, int n, float* latents_out);
 // next: in = (G, eps) of the norm that will consume `out`; out = next->stats when the last conv produced them
@@ -160,4 +181,7 @@ struct tsd_diffusion {
 };
 struct tsd_decoder {
   tsd::Decoder m;
+};
+struct tsd_clip {
+  tsd::Clip m;
 };

@@ -956,7 +956,6 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
 // attention
 // ------------------------------------------------------------------------------------------
 int op_attention_unfused(Ctx* c, const AttnArgs& a) {
-  if (a.causal) return c->fail(TSD_ERR_INVALID, "attention: causal mask is CLIP-only (out of scope)");
   const int C = a.heads * a.d;
   const int ldS = (a.Tk + 3) / 4 * 4;
   const float scale = 1.0f / sqrtf((float)a.d);
@@ -985,7 +984,7 @@ int op_attention_unfused(Ctx* c, const AttnArgs& a) {
     if (rc) return rc;
     if (!c->dry_run) {
       TimedScope ts(c, FAM_ATTN, 0);
-      rc = c->check(launch_softmax(S, BH, a.Tq, a.Tk, ldS, a.softmax_axis, 1.0f, cst, c->stream),
+      rc = c->check(launch_softmax(S, BH, a.Tq, a.Tk, ldS, a.softmax_axis, 1.0f, cst, c->stream, a.causal),
                     "softmax launch");
       if (rc) return rc;
       c->launches += 2;

@@ -137,6 +137,15 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_decoder_get_param", i32, vp, i32, fp)
     sig("tsd_decoder_forward", i32, vp, fp, i32, i32, fp)
     sig("tsd_decoder_forward_dev", i32, vp, fp, i32, i32, fp)
+    sig("tsd_clip_create", i32, vp, i32, i32, C.POINTER(vp))
+    sig("tsd_clip_destroy", i32, vp)
+    sig("tsd_clip_num_params", i64, vp)
+    sig("tsd_clip_load_weights", i32, vp, fp, i64)
+    sig("tsd_clip_init_random", i32, vp, C.c_uint64)
+    sig("tsd_clip_param_count", i32, vp)
+    sig("tsd_clip_param_name", C.c_char_p, vp, i32, c_i64_p, c_i64_p)
+    sig("tsd_clip_forward", i32, vp, vp, i32, fp)
+    sig("tsd_clip_forward_dev", i32, vp, vp, i32, fp)
     sig("tsd_generate_latents", i32, vp, C.POINTER(LoopParams), fp, fp, i32, i32, fp)
     sig("tsd_bench_gemm", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)
     sig("tsd_bench_conv", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)

@@ -335,6 +335,24 @@ class Diffusion(_Model):
         return out
 
 
+class Clip(_Model):
+    """tsd_clip: CLIP text encoder (clip.mojo:56-109): token ids -> the (77, 768) context."""
+    _prefix = "clip"
+
+    def __init__(self, ctx: Context, n_vocab: int = 0, n_layers: int = 0):
+        self.ctx = ctx
+        m = C.c_void_p()
+        ctx._ck(ctx.L.tsd_clip_create(ctx.h, int(n_vocab), int(n_layers), C.byref(m)))
+        self.m = m
+
+    def forward(self, tokens) -> np.ndarray:
+        """CLIP.forward (clip.mojo:88-109): up to 77 token ids (zero-padded) -> (77, 768)."""
+        tok = np.ascontiguousarray(np.asarray(tokens).reshape(-1), np.int32)
+        out = np.empty((77, 768), np.float32)
+        self.ctx._ck(self.ctx.L.tsd_clip_forward(self.m, tok.ctypes.data_as(C.c_void_p), tok.size, _p(out)))
+        return out
+
+
 class Decoder(_Model):
     """tsd_decoder: VAE Decoder (vae.mojo:162-250)."""
     _prefix = "decoder"

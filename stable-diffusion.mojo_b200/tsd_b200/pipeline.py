@@ -1,20 +1,21 @@
 """pipeline.generate (reference pipeline.mojo:13-128) over the C ABI.
 
-The prompt -> CLIP context stage is outside the hot path (CLIP/tokenizer are
-"next"), so `generate` takes the 77x768 context(s) the reference computes at pipeline.mojo:41-53.
-Everything from there on - the denoising loop, CFG, sampler steps, the VAE decode and the final
-rescale/clamp - runs on the device."""
+`generate` takes the 77x768 context(s) the reference computes at pipeline.mojo:41-53, or - with
+`with_clip=True` - the prompt's token ids, which the device CLIP text encoder (clip.mojo:56-109,
+SURVEY section 8 row f1) turns into the context; the tokenizer (row f4) stays outside.  Everything
+from there on - the denoising loop, CFG, sampler steps, the VAE decode and the final rescale/clamp -
+runs on the device."""
 from __future__ import annotations
 
 import numpy as np
 
-from .api import Context, Decoder, Diffusion
+from .api import Clip, Context, Decoder, Diffusion
 from .sampler import DDPMSampler, get_time_embedding
 
 
 class Pipeline:
     def __init__(self, ctx: Context, image_size: int = 512, max_images: int = 1, cfg: bool = True, seed: int = 0,
-                 weights=None):
+                 weights=None, with_clip: bool = False, clip_vocab: int = 0, clip_layers: int = 0):
         if image_size % 32:
             raise ValueError("image_size must be a multiple of 32 (latent side a multiple of 4)")
         self.ctx = ctx
@@ -24,12 +25,23 @@ class Pipeline:
         self.max_images = max_images
         self.diffusion = Diffusion(ctx, self.side, self.side, max_batch=max_images * (2 if cfg else 1))
         self.decoder = Decoder(ctx, self.side, self.side, max_batch=max_images)
+        self.clip = Clip(ctx, clip_vocab, clip_layers) if with_clip else None
         if weights is None:
             self.diffusion.init_random(seed)
             self.decoder.init_random(seed + 1)
+            if self.clip:
+                self.clip.init_random(seed + 2)
         else:
             self.diffusion.load_weights(weights[0])
             self.decoder.load_weights(weights[1])
+            if self.clip:
+                self.clip.load_weights(weights[2])
+
+    def encode_tokens(self, tokens) -> np.ndarray:
+        """clip.forward(tokens) of pipeline.mojo:45-53: token ids (<= 77, zero-padded) -> (77, 768) context."""
+        if self.clip is None:
+            raise ValueError("pipeline was created with with_clip=False")
+        return self.clip.forward(tokens)
 
     def schedule(self, inference_steps: int, time_as_written: bool = False):
         s = DDPMSampler()
@@ -41,9 +53,14 @@ class Pipeline:
                  seed_val: int = 0, latents=None, noise=None, decode: bool = True, rescale: bool = True):
         """Returns (images (n,3,S,S) in [0,255], latents (n,4,S/8,S/8)).  context (n|1,77,768);
         with CFG pass uncond_context of the same shape.  latents/noise default to seeded N(0,1)."""
-        context = np.asarray(context, np.float32)
-        if context.ndim == 2:
-            context = context[None]
+        def as_context(c):
+            c = np.asarray(c)
+            if np.issubdtype(c.dtype, np.integer):      # token ids -> device CLIP
+                return self.encode_tokens(c)[None]
+            c = c.astype(np.float32, copy=False)
+            return c[None] if c.ndim == 2 else c
+
+        context = as_context(context)
         n = self.max_images if latents is None else np.asarray(latents).shape[0]
         rng = np.random.default_rng(seed_val)
         if latents is None:
@@ -55,10 +72,7 @@ class Pipeline:
             raise ValueError("pipeline was created with cfg=False")
         ctx_rows = context
         if use_cfg:
-            u = np.asarray(uncond_context, np.float32)
-            if u.ndim == 2:
-                u = u[None]
-            ctx_rows = np.concatenate([context, u], axis=0)
+            ctx_rows = np.concatenate([context, as_context(uncond_context)], axis=0)
         ts, temb, coef = self.schedule(inference_steps)
         lat = self.diffusion.generate_latents(latents, ctx_rows, ts, temb, coef, noise, cfg=use_cfg,
                                               cfg_scale=cfg_scale)

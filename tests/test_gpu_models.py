@@ -303,3 +303,78 @@ def test_pipeline_generate_small(ctx):
     assert np.isfinite(img).all() and img.min() >= 0 and img.max() <= 255
     img2, lat2 = p.generate(c, u, cfg_scale=7.5, inference_steps=2, seed_val=9)
     assert np.array_equal(lat, lat2) and np.array_equal(img, img2)
+
+
+# ---- CLIP text encoder on the device --------------------------------
+@pytest.fixture(scope="module")
+def clip_small(ctx):
+    from tsd_b200.api import Clip
+    m = Clip(ctx, n_vocab=1000, n_layers=3)
+    m.init_random(77)
+    yield m
+    m.close()
+
+
+def test_clip_param_table_matches_specs(clip_small):
+    specs = synth.clip_specs(1000, 3)
+    table = clip_small.param_table()
+    assert [t[0] for t in table] == [s[0] for s in specs]
+    assert [t[2] for t in table] == [int(np.prod(s[1])) for s in specs]
+    assert clip_small.num_params() == synth.num_params(specs)
+
+
+@pytest.mark.parametrize("axis,ln_mode", [(0, 0), (1, 1), (1, 0), (0, 1)])
+def test_clip_matches_oracle(ctx, clip_small, axis, ln_mode):
+    """CLIP.forward through the C ABI vs the fp64 oracle, reference-faithful defaults (column softmax,
+    global LayerNorm) and the 'intended' switches; causal mask, quick-GELU, zero-padded token row."""
+    W = synth.SynthWeights(synth.clip_specs(1000, 3), 77)
+    tokens = np.random.default_rng(4).integers(0, 1000, 23)
+    sw = O.Switches(softmax_axis="key" if axis else "query", layernorm="token" if ln_mode else "global")
+    ref = O.clip_forward(O.Ops("np", np.float64, sw), W, tokens, n_layers=3)
+    old = (ctx.get_option("softmax_axis"), ctx.get_option("layernorm_mode"))
+    ctx.set_option("softmax_axis", axis)
+    ctx.set_option("layernorm_mode", ln_mode)
+    try:
+        y = clip_small.forward(tokens)
+    finally:
+        ctx.set_option("softmax_axis", old[0])
+        ctx.set_option("layernorm_mode", old[1])
+    e = relerr(y, ref)
+    print(f"clip (3 layers) softmax_axis={axis} layernorm_mode={ln_mode} rel_linf vs fp64 oracle: {e:.2e}")
+    assert y.shape == (77, 768) and e < TOL_MODEL
+
+
+def test_clip_load_weights_and_validation(ctx):
+    from tsd_b200.api import Clip
+    specs = synth.clip_specs(64, 1)
+    blob = synth.random_blob(specs, 9)     # non-zero position embedding
+    m = Clip(ctx, n_vocab=64, n_layers=1)
+    try:
+        with pytest.raises(TsdError):
+            m.forward([1, 2, 3])           # no weights yet
+        m.load_weights(blob)
+        tokens = [5, 63, 0, 17]
+        ref = O.clip_forward(O.Ops("np", np.float64), synth.BlobWeights(specs, blob), tokens, n_layers=1)
+        assert relerr(m.forward(tokens), ref) < TOL_MODEL
+        with pytest.raises(TsdError):
+            m.forward([64])                # token id outside the vocabulary
+        with pytest.raises(TsdError):
+            m.forward(list(range(60)) + list(range(60)))   # more than 77 tokens
+    finally:
+        m.close()
+
+
+def test_pipeline_generate_from_token_ids(ctx):
+    """pipeline.generate with the prompt given as token ids: device CLIP -> context -> loop -> decode equals
+    the same pipeline fed the context computed by the same CLIP handle (pipeline.mojo:41-53, 86-128)."""
+    p = Pipeline(ctx, image_size=64, max_images=1, cfg=True, seed=3, with_clip=True, clip_vocab=500, clip_layers=2)
+    try:
+        cond, uncond = np.arange(1, 12) % 500, np.zeros(1, np.int64)
+        img_a, lat_a = p.generate(cond, uncond, inference_steps=2, seed_val=5)
+        img_b, lat_b = p.generate(p.encode_tokens(cond), p.encode_tokens(uncond), inference_steps=2, seed_val=5)
+        assert img_a.shape == (1, 3, 64, 64) and np.isfinite(img_a).all()
+        assert np.array_equal(lat_a, lat_b) and np.array_equal(img_a, img_b)
+    finally:
+        p.diffusion.close()
+        p.decoder.close()
+        p.clip.close()

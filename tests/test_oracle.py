@@ -206,3 +206,62 @@ def test_full_size_goldens_present():
         assert os.path.exists(os.path.join(GOLDEN, name)), f"run tools/make_golden.py {name[:-4]}"
     u = np.load(os.path.join(GOLDEN, "unet64.npz"))
     assert u["y"].shape == (4, 64, 64) and np.isfinite(u["y"]).all()
+
+
+# ---- CLIP text encoder ------------------------------------------------
+def test_clip_param_inventory():
+    # clip.mojo:71-83: 49408 x 768 token table, 77 x 768 positions, 12 layers of 7 084 800 parameters
+    assert synth.num_params(synth.clip_specs()) == 49408 * 768 + 77 * 768 + 12 * 7_084_800 == 123_022_080
+
+
+def test_clip_intended_switches_vs_torch():
+    """With the 'intended' switches (key-axis softmax, per-token LayerNorm) the oracle's CLIP layer is the
+    standard pre-LN transformer layer with a causal mask and quick-GELU: cross-checked against an
+    independent torch restatement (raw-reshape head split kept, Q4)."""
+    n_vocab, n_layers, c, t, h = 50, 2, 768, 77, 12
+    specs = synth.clip_specs(n_vocab, n_layers)
+    blob = synth.random_blob(specs, 3)
+    W = synth.BlobWeights(specs, blob)
+    tokens = np.random.default_rng(1).integers(0, n_vocab, 11)
+    ops = O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token"))
+    got = O.clip_forward(ops, W, tokens, n_layers=n_layers)
+
+    tw = lambda name: torch.from_numpy(np.asarray(W[name], np.float64))  # noqa: E731
+    tok = np.zeros(t, np.int64)
+    tok[:tokens.size] = tokens
+    x = tw("embedding.token_embedding.weight").view(-1, c)[torch.from_numpy(tok)] + tw("embedding.position_embedding").view(t, c)
+
+    def ln(v):  # (x - mean) / (std + eps), biased std: helpers/utils.mojo:1868-1870 (not sqrt(var + eps))
+        m = v.mean(-1, keepdim=True)
+        s = ((v - m) ** 2).mean(-1, keepdim=True).sqrt()
+        return (v - m) / (s + 1e-5)
+
+    for l in range(1, n_layers + 1):
+        b = f"player{l}"
+        r = x
+        qkv = ln(x) @ tw(b + ".layer2.in_proj.weight").T + tw(b + ".layer2.in_proj.bias")
+        q, k, v = (qkv[:, i * c:(i + 1) * c].contiguous().view(h, t, c // h) for i in range(3))
+        o = F.scaled_dot_product_attention(q[None], k[None], v[None], is_causal=True)[0]
+        o = o.transpose(0, 1).reshape(t, c)
+        x = o @ tw(b + ".layer2.out_proj.weight").T + tw(b + ".layer2.out_proj.bias") + r
+        r = x
+        y = ln(x) @ tw(b + ".layer4.weight").T + tw(b + ".layer4.bias")
+        y = y * torch.sigmoid(1.702 * y)
+        x = y @ tw(b + ".layer5.weight").T + tw(b + ".layer5.bias") + r
+    ref = ln(x).numpy()
+    assert got.shape == (77, 768)
+    assert relerr(got, ref) < 1e-10
+
+
+def test_clip_default_switches_are_the_reference_deviations():
+    """Default switches keep the reference's deterministic deviations: column softmax over the (unmasked)
+    queries (Q3) and one mean/std over the whole (C, T) tensor (Q5)."""
+    n_vocab, n_layers = 40, 1
+    specs = synth.clip_specs(n_vocab, n_layers)
+    W = synth.BlobWeights(specs, synth.random_blob(specs, 5))
+    tokens = np.arange(20) % n_vocab
+    a = O.clip_forward(O.Ops("np", np.float64), W, tokens, n_layers=n_layers)
+    b = O.clip_forward(O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token")), W, tokens, n_layers=n_layers)
+    assert np.isfinite(a).all() and relerr(a, b) > 1e-3   # genuinely different semantics
+    # global LayerNorm: the output as a whole has zero mean and unit (biased) std
+    assert abs(a.mean()) < 1e-9 and abs(a.std() - 1.0) < 1e-4
