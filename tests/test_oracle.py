@@ -265,3 +265,11 @@ def test_clip_default_switches_are_the_reference_deviations():
     assert np.isfinite(a).all() and relerr(a, b) > 1e-3   # genuinely different semantics
     # global LayerNorm: the output as a whole has zero mean and unit (biased) std
     assert abs(a.mean()) < 1e-9 and abs(a.std() - 1.0) < 1e-4
+
+
+def test_clip_golden_reproduced():
+    """tests/golden/clip_small.npz (tools/make_golden.py clip) pins the CLIP restatement."""
+    g = np.load(os.path.join(GOLDEN, "clip_small.npz"))
+    W = synth.SynthWeights(synth.clip_specs(1000, 3), 77)
+    y = O.clip_forward(O.Ops("np", np.float64), W, g["tokens"], n_layers=3)
+    assert relerr(y, g["y_reference_switches"]) < 1e-12

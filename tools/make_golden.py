@@ -7,6 +7,7 @@ checked at the full BASELINE sizes, where running the oracle inside a test would
   python tools/make_golden.py small      # seconds-to-a-minute cases (ops, 8x8 UNet, 8x8 decoder, loop)
   python tools/make_golden.py unet64     # one UNet step at the 64x64 latent of BASELINE config 2
   python tools/make_golden.py decoder64  # one VAE decode 64x64x4 -> 512x512x3 (stored subsampled)
+  python tools/make_golden.py clip       # CLIP text encoder, 1000-token vocabulary, 3 layers, both switch sets
 """
 import os
 import sys
@@ -97,5 +98,20 @@ def decoder64():
                         y_mean=y.mean(axis=(1, 2)), y_std=y.std(axis=(1, 2)), y_absmax=np.abs(y).max())
 
 
+CLIP_SEED, CLIP_VOCAB, CLIP_LAYERS = 77, 1000, 3
+
+
+def clip():
+    W = synth.SynthWeights(synth.clip_specs(CLIP_VOCAB, CLIP_LAYERS), CLIP_SEED)
+    tokens = np.random.default_rng(4).integers(0, CLIP_VOCAB, 23)
+    t0 = time.time()
+    y_ref = O.clip_forward(O.Ops("np", np.float64), W, tokens, n_layers=CLIP_LAYERS)
+    y_int = O.clip_forward(O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token")), W, tokens,
+                           n_layers=CLIP_LAYERS)
+    print(f"clip oracle x2: {time.time() - t0:.1f} s")
+    np.savez_compressed(os.path.join(G, "clip_small.npz"), tokens=tokens, y_reference_switches=y_ref,
+                        y_intended_switches=y_int)
+
+
 if __name__ == "__main__":
-    {"small": small, "unet64": unet64, "decoder64": decoder64}[sys.argv[1]]()
+    {"small": small, "unet64": unet64, "decoder64": decoder64, "clip": clip}[sys.argv[1]]()
