@@ -45,6 +45,7 @@ typedef struct tsd_ctx tsd_ctx;             /* device + stream + workspace */
 typedef struct tsd_diffusion tsd_diffusion; /* Diffusion (diffusion.mojo:294-318) */
 typedef struct tsd_decoder tsd_decoder;     /* VAE Decoder (vae.mojo:162-250) */
 typedef struct tsd_clip tsd_clip;           /* CLIP text encoder (clip.mojo:56-109) */
+typedef struct tsd_encoder tsd_encoder;     /* VAE Encoder (vae.mojo:70-159) */
 
 /* ---- context ------------------------------------------------------------------------ */
 int32_t tsd_init(int32_t device, tsd_ctx** out);
@@ -89,6 +90,12 @@ int32_t tsd_timer_stop(tsd_ctx* ctx, double* ms);
 int32_t tsd_conv2d(tsd_ctx* ctx, const float* x, int32_t n, int32_t cin, int32_t h, int32_t w,
                    const float* weight, const float* bias, int32_t cout, int32_t k, int32_t pad,
                    int32_t stride, float* out);
+/* Matrix.pad((pad,pad_hi),(pad,pad_hi)) (helpers/utils.mojo:1383-1413) followed by Conv2D.forward with
+ * padding (0,0): `pad` zero rows/columns above/left, `pad_hi` below/right.  Encoder.two_stride_pad
+ * (vae.mojo:115-116) is pad = 0, pad_hi = 1.  ho = floor((h+pad+pad_hi-k)/stride)+1. */
+int32_t tsd_conv2d_pad(tsd_ctx* ctx, const float* x, int32_t n, int32_t cin, int32_t h, int32_t w,
+                       const float* weight, const float* bias, int32_t cout, int32_t k, int32_t pad,
+                       int32_t pad_hi, int32_t stride, float* out);
 /* Linear.forward, helpers/utils.mojo:1954-1976 (bias added to every column).
  * x (b,t,in_f); weight (out_f,in_f); bias (out_f) or NULL; out (b,t,out_f). */
 int32_t tsd_linear(tsd_ctx* ctx, const float* x, int32_t b, int32_t t, int32_t in_f,
@@ -132,6 +139,11 @@ int32_t tsd_attention_core(tsd_ctx* ctx, const float* q, const float* k, const f
 int32_t tsd_sampler_step(tsd_ctx* ctx, const float* latents, const float* eps_cond,
                          const float* eps_uncond, float cfg_scale, const float* noise, float sqrt_ab,
                          float sqrt_1mab, float c0, float c1, float sigma, int64_t n, float* out);
+
+/* DDPMSampler.add_noise, sampler.mojo:111-124 (img2img start, pipeline.mojo:78):
+ * out = sqrt_ab * x + sqrt_1mab * noise, with sqrt_ab = sqrt(alphas_cumprod[t]) from the host sampler. */
+int32_t tsd_sampler_add_noise(tsd_ctx* ctx, const float* x, const float* noise, float sqrt_ab,
+                              float sqrt_1mab, int64_t n, float* out);
 
 /* same, device pointers, asynchronous on the context's stream (out may alias latents) */
 int32_t tsd_sampler_step_dev(tsd_ctx* ctx, const float* latents, const float* eps_cond,
@@ -190,6 +202,27 @@ int32_t tsd_decoder_get_param(const tsd_decoder* m, int32_t i, float* out);
 int32_t tsd_decoder_forward(tsd_decoder* m, const float* z, int32_t n, int32_t rescale, float* img);
 int32_t tsd_decoder_forward_dev(tsd_decoder* m, const float* z, int32_t n, int32_t rescale,
                                 float* img);
+
+/* ---- VAE encoder / img2img entry ----------------------------------------
+ * Replaces Encoder.__init__ / Encoder.forward (vae.mojo:91-159): conv 3->128, Res_Blocks, three
+ * two_stride_pad + stride-2 convs (one zero row below / column right, vae.mojo:115-116), Attention_Block,
+ * GroupNorm(32)+SiLU, conv 512->8, conv 1x1 8->8 and metrics_evals (mean / log-variance chunks, clamp
+ * (-30,20), latent = (mean + noise * sqrt(exp(logvar))) * 0.18215; vae.mojo:118-129).
+ * img (n,3,8H,8W): values in (-1,1), or in (0,255) when rescale != 0 (the pipeline's
+ * rescale((0,255),(-1,1)), pipeline.mojo:71).  noise, z: (n,4,H,W).  Parameters in struct order l1..l19. */
+int32_t tsd_encoder_create(tsd_ctx* ctx, int32_t latent_h, int32_t latent_w, int32_t max_batch,
+                           tsd_encoder** out);
+int32_t tsd_encoder_destroy(tsd_encoder* m);
+int64_t tsd_encoder_num_params(const tsd_encoder* m);
+int32_t tsd_encoder_load_weights(tsd_encoder* m, const float* blob, int64_t n_floats);
+int32_t tsd_encoder_init_random(tsd_encoder* m, uint64_t seed);
+int32_t tsd_encoder_param_count(const tsd_encoder* m);
+const char* tsd_encoder_param_name(const tsd_encoder* m, int32_t i, int64_t* offset, int64_t* numel);
+int32_t tsd_encoder_get_param(const tsd_encoder* m, int32_t i, float* out);
+int32_t tsd_encoder_forward(tsd_encoder* m, const float* img, const float* noise, int32_t n, int32_t rescale,
+                            float* z);
+int32_t tsd_encoder_forward_dev(tsd_encoder* m, const float* img, const float* noise, int32_t n,
+                                int32_t rescale, float* z);
 
 /* ---- CLIP text encoder ------------------------------------------------
  * Replaces CLIP.__init__ / CLIP.forward (clip.mojo:70-109): ClipEmbedding (token table + position),

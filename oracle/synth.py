@@ -142,6 +142,36 @@ def decoder_specs():
     return sp
 
 
+def encoder_specs():
+    """VAE Encoder (vae.mojo:71-112) in struct-declaration order."""
+    sp = []
+
+    def res(name, cin, cout):
+        _conv(sp, name + ".conv1", cin, cout, 3)
+        _conv(sp, name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            _conv(sp, name + ".res_conv_layer", cin, cout, 1)
+
+    _conv(sp, "l1", 3, 128, 3)
+    res("l2", 128, 128)
+    res("l3", 128, 128)
+    _conv(sp, "l4", 128, 128, 3)
+    res("l5", 128, 256)
+    res("l6", 256, 256)
+    _conv(sp, "l7", 256, 256, 3)
+    res("l8", 256, 512)
+    res("l9", 512, 512)
+    _conv(sp, "l10", 512, 512, 3)
+    for n in ("l11", "l12", "l13"):
+        res(n, 512, 512)
+    _linear(sp, "l14.attention.in_proj", 512, 1536, True)
+    _linear(sp, "l14.attention.out_proj", 512, 512, True)
+    res("l15", 512, 512)
+    _conv(sp, "l18", 512, 8, 3)
+    _conv(sp, "l19", 8, 8, 1)
+    return sp
+
+
 def clip_specs(n_vocab: int = 49408, n_layers: int = 12, n_embed: int = 768, n_tokens: int = 77):
     """CLIP text encoder (clip.mojo:5-15, 23-34, 56-87) in struct-declaration order.  The embedding
     table and the position embedding are stored flat (device kind P_VEC); LayerNorm owns no tensor."""

@@ -91,9 +91,13 @@ class Ops:
         return np.ascontiguousarray(a, dtype=self.dtype)
 
     # Conv2D.forward, helpers/utils.mojo:1738-1811 (+pad :1383-1413); Appendix C formula
-    def conv2d(self, x, w, b=None, pad=0, stride=1):
+    def conv2d(self, x, w, b=None, pad=0, stride=1, pad_hi=None):
         cout, cin, k, _ = w.shape
         x = x[:cin]  # the loop reads only the first in_channels planes (utils.mojo:1771, Q9)
+        if pad_hi is not None and pad_hi != pad:
+            # Matrix.pad((top,bottom),(left,right)), utils.mojo:1383-1413, then an unpadded Conv2D
+            x = np.pad(self.arr(x), ((0, 0), (pad, pad_hi), (pad, pad_hi)))
+            pad = 0
         _, h, wd = x.shape
         ho, wo = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
         if self.backend == "c32":
@@ -394,14 +398,66 @@ def vae_res_block(ops: Ops, W, base, x, cin, cout):
     return out + res
 
 
-def vae_attn_block(ops: Ops, W, x):
+def vae_attn_block(ops: Ops, W, x, name="l4"):
     """Attention_Block.forward, vae.mojo:17-27: GroupNorm(32) -> 1-head self-attention -> + residue."""
     c, h, w = x.shape
     out = ops.group_norm(x, 32, 1e-5)
     seq = np.ascontiguousarray(out.reshape(c, h * w).T)
-    seq = ops.self_attention(seq, 1, W["l4.attention.in_proj.weight"], W["l4.attention.in_proj.bias"],
-                             W["l4.attention.out_proj.weight"], W["l4.attention.out_proj.bias"])
+    seq = ops.self_attention(seq, 1, W[name + ".attention.in_proj.weight"], W[name + ".attention.in_proj.bias"],
+                             W[name + ".attention.out_proj.weight"], W[name + ".attention.out_proj.bias"])
     return np.ascontiguousarray(seq.T).reshape(c, h, w) + ops.arr(x)
+
+
+def encoder_forward(ops: Ops, W, x, noise):
+    """Encoder.forward, vae.mojo:131-159; x (3,8h,8w) in (-1,1), noise (4,h,w) -> latent (4,h,w).
+    two_stride_pad (:115-116) = one zero row below and one zero column right before each stride-2 conv."""
+    out = ops.conv2d(ops.arr(x), W["l1.weight"], W["l1.bias"], pad=1)
+    out = vae_res_block(ops, W, "l2", out, 128, 128)
+    out = vae_res_block(ops, W, "l3", out, 128, 128)
+    out = ops.conv2d(out, W["l4.weight"], W["l4.bias"], pad=0, stride=2, pad_hi=1)
+    out = vae_res_block(ops, W, "l5", out, 128, 256)
+    out = vae_res_block(ops, W, "l6", out, 256, 256)
+    out = ops.conv2d(out, W["l7.weight"], W["l7.bias"], pad=0, stride=2, pad_hi=1)
+    out = vae_res_block(ops, W, "l8", out, 256, 512)
+    out = vae_res_block(ops, W, "l9", out, 512, 512)
+    out = ops.conv2d(out, W["l10.weight"], W["l10.bias"], pad=0, stride=2, pad_hi=1)
+    for n in ("l11", "l12", "l13"):
+        out = vae_res_block(ops, W, n, out, 512, 512)
+    out = vae_attn_block(ops, W, out, "l14")
+    out = vae_res_block(ops, W, "l15", out, 512, 512)
+    out = ops.group_norm(out, 32, 1e-5)
+    out = ops.silu(out)
+    out = ops.conv2d(out, W["l18.weight"], W["l18.bias"], pad=1)
+    out = ops.conv2d(out, W["l19.weight"], W["l19.bias"])
+    return latent_from_moments(ops, out, noise)
+
+
+def latent_from_moments(ops: Ops, moments, noise):
+    """Encoder.metrics_evals, vae.mojo:118-129: chunk(0,2) -> mean, log-variance; clamp(-30,20);
+    std = sqrt(exp(.)); (mean + noise*std) * 0.18215."""
+    m = ops.arr(moments)
+    half = m.shape[0] // 2
+    mean, logvar = m[:half], np.clip(m[half:], -30.0, 20.0)
+    std = np.sqrt(np.exp(logvar))
+    return (mean + ops.arr(noise) * std) * ops.dtype(0.18215)
+
+
+def rescale_input(img):
+    """Matrix.rescale((0,255),(-1,1)), helpers/utils.mojo:577-597, pipeline.mojo:71."""
+    return np.asarray(img) * 2.0 / 255.0 - 1.0
+
+
+def resize_image(img, new_h, new_w):
+    """resize_image, helpers/utils.mojo:372-402: nearest neighbour, index int(row*old/new).  The
+    reference names dim1 "width" and dim2 "height" (:376-377) and so scales rows by dim2/new_h; for
+    the square images of the pipeline (image_size x image_size) both readings coincide."""
+    img = np.asarray(img)
+    c, h, w = img.shape
+    if h == new_h and w == new_w:
+        return img
+    ys = (np.arange(new_h) * (h / new_h)).astype(np.int64)
+    xs = (np.arange(new_w) * (w / new_w)).astype(np.int64)
+    return img[:, ys][:, :, xs]
 
 
 def rescale_image(img):
@@ -486,6 +542,10 @@ class DDPMSampler:
         if t > 0 and noise is not None:
             out = out + noise * sigma
         return out
+
+    def set_strength(self, strength):  # :67-73 (intended slice timesteps[start:])
+        self.start_step = self.n - int(self.n * strength)
+        self.timesteps = self.timesteps[self.start_step:]
 
     def add_noise(self, x, t, noise):  # :111-124
         ab = self.alphas_cumprod[int(t)]

@@ -194,10 +194,16 @@ int32_t tsd_timer_stop(tsd_ctx* h, double* ms) {
 int32_t tsd_conv2d(tsd_ctx* h, const float* x, int32_t n, int32_t cin, int32_t H, int32_t W,
                    const float* weight, const float* bias, int32_t cout, int32_t k, int32_t pad,
                    int32_t stride, float* out) {
+  return tsd_conv2d_pad(h, x, n, cin, H, W, weight, bias, cout, k, pad, pad, stride, out);
+}
+
+int32_t tsd_conv2d_pad(tsd_ctx* h, const float* x, int32_t n, int32_t cin, int32_t H, int32_t W,
+                       const float* weight, const float* bias, int32_t cout, int32_t k, int32_t pad,
+                       int32_t pad_hi, int32_t stride, float* out) {
   if (!h || !x || !weight || !out) return TSD_ERR_INVALID;
-  if (n <= 0 || cin <= 0 || cout <= 0 || H <= 0 || W <= 0 || k <= 0 || stride <= 0 || pad < 0)
+  if (n <= 0 || cin <= 0 || cout <= 0 || H <= 0 || W <= 0 || k <= 0 || stride <= 0 || pad < 0 || pad_hi < 0)
     return h->c->fail(TSD_ERR_INVALID, "conv2d: non-positive dimension");
-  const int Ho = conv_out_dim(H, k, pad, stride), Wo = conv_out_dim(W, k, pad, stride);
+  const int Ho = conv_out_dim(H, k, pad, stride, pad_hi), Wo = conv_out_dim(W, k, pad, stride, pad_hi);
   if (Ho <= 0 || Wo <= 0) return h->c->fail(TSD_ERR_INVALID, "conv2d: kernel larger than padded input");
   const size_t nx = (size_t)n * cin * H * W, nw = (size_t)cout * cin * k * k,
                no = (size_t)n * cout * Ho * Wo;
@@ -216,7 +222,7 @@ int32_t tsd_conv2d(tsd_ctx* h, const float* x, int32_t n, int32_t cin, int32_t H
     hc.cu(launch_oihw_to_ohwi(w_oihw, w_ohwi, cout, cin, k * k, c->stream), "oihw_to_ohwi");
     ConvArgs a;
     a.x = x_nhwc; a.N = n; a.H = H; a.W = W; a.Cin = cin; a.Cout = cout;
-    a.k = k; a.pad = pad; a.stride = stride; a.w = w_ohwi; a.bias = b; a.out = o_nhwc;
+    a.k = k; a.pad = pad; a.pad_hi = pad_hi; a.stride = stride; a.w = w_ohwi; a.bias = b; a.out = o_nhwc;
     a.force_bn = c->force_bn; a.force_splits = c->force_splits;
     if (!hc.rc) hc.run(op_conv2d(c, a));
     hc.cu(launch_nhwc_to_nchw(o_nhwc, o_nchw, n, cout, Ho * Wo, c->stream), "nhwc_to_nchw");
@@ -540,6 +546,23 @@ int32_t tsd_sampler_step(tsd_ctx* h, const float* latents, const float* eps_cond
     hc.cu(launch_ddpm_step(xd, ec, eu, cfg_scale, nz, sqrt_ab, sqrt_1mab, c0, c1, sigma, od, n,
                            hc.c->stream),
           "ddpm_step");
+    hc.download(out, od, n);
+  }
+  return hc.finish();
+}
+
+// DDPMSampler.add_noise, sampler.mojo:111-124: out = x * sqrt(ab_t) + noise * sqrt(1 - ab_t).
+// Runs on the step kernel with (sqrt_ab, sqrt_1mab, c0, c1, sigma) = (1, 0, sqrt(ab_t), 0, sqrt(1-ab_t)).
+int32_t tsd_sampler_add_noise(tsd_ctx* h, const float* x, const float* noise, float sqrt_ab,
+                              float sqrt_1mab, int64_t n, float* out) {
+  if (!h || !x || !noise || !out || n <= 0) return TSD_ERR_INVALID;
+  HostCall hc(h, 3 * (size_t)n * 4 + (1u << 20));
+  float* xd = hc.upload(x, n);
+  float* nz = hc.upload(noise, n);
+  float* od = hc.dev(n);
+  if (!hc.rc) {
+    hc.cu(launch_ddpm_step(xd, xd, nullptr, 0.0f, nz, 1.0f, 0.0f, sqrt_ab, 0.0f, sqrt_1mab, od, n, hc.c->stream),
+          "add_noise");
     hc.download(out, od, n);
   }
   return hc.finish();

@@ -197,6 +197,79 @@ int32_t tsd_decoder_forward_dev(tsd_decoder* d, const float* z, int32_t n, int32
   return d->m.forward(z, n, rescale, img, false);
 }
 
+// ---- VAE Encoder (vae.mojo:70-159) ---------------------------------------------------------------------------------
+int32_t tsd_encoder_create(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32_t max_batch, tsd_encoder** out) {
+  if (!h || !out) return TSD_ERR_INVALID;
+  *out = nullptr;
+  Guard g(h);
+  tsd_encoder* d = new (std::nothrow) tsd_encoder();
+  if (!d) return h->c->fail(TSD_ERR_OOM, "encoder: host allocation failed");
+  d->m.h = h;
+  d->m.c = h->c;
+  d->m.latent_h = latent_h;
+  d->m.latent_w = latent_w;
+  d->m.max_batch = max_batch;
+  int rc = d->m.create();
+  if (rc) {
+    d->m.destroy();
+    delete d;
+    return rc;
+  }
+  *out = d;
+  return TSD_OK;
+}
+int32_t tsd_encoder_destroy(tsd_encoder* d) {
+  if (!d) return TSD_ERR_INVALID;
+  {
+    Guard g(d->m.h);
+    d->m.destroy();
+  }
+  delete d;
+  return TSD_OK;
+}
+int64_t tsd_encoder_num_params(const tsd_encoder* d) { return d ? d->m.ps.total : 0; }
+int32_t tsd_encoder_load_weights(tsd_encoder* d, const float* blob, int64_t n_floats) {
+  if (!d || !blob) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  return d->m.ps.load(blob, n_floats);
+}
+int32_t tsd_encoder_init_random(tsd_encoder* d, uint64_t seed) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  return d->m.ps.init_random(seed);
+}
+int32_t tsd_encoder_param_count(const tsd_encoder* d) { return d ? (int32_t)d->m.ps.params.size() : 0; }
+const char* tsd_encoder_param_name(const tsd_encoder* d, int32_t i, int64_t* offset, int64_t* numel) {
+  if (!d || i < 0 || i >= (int32_t)d->m.ps.params.size()) return nullptr;
+  const Param& p = d->m.ps.params[i];
+  if (offset) *offset = p.offset;
+  if (numel) *numel = p.numel;
+  return p.name.c_str();
+}
+int32_t tsd_encoder_get_param(const tsd_encoder* d, int32_t i, float* out) {
+  if (!d || !out) return TSD_ERR_INVALID;
+  tsd_encoder* dd = const_cast<tsd_encoder*>(d);
+  Guard g(dd->m.h);
+  return dd->m.ps.get(i, out);
+}
+int32_t tsd_encoder_forward(tsd_encoder* d, const float* img, const float* noise, int32_t n, int32_t rescale,
+                            float* z) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  int rc = d->m.forward(img, noise, n, rescale, z, true);
+  if (rc) {
+    cudaStreamSynchronize(d->m.c->stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
+int32_t tsd_encoder_forward_dev(tsd_encoder* d, const float* img, const float* noise, int32_t n,
+                                int32_t rescale, float* z) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  return d->m.forward(img, noise, n, rescale, z, false);
+}
+
 // ---- CLIP text encoder (clip.mojo:56-109) ------------------------------------------------------
 int32_t tsd_clip_create(tsd_ctx* h, int32_t n_vocab, int32_t n_layers, tsd_clip** out) {
   if (!h || !out) return TSD_ERR_INVALID;

@@ -52,7 +52,8 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
     int c = c0 + i, r = r0 + threadIdx.x;
     if (r < R && c < Cc) {
       float v = tile[threadIdx.x][i];
-      if (rescale) v = fminf(fmaxf((v + 1.0f) * 127.5f, 0.0f), 255.0f);
+      if (rescale == 1) v = fminf(fmaxf((v + 1.0f) * 127.5f, 0.0f), 255.0f);
+      else if (rescale == 2) v = v * 2.0f / 255.0f - 1.0f;  // rescale((0,255),(-1,1)), pipeline.mojo:71
       dst[img + (long long)c * R + r] = v;
     }
   }
@@ -140,7 +141,7 @@ __global__ void upsample2x_planar_kernel(const float* __restrict__ x, float* __r
 }
 
 __global__ void im2col3x3_kernel(const float4* __restrict__ x, float4* __restrict__ col, int N, int H,
-                                 int W, int C4, int stride, int Ho, int Wo) {
+                                 int W, int C4, int stride, int pad_lo, int Ho, int Wo) {
   pdl_wait();
   pdl_launch_dependents();
   const long long total = (long long)N * Ho * Wo * 9 * C4;
@@ -154,7 +155,7 @@ __global__ void im2col3x3_kernel(const float4* __restrict__ x, float4* __restric
     t /= Wo;
     int ho = (int)(t % Ho);
     int n = (int)(t / Ho);
-    int hi = ho * stride + tap / 3 - 1, wi = wo * stride + tap % 3 - 1;
+    int hi = ho * stride + tap / 3 - pad_lo, wi = wo * stride + tap % 3 - pad_lo;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hi >= 0 && hi < H && wi >= 0 && wi < W)
       v = x[(((long long)n * H + hi) * W + wi) * C4 + c];
@@ -1270,6 +1271,36 @@ cudaError_t launch_rescale_to_nchw(const float* src, float* dst, int N, int C, i
                                    cudaStream_t s) {
   return launch_transpose(src, dst, N, HW, C, rescale, s);
 }
+cudaError_t launch_rescale_to_nhwc(const float* src, float* dst, int N, int C, int HW, int rescale,
+                                   cudaStream_t s) {
+  return launch_transpose(src, dst, N, C, HW, rescale ? 2 : 0, s);
+}
+
+// Encoder.metrics_evals, vae.mojo:118-129: moments NHWC [N][HW][8] (mean = channels 0..3,
+// log-variance = 4..7), noise / out NCHW [N][4][HW].
+__global__ void latent_from_moments_kernel(const float* __restrict__ m, const float* __restrict__ noise,
+                                           float* __restrict__ out, int N, int HW) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long total = (long long)N * 4 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % HW);
+    const long long t = i / HW;
+    const int ch = (int)(t % 4);
+    const long long n = t / 4;
+    const float* mp = m + (n * HW + px) * 8;
+    const float mean = mp[ch];
+    const float lv = fminf(fmaxf(mp[4 + ch], -30.0f), 20.0f);
+    const float sd = sqrtf(expf(lv));
+    out[i] = (mean + noise[i] * sd) * 0.18215f;
+  }
+}
+cudaError_t launch_latent_from_moments(const float* m, const float* noise, float* out, int N, int HW,
+                                       cudaStream_t s) {
+  const long long total = (long long)N * 4 * HW;
+  return launch_pdl(latent_from_moments_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, m, noise, out, N, HW);
+}
 cudaError_t launch_transpose_ld(const float* src, float* dst, int B, int R, int Cc, int ld_out,
                                 cudaStream_t s) {
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, B), block(32, 8);
@@ -1300,12 +1331,12 @@ cudaError_t launch_upsample2x_planar(const float* x, float* y, int C, int H, int
   return cudaGetLastError();
 }
 cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, int C, int stride,
-                             int Ho, int Wo, cudaStream_t s) {
+                             int pad_lo, int Ho, int Wo, cudaStream_t s) {
   if (C % 4) return cudaErrorInvalidValue;
   long long total = (long long)N * Ho * Wo * 9 * (C / 4);
   { cudaError_t e_ = launch_pdl(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, reinterpret_cast<const float4*>(x),
                                                         reinterpret_cast<float4*>(col), N, H, W,
-                                                        C / 4, stride, Ho, Wo); if (e_ != cudaSuccess) return e_; }
+                                                        C / 4, stride, pad_lo, Ho, Wo); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 

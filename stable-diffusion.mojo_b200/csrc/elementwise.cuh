@@ -26,8 +26,12 @@ cudaError_t launch_concat_channels(const float* a, int Ca, const float* b, int C
 cudaError_t launch_upsample2x(const float* x, float* y, int N, int H, int W, int C, cudaStream_t s);
 // channel-major (C,H,W) -> (C,2H,2W), any C
 cudaError_t launch_upsample2x_planar(const float* x, float* y, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_rescale_to_nhwc(const float* src, float* dst, int N, int C, int HW, int rescale,
+                                   cudaStream_t s);  // NCHW (0..255 when rescale) -> NHWC (-1..1)
+cudaError_t launch_latent_from_moments(const float* m, const float* noise, float* out, int N, int HW,
+                                       cudaStream_t s);
 cudaError_t launch_im2col3x3(const float* x, float* col, int N, int H, int W, int C, int stride,
-                             int Ho, int Wo, cudaStream_t s);
+                             int pad_lo, int Ho, int Wo, cudaStream_t s);
 
 // ---- normalisation ------------------------------------------------------------------------
 // stats[n][g] = (mean, 1/(std+eps)) with the reference's biased std and eps added to std

@@ -319,9 +319,10 @@ static float* walloc(Ctx* c, long long n) { return c->arena.alloc_n<float>((size
 
 static int conv(Ctx* c, const ParamStore& ps, int wi, const float* x, int N, int H, int W, int cin, int cout,
                 int k, int pad, int stride, const float* bias_override, int bias_img_stride,
-                const float* residual, float* out, int round_out, NormHint* nh = nullptr) {
+                const float* residual, float* out, int round_out, NormHint* nh = nullptr, int pad_hi = -1) {
   ConvArgs a;
   a.nh = nh;
+  a.pad_hi = pad_hi;
   a.x = x; a.N = N; a.H = H; a.W = W; a.Cin = cin; a.Cout = cout; a.k = k; a.pad = pad; a.stride = stride;
   a.w = ps.w(wi);
   a.bias = bias_override ? bias_override : ps.w(wi + 1);
@@ -879,6 +880,27 @@ void Decoder::destroy() {
   ps.free_all();
 }
 
+// Attention_Block.forward, vae.mojo:17-27: GroupNorm(32) -> 1-head self-attention -> + residue
+static int vae_attn_block(Ctx* c, const ParamStore& ps, int attn_in, int attn_out, const float* x, int n,
+                          int H, int W, float* out) {
+  const int C = 512;
+  const long long T = (long long)H * W, M = n * T;
+  const size_t mark = c->arena.mark();
+  WALLOC(a, M * C);
+  TRY(op_group_norm(c, x, a, n, H, W, C, 32, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1));
+  WALLOC(qkv, 3 * M * C);
+  TRY(linear(c, a, M, C, ps.w(attn_in), ps.w(attn_in + 1), 3 * C, qkv, C, nullptr, 1, 0, C, M * C));
+  WALLOC(o, M * C);
+  AttnArgs at;
+  at.Q = qkv; at.K = qkv + M * C; at.V = qkv + 2 * M * C;
+  at.batch = n; at.heads = 1; at.Tq = (int)T; at.Tk = (int)T; at.d = C; at.O = o;
+  at.softmax_axis = c->softmax_axis;
+  TRY(op_attention(c, at));
+  TRY(linear(c, o, M, C, ps.w(attn_out), ps.w(attn_out + 1), C, out, C, x, 0));
+  c->arena.release_to(mark);
+  return TSD_OK;
+}
+
 // Decoder.forward, vae.mojo:221-250; z_in (n,4,h,w) -> img_out (n,3,8h,8w)
 int Decoder::decode(int n, int rescale) {
   int H = latent_h, W = latent_w;
@@ -919,25 +941,8 @@ int Decoder::decode(int n, int rescale) {
     return TSD_OK;
   };
   TRY(RES());  // l3
-  {
-    // Attention_Block.forward, vae.mojo:17-27: GroupNorm(32) -> 1-head self-attention -> + residue
-    const int C = 512;
-    const long long T = (long long)H * W, M = n * T;
-    const size_t mark = c->arena.mark();
-    WALLOC(a, M * C);
-    TRY(op_group_norm(c, cur, a, n, H, W, C, 32, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1));
-    WALLOC(qkv, 3 * M * C);
-    TRY(linear(c, a, M, C, ps.w(attn_in), ps.w(attn_in + 1), 3 * C, qkv, C, nullptr, 1, 0, C, M * C));
-    WALLOC(o, M * C);
-    AttnArgs at;
-    at.Q = qkv; at.K = qkv + M * C; at.V = qkv + 2 * M * C;
-    at.batch = n; at.heads = 1; at.Tq = (int)T; at.Tk = (int)T; at.d = C; at.O = o;
-    at.softmax_axis = c->softmax_axis;
-    TRY(op_attention(c, at));
-    TRY(linear(c, o, M, C, ps.w(attn_out), ps.w(attn_out + 1), C, nxt, C, cur, 0));
-    c->arena.release_to(mark);
-    swap();
-  }
+  TRY(vae_attn_block(c, ps, attn_in, attn_out, cur, n, H, W, nxt));  // l4
+  swap();
   for (int i = 0; i < 4; ++i) TRY(RES());  // l5..l8
   TRY(UPCONV(l10, 512, 512));              // l9, l10
   for (int i = 0; i < 3; ++i) TRY(RES());  // l11..l13
@@ -1006,6 +1011,169 @@ int Decoder::forward(const float* z, int n, int rescale, float* img, bool host_p
   TRY(c->check(cudaMemcpyAsync(img, img_out, n * 3 * 64 * hw * sizeof(float),
                                host_ptrs ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream), "copy img"));
   if (host_ptrs) TRY(c->check(cudaStreamSynchronize(c->stream), "decoder forward sync"));
+  return TSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// VAE Encoder (vae.mojo:70-159)
+// ---------------------------------------------------------------------------------------
+int Encoder::create() {
+  ps.c = c;
+  if (latent_h <= 0 || latent_w <= 0 || max_batch <= 0) return c->fail(TSD_ERR_INVALID, "encoder: bad shape");
+  // parameter order = Encoder struct order l1..l19 (vae.mojo:71-89, 94-112)
+  int ri = 0;
+  auto add_res = [&](const char* name, int cin, int cout) {
+    ResBlockW& w = res[ri++];
+    w.cin = cin; w.cout = cout; w.groups = 16;  // Res_Block GroupNorm(16, .) (vae.mojo:42-43, Q17)
+    std::string b(name);
+    w.conv1 = ps.add_conv(b + ".conv1", cin, cout, 3);
+    w.conv2 = ps.add_conv(b + ".conv2", cout, cout, 3);
+    if (cin != cout) w.skip = ps.add_conv(b + ".res_conv_layer", cin, cout, 1);
+  };
+  l1 = ps.add_conv("l1", 3, 128, 3);
+  add_res("l2", 128, 128);
+  add_res("l3", 128, 128);
+  l4 = ps.add_conv("l4", 128, 128, 3);
+  add_res("l5", 128, 256);
+  add_res("l6", 256, 256);
+  l7 = ps.add_conv("l7", 256, 256, 3);
+  add_res("l8", 256, 512);
+  add_res("l9", 512, 512);
+  l10 = ps.add_conv("l10", 512, 512, 3);
+  add_res("l11", 512, 512);
+  add_res("l12", 512, 512);
+  add_res("l13", 512, 512);
+  attn_in = ps.add_linear("l14.attention.in_proj", 512, 1536, true);
+  attn_out = ps.add_linear("l14.attention.out_proj", 512, 512, true);
+  add_res("l15", 512, 512);
+  l18 = ps.add_conv("l18", 512, 8, 3);
+  l19 = ps.add_conv("l19", 8, 8, 1);
+
+  const size_t B = max_batch, hw = (size_t)latent_h * latent_w;
+  pp_elems = B * hw * 64 * 128;  // largest activation: 128 ch at 8h x 8w
+  auto dmalloc = [&](float** p, size_t n) {
+    return cudaMalloc(p, n * sizeof(float)) == cudaSuccess ? TSD_OK : c->fail(TSD_ERR_OOM, "encoder: buffer allocation failed");
+  };
+  TRY(dmalloc(&img_in, B * 3 * 64 * hw));
+  TRY(dmalloc(&noise_in, B * 4 * hw));
+  TRY(dmalloc(&z_out, B * 4 * hw));
+  TRY(dmalloc(&ping, pp_elems));
+  TRY(dmalloc(&pong, pp_elems));
+  return TSD_OK;
+}
+void Encoder::destroy() {
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (graph.exec) cudaGraphExecDestroy(graph.exec);
+  float* bufs[] = {img_in, noise_in, z_out, ping, pong};
+  for (float* b : bufs)
+    if (b) cudaFree(b);
+  ps.free_all();
+}
+
+// Encoder.forward, vae.mojo:131-159; rescale = the pipeline's rescale((0,255),(-1,1)) (pipeline.mojo:71)
+int Encoder::encode(int n, int rescale) {
+  int H = latent_h * 8, W = latent_w * 8;
+  float* cur = ping;
+  float* nxt = pong;
+  auto swap = [&]() { float* t = cur; cur = nxt; nxt = t; };
+  c->arena.reset();
+  LAUNCH(c, launch_rescale_to_nhwc(img_in, cur, n, 3, H * W, rescale, c->stream), "rescale_to_nhwc");
+  TRY(conv(c, ps, l1, cur, n, H, W, 3, 128, 3, 1, 1, nullptr, 0, nullptr, nxt, 0));
+  swap();
+  int ri = 0;
+  auto RES = [&]() -> int {
+    Act x;
+    x.p = cur; x.N = n; x.H = H; x.W = W; x.C = res[ri].cin;
+    int rc = res_block(c, ps, res[ri], x, nullptr, 0, 1e-5f, nxt);
+    ++ri;
+    swap();
+    return rc;
+  };
+  // two_stride_pad (vae.mojo:115-116: one zero row below, one zero column right) + 3x3 stride-2 conv, no padding
+  auto DOWN = [&](int wi, int ch) -> int {
+    TRY(conv(c, ps, wi, cur, n, H, W, ch, ch, 3, 0, 2, nullptr, 0, nullptr, nxt, 0, nullptr, 1));
+    H = conv_out_dim(H, 3, 0, 2, 1);
+    W = conv_out_dim(W, 3, 0, 2, 1);
+    swap();
+    return TSD_OK;
+  };
+  TRY(RES());  // l2
+  TRY(RES());  // l3
+  TRY(DOWN(l4, 128));
+  TRY(RES());  // l5
+  TRY(RES());  // l6
+  TRY(DOWN(l7, 256));
+  TRY(RES());  // l8
+  TRY(RES());  // l9
+  TRY(DOWN(l10, 512));
+  for (int i = 0; i < 3; ++i) TRY(RES());  // l11..l13
+  TRY(vae_attn_block(c, ps, attn_in, attn_out, cur, n, H, W, nxt));  // l14
+  swap();
+  TRY(RES());  // l15
+  {
+    // l16 GroupNorm(32,512), l17 SiLU, l18 conv 512->8, l19 conv 1x1 8->8, metrics_evals (vae.mojo:118-129)
+    const size_t mark = c->arena.mark();
+    WALLOC(f, (long long)n * H * W * 512);
+    TRY(op_group_norm(c, cur, f, n, H, W, 512, 32, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1));
+    WALLOC(m8, (long long)n * H * W * 8);
+    TRY(conv(c, ps, l18, f, n, H, W, 512, 8, 3, 1, 1, nullptr, 0, nullptr, m8, 0));
+    TRY(conv(c, ps, l19, m8, n, H, W, 8, 8, 1, 0, 1, nullptr, 0, nullptr, nxt, 0));
+    c->arena.release_to(mark);
+    LAUNCH(c, launch_latent_from_moments(nxt, noise_in, z_out, n, H * W, c->stream), "latent_from_moments");
+  }
+  return TSD_OK;
+}
+
+size_t Encoder::workspace_bytes(int n) const {
+  Encoder* self = const_cast<Encoder*>(this);
+  Ctx* cc = self->c;
+  const bool was = cc->dry_run;
+  cc->dry_run = true;
+  cc->arena.set_virtual(true);
+  int rc = self->encode(n, 0);
+  size_t hw = cc->arena.high_water();
+  cc->arena.set_virtual(false);
+  cc->dry_run = was;
+  return rc ? 0 : hw + (64u << 20);
+}
+int Encoder::forward(const float* img, const float* noise, int n, int rescale, float* z, bool host_ptrs) {
+  if (!ps.loaded) return c->fail(TSD_ERR_STATE, "encoder: forward before load_weights / init_random");
+  if (n <= 0 || n > max_batch) return c->fail(TSD_ERR_INVALID, "encoder: batch exceeds max_batch");
+  if (!img || !noise || !z) return c->fail(TSD_ERR_INVALID, "encoder: null buffer");
+  cudaSetDevice(c->device);
+  const size_t need = workspace_bytes(n);
+  if (need == 0) return TSD_ERR_OOM;
+  if (need > c->arena.capacity()) {
+    cudaStreamSynchronize(c->stream);
+    if (c->arena.reserve(need) != TSD_OK) return c->fail(TSD_ERR_OOM, "encoder: workspace allocation failed");
+  }
+  const size_t hw = (size_t)latent_h * latent_w;
+  const cudaMemcpyKind in_kind = host_ptrs ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  TRY(c->check(cudaMemcpyAsync(img_in, img, n * 3 * 64 * hw * sizeof(float), in_kind, c->stream), "copy image"));
+  TRY(c->check(cudaMemcpyAsync(noise_in, noise, n * 4 * hw * sizeof(float), in_kind, c->stream), "copy noise"));
+  GraphSlot& g = graph;
+  const bool use = h->use_graph && !c->timer;
+  const bool valid = g.exec && g.n == n && g.n_ctx == rescale && g.epoch == h->option_epoch &&
+                     g.arena_base == c->arena.base();
+  if (!use) {
+    TRY(encode(n, rescale));
+  } else if (!valid) {
+    TRY(encode(n, rescale));
+    TRY(c->check(cudaStreamSynchronize(c->stream), "encoder eager pass"));
+    TRY(capture_begin(c));
+    int rc = encode(n, rescale);
+    int rc2 = capture_end(c, &g);
+    if (rc) return rc;
+    if (rc2) return rc2;
+    g.n = n; g.n_ctx = rescale; g.epoch = h->option_epoch; g.arena_base = c->arena.base();
+  } else {
+    TRY(c->check(cudaGraphLaunch(g.exec, c->stream), "graph launch"));
+    c->launches += g.nodes;
+  }
+  TRY(c->check(cudaMemcpyAsync(z, z_out, n * 4 * hw * sizeof(float),
+                               host_ptrs ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream), "copy latent"));
+  if (host_ptrs) TRY(c->check(cudaStreamSynchronize(c->stream), "encoder forward sync"));
   return TSD_OK;
 }
 

@@ -147,6 +147,29 @@ struct Decoder {
   int forward(const float* z, int n, int rescale, float* img, bool host_ptrs);
 };
 
+// VAE Encoder (vae.mojo:70-159): image (n,3,8h,8w) + noise (n,4,h,w) -> latent (n,4,h,w)
+struct Encoder {
+  tsd_ctx* h = nullptr;
+  Ctx* c = nullptr;
+  int latent_h = 0, latent_w = 0, max_batch = 1;
+  ParamStore ps;
+  int l1 = -1, l4 = -1, l7 = -1, l10 = -1, l18 = -1, l19 = -1, attn_in = -1, attn_out = -1;
+  ResBlockW res[10];  // l2 l3 l5 l6 l8 l9 l11 l12 l13 l15
+  float* img_in = nullptr;    // [max_batch][3][8h][8w]
+  float* noise_in = nullptr;  // [max_batch][4][h][w]
+  float* z_out = nullptr;     // [max_batch][4][h][w]
+  float* ping = nullptr;
+  float* pong = nullptr;
+  size_t pp_elems = 0;
+  GraphSlot graph;
+
+  int create();
+  void destroy();
+  size_t workspace_bytes(int n) const;
+  int encode(int n, int rescale);  // img_in, noise_in -> z_out
+  int forward(const float* img, const float* noise, int n, int rescale, float* z, bool host_ptrs);
+};
+
 // CLIP text encoder (clip.mojo:5-109) - models_clip.cu
 struct Clip {
   static constexpr int kMaxLayers = 24;
@@ -184,4 +207,7 @@ struct tsd_decoder {
 };
 struct tsd_clip {
   tsd::Clip m;
+};
+struct tsd_encoder {
+  tsd::Encoder m;
 };

@@ -793,7 +793,8 @@ int op_gemm(Ctx* c, const GemmArgs& a) {
 }
 
 int op_conv2d(Ctx* c, const ConvArgs& a) {
-  const int Ho = conv_out_dim(a.H, a.k, a.pad, a.stride), Wo = conv_out_dim(a.W, a.k, a.pad, a.stride);
+  const int Ho = conv_out_dim(a.H, a.k, a.pad, a.stride, a.pad_hi), Wo = conv_out_dim(a.W, a.k, a.pad, a.stride, a.pad_hi);
+  const bool sym = a.pad_hi < 0 || a.pad_hi == a.pad;
   if (Ho <= 0 || Wo <= 0 || a.Cin <= 0 || a.Cout <= 0) return c->fail(TSD_ERR_INVALID, "conv2d: empty output");
   const int ktot = a.k * a.k * a.Cin;
   // rows of w past Cout are out of bounds for the B tensor map and read as zeros
@@ -811,7 +812,7 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
   p.split_n = 1 << 30;
   p.round_tf32 = a.round_tf32;
   p.b_static = 1;  // convolution kernels are parameters
-  if (tensor_ok && ((a.k == 3 && a.pad == 1) || (a.k == 1 && a.pad == 0)) && a.stride == 1) {
+  if (tensor_ok && sym && ((a.k == 3 && a.pad == 1) || (a.k == 1 && a.pad == 0)) && a.stride == 1) {
     ASpec A{};
     A.base = a.x;
     A.K = a.Cin;
@@ -835,15 +836,16 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
     return run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops, nh);
   }
   if (a.nh) a.nh->req = NormStatsReq();
-  if (tensor_ok && a.k == 3 && a.pad == 1 && a.stride > 1) {
-    // stride-2 downsample convs (diffusion.mojo:180,183): explicit im2col then GEMM
+  if (tensor_ok && a.k == 3 && (a.pad == 1 || a.pad == 0) && a.stride > 1) {
+    // stride-2 downsample convs (diffusion.mojo:180,183; vae.mojo:97,100,103 with the bottom/right
+    // padding of two_stride_pad): explicit im2col then GEMM
     const size_t mark = c->arena.mark();
     const long long M = (long long)a.N * Ho * Wo;
     float* col = c->arena.alloc_n<float>((size_t)M * ktot);
     if (!col) return c->fail(TSD_ERR_OOM, "conv2d: arena exhausted (im2col)");
     if (!c->dry_run) {
       TimedScope ts(c, FAM_OTHER, 0);
-      int rc = c->check(launch_im2col3x3(a.x, col, a.N, a.H, a.W, a.Cin, a.stride, Ho, Wo, c->stream),
+      int rc = c->check(launch_im2col3x3(a.x, col, a.N, a.H, a.W, a.Cin, a.stride, a.pad, Ho, Wo, c->stream),
                         "im2col launch");
       if (rc) return rc;
       c->launches++;

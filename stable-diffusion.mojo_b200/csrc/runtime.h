@@ -184,6 +184,7 @@ struct ConvArgs {
   const float* x = nullptr;  // [N][H][W][Cin]
   int N = 1, H = 0, W = 0, Cin = 0, Cout = 0;
   int k = 3, pad = 1, stride = 1;
+  int pad_hi = -1;  // bottom/right padding; -1 = same as pad (top/left).  Encoder: pad 0, pad_hi 1 (vae.mojo:115-116)
   const float* w = nullptr;     // [Cout][k*k*Cin]  (O,(kh,kw),I)
   const float* bias = nullptr;  // [Cout] (image i uses bias + i * bias_img_stride)
   int bias_img_stride = 0;
@@ -194,7 +195,9 @@ struct ConvArgs {
   NormHint* nh = nullptr;  // optional: statistics of `out` for the next norm
 };
 int op_conv2d(Ctx* c, const ConvArgs& a);
-inline int conv_out_dim(int in, int k, int pad, int stride) { return (in + 2 * pad - k) / stride + 1; }
+inline int conv_out_dim(int in, int k, int pad, int stride, int pad_hi = -1) {
+  return (in + pad + (pad_hi < 0 ? pad : pad_hi) - k) / stride + 1;
+}
 
 // GroupNorm(+SiLU)(+2x nearest upsample). stats scratch comes from the arena.
 int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,

@@ -101,6 +101,7 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_timer_start", i32, vp)
     sig("tsd_timer_stop", i32, vp, c_double_p)
     sig("tsd_conv2d", i32, vp, fp, i32, i32, i32, i32, fp, fp, i32, i32, i32, i32, fp)
+    sig("tsd_conv2d_pad", i32, vp, fp, i32, i32, i32, i32, fp, fp, i32, i32, i32, i32, i32, fp)
     sig("tsd_linear", i32, vp, fp, i32, i32, i32, fp, fp, i32, fp)
     sig("tsd_matmul", i32, vp, fp, fp, i32, i32, i32, i32, fp)
     sig("tsd_groupnorm", i32, vp, fp, i32, i32, i32, i32, i32, f32, fp, fp, fp)
@@ -114,6 +115,7 @@ def _declare(L: C.CDLL) -> None:
         fp, fp)
     sig("tsd_attention_core", i32, vp, fp, fp, fp, i32, i32, i32, i32, fp)
     sig("tsd_sampler_step", i32, vp, fp, fp, fp, f32, fp, f32, f32, f32, f32, f32, i64, fp)
+    sig("tsd_sampler_add_noise", i32, vp, fp, fp, f32, f32, i64, fp)
     sig("tsd_sampler_step_dev", i32, vp, fp, fp, fp, f32, fp, f32, f32, f32, f32, f32, i64, fp)
     sig("tsd_diffusion_create", i32, vp, C.POINTER(DiffusionConfig), C.POINTER(vp))
     sig("tsd_diffusion_destroy", i32, vp)
@@ -137,6 +139,16 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_decoder_get_param", i32, vp, i32, fp)
     sig("tsd_decoder_forward", i32, vp, fp, i32, i32, fp)
     sig("tsd_decoder_forward_dev", i32, vp, fp, i32, i32, fp)
+    sig("tsd_encoder_create", i32, vp, i32, i32, i32, C.POINTER(vp))
+    sig("tsd_encoder_destroy", i32, vp)
+    sig("tsd_encoder_num_params", i64, vp)
+    sig("tsd_encoder_load_weights", i32, vp, fp, i64)
+    sig("tsd_encoder_init_random", i32, vp, C.c_uint64)
+    sig("tsd_encoder_param_count", i32, vp)
+    sig("tsd_encoder_param_name", C.c_char_p, vp, i32, c_i64_p, c_i64_p)
+    sig("tsd_encoder_get_param", i32, vp, i32, fp)
+    sig("tsd_encoder_forward", i32, vp, fp, fp, i32, i32, fp)
+    sig("tsd_encoder_forward_dev", i32, vp, fp, fp, i32, i32, fp)
     sig("tsd_clip_create", i32, vp, i32, i32, C.POINTER(vp))
     sig("tsd_clip_destroy", i32, vp)
     sig("tsd_clip_num_params", i64, vp)

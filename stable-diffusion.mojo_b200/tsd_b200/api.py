@@ -80,7 +80,8 @@ class Context:
         return ms.value
 
     # -- ops ----------------------------------------------------------------------------------
-    def conv2d(self, x, weight, bias=None, pad=0, stride=1):
+    def conv2d(self, x, weight, bias=None, pad=0, stride=1, pad_hi=None):
+        """Conv2D.forward; pad_hi != None: Matrix.pad((pad,pad_hi),(pad,pad_hi)) first (vae.mojo:115-116)."""
         x = _f32(x)
         squeeze = x.ndim == 3
         if squeeze:
@@ -90,11 +91,12 @@ class Context:
         cout, cin2, k, k2 = weight.shape
         if cin2 != cin or k != k2:
             raise TsdError(1, "conv2d: weight shape does not match input channels")
-        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        ph = pad if pad_hi is None else pad_hi
+        ho, wo = (h + pad + ph - k) // stride + 1, (w + pad + ph - k) // stride + 1
         out = np.empty((n, cout, max(ho, 0), max(wo, 0)), np.float32)
         b = None if bias is None else _f32(bias)
-        self._ck(self.L.tsd_conv2d(self.h, _p(x), n, cin, h, w, _p(weight), _p(b), cout, k, pad, stride,
-                                   _p(out)))
+        self._ck(self.L.tsd_conv2d_pad(self.h, _p(x), n, cin, h, w, _p(weight), _p(b), cout, k, pad, ph, stride,
+                                       _p(out)))
         return out[0] if squeeze else out
 
     def linear(self, x, weight, bias=None):
@@ -203,6 +205,16 @@ class Context:
         out = np.empty_like(latents)
         self._ck(self.L.tsd_sampler_step(self.h, _p(latents), _p(eps_cond), _p(eu), cfg_scale, _p(nz),
                                          sqrt_ab, sqrt_1mab, c0, c1, sigma, latents.size, _p(out)))
+        return out
+
+    def sampler_add_noise(self, x, noise, sqrt_ab, sqrt_1mab):
+        """DDPMSampler.add_noise (sampler.mojo:111-124) with the host sampler's add_noise_coefficients(t)."""
+        x, noise = _f32(x), _f32(noise)
+        if x.shape != noise.shape:
+            raise TsdError(1, "add_noise: shapes differ")
+        out = np.empty_like(x)
+        self._ck(self.L.tsd_sampler_add_noise(self.h, _p(x), _p(noise), float(sqrt_ab), float(sqrt_1mab), x.size,
+                                              _p(out)))
         return out
 
     def sampler_step_dev(self, latents_dev, eps_dev, eps_uncond_dev, cfg_scale, noise_dev, coef, n, out_dev):
@@ -376,3 +388,33 @@ class Decoder(_Model):
 
     def forward_dev(self, z_dev, n, rescale, img_dev):
         self.ctx._ck(self.ctx.L.tsd_decoder_forward_dev(self.m, z_dev, n, int(rescale), img_dev))
+
+
+class Encoder(_Model):
+    """tsd_encoder: VAE Encoder (vae.mojo:70-159).  forward(x, noise) as Encoder.forward (:131-159):
+    x (3,8h,8w) [or (n,3,8h,8w)] in (-1,1) - or in (0,255) with rescale=True, the pipeline's
+    rescale((0,255),(-1,1)) (pipeline.mojo:71) - and noise (4,h,w) -> latent (4,h,w)."""
+    _prefix = "encoder"
+
+    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1):
+        self.ctx = ctx
+        self.shape = (latent_h, latent_w)
+        m = C.c_void_p()
+        ctx._ck(ctx.L.tsd_encoder_create(ctx.h, latent_h, latent_w, max_batch, C.byref(m)))
+        self.m = m
+
+    def forward(self, x, noise, rescale=False):
+        x, noise = _f32(x), _f32(noise)
+        squeeze = x.ndim == 3
+        if squeeze:
+            x, noise = x[None], noise[None]
+        n, ch, h, w = x.shape
+        lh, lw = self.shape
+        if ch != 3 or (h, w) != (8 * lh, 8 * lw) or noise.shape != (n, 4, lh, lw):
+            raise TsdError(1, "encoder: image must be (3,8h,8w) and noise (4,h,w) for the latent size of the model")
+        z = np.empty((n, 4, lh, lw), np.float32)
+        self.ctx._ck(self.ctx.L.tsd_encoder_forward(self.m, _p(x), _p(noise), n, int(rescale), _p(z)))
+        return z[0] if squeeze else z
+
+    def forward_dev(self, img_dev, noise_dev, n, rescale, z_dev):
+        self.ctx._ck(self.ctx.L.tsd_encoder_forward_dev(self.m, img_dev, noise_dev, n, int(rescale), z_dev))

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .api import Clip, Context, Decoder, Diffusion
+from .api import Clip, Context, Decoder, Diffusion, Encoder
 from .sampler import DDPMSampler, get_time_embedding
 
 
@@ -26,6 +26,8 @@ class Pipeline:
         self.diffusion = Diffusion(ctx, self.side, self.side, max_batch=max_images * (2 if cfg else 1))
         self.decoder = Decoder(ctx, self.side, self.side, max_batch=max_images)
         self.clip = Clip(ctx, clip_vocab, clip_layers) if with_clip else None
+        self.encoder = None
+        self._weights, self._seed = weights, seed
         if weights is None:
             self.diffusion.init_random(seed)
             self.decoder.init_random(seed + 1)
@@ -43,16 +45,55 @@ class Pipeline:
             raise ValueError("pipeline was created with with_clip=False")
         return self.clip.forward(tokens)
 
-    def schedule(self, inference_steps: int, time_as_written: bool = False):
+    def _encoder(self):
+        """The reference builds Encoder() only when an input image is given (pipeline.mojo:66-67)."""
+        if self.encoder is None:
+            self.encoder = Encoder(self.ctx, self.side, self.side, max_batch=self.max_images)
+            if self._weights is None or len(self._weights) < 4:
+                self.encoder.init_random(self._seed + 3)
+            else:
+                self.encoder.load_weights(self._weights[3])
+        return self.encoder
+
+    @staticmethod
+    def resize_image(img, new_h: int, new_w: int):
+        """resize_image, helpers/utils.mojo:372-402: nearest neighbour, source index int(i * old / new).
+        Pure indexing of the host-side input image (no arithmetic on pixel values)."""
+        img = np.asarray(img)
+        _, h, w = img.shape
+        if (h, w) == (new_h, new_w):
+            return img
+        ys = (np.arange(new_h) * (h / new_h)).astype(np.int64)
+        xs = (np.arange(new_w) * (w / new_w)).astype(np.int64)
+        return img[:, ys][:, :, xs]
+
+    def encode_image(self, input_image, encoder_noise):
+        """pipeline.mojo:69-77: resize to image_size, rescale (0,255)->(-1,1) and Encoder.forward, on the device."""
+        x = np.asarray(input_image, np.float32)
+        squeeze = x.ndim == 3
+        if squeeze:
+            x, encoder_noise = x[None], np.asarray(encoder_noise)[None]
+        x = np.stack([self.resize_image(i, self.image_size, self.image_size) for i in x])
+        z = self._encoder().forward(x, encoder_noise, rescale=True)
+        return z[0] if squeeze else z
+
+    def schedule(self, inference_steps: int, time_as_written: bool = False, strength=None):
         s = DDPMSampler()
         s.set_inference_timesteps(inference_steps)
+        if strength is not None:
+            s.set_strength(strength)               # pipeline.mojo:77, sampler.mojo:67-73
         temb = np.stack([get_time_embedding(float(t), time_as_written) for t in s.timesteps])
         return s.timesteps.astype(np.int32), temb.astype(np.float32), s.coefficient_table()
 
     def generate(self, context, uncond_context=None, cfg_scale: float = 7.5, inference_steps: int = 20,
-                 seed_val: int = 0, latents=None, noise=None, decode: bool = True, rescale: bool = True):
+                 seed_val: int = 0, latents=None, noise=None, decode: bool = True, rescale: bool = True,
+                 input_image=None, strength: float = 0.8, encoder_noise=None, start_noise=None):
         """Returns (images (n,3,S,S) in [0,255], latents (n,4,S/8,S/8)).  context (n|1,77,768);
-        with CFG pass uncond_context of the same shape.  latents/noise default to seeded N(0,1)."""
+        with CFG pass uncond_context of the same shape.  latents/noise default to seeded N(0,1).
+        input_image ((3,h,w) or (n,3,h,w), values 0..255) selects the img2img start of pipeline.mojo:66-79:
+        latents = add_noise(Encoder(rescaled image, encoder_noise), timesteps[0]) after set_strength."""
+        if not 0.0 <= strength <= 1.0:             # pipeline.mojo:23-29
+            raise ValueError("Strength must be between 0 and 1")
         def as_context(c):
             c = np.asarray(c)
             if np.issubdtype(c.dtype, np.integer):      # token ids -> device CLIP
@@ -62,8 +103,10 @@ class Pipeline:
 
         context = as_context(context)
         n = self.max_images if latents is None else np.asarray(latents).shape[0]
+        if input_image is not None:
+            n = 1 if np.ndim(input_image) == 3 else np.shape(input_image)[0]
         rng = np.random.default_rng(seed_val)
-        if latents is None:
+        if latents is None and input_image is None:
             latents = rng.standard_normal((n, 4, self.side, self.side), dtype=np.float32)
         if noise is None:
             noise = rng.standard_normal((inference_steps, n, 4, self.side, self.side), dtype=np.float32)
@@ -73,7 +116,20 @@ class Pipeline:
         ctx_rows = context
         if use_cfg:
             ctx_rows = np.concatenate([context, as_context(uncond_context)], axis=0)
-        ts, temb, coef = self.schedule(inference_steps)
+        ts, temb, coef = self.schedule(inference_steps, strength=None if input_image is None else strength)
+        if input_image is not None:
+            img = np.asarray(input_image, np.float32)
+            img = img[None] if img.ndim == 3 else img
+            if encoder_noise is None:
+                encoder_noise = rng.standard_normal((n, 4, self.side, self.side), dtype=np.float32)
+            if start_noise is None:
+                start_noise = rng.standard_normal((n, 4, self.side, self.side), dtype=np.float32)
+            if len(ts) == 0:
+                raise ValueError("strength leaves no denoising step")
+            z = self.encode_image(img, encoder_noise)
+            sa, sb = DDPMSampler().add_noise_coefficients(int(ts[0]))
+            latents = self.ctx.sampler_add_noise(z, start_noise, sa, sb)
+            noise = np.asarray(noise)[inference_steps - len(ts):]
         lat = self.diffusion.generate_latents(latents, ctx_rows, ts, temb, coef, noise, cfg=use_cfg,
                                               cfg_scale=cfg_scale)
         if not decode:

@@ -11,7 +11,7 @@ import pytest
 import synth
 import tsd_oracle as O
 from conftest import GOLDEN, relerr
-from tsd_b200.api import Decoder, Diffusion
+from tsd_b200.api import Decoder, Diffusion, Encoder
 from tsd_b200._lib import TsdError
 from tsd_b200.pipeline import Pipeline
 from tsd_b200 import sampler as host_sampler
@@ -24,7 +24,7 @@ TOL_MODEL = 2e-2
 # a TF32 rounding of an intermediate activation (2^-11 relative) and propagate.  Bit-exactness is
 # asserted only for repeated evaluation of the same configuration.
 TOL_BATCH = 5e-3
-UNET_SEED, DEC_SEED = 1234, 1235
+UNET_SEED, DEC_SEED, ENC_SEED = 1234, 1235, 1236
 
 
 @pytest.fixture(scope="module")
@@ -384,3 +384,124 @@ def test_pipeline_generate_from_token_ids(ctx):
         p.diffusion.close()
         p.decoder.close()
         p.clip.close()
+
+
+# ---- VAE Encoder / img2img ---------------------------------------------
+@pytest.fixture(scope="module")
+def enc_golden():
+    return np.load(os.path.join(GOLDEN, "encoder_small.npz"))
+
+
+def test_encoder_param_table_matches_specs(ctx):
+    m = Encoder(ctx, 4, 4)
+    try:
+        specs = synth.encoder_specs()
+        assert m.num_params() == synth.num_params(specs) == 34_147_024
+        table = m.param_table()
+        assert [t[0] for t in table] == [s[0] for s in specs]
+        assert [t[2] for t in table] == [int(np.prod(s[1])) for s in specs]
+        with pytest.raises(TsdError):          # forward before weights
+            m.forward(np.zeros((3, 32, 32), np.float32), np.zeros((4, 4, 4), np.float32))
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("side", [4, 16])
+@pytest.mark.parametrize("axis,ln_mode,key", [(0, 0, "z%d"), (1, 1, "z%d_intended")])
+def test_encoder_matches_oracle_golden(ctx, enc_golden, side, axis, ln_mode, key):
+    """Encoder.forward (vae.mojo:131-159) at 32x32 and 128x128 images, reference and intended switches;
+    the image goes in as 0..255 and is rescaled on the device (pipeline.mojo:71)."""
+    g = enc_golden
+    m = Encoder(ctx, side, side, max_batch=2)
+    old = ctx.get_option("softmax_axis"), ctx.get_option("layernorm_mode")
+    try:
+        m.init_random(ENC_SEED)
+        ctx.set_option("softmax_axis", axis)
+        ctx.set_option("layernorm_mode", ln_mode)
+        img, noise, want = g[f"img{side}"], g[f"noise{side}"], g[key % side]
+        z = m.forward(img, noise, rescale=True)
+        e = relerr(z, want)
+        print(f"encoder {8 * side}x{8 * side} image, softmax_axis={axis}: rel_linf vs fp64 oracle {e:.2e}")
+        assert z.shape == (4, side, side) and e < TOL_MODEL
+        # already-rescaled input gives the same latent; a batch of two reproduces the single image
+        z1 = m.forward(img * np.float32(2.0) / np.float32(255.0) - np.float32(1.0), noise)
+        assert relerr(z1, z) < 1e-5
+        z2 = m.forward(np.stack([img, img[:, ::-1].copy()]), np.stack([noise, noise]), rescale=True)
+        assert relerr(z2[0], z) < TOL_BATCH
+        # zero reparameterisation noise -> the scaled mean; the noise enters linearly (vae.mojo:127-128)
+        z0 = m.forward(img, np.zeros_like(noise), rescale=True)
+        zh = m.forward(img, 0.5 * noise, rescale=True)
+        assert np.allclose(zh - z0, 0.5 * (z - z0), atol=1e-5 * float(np.abs(z).max()) + 1e-7)
+    finally:
+        ctx.set_option("softmax_axis", old[0])
+        ctx.set_option("layernorm_mode", old[1])
+        m.close()
+
+
+def test_encoder64_full_size_golden(ctx):
+    """512x512x3 -> 64x64x4 against tests/golden/encoder64.npz; the image is regenerated from its seed."""
+    g = np.load(os.path.join(GOLDEN, "encoder64.npz"))
+    rng = np.random.default_rng(51)
+    img = rng.uniform(0.0, 255.0, (3, 512, 512)).astype(np.float32)
+    noise = rng.standard_normal((4, 64, 64), dtype=np.float32)
+    assert np.array_equal(noise, g["noise"])
+    m = Encoder(ctx, 64, 64)
+    try:
+        m.init_random(ENC_SEED)
+        z = m.forward(img, noise, rescale=True)
+        e = relerr(z, g["z"])
+        print(f"encoder 512x512 image rel_linf vs fp64 oracle golden: {e:.2e}")
+        assert z.shape == (4, 64, 64) and e < TOL_MODEL
+        assert np.array_equal(m.forward(img, noise, rescale=True), z)     # graph replay == first pass
+    finally:
+        m.close()
+
+
+def test_encoder_validation(ctx):
+    m = Encoder(ctx, 4, 4)
+    try:
+        m.init_random(1)
+        with pytest.raises(TsdError):
+            m.forward(np.zeros((3, 16, 16), np.float32), np.zeros((4, 4, 4), np.float32))
+        with pytest.raises(TsdError):
+            m.forward(np.zeros((2, 3, 32, 32), np.float32), np.zeros((2, 4, 4, 4), np.float32))  # > max_batch
+        with pytest.raises(TsdError):
+            m.load_weights(np.zeros(10, np.float32))
+    finally:
+        m.close()
+
+
+def test_pipeline_img2img_start_and_loop(ctx, enc_golden):
+    """pipeline.mojo:66-79: resize -> rescale -> Encoder -> set_strength -> add_noise, then the loop over the
+    remaining timesteps.  The start latents are checked against the oracle golden; the loop against the same
+    pipeline started from those latents."""
+    g = enc_golden
+    p = Pipeline(ctx, image_size=128, max_images=1, cfg=False, seed=ENC_SEED - 3)   # encoder seed = seed + 3
+    try:
+        rng = np.random.default_rng(8)
+        cx = rng.standard_normal((1, 77, 768), dtype=np.float32)
+        noise = rng.standard_normal((5, 1, 4, 16, 16), dtype=np.float32)
+        small = g["img16"][:, ::2, ::2]                                    # 64x64 input, resized x2 on the way in
+        z = p.encode_image(small, g["noise16"])
+        want_z = O.encoder_forward(O.Ops("np", np.float64), synth.SynthWeights(synth.encoder_specs(), ENC_SEED),
+                                   O.rescale_input(O.resize_image(small.astype(np.float64), 128, 128)), g["noise16"])
+        assert relerr(z, want_z) < TOL_MODEL
+        ts, temb, coef = p.schedule(5, strength=0.6)
+        assert np.array_equal(ts, g["i2i_timesteps"]) and temb.shape == (3, 320) and coef.shape == (3, 5)
+        sa, sb = host_sampler.DDPMSampler().add_noise_coefficients(int(ts[0]))
+        start = ctx.sampler_add_noise(p.encode_image(g["img16"], g["noise16"]), g["i2i_start_noise"], sa, sb)
+        assert relerr(start, g["i2i_start"]) < TOL_MODEL
+        _, lat_a = p.generate(cx, inference_steps=5, input_image=g["img16"], strength=0.6,
+                              encoder_noise=g["noise16"][None], start_noise=g["i2i_start_noise"][None], noise=noise,
+                              decode=False)
+        lat_b = p.diffusion.generate_latents(start[None], cx, ts, temb, coef, noise[2:])
+        assert np.array_equal(lat_a, lat_b)
+        with pytest.raises(ValueError):
+            p.generate(cx, input_image=g["img16"], strength=1.5)
+        with pytest.raises(ValueError):
+            p.generate(cx, inference_steps=2, input_image=g["img16"], strength=0.0)   # no step left
+    finally:
+        p.diffusion.close()
+        p.decoder.close()
+        if p.encoder:
+            p.encoder.close()

@@ -49,6 +49,28 @@ def test_conv2d(ctx, ops, n, cin, h, w, cout, k, pad, stride):
     assert relerr(y, ref) < tol
 
 
+@pytest.mark.parametrize("n,cin,h,w,cout,stride", [
+    (1, 128, 32, 32, 128, 2),     # Encoder l4 geometry (vae.mojo:97): two_stride_pad + stride-2, tensor-core path
+    (2, 256, 16, 16, 256, 2),     # l7, batched
+    (1, 64, 9, 13, 48, 2),        # odd sizes: the last output row/column reads the zero row/column
+    (1, 8, 10, 10, 8, 2),         # CUDA-core direct path
+    (1, 64, 12, 12, 32, 1),       # stride 1 with one-sided padding
+])
+def test_conv2d_bottom_right_padding(ctx, ops, n, cin, h, w, cout, stride):
+    """Matrix.pad((0,1),(0,1)) + unpadded Conv2D (Encoder.two_stride_pad, vae.mojo:115-116) in one call."""
+    rng = np.random.default_rng(cin + h)
+    x = rng.standard_normal((n, cin, h, w), dtype=np.float32)
+    wt = (rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32)
+    b = rng.standard_normal(cout, dtype=np.float32)
+    y = ctx.conv2d(x, wt, b, pad=0, stride=stride, pad_hi=1)
+    ref = np.stack([ops.conv2d(x[i], wt, b, pad=0, stride=stride, pad_hi=1) for i in range(n)])
+    assert y.shape == ref.shape == (n, cout, (h + 1 - 3) // stride + 1, (w + 1 - 3) // stride + 1)
+    assert relerr(y, ref) < (TOL_FP32 if cin < 32 else TOL_TF32)
+    # the explicit pad followed by the plain conv gives the same result
+    xp = np.pad(x, ((0, 0), (0, 0), (0, 1), (0, 1)))
+    assert relerr(ctx.conv2d(xp, wt, b, pad=0, stride=stride), ref) < (TOL_FP32 if cin < 32 else TOL_TF32)
+
+
 def test_conv2d_no_bias_and_errors(ctx, ops):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((64, 8, 8), dtype=np.float32)
@@ -177,6 +199,19 @@ def test_sampler_step(ctx):
         assert relerr(got, want) < TOL_FP32
     got = ctx.sampler_step(lat, ec, None, 1.0, None, *[float(v) for v in sm.coefficients(500)])
     assert relerr(got, sm.step(500, lat.astype(np.float64), ec.astype(np.float64), None)) < TOL_FP32
+
+
+def test_sampler_add_noise(ctx):
+    """DDPMSampler.add_noise, sampler.mojo:111-124."""
+    rng = np.random.default_rng(10)
+    x, nz = (rng.standard_normal((4, 16, 16)).astype(np.float32) for _ in range(2))
+    sm = O.DDPMSampler()
+    for t in (999, 400, 0):
+        ab = sm.alphas_cumprod[t]
+        got = ctx.sampler_add_noise(x, nz, np.sqrt(ab), np.sqrt(1 - ab))
+        assert got.shape == x.shape and relerr(got, sm.add_noise(x.astype(np.float64), t, nz)) < TOL_FP32
+    with pytest.raises(TsdError):
+        ctx.sampler_add_noise(x, nz[:2], 1.0, 0.0)
 
 
 # ------------------------------------------------------------------------------------------------

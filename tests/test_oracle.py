@@ -273,3 +273,138 @@ def test_clip_golden_reproduced():
     W = synth.SynthWeights(synth.clip_specs(1000, 3), 77)
     y = O.clip_forward(O.Ops("np", np.float64), W, g["tokens"], n_layers=3)
     assert relerr(y, g["y_reference_switches"]) < 1e-12
+
+
+# ---- VAE Encoder / img2img ---------------------------------------------
+def test_encoder_param_inventory():
+    # vae.mojo:94-112, GroupNorm owns no tensor (utils.mojo:1825-1872)
+    def conv(ci, co, k):
+        return co * ci * k * k + co
+
+    def res(ci, co):
+        return conv(ci, co, 3) + conv(co, co, 3) + (conv(ci, co, 1) if ci != co else 0)
+
+    want = (conv(3, 128, 3) + 2 * res(128, 128) + conv(128, 128, 3) + res(128, 256) + res(256, 256) + conv(256, 256, 3)
+            + res(256, 512) + res(512, 512) + conv(512, 512, 3) + 4 * res(512, 512) + (512 * 1536 + 1536)
+            + (512 * 512 + 512) + conv(512, 8, 3) + conv(8, 8, 1))
+    # = the published SD-v1 VAE encoder (34 163 592) - its GroupNorm affine tensors (16 640) + quant_conv 8->8 (72)
+    assert synth.num_params(synth.encoder_specs()) == want == 34_163_592 - 16_640 + 72
+
+
+def test_asymmetric_pad_conv_vs_torch(ops64, opsc):
+    """two_stride_pad + stride-2 conv (vae.mojo:97,115-116) = F.pad(x, (0,1,0,1)) + conv2d(stride 2)."""
+    rng = np.random.default_rng(3)
+    for (h, w) in ((8, 8), (7, 10), (2, 2)):
+        x = rng.standard_normal((5, h, w))
+        wt = rng.standard_normal((6, 5, 3, 3)) * 0.2
+        b = rng.standard_normal(6)
+        ref = F.conv2d(F.pad(torch.from_numpy(x)[None], (0, 1, 0, 1)), torch.from_numpy(wt), torch.from_numpy(b),
+                       stride=2)[0].numpy()
+        got = ops64.conv2d(x, wt, b, pad=0, stride=2, pad_hi=1)
+        assert got.shape == ref.shape == (6, (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1)
+        assert relerr(got, ref) < 1e-12
+        assert relerr(opsc.conv2d(x, wt, b, pad=0, stride=2, pad_hi=1), ref) < 1e-5
+
+
+def test_latent_from_moments_definition(ops64):
+    """metrics_evals, vae.mojo:118-129, including the (-30, 20) clamp of the log-variance."""
+    m = np.zeros((8, 1, 3))
+    m[:4, 0] = [[1.0, -2.0, 0.5]] * 4
+    m[4:, 0] = [[0.0, 100.0, -100.0]] * 4          # -> std 1, e^10, e^-15
+    noise = np.full((4, 1, 3), 2.0)
+    got = O.latent_from_moments(ops64, m, noise)
+    want = (np.array([1.0, -2.0, 0.5]) + 2.0 * np.array([1.0, np.exp(10.0), np.exp(-15.0)])) * 0.18215
+    assert np.allclose(got[2, 0], want, rtol=1e-14)
+
+
+def test_resize_and_rescale_input():
+    img = np.arange(2 * 4 * 6, dtype=np.float64).reshape(2, 4, 6)
+    assert O.resize_image(img, 4, 6) is img
+    up = O.resize_image(img, 8, 12)            # nearest neighbour: every source pixel doubled
+    assert np.array_equal(up, img.repeat(2, 1).repeat(2, 2))
+    down = O.resize_image(img, 2, 3)
+    assert np.array_equal(down, img[:, ::2, ::2])
+    assert np.allclose(O.rescale_input(np.array([0.0, 127.5, 255.0])), [-1.0, 0.0, 1.0])
+
+
+def test_set_strength_slices_the_schedule():
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(20)
+    full = sm.timesteps.copy()
+    sm.set_strength(0.8)                       # start_step = 20 - int(16.0) = 4 (sampler.mojo:67-73)
+    assert sm.start_step == 4 and np.array_equal(sm.timesteps, full[4:])
+    x, nz = np.ones(5), np.full(5, 2.0)
+    ab = sm.alphas_cumprod[int(sm.timesteps[0])]
+    assert np.allclose(sm.add_noise(x, sm.timesteps[0], nz), np.sqrt(ab) + 2.0 * np.sqrt(1 - ab))
+
+
+def test_encoder_intended_switches_vs_torch():
+    """Independent torch restatement of Encoder.forward (key-axis softmax; GroupNorm keeps the reference's
+    (x - mean) / (std + eps) formula) at a 32x32 image."""
+    specs = synth.encoder_specs()
+    W = synth.BlobWeights(specs, synth.random_blob(specs, 9))
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, (3, 32, 32))
+    noise = rng.standard_normal((4, 4, 4))
+    got = O.encoder_forward(O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token")), W, x, noise)
+
+    tw = lambda name: torch.from_numpy(np.asarray(W[name], np.float64))  # noqa: E731
+
+    def gn(v, g):
+        c, h, w = v.shape
+        r = v.reshape(g, -1)
+        m = r.mean(1, keepdim=True)
+        s = ((r - m) ** 2).mean(1, keepdim=True).sqrt()
+        return ((r - m) / (s + 1e-5)).reshape(c, h, w)
+
+    def conv(v, name, pad=0, stride=1):
+        return F.conv2d(v[None], tw(name + ".weight"), tw(name + ".bias"), padding=pad, stride=stride)[0]
+
+    def res(v, name, ci, co):
+        o = conv(F.silu(gn(v, 16)), name + ".conv1", 1)
+        o = conv(F.silu(gn(o, 16)), name + ".conv2", 1)
+        return o + (conv(v, name + ".res_conv_layer") if ci != co else v)
+
+    def down(v, name):
+        return conv(F.pad(v, (0, 1, 0, 1)), name, 0, 2)
+
+    v = conv(torch.from_numpy(x), "l1", 1)
+    v = res(res(v, "l2", 128, 128), "l3", 128, 128)
+    v = down(v, "l4")
+    v = res(res(v, "l5", 128, 256), "l6", 256, 256)
+    v = down(v, "l7")
+    v = res(res(v, "l8", 256, 512), "l9", 512, 512)
+    v = down(v, "l10")
+    for n in ("l11", "l12", "l13"):
+        v = res(v, n, 512, 512)
+    c, h, w = v.shape
+    seq = gn(v, 32).reshape(c, h * w).T
+    qkv = seq @ tw("l14.attention.in_proj.weight").T + tw("l14.attention.in_proj.bias")
+    q, k, vv = (qkv[:, i * c:(i + 1) * c] for i in range(3))
+    o = F.scaled_dot_product_attention(q[None, None], k[None, None], vv[None, None])[0, 0]
+    o = o @ tw("l14.attention.out_proj.weight").T + tw("l14.attention.out_proj.bias")
+    v = o.T.reshape(c, h, w) + v
+    v = res(v, "l15", 512, 512)
+    v = conv(F.silu(gn(v, 32)), "l18", 1)
+    v = conv(v, "l19")
+    mean, logvar = v[:4], v[4:].clamp(-30, 20)
+    ref = ((mean + torch.from_numpy(noise) * (0.5 * logvar).exp()) * 0.18215).numpy()
+    assert got.shape == (4, 4, 4)
+    assert relerr(got, ref) < 1e-10
+
+
+def test_encoder_golden_reproduced(opsc):
+    """tests/golden/encoder_small.npz (tools/make_golden.py encoder) pins the Encoder restatement; the C
+    loops (fp32) agree with the fp64 evaluation."""
+    g = np.load(os.path.join(GOLDEN, "encoder_small.npz"))
+    W = synth.SynthWeights(synth.encoder_specs(), 1236)
+    x = O.rescale_input(g["img4"].astype(np.float64))
+    z = O.encoder_forward(O.Ops("np", np.float64), W, x, g["noise4"])
+    assert relerr(z, g["z4"]) < 1e-12
+    assert relerr(O.encoder_forward(opsc, W, x.astype(np.float32), g["noise4"]), g["z4"]) < 2e-4
+    assert os.path.exists(os.path.join(GOLDEN, "encoder64.npz")), "run tools/make_golden.py encoder64"
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(5)
+    sm.set_strength(0.6)
+    assert np.array_equal(sm.timesteps, g["i2i_timesteps"])
+    assert relerr(sm.add_noise(g["z16"], sm.timesteps[0], g["i2i_start_noise"].astype(np.float64)), g["i2i_start"]) < 1e-14

@@ -8,6 +8,8 @@ checked at the full BASELINE sizes, where running the oracle inside a test would
   python tools/make_golden.py unet64     # one UNet step at the 64x64 latent of BASELINE config 2
   python tools/make_golden.py decoder64  # one VAE decode 64x64x4 -> 512x512x3 (stored subsampled)
   python tools/make_golden.py clip       # CLIP text encoder, 1000-token vocabulary, 3 layers, both switch sets
+  python tools/make_golden.py encoder    # VAE Encoder at 32x32 / 128x128 images + the img2img start latents
+  python tools/make_golden.py encoder64  # VAE Encoder 512x512x3 -> 64x64x4
 """
 import os
 import sys
@@ -113,5 +115,50 @@ def clip():
                         y_intended_switches=y_int)
 
 
+ENC_SEED = 1236
+
+
+def encoder_inputs(seed, side):
+    """image in (0,255) of (3, 8*side, 8*side) and the reparameterisation noise (4, side, side)"""
+    rng = np.random.default_rng(seed)
+    img = rng.uniform(0.0, 255.0, (3, 8 * side, 8 * side)).astype(np.float32)
+    noise = rng.standard_normal((4, side, side), dtype=np.float32)
+    return img, noise
+
+
+def encoder():
+    """VAE Encoder (row f3) at 32x32 and 128x128 images (latents 4x4 and 16x16), both switch sets."""
+    We = synth.SynthWeights(synth.encoder_specs(), ENC_SEED)
+    out = {}
+    t0 = time.time()
+    for side in (4, 16):
+        img, noise = encoder_inputs(40 + side, side)
+        out[f"img{side}"], out[f"noise{side}"] = img, noise
+        out[f"z{side}"] = O.encoder_forward(O.Ops("np", np.float64), We, O.rescale_input(img.astype(np.float64)), noise)
+        out[f"z{side}_intended"] = O.encoder_forward(
+            O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token")), We,
+            O.rescale_input(img.astype(np.float64)), noise)
+    # img2img start (pipeline.mojo:66-79) at the 16x16 latent: strength 0.6 of 5 steps
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(5)
+    sm.set_strength(0.6)
+    start_noise = np.random.default_rng(77).standard_normal((4, 16, 16), dtype=np.float32)
+    out.update(i2i_timesteps=sm.timesteps, i2i_start_noise=start_noise,
+               i2i_start=sm.add_noise(out["z16"], sm.timesteps[0], start_noise.astype(np.float64)))
+    print(f"encoder oracle: {time.time() - t0:.1f} s")
+    np.savez_compressed(os.path.join(G, "encoder_small.npz"), **out)
+
+
+def encoder64():
+    We = synth.SynthWeights(synth.encoder_specs(), ENC_SEED)
+    img, noise = encoder_inputs(51, 64)
+    t0 = time.time()
+    z = O.encoder_forward(O.Ops("np", np.float64), We, O.rescale_input(img.astype(np.float64)), noise)
+    print("encoder64 oracle seconds", time.time() - t0, flush=True)
+    # the 512x512 image is regenerated from its seed in the test; only the latent is stored
+    np.savez_compressed(os.path.join(G, "encoder64.npz"), noise=noise, z=z.astype(np.float64))
+
+
 if __name__ == "__main__":
-    {"small": small, "unet64": unet64, "decoder64": decoder64, "clip": clip}[sys.argv[1]]()
+    {"small": small, "unet64": unet64, "decoder64": decoder64, "clip": clip, "encoder": encoder,
+     "encoder64": encoder64}[sys.argv[1]]()
