@@ -46,6 +46,7 @@ typedef struct tsd_diffusion tsd_diffusion; /* Diffusion (diffusion.mojo:294-318
 typedef struct tsd_decoder tsd_decoder;     /* VAE Decoder (vae.mojo:162-250) */
 typedef struct tsd_clip tsd_clip;           /* CLIP text encoder (clip.mojo:56-109) */
 typedef struct tsd_encoder tsd_encoder;     /* VAE Encoder (vae.mojo:70-159) */
+typedef struct tsd_tokenizer tsd_tokenizer; /* Tokenizer (helpers/utils.mojo:228-292) */
 
 /* ---- context ------------------------------------------------------------------------ */
 int32_t tsd_init(int32_t device, tsd_ctx** out);
@@ -255,6 +256,34 @@ typedef struct tsd_loop_params {
 /* latents (n,4,H,W) in/out; context (n_ctx,77,768): cond rows first, then (if cfg) uncond rows */
 int32_t tsd_generate_latents(tsd_diffusion* m, const tsd_loop_params* lp, const float* latents_in,
                              const float* context, int32_t n_ctx, int32_t n, float* latents_out);
+
+/* ---- host-side data formats: no device, no tsd_ctx ------------------------
+ * Tokenizer(vocab_size, buf) (helpers/utils.mojo:236-249) over the tokenizer_clip.bin layout written by
+ * tokenizer_creation.py:44-48: uint32 max_token_length, then per token float32 score, uint32 length,
+ * bytes.  A truncated file is an error (the reference prints and carries on with zeros).  Token strings
+ * are C strings as in the reference (cut at the first NUL byte). */
+int32_t tsd_tokenizer_load(const char* path, int32_t vocab_size, tsd_tokenizer** out);
+int32_t tsd_tokenizer_from_memory(const void* buf, int64_t size, int32_t vocab_size, tsd_tokenizer** out);
+int32_t tsd_tokenizer_destroy(tsd_tokenizer* t);
+int32_t tsd_tokenizer_vocab_size(const tsd_tokenizer* t);
+int32_t tsd_tokenizer_max_token_length(const tsd_tokenizer* t);
+const uint8_t* tsd_tokenizer_token(const tsd_tokenizer* t, int32_t id, int32_t* len, float* score);
+/* Tokenizer.find (utils.mojo:276-292) including wrap (:197-206); -1 when absent. */
+int32_t tsd_tokenizer_find(const tsd_tokenizer* t, const uint8_t* s, int32_t len);
+/* bpe_encode (utils.mojo:294-327): one token per byte, then greedy merges of the adjacent pair whose
+ * concatenation has the highest score (first wins on ties).  concat_mode 0 = str_concat as written
+ * (utils.mojo:214-224: each output position receives the first byte of its source string), 1 = plain
+ * concatenation (the intent).  A byte without a token: TSD_ERR_INVALID with the ids collected so far in
+ * ids / n_out (the reference prints "Not a good prompt token" and returns that prefix).  n_out > cap:
+ * TSD_ERR_OOM, nothing written.  The caller applies prompt.replace(" ", "</w>") (pipeline.mojo:39-40). */
+int32_t tsd_tokenizer_encode(const tsd_tokenizer* t, const uint8_t* text, int32_t len, int32_t concat_mode,
+                             int32_t* ids, int32_t cap, int32_t* n_out);
+/* 8-bit PNG of the (c,h,w) planar float image pipeline.generate returns (values 0..255 after
+ * rescale(clamp), pipeline.mojo:127-128; c = 1, 3 or 4): round half up, clamp, filter 0, stored deflate
+ * blocks.  tsd_png_encode with out == NULL returns the size needed. */
+int32_t tsd_png_encode(const float* img, int32_t c, int32_t h, int32_t w, uint8_t* out, int64_t cap,
+                       int64_t* size);
+int32_t tsd_png_write(const char* path, const float* img, int32_t c, int32_t h, int32_t w);
 
 /* ---- tuning probes (synthetic device-resident operands, CUDA-event ms per launch) ------------ */
 int32_t tsd_bench_gemm(tsd_ctx* ctx, int32_t m, int32_t n, int32_t k, int32_t batch, int32_t geglu,

@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -Wno-deprecated-gpu-targets -std=c++17 -Xcompiler -fPIC
        -Xcompiler -fvisibility=hidden -DTSD_BUILD)
 mkdir -p build
-SRCS=(gemm_tcgen05.cu attention_tcgen05.cu elementwise.cu runtime.cu models.cu models_clip.cu c_api.cu c_api_models.cu)
+SRCS=(gemm_tcgen05.cu attention_tcgen05.cu elementwise.cu runtime.cu models.cu models_clip.cu c_api.cu c_api_models.cu host_io.cu)
 pids=()
 for s in "${SRCS[@]}"; do
   [ -f "$s" ] || continue

@@ -143,7 +143,8 @@ size_t Clip::workspace_bytes() const {
 
 int Clip::forward(const int32_t* tokens, int n, float* out, bool host_ptrs) {
   if (!ps.loaded) return c->fail(TSD_ERR_STATE, "clip: forward before load_weights / init_random");
-  if (!tokens || !out || n <= 0 || n > n_tokens) return c->fail(TSD_ERR_INVALID, "clip: bad token buffer");
+  // n = 0 is the empty prompt (the default backup_prompt, pipeline.mojo:15): 77 zero ids after the padding
+  if (!out || n < 0 || n > n_tokens || (!tokens && n)) return c->fail(TSD_ERR_INVALID, "clip: bad token buffer");
   cudaSetDevice(c->device);
   // reshaped_tokens = zeros(77); first n entries = tokens (clip.mojo:90-92)
   std::vector<int32_t> padded(n_tokens, 0);
@@ -166,7 +167,7 @@ int Clip::forward(const int32_t* tokens, int n, float* out, bool host_ptrs) {
     TRY(c->check(cudaStreamSynchronize(c->stream), "clip token upload"));  // `padded` is a stack-lifetime buffer
   } else {
     TRY(c->check(cudaMemsetAsync(tokens_dev, 0, sizeof(int32_t) * n_tokens, c->stream), "clear tokens"));
-    TRY(c->check(cudaMemcpyAsync(tokens_dev, tokens, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, c->stream), "copy tokens"));
+    if (n) TRY(c->check(cudaMemcpyAsync(tokens_dev, tokens, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, c->stream), "copy tokens"));
   }
   TRY(encode());
   TRY(c->check(cudaMemcpyAsync(out, out_dev, sizeof(float) * (size_t)n_tokens * n_embed,

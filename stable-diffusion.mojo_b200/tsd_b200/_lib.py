@@ -129,6 +129,17 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_diffusion_forward_dev", i32, vp, fp, fp, i32, fp, i32, i32, fp)
     sig("tsd_diffusion_profile", i32, vp, fp, fp, i32, fp, i32, i32, fp, c_double_p, c_double_p,
         c_i64_p)
+    i32p = C.POINTER(C.c_int32)
+    sig("tsd_tokenizer_load", i32, C.c_char_p, i32, C.POINTER(vp))
+    sig("tsd_tokenizer_from_memory", i32, vp, i64, i32, C.POINTER(vp))
+    sig("tsd_tokenizer_destroy", i32, vp)
+    sig("tsd_tokenizer_vocab_size", i32, vp)
+    sig("tsd_tokenizer_max_token_length", i32, vp)
+    sig("tsd_tokenizer_token", vp, vp, i32, i32p, C.POINTER(C.c_float))
+    sig("tsd_tokenizer_find", i32, vp, C.c_char_p, i32)
+    sig("tsd_tokenizer_encode", i32, vp, C.c_char_p, i32, i32, i32p, i32, i32p)
+    sig("tsd_png_encode", i32, fp, i32, i32, i32, vp, i64, C.POINTER(i64))
+    sig("tsd_png_write", i32, C.c_char_p, fp, i32, i32, i32)
     sig("tsd_decoder_create", i32, vp, i32, i32, i32, C.POINTER(vp))
     sig("tsd_decoder_destroy", i32, vp)
     sig("tsd_decoder_num_params", i64, vp)

@@ -11,11 +11,13 @@ import numpy as np
 
 from .api import Clip, Context, Decoder, Diffusion, Encoder
 from .sampler import DDPMSampler, get_time_embedding
+from .tokenizer import Tokenizer, prompt_tokens
 
 
 class Pipeline:
     def __init__(self, ctx: Context, image_size: int = 512, max_images: int = 1, cfg: bool = True, seed: int = 0,
-                 weights=None, with_clip: bool = False, clip_vocab: int = 0, clip_layers: int = 0):
+                 weights=None, with_clip: bool = False, clip_vocab: int = 0, clip_layers: int = 0,
+                 tokenizer=None, tokenizer_vocab: int = 49408, concat_as_written: bool = True):
         if image_size % 32:
             raise ValueError("image_size must be a multiple of 32 (latent side a multiple of 4)")
         self.ctx = ctx
@@ -27,6 +29,9 @@ class Pipeline:
         self.decoder = Decoder(ctx, self.side, self.side, max_batch=max_images)
         self.clip = Clip(ctx, clip_vocab, clip_layers) if with_clip else None
         self.encoder = None
+        # Tokenizer(49408, read_file("tokenizer_clip.bin")), pipeline.mojo:32-37: a path, the file's bytes or a Tokenizer
+        self.tokenizer = tokenizer if tokenizer is None or isinstance(tokenizer, Tokenizer) else Tokenizer(tokenizer, tokenizer_vocab)
+        self.concat_as_written = concat_as_written
         self._weights, self._seed = weights, seed
         if weights is None:
             self.diffusion.init_random(seed)
@@ -38,6 +43,11 @@ class Pipeline:
             self.decoder.load_weights(weights[1])
             if self.clip:
                 self.clip.load_weights(weights[2])
+
+    def close(self):
+        for m in (self.diffusion, self.decoder, self.clip, self.encoder):
+            if m is not None:
+                m.close()
 
     def encode_tokens(self, tokens) -> np.ndarray:
         """clip.forward(tokens) of pipeline.mojo:45-53: token ids (<= 77, zero-padded) -> (77, 768) context."""
@@ -95,6 +105,10 @@ class Pipeline:
         if not 0.0 <= strength <= 1.0:             # pipeline.mojo:23-29
             raise ValueError("Strength must be between 0 and 1")
         def as_context(c):
+            if isinstance(c, str):                      # prompt -> bpe_encode -> token ids (pipeline.mojo:39-53)
+                if self.tokenizer is None:
+                    raise ValueError("pipeline was created without a tokenizer")
+                c = prompt_tokens(c, self.tokenizer, self.concat_as_written)
             c = np.asarray(c)
             if np.issubdtype(c.dtype, np.integer):      # token ids -> device CLIP
                 return self.encode_tokens(c)[None]
@@ -135,3 +149,25 @@ class Pipeline:
         if not decode:
             return None, lat
         return self.decoder.forward(lat, rescale=rescale), lat
+
+
+def generate(prompt: str, backup_prompt: str = "", strength: float = 0.8, cfg: bool = True, cfg_scale: float = 7.5,
+             inference_steps: int = 1, seed_val: int = 0, input_image=None, *, image_size: int = 512, ctx=None,
+             tokenizer="tokenizer_clip.bin", weights=None, pipeline: Pipeline | None = None):
+    """pipeline.generate (pipeline.mojo:13-128) with the reference's argument list: prompt -> tokenizer -> CLIP
+    -> (optional img2img start) -> denoising loop -> Decoder -> (3, image_size, image_size) image in 0..255.
+    Weights are random as in the reference unless `weights` = (diffusion, decoder, clip[, encoder]) blobs.
+    Pass `pipeline` to reuse the model handles between calls (the reference rebuilds them every time)."""
+    if not 0.0 <= strength <= 1.0:                                   # pipeline.mojo:23-29
+        raise ValueError("Strength must be between 0 and 1")
+    own = pipeline is None
+    p = pipeline or Pipeline(ctx or Context(0), image_size=image_size, max_images=1, cfg=cfg, seed=seed_val,
+                             weights=weights, with_clip=True, tokenizer=tokenizer)
+    try:
+        img, _ = p.generate(prompt, backup_prompt if cfg else None, cfg_scale=cfg_scale,
+                            inference_steps=inference_steps, seed_val=seed_val, input_image=input_image,
+                            strength=strength)
+        return img[0]
+    finally:
+        if own:
+            p.close()

@@ -362,6 +362,9 @@ def test_clip_load_weights_and_validation(ctx):
         tokens = [5, 63, 0, 17]
         ref = O.clip_forward(O.Ops("np", np.float64), synth.BlobWeights(specs, blob), tokens, n_layers=1)
         assert relerr(m.forward(tokens), ref) < TOL_MODEL
+        # the empty prompt (default backup_prompt, pipeline.mojo:15) = 77 zero ids (clip.mojo:90-92)
+        empty = m.forward([])
+        assert np.array_equal(empty, m.forward([0])) and np.array_equal(empty, m.forward([0] * 77))
         with pytest.raises(TsdError):
             m.forward([64])                # token id outside the vocabulary
         with pytest.raises(TsdError):
@@ -505,3 +508,37 @@ def test_pipeline_img2img_start_and_loop(ctx, enc_golden):
         p.decoder.close()
         if p.encoder:
             p.encoder.close()
+
+
+# ---- prompt string -> image (rows f1 + f4 around the hot path) -------------------------------------
+def test_generate_from_prompt_string(ctx, tmp_path):
+    """pipeline.generate(prompt, backup_prompt, ...) with the reference's argument list (pipeline.mojo:13-22):
+    tokenizer .bin -> bpe_encode -> CLIP -> loop with CFG -> Decoder; equal to feeding the token ids, and the
+    returned image is written as a PNG."""
+    from tsd_b200 import pipeline as PL
+    from tsd_b200.image import save_png
+    from tsd_b200.tokenizer import Tokenizer, prompt_tokens
+    tok_path = os.path.join(GOLDEN, "tokenizer_small.bin")
+    p = Pipeline(ctx, image_size=64, max_images=1, cfg=True, seed=3, with_clip=True, clip_vocab=400, clip_layers=2,
+                 tokenizer=tok_path, tokenizer_vocab=341)
+    try:
+        prompt, backup = "a cat flying a spaceship", ""
+        img = PL.generate(prompt, backup, cfg=True, cfg_scale=7.5, inference_steps=2, seed_val=5, pipeline=p)
+        tok = Tokenizer(tok_path, 341)
+        ids, ids_b = prompt_tokens(prompt, tok), prompt_tokens(backup, tok)
+        assert ids.size == 31 and ids_b.size == 0
+        img_ids, _ = p.generate(ids, ids_b, inference_steps=2, seed_val=5)
+        assert img.shape == (3, 64, 64) and np.array_equal(img, img_ids[0])
+        assert img.min() >= 0 and img.max() <= 255
+        # img2img through the same call: strength 0.5 of 2 steps leaves one step
+        img2 = PL.generate(prompt, backup, strength=0.5, cfg=False, inference_steps=2, seed_val=5,
+                           input_image=img, pipeline=p)
+        assert img2.shape == (3, 64, 64) and np.isfinite(img2).all()
+        with pytest.raises(ValueError):
+            PL.generate(prompt, strength=1.2, pipeline=p)
+        save_png(tmp_path / "out.png", img)
+        from PIL import Image
+        got = np.asarray(Image.open(tmp_path / "out.png"))
+        assert np.array_equal(got, np.floor(img + 0.5).astype(np.uint8).transpose(1, 2, 0))
+    finally:
+        p.close()

@@ -10,6 +10,7 @@ checked at the full BASELINE sizes, where running the oracle inside a test would
   python tools/make_golden.py clip       # CLIP text encoder, 1000-token vocabulary, 3 layers, both switch sets
   python tools/make_golden.py encoder    # VAE Encoder at 32x32 / 128x128 images + the img2img start latents
   python tools/make_golden.py encoder64  # VAE Encoder 512x512x3 -> 64x64x4
+  python tools/make_golden.py tokenizer  # synthetic tokenizer .bin + known-answer token ids
 """
 import os
 import sys
@@ -159,6 +160,32 @@ def encoder64():
     np.savez_compressed(os.path.join(G, "encoder64.npz"), noise=noise, z=z.astype(np.float64))
 
 
+TOK_PROMPTS = ["a cat flying a spaceship", "photo of an astronaut riding a horse on mars", "", "x",
+               "it's a \"quoted\" prompt", "tab\there", "caf\u00e9 at night", "the  double  space",
+               "highly detailed oil painting of an old castle at sunset"]
+
+
+def tokenizer():
+    """Row f4: a synthetic vocabulary in tokenizer_clip.bin layout (written by the restatement of
+    tokenizer_creation.py) and the ids the restated bpe_encode gives, for both str_concat readings."""
+    import json
+    import tokenizer_oracle as T
+    keys, merges = T.synthetic_vocab()
+    blob = T.tokenizer_bin(keys, merges)
+    with open(os.path.join(G, "tokenizer_small.bin"), "wb") as f:
+        f.write(blob)
+    tok = T.Tokenizer(len(keys), blob)
+    cases = []
+    for p in TOK_PROMPTS:
+        text = T.preprocess_prompt(p)
+        a, ok_a = T.bpe_encode(text, tok, True)
+        b, ok_b = T.bpe_encode(text, tok, False)
+        cases.append(dict(prompt=p, as_written=a, intended=b, complete=ok_a and ok_b))
+    with open(os.path.join(G, "tokenizer_small.json"), "w") as f:
+        json.dump(dict(vocab_size=len(keys), n_merges=len(merges), cases=cases), f)
+    print("tokenizer golden:", len(keys), "tokens,", len(blob), "bytes")
+
+
 if __name__ == "__main__":
-    {"small": small, "unet64": unet64, "decoder64": decoder64, "clip": clip, "encoder": encoder,
+    {"tokenizer": tokenizer, "small": small, "unet64": unet64, "decoder64": decoder64, "clip": clip, "encoder": encoder,
      "encoder64": encoder64}[sys.argv[1]]()
