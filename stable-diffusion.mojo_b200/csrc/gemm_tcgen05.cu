@@ -13,16 +13,18 @@ namespace {
 __device__ __forceinline__ float gelu_tanh(float x) {
   // reference Gelu.forward, helpers/utils.mojo:1908-1919 (tanh form)
   const float k = 0.7978845608028654f;  // sqrt(2/pi)
-  float u = k * (x + 0.044715f * x * x * x);
+  const float u = x * fmaf(x * x, 0.044715f * k, k);  // k (x + 0.044715 x^3)
   float t;
   asm("tanh.approx.f32 %0, %1;\n" : "=f"(t) : "f"(u));  // MUFU.TANH, rel. error 2^-11 (TF32 level)
-  return 0.5f * x * (1.0f + t);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
+// Round to nearest (ties away) at TF32 precision.  ptxas expands cvt.rna.tf32.f32 into this add-and-mask plus an
+// Inf/NaN guard per element; the unguarded form gives the same bits for every finite input, keeps +-Inf, turns an
+// overflowing finite value into Inf as rounding must, and keeps NaN a NaN (except the all-ones payload).
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 }  // namespace
@@ -128,6 +130,62 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+// Store phase of one 32-column chunk: this lane's 8 rows x 4 columns, staged tile -> (scale, bias, residual,
+// TF32 rounding) -> global, plus the per-column (sum, sum^2) of what was stored.  Compile-time variants keep the
+// row loop free of branches and of re-derived predicates: measured, the branchy runtime form cost ~130 cycles per
+// row (a constant-bank reload and a branch per row, nothing overlapping) against ~25 here.
+//   FULL  - all 8 rows of every lane of the warp lie inside the image (no row predicate at all)
+//   RES / ROUND / STATS - residual add, TF32 rounding of the output, column statistics
+template <bool FULL, bool RES, bool ROUND, bool STATS>
+__device__ __forceinline__ void store_chunk_rows(const float* __restrict__ st, float sc, float4 b4,
+                                                 float* const (&drow)[8], const float* const (&rrow)[8],
+                                                 long long col, int n, float4& ss, float4& qq) {
+  float4 t[8], rr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(st + i * (4 * 36));
+  if (RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      rr[i] = (FULL || drow[i] != nullptr) ? *reinterpret_cast<const float4*>(rrow[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 u = t[i];
+    u.x = fmaf(u.x, sc, b4.x); u.y = fmaf(u.y, sc, b4.y); u.z = fmaf(u.z, sc, b4.z); u.w = fmaf(u.w, sc, b4.w);
+    if (RES) {
+      u.x += rr[i].x; u.y += rr[i].y; u.z += rr[i].z; u.w += rr[i].w;
+    }
+    if (ROUND) {
+      u.x = round_tf32(u.x); u.y = round_tf32(u.y); u.z = round_tf32(u.z); u.w = round_tf32(u.w);
+    }
+    if (FULL) {
+      *reinterpret_cast<float4*>(drow[i] + col) = u;
+      if (STATS) {
+        ss.x += u.x; ss.y += u.y; ss.z += u.z; ss.w += u.w;
+        qq.x = fmaf(u.x, u.x, qq.x); qq.y = fmaf(u.y, u.y, qq.y); qq.z = fmaf(u.z, u.z, qq.z); qq.w = fmaf(u.w, u.w, qq.w);
+      }
+    } else if (drow[i] != nullptr) {
+      *reinterpret_cast<float4*>(drow[i] + col) = u;
+      if (STATS) {
+        ss.x += u.x; ss.y += u.y; ss.z += u.z; ss.w += u.w;
+        qq.x = fmaf(u.x, u.x, qq.x); qq.y = fmaf(u.y, u.y, qq.y); qq.z = fmaf(u.z, u.z, qq.z); qq.w = fmaf(u.w, u.w, qq.w);
+      }
+    }
+  }
+}
+template <bool FULL, bool RES>
+__device__ __forceinline__ void store_chunk_dispatch(bool round_out, bool stats, const float* __restrict__ st, float sc,
+                                                     float4 b4, float* const (&drow)[8], const float* const (&rrow)[8],
+                                                     long long col, int n, float4& ss, float4& qq) {
+  if (round_out) {
+    if (stats) store_chunk_rows<FULL, RES, true, true>(st, sc, b4, drow, rrow, col, n, ss, qq);
+    else store_chunk_rows<FULL, RES, true, false>(st, sc, b4, drow, rrow, col, n, ss, qq);
+  } else {
+    if (stats) store_chunk_rows<FULL, RES, false, true>(st, sc, b4, drow, rrow, col, n, ss, qq);
+    else store_chunk_rows<FULL, RES, false, false>(st, sc, b4, drow, rrow, col, n, ss, qq);
+  }
+}
+
 // ===================== epilogue (8 warps: kernel warps 2..9) =====================
 // TMEM -> registers (thread = output row) -> per-warp shared staging tile -> coalesced global
 // stores (8 lanes x 16 B cover 128 B of one row; a warp instruction writes 4 full rows).
@@ -203,6 +261,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
     drow[i] = ok ? dbase + g * ldd : nullptr;
     rrow[i] = rbase ? rbase + g * p.ldr : nullptr;
   }
+  bool rows_all = true;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rows_all = rows_all && (drow[i] != nullptr);
+  const bool rows_full = __all_sync(0xffffffffu, rows_all) != 0;  // warp-uniform: no row predicates in the store phase
   const bool routed = !partial && p.split_n < (1 << 30);
   const bool vec_ok = partial || (((n_valid | p.ldd | p.split_n) & 3) == 0 && (p.split_stride & 3) == 0 &&
                                   (rbase == nullptr || (p.ldr & 3) == 0) &&
@@ -220,6 +282,30 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
     named_bar_sync(3, 256);
     ln_r = ln_st[0].y;
     ln_rmu = ln_st[0].x * ln_st[0].y;
+  }
+  // Effective column bias of this tile, bias[n] - r*mu*rowsum(W)[n] (LayerNorm fold), staged in shared memory
+  // while the K loop is still running: the thread = row GEGLU math reads it as broadcast LDS.128 and the store
+  // phase as one LDS.128 per chunk, instead of global loads on the critical path after the accumulator barrier.
+  // GEGLU: [0, out_cols) value half, [128, 128 + out_cols) gate half.
+  __shared__ __align__(16) float eb[256];
+  const bool use_eb = !partial || fixup;
+  if (use_eb) {
+    const int te = threadIdx.x - 64;
+    const float* cb = p.bias ? p.bias + (long long)img * p.bias_img_stride : nullptr;
+    float e = 0.0f;
+    int nsrc = -1;
+    if (geglu) {
+      const int hcol = te & 127;
+      if (hcol < out_cols && n0 + hcol < n_valid) nsrc = (te >> 7) * p.n_half + n0 + hcol;
+    } else if (te < p.BN && n0 + te < n_valid) {
+      nsrc = n0 + te;
+    }
+    if (nsrc >= 0) {
+      if (cb != nullptr) e = __ldg(cb + nsrc);
+      if (ln_fold) e -= ln_rmu * __ldg(p.wsum + nsrc);
+    }
+    eb[te] = e;
+    named_bar_sync(3, 256);
   }
   // producer-side norm statistics: per-column (sum, sum^2) of the stored values of this tile
   const bool want_stats = p.ns.partial != nullptr && (!partial || fixup);
@@ -252,33 +338,35 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
 #pragma unroll
         for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(__uint_as_float(g[j]) + __uint_as_float(g1[j]));
       }
-      float bo[32], bg[32];
+      if (threadIdx.x == 64 && c == 0) tr[8] = clock64();
+      tmem_ld_wait();
+      if (threadIdx.x == 64 && c == 0) tr[9] = clock64();
+      const float4* bo4 = reinterpret_cast<const float4*>(eb + c);
+      const float4* bg4 = reinterpret_cast<const float4*>(eb + 128 + c);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c + j;
-        const bool okb = cbias != nullptr && n < n_valid && c + j < out_cols;
-        bo[j] = okb ? __ldg(cbias + n) : 0.0f;
-        bg[j] = okb ? __ldg(cbias + p.n_half + n) : 0.0f;
-        if (ln_fold && n < n_valid && c + j < out_cols) {
-          bo[j] -= ln_rmu * __ldg(p.wsum + n);
-          bg[j] -= ln_rmu * __ldg(p.wsum + p.n_half + n);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float4 bo = bo4[j], bg = bg4[j];
+        v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), ln_r, bo.x) * gelu_tanh(fmaf(__uint_as_float(g[4 * j + 0]), ln_r, bg.x)));
+        v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), ln_r, bo.y) * gelu_tanh(fmaf(__uint_as_float(g[4 * j + 1]), ln_r, bg.y)));
+        v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), ln_r, bo.z) * gelu_tanh(fmaf(__uint_as_float(g[4 * j + 2]), ln_r, bg.z)));
+        v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), ln_r, bo.w) * gelu_tanh(fmaf(__uint_as_float(g[4 * j + 3]), ln_r, bg.w)));
       }
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), ln_r, bo[j]) * gelu_tanh(fmaf(__uint_as_float(g[j]), ln_r, bg[j])));
     } else {
+      if (threadIdx.x == 64 && c == 0) tr[8] = clock64();
       tmem_ld_wait();
+      if (threadIdx.x == 64 && c == 0) tr[9] = clock64();
       if (!plain) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), alpha, rb));
       }
     }
+    if (threadIdx.x == 64 && c == 0) tr[10] = clock64();
     uint4* srow = reinterpret_cast<uint4*>(stg + lane * ST);
 #pragma unroll
     for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
+    if (threadIdx.x == 64 && c == 0) tr[11] = clock64();
+    if (threadIdx.x == 64 && c == 64) tr[13] = clock64();
     const int n = n0 + c + c4;  // first of this lane's 4 columns
     float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c + c4 < out_cols && n < n_lim) {
@@ -288,28 +376,18 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       else col = n;
       if (vec_ok) {
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cbias != nullptr && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(cbias + n));
         float sc = 1.0f;
-        if (ln_fold && !geglu && !partial) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.wsum + n));
-          b4.x -= ln_rmu * w4.x; b4.y -= ln_rmu * w4.y; b4.z -= ln_rmu * w4.z; b4.w -= ln_rmu * w4.w;
-          sc = ln_r;
+        if (!geglu && !partial) {
+          b4 = *reinterpret_cast<const float4*>(eb + c + c4);
+          if (ln_fold) sc = ln_r;
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (drow[i] == nullptr) continue;
-          float4 t = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * ST + c4);
-          t.x = fmaf(t.x, sc, b4.x); t.y = fmaf(t.y, sc, b4.y); t.z = fmaf(t.z, sc, b4.z); t.w = fmaf(t.w, sc, b4.w);
-          if (rbase != nullptr) {
-            const float4 rr = *reinterpret_cast<const float4*>(rrow[i] + n);
-            t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
-          }
-          if (round_out) {
-            t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
-          }
-          *reinterpret_cast<float4*>(drow[i] + col) = t;
-          ss.x += t.x; ss.y += t.y; ss.z += t.z; ss.w += t.w;
-          qq.x = fmaf(t.x, t.x, qq.x); qq.y = fmaf(t.y, t.y, qq.y); qq.z = fmaf(t.z, t.z, qq.z); qq.w = fmaf(t.w, t.w, qq.w);
+        const float* st = stg + sub * ST + c4;
+        if (rows_full) {
+          if (rbase != nullptr) store_chunk_dispatch<true, true>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
+          else store_chunk_dispatch<true, false>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
+        } else {
+          if (rbase != nullptr) store_chunk_dispatch<false, true>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
+          else store_chunk_dispatch<false, false>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
         }
       } else {
 #pragma unroll
@@ -330,6 +408,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         }
       }
     }
+    if (threadIdx.x == 64 && c == 0) tr[12] = clock64();
+    if (threadIdx.x == 64 && c == 64) tr[14] = clock64();
     if (stats_pass1) {
       // fold the 4 row groups of the warp (lanes with equal lane % 8): fixed xor tree, all lanes take part
 #pragma unroll
@@ -473,7 +553,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ long long tr[8];  // lab trace (debug bit 3)
+  __shared__ long long tr[16];  // lab trace (debug bit 3)
   if (threadIdx.x == 0) tr[0] = clock64();
 
   const int warp = threadIdx.x >> 5;
@@ -726,6 +806,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     printf("gemm trace: setup %lld producer_done %lld mma_issued %lld accum_ready %lld epilogue_done %lld end %lld (clk since entry)\n",
            tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], clock64() - tr[0]);
+  if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    printf("  epilogue chunk 0 of warp 2: loads issued %lld tmem ready %lld math done %lld staged %lld stored %lld; chunk 1: staged %lld stored %lld\n",
+           tr[8] - tr[4], tr[9] - tr[4], tr[10] - tr[4], tr[11] - tr[4], tr[12] - tr[4], tr[13] - tr[4], tr[14] - tr[4]);
+
   if constexpr (CG == 2) cluster_sync_all();  // neither CTA may release TMEM / exit while the pair is in flight
   if (warp == 1) {
     tc_fence_after_sync();
@@ -763,7 +847,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t b_full[HALO_SB_MAX], b_empty[HALO_SB_MAX];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ long long tr[8];
+  __shared__ long long tr[16];
   if (threadIdx.x == 0) tr[0] = clock64();
 
   const int warp = threadIdx.x >> 5;
