@@ -8,6 +8,14 @@
 
 namespace tsd {
 
+// Lab instrumentation: in-kernel cycle stamps (gemm_debug bit 3 prints them).  Compiled in only with -DTSD_LAB_TRACE
+// (csrc/build.sh honours TSD_LAB_TRACE=1): the stamps re-read %tid and the clock in the hot loops.
+#ifdef TSD_LAB_TRACE
+#define TSD_TRACE(cond, slot) do { if (cond) tr[slot] = clock64(); } while (0)
+#else
+#define TSD_TRACE(cond, slot) do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -173,16 +181,25 @@ __device__ __forceinline__ void store_chunk_rows(const float* __restrict__ st, f
     }
   }
 }
-template <bool FULL, bool RES>
-__device__ __forceinline__ void store_chunk_dispatch(bool round_out, bool stats, const float* __restrict__ st, float sc,
-                                                     float4 b4, float* const (&drow)[8], const float* const (&rrow)[8],
-                                                     long long col, int n, float4& ss, float4& qq) {
-  if (round_out) {
-    if (stats) store_chunk_rows<FULL, RES, true, true>(st, sc, b4, drow, rrow, col, n, ss, qq);
-    else store_chunk_rows<FULL, RES, true, false>(st, sc, b4, drow, rrow, col, n, ss, qq);
-  } else {
-    if (stats) store_chunk_rows<FULL, RES, false, true>(st, sc, b4, drow, rrow, col, n, ss, qq);
-    else store_chunk_rows<FULL, RES, false, false>(st, sc, b4, drow, rrow, col, n, ss, qq);
+// Ragged tiles (some rows outside the image / past M): one generic variant with run-time switches and row predicates.
+__device__ __forceinline__ void store_chunk_rows_ragged(const float* __restrict__ st, float sc, float4 b4,
+                                                     float* const (&drow)[8], const float* const (&rrow)[8],
+                                                     long long col, int n, uint32_t flags, float4& ss, float4& qq) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (drow[i] == nullptr) continue;
+    float4 u = *reinterpret_cast<const float4*>(st + i * (4 * 36));
+    u.x = fmaf(u.x, sc, b4.x); u.y = fmaf(u.y, sc, b4.y); u.z = fmaf(u.z, sc, b4.z); u.w = fmaf(u.w, sc, b4.w);
+    if (flags & 2u) {
+      const float4 r = *reinterpret_cast<const float4*>(rrow[i] + n);
+      u.x += r.x; u.y += r.y; u.z += r.z; u.w += r.w;
+    }
+    if (flags & 4u) {
+      u.x = round_tf32(u.x); u.y = round_tf32(u.y); u.z = round_tf32(u.z); u.w = round_tf32(u.w);
+    }
+    *reinterpret_cast<float4*>(drow[i] + col) = u;
+    ss.x += u.x; ss.y += u.y; ss.z += u.z; ss.w += u.w;
+    qq.x = fmaf(u.x, u.x, qq.x); qq.y = fmaf(u.y, u.y, qq.y); qq.z = fmaf(u.z, u.z, qq.z); qq.w = fmaf(u.w, u.w, qq.w);
   }
 }
 
@@ -207,7 +224,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
   const uint32_t accum_a = ec.accum_bar;
   const int n_iters = ec.n_iters;
   const int nt = ec.nt, img = ec.img, h0 = ec.h0, w0 = ec.w0, batch = ec.batch, split = ec.split;
-  long long* const tr = ec.tr;
+  [[maybe_unused]] long long* const tr = ec.tr;
   pdl_wait();                // before the first global access of this role (row bias, residual, D)
   const int ew = warp - 2;   // 0..7
   const int q = warp & 3;    // TMEM lane quadrant this warp may read
@@ -312,35 +329,48 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
   const bool stats_pass1 = want_stats && !partial;
   float2* cs = reinterpret_cast<float2*>(smem_ring + 8 * 32 * ST * 4);  // [4][256]
 
-  mbar_wait_a(accum_a, 0);
-  tc_fence_after_sync();
-  if (threadIdx.x == 64) tr[4] = clock64();
-
   const bool two_acc = n_iters > 1 && GEMM_ROLE_PAIRS > 1;
   const uint32_t trow1 = trow + (uint32_t)p.acc_stride;  // the odd-K-step issuer's accumulator
+  // Every decision of the chunk loop is a bit of one register that the compiler cannot re-derive: left to itself it
+  // re-read the kernel parameters from the constant bank and branched on them in every chunk (a chain of ~6 dependent
+  // constant loads, ~300 cycles per chunk with only two epilogue warps per scheduler to hide them).
+  enum : uint32_t { F_FULL = 1, F_RES = 2, F_ROUND = 4, F_STATS = 8, F_GEGLU = 16, F_TWOACC = 32, F_PLAIN = 64,
+                    F_PARTIAL = 128, F_ROUTED = 256, F_VEC = 512, F_B4 = 1024, F_STATS1 = 2048 };
+  uint32_t flags = (rows_full ? F_FULL : 0u) | (rbase != nullptr ? F_RES : 0u) | (round_out ? F_ROUND : 0u) |
+                   (want_stats ? F_STATS : 0u) | (geglu ? F_GEGLU : 0u) | (two_acc ? F_TWOACC : 0u) |
+                   (plain ? F_PLAIN : 0u) | (partial ? F_PARTIAL : 0u) | (routed ? F_ROUTED : 0u) |
+                   (vec_ok ? F_VEC : 0u) | ((!geglu && !partial) ? F_B4 : 0u) | (stats_pass1 ? F_STATS1 : 0u);
+  asm volatile("mov.b32 %0, %0;\n" : "+r"(flags));
+  const float sc_store = (!geglu && !partial && ln_fold) ? ln_r : 1.0f;
+  const long long partial_col0 = (long long)nt * p.BN;
+
+  mbar_wait_a(accum_a, 0);
+  tc_fence_after_sync();
+  TSD_TRACE(threadIdx.x == 64, 4);
+
   for (int c = half * 32; c < out_cols; c += 64) {
     uint32_t v[32];
     tmem_ld32(trow + c, v);
-    if (two_acc) {
+    if (flags & F_TWOACC) {
       uint32_t v1[32];
       tmem_ld32(trow1 + c, v1);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
     }
-    if (geglu) {
+    if (flags & F_GEGLU) {
       uint32_t g[32];
       tmem_ld32(trow + out_cols + c, g);
-      if (two_acc) {
+      if (flags & F_TWOACC) {
         uint32_t g1[32];
         tmem_ld32(trow1 + out_cols + c, g1);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(__uint_as_float(g[j]) + __uint_as_float(g1[j]));
       }
-      if (threadIdx.x == 64 && c == 0) tr[8] = clock64();
+      TSD_TRACE(threadIdx.x == 64 && c == 0, 8);
       tmem_ld_wait();
-      if (threadIdx.x == 64 && c == 0) tr[9] = clock64();
+      TSD_TRACE(threadIdx.x == 64 && c == 0, 9);
       const float4* bo4 = reinterpret_cast<const float4*>(eb + c);
       const float4* bg4 = reinterpret_cast<const float4*>(eb + 128 + c);
 #pragma unroll
@@ -352,44 +382,55 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), ln_r, bo.w) * gelu_tanh(fmaf(__uint_as_float(g[4 * j + 3]), ln_r, bg.w)));
       }
     } else {
-      if (threadIdx.x == 64 && c == 0) tr[8] = clock64();
+      TSD_TRACE(threadIdx.x == 64 && c == 0, 8);
       tmem_ld_wait();
-      if (threadIdx.x == 64 && c == 0) tr[9] = clock64();
-      if (!plain) {
+      TSD_TRACE(threadIdx.x == 64 && c == 0, 9);
+      if (!(flags & F_PLAIN)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), alpha, rb));
       }
     }
-    if (threadIdx.x == 64 && c == 0) tr[10] = clock64();
+    TSD_TRACE(threadIdx.x == 64 && c == 0, 10);
     uint4* srow = reinterpret_cast<uint4*>(stg + lane * ST);
 #pragma unroll
     for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
-    if (threadIdx.x == 64 && c == 0) tr[11] = clock64();
-    if (threadIdx.x == 64 && c == 64) tr[13] = clock64();
+    TSD_TRACE(threadIdx.x == 64 && c == 0, 11);
+    TSD_TRACE(threadIdx.x == 64 && c == 64, 13);
     const int n = n0 + c + c4;  // first of this lane's 4 columns
     float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c + c4 < out_cols && n < n_lim) {
       long long col;
-      if (partial) col = (long long)nt * p.BN + c + c4;
-      else if (routed) col = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
+      if (flags & F_PARTIAL) col = partial_col0 + c + c4;
+      else if (flags & F_ROUTED) col = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
       else col = n;
-      if (vec_ok) {
+      if (flags & F_VEC) {
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float sc = 1.0f;
-        if (!geglu && !partial) {
-          b4 = *reinterpret_cast<const float4*>(eb + c + c4);
-          if (ln_fold) sc = ln_r;
-        }
+        if (flags & F_B4) b4 = *reinterpret_cast<const float4*>(eb + c + c4);
         const float* st = stg + sub * ST + c4;
-        if (rows_full) {
-          if (rbase != nullptr) store_chunk_dispatch<true, true>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
-          else store_chunk_dispatch<true, false>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
+#define TSD_STORE_CASE(k)                                                                                      \
+  case k:                                                                                                      \
+    store_chunk_rows<true, ((k) & 1) != 0, ((k) & 2) != 0, ((k) & 4) != 0>(st, sc_store, b4, drow, rrow, col, n, ss, qq); \
+    break;
+        if (flags & F_FULL) {
+          switch ((flags >> 1) & 7u) {
+            TSD_STORE_CASE(0) TSD_STORE_CASE(1) TSD_STORE_CASE(2) TSD_STORE_CASE(3)
+            TSD_STORE_CASE(4) TSD_STORE_CASE(5) TSD_STORE_CASE(6) TSD_STORE_CASE(7)
+          }
         } else {
-          if (rbase != nullptr) store_chunk_dispatch<false, true>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
-          else store_chunk_dispatch<false, false>(round_out, want_stats, st, sc, b4, drow, rrow, col, n, ss, qq);
+          store_chunk_rows_ragged(st, sc_store, b4, drow, rrow, col, n, flags, ss, qq);
         }
+#undef TSD_STORE_CASE
       } else {
+        // unaligned shapes (rare): scalar stores, output routing resolved once per column
+        long long co[4];
+        float badd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int nn = n + j;
+          co[j] = nn < n_valid ? (long long)(nn / p.split_n) * p.split_stride + (nn % p.split_n) : -1;
+          badd[j] = (nn < n_valid && cbias != nullptr && !(flags & F_GEGLU)) ? cbias[nn] : 0.0f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (drow[i] == nullptr) continue;
@@ -397,20 +438,18 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
           const float e[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int nn = n + j;
-            if (nn >= n_valid) break;
-            float a = e[j];
-            if (cbias != nullptr && !geglu) a += cbias[nn];
-            if (rbase != nullptr) a += rrow[i][nn];
-            if (round_out) a = round_tf32(a);
-            drow[i][(long long)(nn / p.split_n) * p.split_stride + (nn % p.split_n)] = a;
+            if (co[j] < 0) continue;
+            float a = e[j] + badd[j];
+            if (rbase != nullptr) a += rrow[i][n + j];
+            if (flags & F_ROUND) a = round_tf32(a);
+            drow[i][co[j]] = a;
           }
         }
       }
     }
-    if (threadIdx.x == 64 && c == 0) tr[12] = clock64();
-    if (threadIdx.x == 64 && c == 64) tr[14] = clock64();
-    if (stats_pass1) {
+    TSD_TRACE(threadIdx.x == 64 && c == 0, 12);
+    TSD_TRACE(threadIdx.x == 64 && c == 64, 14);
+    if (flags & F_STATS1) {
       // fold the 4 row groups of the warp (lanes with equal lane % 8): fixed xor tree, all lanes take part
 #pragma unroll
       for (int o = 8; o <= 16; o <<= 1) {
@@ -532,7 +571,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       }
     }
   }
-  if (threadIdx.x == 64) tr[5] = clock64();
+  TSD_TRACE(threadIdx.x == 64, 5);
 }
 
 // Role loops are single-thread instruction streams: every dependent SASS instruction costs ~4-6
@@ -554,7 +593,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ long long tr[16];  // lab trace (debug bit 3)
-  if (threadIdx.x == 0) tr[0] = clock64();
+  TSD_TRACE(threadIdx.x == 0, 0);
 
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -612,7 +651,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
-  if (threadIdx.x == 0) tr[1] = clock64();
+  TSD_TRACE(threadIdx.x == 0, 1);
   pdl_launch_dependents();  // resources are held: the next kernel may start its own prologue
 
   // Role warps: 0 / 10 = TMA producers, 1 / 11 = MMA issuers (1 also owns TMEM), 2..9 = epilogue.
@@ -731,7 +770,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           phase ^= 1u;
         }
       }
-      if (role_parity == 0) tr[2] = clock64();
+      TSD_TRACE(role_parity == 0, 2);
     }
   } else if ((warp == 1 || warp == 11) && role_parity < n_par) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
@@ -787,7 +826,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       umma_commit_cg<CG>(accum_a);  // this issuer's accumulator complete
-      if (role_parity == 0) tr[3] = clock64();
+      TSD_TRACE(role_parity == 0, 3);
     }
   } else if (warp >= 2 && warp < 10) {
     // ===================== epilogue (warps 2..9) =====================
@@ -803,12 +842,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   __syncthreads();
+#ifdef TSD_LAB_TRACE
   if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     printf("gemm trace: setup %lld producer_done %lld mma_issued %lld accum_ready %lld epilogue_done %lld end %lld (clk since entry)\n",
            tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], clock64() - tr[0]);
   if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     printf("  epilogue chunk 0 of warp 2: loads issued %lld tmem ready %lld math done %lld staged %lld stored %lld; chunk 1: staged %lld stored %lld\n",
            tr[8] - tr[4], tr[9] - tr[4], tr[10] - tr[4], tr[11] - tr[4], tr[12] - tr[4], tr[13] - tr[4], tr[14] - tr[4]);
+#endif
 
   if constexpr (CG == 2) cluster_sync_all();  // neither CTA may release TMEM / exit while the pair is in flight
   if (warp == 1) {
@@ -848,7 +889,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ long long tr[16];
-  if (threadIdx.x == 0) tr[0] = clock64();
+  TSD_TRACE(threadIdx.x == 0, 0);
 
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -907,7 +948,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
-  if (threadIdx.x == 0) tr[1] = clock64();
+  TSD_TRACE(threadIdx.x == 0, 1);
   pdl_launch_dependents();
 
   if (warp == 0) {
@@ -952,7 +993,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           load_b(jb);
         }
       }
-      tr[2] = clock64();
+      TSD_TRACE(true, 2);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
@@ -1005,7 +1046,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       umma_commit_cg<CG>(accum_a);
-      tr[3] = clock64();
+      TSD_TRACE(true, 3);
     }
   } else if (warp >= 2 && warp < 10) {
     EpilogueCtx ec;
@@ -1020,9 +1061,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   __syncthreads();
+#ifdef TSD_LAB_TRACE
   if ((p.debug & 8) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     printf("halo trace: setup %lld producer_done %lld mma_issued %lld accum_ready %lld epilogue_done %lld end %lld (clk since entry)\n",
            tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], clock64() - tr[0]);
+#endif
   if constexpr (CG == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after_sync();

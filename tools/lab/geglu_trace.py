@@ -1,4 +1,5 @@
-"""In-kernel cycle trace of the GEMM epilogue (gemm_debug bit 3) for GEGLU and plain tiles."""
+"""In-kernel cycle trace of the GEMM epilogue (gemm_debug bit 3) for GEGLU and plain tiles.
+Needs a lab build of the library: TSD_LAB_TRACE=1 bash stable-diffusion.mojo_b200/csrc/build.sh (touch gemm_tcgen05.cu first)."""
 import os
 import sys
 
