@@ -590,7 +590,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
 template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmKParams p) {
+                 const __grid_constant__ CUtensorMap tmA2, const GemmKParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
@@ -638,6 +638,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    if (p.cin2 > 0) prefetch_tensormap(&tmA2);
   }
   if (warp == 1) {
     if constexpr (CG == 1) {
@@ -690,11 +691,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool two_b = geglu && CG == 1;
       const int step = n_par;
       // (tap, channel chunk) of this thread's first iteration; afterwards advanced incrementally
+      // Second K segment (p.cin2 > 0): after the taps over the first operand, `cin2` more channels of a second
+      // NHWC tensor (tmA2, no spatial shift) against the weight columns that follow - a ResBlock's 1x1 skip
+      // convolution accumulated into its second 3x3 convolution (diffusion.mojo:66-72) instead of a GEMM of its own.
       const int it_first = it_begin + role_parity;
+      const int taps = p.taps, cin2 = p.cin2;
       int tap = it_first / p.chunks_per_tap;
       int kc = (it_first - tap * p.chunks_per_tap) * bk;
       int dy = 0, dx = 0;
-      if (p.taps == 9) {
+      int cin_cur = cin;
+      if (tap >= taps) {  // this split starts inside the second segment
+        kc = (it_first - taps * p.chunks_per_tap) * bk;
+        tap = taps;
+        cin_cur = cin2;
+      } else if (taps == 9) {
         dy = tap / 3 - 1;
         dx = tap - (tap / 3) * 3 - 1;
       }
@@ -703,13 +713,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < step; ++s) {
           kc += bk;
           kb += bk;
-          if (kc >= cin) {
+          if (kc >= cin_cur) {
             kc = 0;
             ++tap;
             kb = tap * cin;
             if (++dx > 1) {
               dx = -1;
               ++dy;
+            }
+            if (tap >= taps) {
+              cin_cur = cin2;
+              dx = 0;
+              dy = 0;
             }
           }
         }
@@ -737,7 +752,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int pre_end = role_parity;  // iterations < pre_end (of this parity) already have their B tile in flight
       if (p.b_static && !(debug & 4)) {
         pre_end = n_iters < num_stages ? n_iters : num_stages;
-        int kc2 = kc, tap2 = tap, kb2 = kb;
+        int kc2 = kc, tap2 = tap, kb2 = kb, cin_cur2 = cin_cur;
         for (int it = role_parity; it < pre_end; it += step) {
           const uint32_t fb2 = full0 + 8u * it;
           if (CG == 1 || rank == 0) mbar_expect_tx_a(fb2, tx);
@@ -745,10 +760,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int s = 0; s < step; ++s) {
             kc2 += bk;
             kb2 += bk;
-            if (kc2 >= cin) {
+            if (kc2 >= cin_cur2) {
               kc2 = 0;
               ++tap2;
               kb2 = tap2 * cin;
+              if (tap2 >= taps) cin_cur2 = cin2;
             }
           }
         }
@@ -764,8 +780,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(debug & 4)) load_b(sa, fbs, kb);
         }
         if (!(debug & 2)) {
-          tma_a_4d<CG>(sa, &tmA, fbs, kc, w0 + dx, h0 + dy, c3);
-          if (natoms == 2) tma_a_4d<CG>(sa + a_atom, &tmA, fbs, kc + 32, w0 + dx, h0 + dy, c3);
+          const CUtensorMap* ta = tap >= taps ? &tmA2 : &tmA;
+          tma_a_4d<CG>(sa, ta, fbs, kc, w0 + dx, h0 + dy, c3);
+          if (natoms == 2) tma_a_4d<CG>(sa + a_atom, ta, fbs, kc + 32, w0 + dx, h0 + dy, c3);
         }
         advance();
         stage += step;
@@ -1149,8 +1166,8 @@ void gemm_pick_ring(int BN, int cg, int* bk, int* stages) {
 }
 
 template <int CG>
-static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
-                                  size_t smem_bytes, cudaStream_t stream) {
+static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                                  const GemmKParams& p, dim3 grid, size_t smem_bytes, cudaStream_t stream) {
   // static + dynamic shared memory must fit the 227 KiB opt-in limit together
   static int max_dyn = -1;
   if (max_dyn < 0) {
@@ -1181,7 +1198,7 @@ static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<CG>, tmA, tmB, p);
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<CG>, tmA, tmB, tmA2, p);
 }
 
 // halo convolution: B ring depth that fits next to the two halo tiles (0: configuration unsupported)
@@ -1242,9 +1259,10 @@ cudaError_t launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, con
 }
 
 cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
-                             dim3 grid, size_t smem_bytes, cudaStream_t stream) {
-  if (p.cg == 2) return launch_gemm_cg<2>(tmA, tmB, p, grid, smem_bytes, stream);
-  return launch_gemm_cg<1>(tmA, tmB, p, grid, smem_bytes, stream);
+                             dim3 grid, size_t smem_bytes, cudaStream_t stream, const CUtensorMap* tmA2) {
+  const CUtensorMap& a2 = tmA2 ? *tmA2 : tmA;
+  if (p.cg == 2) return launch_gemm_cg<2>(tmA, tmB, a2, p, grid, smem_bytes, stream);
+  return launch_gemm_cg<1>(tmA, tmB, a2, p, grid, smem_bytes, stream);
 }
 
 // Slab variant with producer-side norm statistics (norm_stats.cuh): a block owns `slab_rows` rows x all

@@ -39,6 +39,7 @@ struct GemmKParams {
   int m_per_batch;  // img_n * H * W : rows of D per batch entry
   // K loop
   int taps, cin, chunks_per_tap, total_iters, splits, iters_per_split;
+  int cin2;                // > 0: second K segment - cin2 channels of a second NHWC operand (tmA2) after the taps
   int a_box_bytes;
   // N tiling
   int BN, n_valid, geglu, n_half;
@@ -93,7 +94,7 @@ struct SplitKReduceParams {
 };
 
 cudaError_t launch_gemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
-                             dim3 grid, size_t smem_bytes, cudaStream_t stream);
+                             dim3 grid, size_t smem_bytes, cudaStream_t stream, const CUtensorMap* tmA2 = nullptr);
 cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t stream);
 int halo_pick_sb(int BN, int cg);
 size_t halo_smem_bytes(int BN, int cg, int sb);

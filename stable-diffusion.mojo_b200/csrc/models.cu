@@ -193,6 +193,10 @@ void ParamStore::free_all() {
     if (r) cudaFree(r);
   rowsum_dev.clear();
   rowsum_gen.clear();
+  for (float* r : fskip_dev)
+    if (r) cudaFree(r);
+  fskip_dev.clear();
+  fskip_gen.clear();
   if (block) cudaFree(block);
   block = nullptr;
 }
@@ -289,6 +293,49 @@ __global__ void weight_rowsum_kernel(const float* __restrict__ w, float* __restr
   if (lane == 0) out[row] = s;
 }
 
+__global__ void fuse_skip_weights_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                         float* __restrict__ out, int O, int K1, int K2) {
+  const long long K = (long long)K1 + K2, total = (long long)O * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + O;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < total) {
+      const long long o = i / K, k = i - o * K;
+      out[i] = k < K1 ? w1[o * K1 + k] : w2[o * K2 + (k - K1)];
+    } else {
+      const long long o = i - total;
+      out[i] = b1[o] + b2[o];
+    }
+  }
+}
+
+int ParamStore::fused_skip(int conv_w, int skip_w, const float** w, const float** b) {
+  if (fskip_dev.size() != params.size()) {
+    fskip_dev.assign(params.size(), nullptr);
+    fskip_gen.assign(params.size(), -1);
+  }
+  const Param& p1 = params[conv_w];
+  const Param& p2 = params[skip_w];
+  const int K1 = p1.I * p1.KK, K2 = p2.I * p2.KK;
+  const size_t elems = (size_t)p1.O * (K1 + K2);
+  if (p2.O != p1.O) return c->fail(TSD_ERR_INVALID, "fused skip: output channels differ");
+  if (!fskip_dev[conv_w]) {
+    if (cudaMalloc(&fskip_dev[conv_w], sizeof(float) * (elems + p1.O)) != cudaSuccess) {
+      cudaGetLastError();
+      return c->fail(TSD_ERR_OOM, "fused skip weights: allocation failed");
+    }
+  }
+  if (fskip_gen[conv_w] != gen && !c->dry_run) {
+    fuse_skip_weights_kernel<<<1184, 256, 0, c->stream>>>(p1.dev, params[conv_w + 1].dev, p2.dev, params[skip_w + 1].dev,
+                                                        fskip_dev[conv_w], p1.O, K1, K2);
+    TRY(c->check(cudaGetLastError(), "fuse_skip_weights launch"));
+    fskip_gen[conv_w] = gen;
+  }
+  *w = fskip_dev[conv_w];
+  *b = fskip_dev[conv_w] + elems;
+  return TSD_OK;
+}
+
 const float* ParamStore::rowsum(int i) {
   if (rowsum_dev.size() != params.size()) {
     rowsum_dev.assign(params.size(), nullptr);
@@ -319,12 +366,15 @@ static float* walloc(Ctx* c, long long n) { return c->arena.alloc_n<float>((size
 
 static int conv(Ctx* c, const ParamStore& ps, int wi, const float* x, int N, int H, int W, int cin, int cout,
                 int k, int pad, int stride, const float* bias_override, int bias_img_stride,
-                const float* residual, float* out, int round_out, NormHint* nh = nullptr, int pad_hi = -1) {
+                const float* residual, float* out, int round_out, NormHint* nh = nullptr, int pad_hi = -1,
+                const float* x2 = nullptr, int cin2 = 0, const float* w_override = nullptr) {
   ConvArgs a;
   a.nh = nh;
   a.pad_hi = pad_hi;
+  a.x2 = x2;
+  a.Cin2 = cin2;
   a.x = x; a.N = N; a.H = H; a.W = W; a.Cin = cin; a.Cout = cout; a.k = k; a.pad = pad; a.stride = stride;
-  a.w = ps.w(wi);
+  a.w = w_override ? w_override : ps.w(wi);
   a.bias = bias_override ? bias_override : ps.w(wi + 1);
   a.bias_img_stride = bias_override ? bias_img_stride : 0;
   a.residual = residual;
@@ -376,6 +426,15 @@ int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, co
   WALLOC(h3, px * w.cout);
   TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, mid.ready()));
   const float* r = x.p;
+  if (w.cin != w.cout && c->fuse_skip && w.cin % 64 == 0 && w.cout % 64 == 0) {
+    // res_conv_layer (1x1, diffusion.mojo:66-70 / vae.mojo:64-66) rides in the K loop of conv2: one GEMM over
+    // K = 9*cout + cin with the concatenated weights and the summed biases, no residual operand
+    const float *wcat = nullptr, *bcat = nullptr;
+    TRY(const_cast<ParamStore&>(ps).fused_skip(w.conv2, w.skip, &wcat, &bcat));
+    TRY(conv(c, ps, w.conv2, h3, N, H, W, w.cout, w.cout, 3, 1, 1, bcat, 0, nullptr, out, 0, next, -1, x.p, w.cin, wcat));
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
   if (w.cin != w.cout) {
     WALLOC(rr, px * w.cout);
     TRY(conv(c, ps, w.skip, x.p, N, H, W, w.cin, w.cout, 1, 0, 1, nullptr, 0, nullptr, rr, 0));

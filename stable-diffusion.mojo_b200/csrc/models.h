@@ -52,6 +52,12 @@ struct ParamStore {
   const float* rowsum(int i);
   std::vector<float*> rowsum_dev;
   std::vector<int> rowsum_gen;
+  // [O][KK*I + I2] = conv weight rows followed by the rows of a 1x1 convolution with the same O, and the sum of
+  // the two biases: the operands of the fused ResBlock tail (conv2 + skip convolution in one GEMM).  Built on first
+  // use after every (re)load, keyed by the conv weight's index.
+  int fused_skip(int conv_w, int skip_w, const float** w, const float** b);
+  std::vector<float*> fskip_dev;
+  std::vector<int> fskip_gen;
   int gen = 0;  // bumped by load / init_random
   void free_all();
 };

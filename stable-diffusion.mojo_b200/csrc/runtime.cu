@@ -302,7 +302,15 @@ struct ASpec {
   int batch;
   long long ld_batch;
   int taps;
+  // optional second K segment: K2 channels of a dense NHWC tensor of the same pixel grid (no spatial shift),
+  // multiplied by the weight columns [taps*K, taps*K + K2)
+  const float* base2;
+  int K2;
 };
+// K steps of the provisional 64-wide kind (tile selection happens before the ring picks 64 or 32)
+static int provisional_iters(const ASpec& A) {
+  return A.taps * ((A.K + GEMM_BK - 1) / GEMM_BK) + (A.K2 + GEMM_BK - 1) / GEMM_BK;
+}
 
 }  // namespace
 
@@ -310,7 +318,7 @@ struct ASpec {
 // `ws_splits_plan` > 0 (planning pass): reserve split-K workspace for that many splits.
 // 3x3 / stride 1 / pad 1 convolution over an NHWC image that the halo kernel can take
 static bool conv_halo_eligible(const Ctx* c, const ASpec& A, int N, const GemmKParams& p) {
-  return c->conv_halo > 0 && A.taps == 9 && A.batch == 1 && A.K % 4 == 0 && A.W >= c->halo_min_w && A.H >= c->halo_min_h &&
+  return c->conv_halo > 0 && A.K2 == 0 && A.taps == 9 && A.batch == 1 && A.K % 4 == 0 && A.W >= c->halo_min_w && A.H >= c->halo_min_h &&
          !p.geglu && p.row_bias == nullptr && N >= 16;
 }
 
@@ -320,6 +328,8 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   if (nh) nh->req = NormStatsReq();
   if (A.K % 4) return c->fail(TSD_ERR_INVALID, "gemm: K must be a multiple of 4");
   if (A.batch > 1 && A.imgs > 1) return c->fail(TSD_ERR_INVALID, "gemm: batch and images are exclusive");
+  if (A.K2 > 0 && (A.K % GEMM_BK || A.K2 % GEMM_BK || A.batch > 1 || !A.base2))
+    return c->fail(TSD_ERR_INVALID, "gemm: a second K segment needs both channel counts to be multiples of 64");
   // pixel box of 128 rows
   int bw = std::min(A.W, 128);
   while (128 % bw) --bw;  // largest divisor of 128 not above W
@@ -329,8 +339,9 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   p.m_per_batch = A.imgs * A.H * A.W;
   p.taps = A.taps;
   p.cin = A.K;
+  p.cin2 = A.K2;
   p.chunks_per_tap = (A.K + GEMM_BK - 1) / GEMM_BK;  // provisional (K steps of 64): the ring below may pick 32
-  p.total_iters = p.taps * p.chunks_per_tap;
+  p.total_iters = provisional_iters(A);
   long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
   const int nbatch = A.batch;
   const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
@@ -372,7 +383,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     gemm_pick_ring(p.BN, p.cg, &p.bk, &p.num_stages);
     if (c->force_stages >= 2 && c->force_stages < p.num_stages) p.num_stages = GEMM_ROLE_PAIRS > 1 ? (c->force_stages & ~1) : c->force_stages;
     p.chunks_per_tap = (A.K + p.bk - 1) / p.bk;
-    p.total_iters = p.taps * p.chunks_per_tap;
+    p.total_iters = p.taps * p.chunks_per_tap + A.K2 / p.bk;
   }
   p.splits = std::min(cfg.splits, p.total_iters);
   p.iters_per_split = (p.total_iters + p.splits - 1) / p.splits;
@@ -390,7 +401,14 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   const int n_out = p.geglu ? N / 2 : N;
   const int n_tiles = (((p.geglu ? n_out : p.n_pad)) + out_cols_per_tile - 1) / out_cols_per_tile;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA2;
+  if (!c->dry_run && A.K2 > 0) {
+    uint64_t dims[4] = {(uint64_t)A.K2, (uint64_t)A.W, (uint64_t)A.H, (uint64_t)A.imgs};
+    uint64_t str[4] = {1, (uint64_t)A.K2, (uint64_t)A.K2 * A.W, (uint64_t)A.K2 * A.W * A.H};
+    uint32_t box[4] = {32u, (uint32_t)bw, (uint32_t)bh, 1};
+    int rc = make_tmap_f32(c, &tmA2, A.base2, 4, dims, str, box, 0);
+    if (rc) return rc;
+  }
   if (!c->dry_run) {
     uint64_t dims[4] = {(uint64_t)A.K, (uint64_t)A.W, (uint64_t)A.H,
                         (uint64_t)(A.batch > 1 ? A.batch : A.imgs)};
@@ -404,7 +422,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     if (rc) return rc;
   }
   if (!c->dry_run) {
-    const int ktot = A.taps * A.K;
+    const int ktot = A.taps * A.K + A.K2;
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
     uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
     uint32_t box[3] = {32u, (uint32_t)((p.geglu || p.cg == 2) ? p.BN / 2 : p.BN), 1};
@@ -510,7 +528,8 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     TimedScope ts(c, FAM_GEMM, flops);
     int rc = p.halo ? c->check(launch_conv_halo(tmA, tmB, p, grid, halo_smem_bytes(p.BN, p.cg, p.num_stages), c->stream),
                                "conv3x3_halo_kernel launch")
-                    : c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg, p.bk), c->stream),
+                    : c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg, p.bk), c->stream,
+                                              A.K2 > 0 ? &tmA2 : nullptr),
                                "gemm_tf32_kernel launch");
     if (rc) return rc;
     c->launches++;
@@ -650,7 +669,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     while (128 % bw) --bw;
     const int bh = std::min(128 / bw, A.H);
     const long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
-    const int total_iters = A.taps * ((A.K + GEMM_BK - 1) / GEMM_BK);
+    const int total_iters = provisional_iters(A);
     int max_sp = 0;
     if (allow_split)
       for (const TileCfg& t : tune_candidates(c->sm_count, m_tiles, N, total_iters, p.geglu != 0, true, c->gemm_cg,
@@ -667,7 +686,8 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     int bw = std::min(A.W, 128);
     while (128 % bw) --bw;
     int i = 0;
-    key.v[i++] = A.K; key.v[i++] = A.W; key.v[i++] = A.H; key.v[i++] = A.imgs; key.v[i++] = A.batch; key.v[i++] = A.taps;
+    key.v[i++] = A.K; key.v[i++] = A.W; key.v[i++] = A.H; key.v[i++] = A.imgs; key.v[i++] = A.batch;
+    key.v[i++] = A.taps + 16 * (A.K2 / 32);
     key.v[i++] = N; key.v[i++] = p.geglu; key.v[i++] = allow_split ? 1 : 0; key.v[i++] = p.residual ? 1 : 0;
     key.v[i++] = (nh && nh->G > 0 && c->producer_stats) ? nh->G : 0; key.v[i++] = c->gemm_cg * 4 + c->conv_halo;
   }
@@ -685,7 +705,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   while (128 % bw) --bw;
   const int bh = std::min(128 / bw, A.H);
   const long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
-  const int total_iters = A.taps * ((A.K + GEMM_BK - 1) / GEMM_BK);
+  const int total_iters = provisional_iters(A);
   const int halo_cin = conv_halo_eligible(c, A, N, p) ? A.K : 0;
   std::vector<TileCfg> cands = tune_candidates(c->sm_count, m_tiles, N, total_iters, p.geglu != 0, allow_split, c->gemm_cg,
                                                halo_cin, A.H, A.W, A.imgs);
@@ -796,10 +816,12 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
   const int Ho = conv_out_dim(a.H, a.k, a.pad, a.stride, a.pad_hi), Wo = conv_out_dim(a.W, a.k, a.pad, a.stride, a.pad_hi);
   const bool sym = a.pad_hi < 0 || a.pad_hi == a.pad;
   if (Ho <= 0 || Wo <= 0 || a.Cin <= 0 || a.Cout <= 0) return c->fail(TSD_ERR_INVALID, "conv2d: empty output");
-  const int ktot = a.k * a.k * a.Cin;
+  const int ktot = a.k * a.k * a.Cin + a.Cin2;
   // rows of w past Cout are out of bounds for the B tensor map and read as zeros
   const bool tensor_ok = a.Cin >= 32 && a.Cin % 4 == 0 && (a.Cout % 4 == 0 || a.Cout < 16);
   const double flops = 2.0 * a.N * Ho * (double)Wo * a.Cout * ktot;
+  if (a.Cin2 > 0 && !(tensor_ok && sym && a.k == 3 && a.pad == 1 && a.stride == 1 && a.x2))
+    return c->fail(TSD_ERR_INVALID, "conv2d: the fused second operand needs the 3x3 / stride 1 tensor-core path");
   GemmKParams p{};
   p.D = a.out;
   p.ldd = a.Cout;
@@ -824,6 +846,8 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
     A.ld_img = (long long)a.H * a.W * a.Cin;
     A.batch = 1;
     A.taps = a.k * a.k;
+    A.base2 = a.x2;
+    A.K2 = a.Cin2;
     if (a.k == 1) {  // a 1x1 conv is a plain GEMM over all pixels
       A.W = a.N * a.H * a.W;
       A.H = 1;

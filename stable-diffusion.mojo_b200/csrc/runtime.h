@@ -112,6 +112,7 @@ struct Ctx {
   int gn_partial = 1;              // GroupNorm consumes producer-side partial statistics (0: always the stand-alone fused norm)
   int gn_partial_max_groups = 64;  // ... only up to this many groups (every block folds all groups of its image)
   int ln_fold = 1;                 // fold global-statistics LayerNorm into the consuming GEMM epilogue (0: separate pass)
+  int fuse_skip = 1;               // ResBlock 1x1 skip convolution as a second K segment of conv2 (0: GEMM of its own + residual add)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;
@@ -193,6 +194,10 @@ struct ConvArgs {
   int round_tf32 = 0;
   int force_bn = 0, force_splits = 0;
   NormHint* nh = nullptr;  // optional: statistics of `out` for the next norm
+  // optional fused 1x1 convolution of a second tensor accumulated into the same output (3x3 / stride 1 / pad 1
+  // only): x2 [N][H][W][Cin2]; `w` then is [Cout][k*k*Cin + Cin2] and `bias` the sum of both biases
+  const float* x2 = nullptr;
+  int Cin2 = 0;
 };
 int op_conv2d(Ctx* c, const ConvArgs& a);
 inline int conv_out_dim(int in, int k, int pad, int stride, int pad_hi = -1) {

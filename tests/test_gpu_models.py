@@ -123,6 +123,8 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
 
 @pytest.mark.parametrize("opts", [
     {"ln_fold": 0},                       # LayerNorm as a separate pass instead of the GEMM-epilogue fold
+    {"fuse_skip": 0},                     # skip convolution as its own GEMM + residual add
+    {"fuse_skip": 1, "force_splits": 8},  # second K segment under split-K (the last split starts inside it)
     {"producer_stats": 0},                # every norm computes its own statistics (no epilogue partial sums)
     {"producer_stats": 0, "norm_v2": 1},  # ... with the register-resident fused norm kernel
     {"pdl": 0},                           # no programmatic dependent launch
@@ -155,7 +157,7 @@ def test_unet64_switches_agree_at_full_size(ctx, diff64):
     cx = rng.standard_normal((77, 768), dtype=np.float32)
     t = host_sampler.get_time_embedding(500.0)
     y_default = diff64.forward(x, cx, t)
-    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}):
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}):
         old = {k: ctx.get_option(k) for k in opts}
         for k, v in opts.items():
             ctx.set_option(k, v)
