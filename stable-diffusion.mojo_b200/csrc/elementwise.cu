@@ -1132,6 +1132,47 @@ __global__ void gemv_kernel(const float* __restrict__ x, int K, const float* __r
   }
 }
 
+// Several GEMVs over the same input vector(s) in one launch: output row n of the concatenation belongs to the
+// segment whose [row0, row0 + N) holds it.  Used for the nine per-ResBlock Linear(SiLU(t)) (diffusion.mojo:61-62),
+// which depend only on the time embedding.
+__global__ void gemv_multi_kernel(const float* __restrict__ x, int K, const GemvMulti m, int silu_in) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warps = blockDim.x >> 5;
+  const int ng = blockIdx.x * warps + (threadIdx.x >> 5);
+  const int r = blockIdx.y;
+  if (ng >= m.total) return;
+  int s = 0;
+#pragma unroll 1
+  while (s + 1 < m.nseg && ng >= m.seg[s + 1].row0) ++s;
+  const GemvSeg sg = m.seg[s];
+  const int n = ng - sg.row0;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)r * K;
+  const float* wr = sg.W + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 a = *reinterpret_cast<const float4*>(xr + k);
+    const float4 b = *reinterpret_cast<const float4*>(wr + k);
+    if (silu_in) {
+      a.x = a.x / (1.0f + expf(-a.x));
+      a.y = a.y / (1.0f + expf(-a.y));
+      a.z = a.z / (1.0f + expf(-a.z));
+      a.w = a.w / (1.0f + expf(-a.w));
+    }
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    acc = fmaf(a.w, b.w, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+  if (lane == 0) {
+    if (sg.bias) acc += sg.bias[n];
+    if (sg.bias2) acc += sg.bias2[n];
+    sg.y[(long long)r * sg.N + n] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // softmax (unfused attention path)
 // ------------------------------------------------------------------------------------------
@@ -1605,6 +1646,12 @@ cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias
   return cudaGetLastError();
 }
 
+cudaError_t launch_gemv_multi(const float* x, int rows, int K, const GemvMulti& m, int silu_in, cudaStream_t s) {
+  if (K % 4 || m.nseg <= 0 || m.nseg > GemvMulti::kMax) return cudaErrorInvalidValue;
+  const int warps = 8;
+  dim3 grid((m.total + warps - 1) / warps, rows);
+  return launch_pdl(gemv_multi_kernel, grid, dim3(warps * 32), 0, s, x, K, m, silu_in);
+}
 cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const float* bias,
                         const float* bias2, float* y, int N, int silu_in, int silu_out,
                         cudaStream_t s) {

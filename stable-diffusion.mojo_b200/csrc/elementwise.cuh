@@ -96,6 +96,19 @@ cudaError_t launch_conv_direct(const float* x, const float* w, const float* bias
                                int Wo, cudaStream_t s);
 
 // ---- GEMV: y[r][n] = sum_k act(x[r][k]) * Wt[n][k] + bias[n] + bias2[n] ---------------------
+struct GemvSeg {
+  const float* W;      // [N][K]
+  const float* bias;   // [N] or nullptr
+  const float* bias2;  // [N] or nullptr
+  float* y;            // [rows][N]
+  int N, row0;
+};
+struct GemvMulti {
+  static constexpr int kMax = 12;
+  GemvSeg seg[kMax];
+  int nseg, total;
+};
+cudaError_t launch_gemv_multi(const float* x, int rows, int K, const GemvMulti& m, int silu_in, cudaStream_t s);
 cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const float* bias,
                         const float* bias2, float* y, int N, int silu_in, int silu_out,
                         cudaStream_t s);

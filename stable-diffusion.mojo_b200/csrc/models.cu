@@ -646,6 +646,20 @@ int Diffusion::prepare_time(int rows, const float* time_dev, float* const* tb_ou
   }
   LAUNCH(c, launch_gemv(time_dev, rows, 320, ps.w(te1), ps.w(te1 + 1), nullptr, t1, 1280, 0, 1, c->stream), "gemv");
   LAUNCH(c, launch_gemv(t1, rows, 1280, ps.w(te2), ps.w(te2 + 1), nullptr, t2, 1280, 0, 0, c->stream), "gemv");
+  if (!cfg.mojo_alias_time) {
+    // the nine block linears read the same SiLU(t_emb): one launch over the concatenated output rows
+    GemvMulti gm{};
+    gm.nseg = 9;
+    int row0 = 0;
+    for (int r = 0; r < 9; ++r) {
+      gm.seg[r] = GemvSeg{ps.w(res[r].lin_t), ps.w(res[r].lin_t + 1), ps.w(res[r].conv1 + 1), tb_out[r], res[r].cout, row0};
+      row0 += res[r].cout;
+    }
+    gm.total = row0;
+    LAUNCH(c, launch_gemv_multi(t2, rows, 1280, gm, 1, c->stream), "gemv_multi");
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
   float* cur = t2;
   float* other = t1;  // t1 (SiLU(layer1)) is dead once layer2 has run
   for (int r = 0; r < 9; ++r) {
