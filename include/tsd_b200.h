@@ -71,6 +71,8 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *   "ln_fold"          1 = global-statistics LayerNorm folded into the consuming GEMM epilogue [default]
  *   "fuse_skip"        1 = a ResBlock's 1x1 skip convolution is a second K segment of its conv2 GEMM [default],
  *                          0 = a GEMM of its own whose result conv2 adds as a residual
+ *   "defer_reduce"     1 = where a split-K GEMM feeds a norm directly, the norm kernel sums the partial tiles
+ *                          (no reduce kernel) [default]
  *   "norm_v2"          0/1 = which single-launch fused norm kernel serves the remaining norms
  *   "splitk_fixup"     1 = split-K partials reduced in-kernel by the last CTA of each tile, 0 = reduce kernel [default]
  *   "pdl"              1 = programmatic dependent launch between the kernels of a graph [default]

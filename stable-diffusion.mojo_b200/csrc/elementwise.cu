@@ -1093,6 +1093,8 @@ conv_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 __global__ void gemv_kernel(const float* __restrict__ x, int K, const float* __restrict__ Wt,
                             const float* __restrict__ bias, const float* __restrict__ bias2,
                             float* __restrict__ y, int N, int silu_in, int silu_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warps = blockDim.x >> 5;
   const int n = blockIdx.x * warps + (threadIdx.x >> 5);
   const int r = blockIdx.y;
@@ -1657,8 +1659,7 @@ cudaError_t launch_gemv(const float* x, int rows, int K, const float* Wt, const 
                         cudaStream_t s) {
   const int warps = 8;
   dim3 grid((N + warps - 1) / warps, rows);
-  gemv_kernel<<<grid, warps * 32, 0, s>>>(x, K, Wt, bias, bias2, y, N, silu_in, silu_out);
-  return cudaGetLastError();
+  return launch_pdl(gemv_kernel, grid, dim3(warps * 32), 0, s, x, K, Wt, bias, bias2, y, N, silu_in, silu_out);
 }
 
 cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, float scale,

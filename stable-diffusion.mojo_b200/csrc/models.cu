@@ -419,12 +419,14 @@ int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, co
   NormHint mid;
   mid.G = w.groups;
   mid.eps = eps;
+  mid.imgs = N;
+  mid.allow_defer = true;  // h2 has one reader, the GroupNorm right below
   mid.scratch_elems = norm_scratch_elems(N, (long long)H * W, w.cout, w.groups);
   mid.scratch = c->arena.alloc_n<float2>(mid.scratch_elems);
   if (!mid.scratch) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
   TRY(conv(c, ps, w.conv1, h1, N, H, W, w.cin, w.cout, 3, 1, 1, tbias, tbias_stride, nullptr, h2, 0, &mid));
   WALLOC(h3, px * w.cout);
-  TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, mid.ready()));
+  TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, mid.ready(), mid.deferred()));
   const float* r = x.p;
   if (w.cin != w.cout && c->fuse_skip && w.cin % 64 == 0 && w.cout % 64 == 0) {
     // res_conv_layer (1x1, diffusion.mojo:66-70 / vae.mojo:64-66) rides in the K loop of conv2: one GEMM over

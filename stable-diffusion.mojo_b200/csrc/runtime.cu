@@ -325,7 +325,10 @@ static bool conv_halo_eligible(const Ctx* c, const ASpec& A, int N, const GemmKP
 static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
                         int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh,
                         const TileCfg* use, int ws_splits_plan) {
-  if (nh) nh->req = NormStatsReq();
+  if (nh) {
+    nh->req = NormStatsReq();
+    nh->def = NormHint::Deferred();
+  }
   if (A.K % 4) return c->fail(TSD_ERR_INVALID, "gemm: K must be a multiple of 4");
   if (A.batch > 1 && A.imgs > 1) return c->fail(TSD_ERR_INVALID, "gemm: batch and images are exclusive");
   if (A.K2 > 0 && (A.K % GEMM_BK || A.K2 % GEMM_BK || A.batch > 1 || !A.base2))
@@ -432,10 +435,18 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
 
   SplitKReduceParams rp{};
   size_t mark = c->arena.mark();
+  // deferred reduction: possible when the consumer allows it and the output is a dense [rows][N] matrix that the
+  // fused norm kernel can take (one image per m_per_batch / imgs rows)
+  const int def_imgs = (A.H > 1 || A.imgs > 1) ? A.imgs : ((nh && nh->imgs > 0) ? nh->imgs : 1);
+  const bool can_defer = nh && nh->allow_defer && c->defer_reduce && nh->G > 0 && nbatch == 1 && N % 4 == 0 && p.ldd == N &&
+                         (!p.residual || p.ldr == N) && p.n_pad == N && p.m_per_batch % def_imgs == 0 &&
+                         (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                         norm_fused2_supported(def_imgs, p.m_per_batch / def_imgs, N, nh->G, c->sm_count);
   if (c->dry_run && ws_splits_plan > p.splits) {
     // planning pass: the autotuner may later pick more splits than the model did
     if (!c->arena.alloc_n<float>((size_t)ws_splits_plan * p.m_per_batch * p.n_pad))
       return c->fail(TSD_ERR_OOM, "gemm: arena exhausted (split-K workspace plan)");
+    if (can_defer) return TSD_OK;  // a deferred reduction keeps the workspace until the caller's release
     c->arena.release_to(mark);
   }
   if (p.splits > 1) {
@@ -533,11 +544,25 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
                                "gemm_tf32_kernel launch");
     if (rc) return rc;
     c->launches++;
-    if (p.splits > 1 && !p.fixup) {
+    if (p.splits > 1 && !p.fixup && !can_defer) {
       rc = c->check(launch_splitk_reduce(rp, c->stream), "splitk_reduce launch");
       if (rc) return rc;
       c->launches++;
     }
+  }
+  if (p.splits > 1 && !p.fixup && can_defer) {
+    NormHint::Deferred& d = nh->def;
+    d.ws = rp.partial;
+    d.splits = p.splits;
+    d.ld = p.n_pad;
+    d.split_stride = rp.split_stride;
+    d.bias = p.bias;
+    d.bias_img_stride = p.bias_img_stride;
+    d.residual = p.residual;
+    d.raw = p.D;
+    d.rows = p.m_per_batch;
+    d.C = N;
+    return TSD_OK;  // the partial buffer stays allocated: the caller's arena mark releases it after the norm
   }
   c->arena.release_to(mark);  // stream-ordered: the next op may reuse the partial buffer
   return TSD_OK;
@@ -725,6 +750,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   float best_ms = 1e30f;
   TileCfg best = model;
   int rc = TSD_OK;
+  const size_t tune_mark = c->arena.mark();
   for (const TileCfg& cand : cands) {
     float ms_c = 1e30f;
     for (int rep = 0; rep < 3 && !rc; ++rep) {
@@ -732,6 +758,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
       cudaEventRecord(e0, c->stream);
       rc = run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, &cand, 0);
       cudaEventRecord(e1, c->stream);
+      c->arena.release_to(tune_mark);  // a deferred split-K reduction leaves its workspace allocated
       if (rc) break;
       if (cudaEventSynchronize(e1) != cudaSuccess) {
         rc = c->check(cudaGetLastError(), "gemm autotune");
@@ -910,8 +937,44 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
 
 int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,
                   const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
-                  int round_tf32, const NormStatsReq* pre) {
+                  int round_tf32, const NormStatsReq* pre, const NormHint::Deferred* def) {
   if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
+  if (def != nullptr && def->ws != nullptr) {
+    // the producer was a split-K GEMM that left its partial tiles: sum them, add bias / residual, write the raw
+    // output (x) and normalise in one launch
+    if (upsample || def->raw != x || def->C != C || def->rows != (long long)N * H * W ||
+        !norm_fused2_supported(N, (long long)H * W, C, G, c->sm_count))
+      return c->fail(TSD_ERR_STATE, "group_norm: deferred split-K reduction does not match its consumer");
+    const size_t mark = c->arena.mark();
+    void* scratch = c->arena.alloc(norm_fused2_scratch_bytes(N, (long long)H * W, C, G, c->sm_count));
+    if (!scratch) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+    if (!c->dry_run) {
+      TimedScope ts(c, FAM_NORM, 0);
+      NormFused2Src src;
+      src.x = def->ws;
+      src.splits = def->splits;
+      src.split_stride = def->split_stride;
+      src.ldx = def->ld;
+      src.bias = def->bias;
+      src.bias_img_stride = def->bias_img_stride;
+      src.residual = def->residual;
+      src.raw = def->raw;
+      int rc = c->check(launch_norm_fused2(src, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
+                                           round_tf32, scratch, c->norm_bar, c->sm_count, c->stream),
+                        "norm_fused2 (split-K source) launch");
+      if (rc) return rc;
+      c->launches += 1;
+    }
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
+  if (c->dry_run && !upsample && norm_fused2_supported(N, (long long)H * W, C, G, c->sm_count)) {
+    // planning pass: whichever fused norm the run takes, its scratch fits
+    const size_t mark = c->arena.mark();
+    if (!c->arena.alloc(norm_fused2_scratch_bytes(N, (long long)H * W, C, G, c->sm_count)))
+      return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+    c->arena.release_to(mark);
+  }
   if (pre != nullptr && pre->partial != nullptr && !upsample && pre->G == G && pre->C == C && pre->imgs == N &&
       c->gn_partial && G <= c->gn_partial_max_groups && norm_apply_partial_supported(C, G)) {
     // the producer left per-tile partial sums: one normalise pass that folds them per block

@@ -74,6 +74,21 @@ struct NormHint {
   size_t scratch_elems = 0;
   NormStatsReq req;
   const NormStatsReq* ready() const { return req.partial ? &req : nullptr; }
+  // Deferred split-K reduction: the consumer promises that the very next reader of the producer's output is its
+  // norm.  A split-K producer then leaves its partial tiles in the arena (not released) and launches no reduce
+  // kernel; the norm kernel sums them, adds bias / residual, writes the raw output and normalises in one launch.
+  bool allow_defer = false;
+  struct Deferred {
+    const float* ws = nullptr;  // [splits][rows][ld]
+    int splits = 0, ld = 0;
+    long long split_stride = 0;
+    const float* bias = nullptr;
+    int bias_img_stride = 0;
+    const float* residual = nullptr;
+    float* raw = nullptr;       // [rows][C] un-normalised output
+    int rows = 0, C = 0;
+  } def;
+  const Deferred* deferred() const { return def.ws ? &def : nullptr; }
 };
 // upper bound of the partial entries a producer may write for an [imgs][rows_per_img][C] activation
 inline size_t norm_scratch_elems(int imgs, long long rows_per_img, int C, int G) {
@@ -112,6 +127,7 @@ struct Ctx {
   int gn_partial = 1;              // GroupNorm consumes producer-side partial statistics (0: always the stand-alone fused norm)
   int gn_partial_max_groups = 64;  // ... only up to this many groups (every block folds all groups of its image)
   int ln_fold = 1;                 // fold global-statistics LayerNorm into the consuming GEMM epilogue (0: separate pass)
+  int defer_reduce = 1;            // split-K partials summed by the consuming norm kernel where the call site allows it
   int fuse_skip = 1;               // ResBlock 1x1 skip convolution as a second K segment of conv2 (0: GEMM of its own + residual add)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
@@ -207,7 +223,7 @@ inline int conv_out_dim(int in, int k, int pad, int stride, int pad_hi = -1) {
 // GroupNorm(+SiLU)(+2x nearest upsample). stats scratch comes from the arena.
 int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, int G, float eps,
                   const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
-                  int round_tf32, const NormStatsReq* pre = nullptr);
+                  int round_tf32, const NormStatsReq* pre = nullptr, const NormHint::Deferred* def = nullptr);
 
 struct AttnArgs {
   // per (batch b, head h): Q [Tq][d], K [Tk][d], V [Tk][d], contiguous blocks

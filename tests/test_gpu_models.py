@@ -124,6 +124,8 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
 @pytest.mark.parametrize("opts", [
     {"ln_fold": 0},                       # LayerNorm as a separate pass instead of the GEMM-epilogue fold
     {"fuse_skip": 0},                     # skip convolution as its own GEMM + residual add
+    {"defer_reduce": 0},                  # split-K always through the reduce kernel
+    {"defer_reduce": 1, "force_splits": 4},  # split-K partials summed by the consuming GroupNorm kernel
     {"fuse_skip": 1, "force_splits": 8},  # second K segment under split-K (the last split starts inside it)
     {"producer_stats": 0},                # every norm computes its own statistics (no epilogue partial sums)
     {"producer_stats": 0, "norm_v2": 1},  # ... with the register-resident fused norm kernel
@@ -157,7 +159,7 @@ def test_unet64_switches_agree_at_full_size(ctx, diff64):
     cx = rng.standard_normal((77, 768), dtype=np.float32)
     t = host_sampler.get_time_embedding(500.0)
     y_default = diff64.forward(x, cx, t)
-    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}):
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}):
         old = {k: ctx.get_option(k) for k in opts}
         for k, v in opts.items():
             ctx.set_option(k, v)
