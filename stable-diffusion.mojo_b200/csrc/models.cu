@@ -414,7 +414,9 @@ int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, co
   const size_t mark = c->arena.mark();
   WALLOC(h1, px * w.cin);
   const NormStatsReq* xs = (x.ns.G == w.groups && x.ns.eps == eps && x.C == w.cin) ? x.ns.ready() : nullptr;
-  TRY(op_group_norm(c, x.p, h1, N, H, W, w.cin, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, xs));
+  const bool xmatch = x.ns.G == w.groups && x.ns.eps == eps && x.C == w.cin;
+  TRY(op_group_norm(c, x.p, h1, N, H, W, w.cin, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, xs,
+                    xmatch ? x.ns.deferred() : nullptr));
   WALLOC(h2, px * w.cout);
   NormHint mid;
   mid.G = w.groups;
@@ -462,7 +464,8 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   const size_t mark = c->arena.mark();
   WALLOC(a, M * C);
   const NormStatsReq* xs = (x.ns.G == 32 && x.ns.eps == 1e-6f) ? x.ns.ready() : nullptr;
-  TRY(op_group_norm(c, x.p, a, N, x.H, x.W, C, 32, 1e-6f, nullptr, nullptr, 1.0f, 0, 0, 1, xs));
+  TRY(op_group_norm(c, x.p, a, N, x.H, x.W, C, 32, 1e-6f, nullptr, nullptr, 1.0f, 0, 0, 1, xs,
+                    (x.ns.G == 32 && x.ns.eps == 1e-6f) ? x.ns.deferred() : nullptr));
   // LayerNorm with global statistics (Q5) = one group per image: the producing GEMMs fold the sums
   NormHint ln;
   ln.G = c->layernorm_mode == 0 ? 1 : 0;
@@ -698,6 +701,16 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
     a.ns.scratch = c->arena.alloc_n<float2>(a.ns.scratch_elems);
     return a.ns.scratch != nullptr;
   };
+  // The first reader of these activations is the GroupNorm of the next block: a split-K producer may leave its
+  // partial tiles for that norm kernel (NormHint::allow_defer).  Only where split-K happens (<= 32x32 latents).
+  auto defer_ws = [&](Act& a) -> bool {
+    if (!c->defer_reduce || a.pixels() * a.C > 1024ll * 1280) return true;
+    a.ns.imgs = a.N;
+    a.ns.defer_ws_elems = (size_t)8 * a.pixels() * a.C;  // up to 8 splits
+    a.ns.defer_ws = c->arena.alloc_n<float>(a.ns.defer_ws_elems);
+    a.ns.allow_defer = a.ns.defer_ws != nullptr;
+    return a.ns.allow_defer;
+  };
   auto RES = [&](int i, const Act& in, Act& out_) -> int {
     out_ = act(res[i].cout, in.H, in.W);
     if (!out_.p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)");
@@ -707,6 +720,7 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
     out_.ns.G = 32;
     out_.ns.eps = 1e-6f;
     if (!hint_scratch(out_)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+    if (!defer_ws(out_)) return c->fail(TSD_ERR_OOM, "workspace exhausted (split-K partial tiles)");
     return res_block(c, ps, res[i], v, tbias[i], tstride * res[i].cout, 1e-5f, out_.p, &out_.ns);
   };
   auto ATT = [&](int i, const Act& in, Act& out_) -> int {
@@ -754,6 +768,7 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
   d4.ns.G = 32;  // consumed by ResBlock 1's first GroupNorm
   d4.ns.eps = 1e-5f;
   if (!hint_scratch(d4)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+  if (!defer_ws(d4)) return c->fail(TSD_ERR_OOM, "workspace exhausted (split-K partial tiles)");
   TRY(conv(c, ps, down1, a3.p, n, H, W, 320, 320, 3, 1, 2, nullptr, 0, nullptr, d4.p, 0, &d4.ns));
   TRY(RES(1, d4, r5));
   TRY(ATT(1, r5, a6));  // skip4: dead input of layer15 (Q9)
@@ -762,6 +777,7 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
   d7.ns.G = 32;
   d7.ns.eps = 1e-5f;
   if (!hint_scratch(d7)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+  if (!defer_ws(d7)) return c->fail(TSD_ERR_OOM, "workspace exhausted (split-K partial tiles)");
   TRY(conv(c, ps, down2, a6.p, n, H / 2, W / 2, 640, 640, 3, 1, 2, nullptr, 0, nullptr, d7.p, 0, &d7.ns));
   TRY(RES(2, d7, r8));
   TRY(ATT(2, r8, a9));

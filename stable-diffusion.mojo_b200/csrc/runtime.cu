@@ -441,17 +441,20 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   const bool can_defer = nh && nh->allow_defer && c->defer_reduce && nh->G > 0 && nbatch == 1 && N % 4 == 0 && p.ldd == N &&
                          (!p.residual || p.ldr == N) && p.n_pad == N && p.m_per_batch % def_imgs == 0 &&
                          (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
-                         norm_fused2_supported(def_imgs, p.m_per_batch / def_imgs, N, nh->G, c->sm_count);
+                         norm_fused2_supported(def_imgs, p.m_per_batch / def_imgs, N, nh->G, c->sm_count) &&
+                         (nh->defer_ws == nullptr ||
+                          (size_t)std::max(p.splits, 1) * p.m_per_batch * p.n_pad <= nh->defer_ws_elems);
+  const bool own_ws = can_defer && nh->defer_ws != nullptr;  // partials go to the consumer-lifetime buffer
   if (c->dry_run && ws_splits_plan > p.splits) {
     // planning pass: the autotuner may later pick more splits than the model did
     if (!c->arena.alloc_n<float>((size_t)ws_splits_plan * p.m_per_batch * p.n_pad))
       return c->fail(TSD_ERR_OOM, "gemm: arena exhausted (split-K workspace plan)");
-    if (can_defer) return TSD_OK;  // a deferred reduction keeps the workspace until the caller's release
+    if (can_defer && !own_ws) return TSD_OK;  // a deferred reduction keeps the workspace until the caller's release
     c->arena.release_to(mark);
   }
   if (p.splits > 1) {
     const size_t elems = (size_t)p.splits * p.m_per_batch * p.n_pad;
-    float* ws = c->arena.alloc_n<float>(elems);
+    float* ws = own_ws ? nh->defer_ws : c->arena.alloc_n<float>(elems);
     if (!ws) return c->fail(TSD_ERR_OOM, "gemm: arena exhausted (split-K workspace)");
     rp.partial = ws;
     rp.splits = p.splits;

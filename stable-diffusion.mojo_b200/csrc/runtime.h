@@ -78,6 +78,10 @@ struct NormHint {
   // norm.  A split-K producer then leaves its partial tiles in the arena (not released) and launches no reduce
   // kernel; the norm kernel sums them, adds bias / residual, writes the raw output and normalises in one launch.
   bool allow_defer = false;
+  // Partial-tile buffer that outlives the producer's own arena scope (consumer in another block); nullptr: the
+  // producer allocates from the arena and leaves it to the caller's mark.  Capacity in floats.
+  float* defer_ws = nullptr;
+  size_t defer_ws_elems = 0;
   struct Deferred {
     const float* ws = nullptr;  // [splits][rows][ld]
     int splits = 0, ld = 0;
