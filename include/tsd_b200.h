@@ -73,6 +73,8 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *                          0 = a GEMM of its own whose result conv2 adds as a residual
  *   "defer_reduce"     1 = where a split-K GEMM feeds a norm directly, the norm kernel sums the partial tiles
  *                          (no reduce kernel) [default]
+ *   "virtual_concat"   1 = the channel concats of the UNet are read (and written out) by the GroupNorm kernel of the
+ *                          ResBlock they feed instead of a concat kernel of their own; 0 [default] (measured neutral)
  *   "norm_v2"          0/1 = which single-launch fused norm kernel serves the remaining norms
  *   "splitk_fixup"     1 = split-K partials reduced in-kernel by the last CTA of each tile, 0 = reduce kernel [default]
  *   "pdl"              1 = programmatic dependent launch between the kernels of a graph [default]

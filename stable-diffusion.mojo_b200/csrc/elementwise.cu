@@ -496,7 +496,9 @@ struct NormFused2Params {
   const float* bias;    // split-K source only: [C] per image (bias + img * bias_img_stride) or nullptr
   int bias_img_stride;
   const float4* residual;  // split-K source only
-  float4* raw;          // split-K source only: un-normalised result (nullptr: not needed)
+  float4* raw;          // split-K / two-source: un-normalised result (nullptr: not needed)
+  const float4* x2;     // two-source (channel concat): channels [c4a*4, C) come from x2 [rows][C4 - c4a]
+  int c4a;
   float4* y;
   int pixels, C4, G, cpg;
   int slabs_per_img, slab, subs_per_img;
@@ -536,6 +538,11 @@ norm_fused2_kernel(const NormFused2Params p) {
 
   auto load = [&](int px, int qd) -> float4 {
     const long long row = (long long)n * p.pixels + px;
+    if (p.x2 != nullptr) {  // channel concat of two tensors, written out as a by-product
+      const float4 a = qd < p.c4a ? p.x[row * p.c4a + qd] : p.x2[row * (C4 - p.c4a) + (qd - p.c4a)];
+      if (p.raw) p.raw[row * C4 + qd] = a;
+      return a;
+    }
     float4 a = p.x[row * p.ldx4 + qd];
     if (p.splits > 1) {
       for (int s = 1; s < p.splits; ++s) {
@@ -787,8 +794,9 @@ norm_fused2_kernel(const NormFused2Params p) {
       }
     }
   } else {
-    const float4* src = (p.splits > 1) ? p.raw : p.x;  // re-read mode of a split-K source reads back the raw sum
-    const int ld = (p.splits > 1) ? C4 : p.ldx4;
+    const bool from_raw = p.splits > 1 || p.x2 != nullptr;  // re-read mode of a split-K / two-source input reads back
+    const float4* src = from_raw ? p.raw : p.x;             // the raw tensor this kernel wrote in phase 1
+    const int ld = from_raw ? C4 : p.ldx4;
 #pragma unroll 2
     for (int px = p0 + pl; px < p1; px += ppl) {
 #pragma unroll
@@ -1524,6 +1532,9 @@ cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long l
   p.bias_img_stride = src.bias_img_stride;
   p.residual = reinterpret_cast<const float4*>(src.residual);
   p.raw = reinterpret_cast<float4*>(src.raw);
+  p.x2 = reinterpret_cast<const float4*>(src.x2);
+  p.c4a = src.c_a / 4;
+  if (src.x2 != nullptr && (src.splits > 1 || src.c_a <= 0 || src.c_a >= C || src.c_a % 4)) return cudaErrorInvalidValue;
   p.y = reinterpret_cast<float4*>(y);
   p.pixels = (int)pixels;
   p.C4 = C / 4;
@@ -1548,7 +1559,7 @@ cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long l
     p.trace = tr;
   }
   bool cache = pl.cache;
-  if (p.splits > 1 && !cache && p.raw == nullptr) return cudaErrorInvalidValue;  // re-read mode needs the raw sum
+  if ((p.splits > 1 || p.x2 != nullptr) && !cache && p.raw == nullptr) return cudaErrorInvalidValue;  // re-read mode needs the raw tensor
   const int grid = N * pl.slabs_per_img;
   size_t smem = (size_t)pl.ppl * 2 * C * sizeof(float);
   if (smem < (size_t)G * sizeof(float2)) smem = (size_t)G * sizeof(float2);

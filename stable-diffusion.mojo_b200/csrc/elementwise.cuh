@@ -54,6 +54,8 @@ struct NormFused2Src {
   int bias_img_stride = 0;
   const float* residual = nullptr;  // split-K source: [N*pixels][C]
   float* raw = nullptr;             // split-K source: un-normalised result [N*pixels][C] (nullptr: not needed)
+  const float* x2 = nullptr;        // two-source (channel concat [x | x2]): x is [rows][c_a], x2 [rows][C - c_a];
+  int c_a = 0;                      //   raw (optional) receives the concatenated tensor
 };
 bool norm_fused2_supported(int N, long long pixels, int C, int G, int sm_count);
 size_t norm_fused2_scratch_bytes(int N, long long pixels, int C, int G, int sm_count);

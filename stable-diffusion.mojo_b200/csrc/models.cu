@@ -745,6 +745,23 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
   auto CAT = [&](const Act& a, const Act& b, Act& out_) -> int {
     out_ = act(a.C + b.C, a.H, a.W);
     if (!out_.p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)");
+    if (c->virtual_concat && a.C % 4 == 0 && b.C % 4 == 0 &&
+        norm_fused2_supported(a.N, (long long)a.H * a.W, a.C + b.C, 32, c->sm_count)) {
+      // every concat of the UNet feeds a ResBlock whose first GroupNorm(32, eps 1e-5) is its first reader: that
+      // kernel reads the two tensors and writes the concatenation (for the block's convolutions) as a by-product
+      out_.ns.G = 32;
+      out_.ns.eps = 1e-5f;
+      out_.ns.imgs = a.N;
+      NormHint::Deferred& d = out_.ns.def;
+      d.ws = a.p;
+      d.x2 = b.p;
+      d.c_a = a.C;
+      d.splits = 1;
+      d.raw = out_.p;
+      d.rows = (int)a.pixels();
+      d.C = a.C + b.C;
+      return TSD_OK;
+    }
     LAUNCH(c, launch_concat_channels(a.p, a.C, b.p, b.C, out_.p, a.pixels(), c->stream), "concat");
     return TSD_OK;
   };

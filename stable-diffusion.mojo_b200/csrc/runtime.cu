@@ -962,6 +962,8 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
       src.bias_img_stride = def->bias_img_stride;
       src.residual = def->residual;
       src.raw = def->raw;
+      src.x2 = def->x2;
+      src.c_a = def->c_a;
       int rc = c->check(launch_norm_fused2(src, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
                                            round_tf32, scratch, c->norm_bar, c->sm_count, c->stream),
                         "norm_fused2 (split-K source) launch");

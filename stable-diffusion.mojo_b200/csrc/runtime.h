@@ -91,6 +91,10 @@ struct NormHint {
     const float* residual = nullptr;
     float* raw = nullptr;       // [rows][C] un-normalised output
     int rows = 0, C = 0;
+    // virtual channel concat (splits == 1): ws = first tensor [rows][c_a], x2 = second [rows][C - c_a]; the norm
+    // kernel writes the concatenated tensor to `raw` as a by-product
+    const float* x2 = nullptr;
+    int c_a = 0;
   } def;
   const Deferred* deferred() const { return def.ws ? &def : nullptr; }
 };
@@ -132,6 +136,7 @@ struct Ctx {
   int gn_partial_max_groups = 64;  // ... only up to this many groups (every block folds all groups of its image)
   int ln_fold = 1;                 // fold global-statistics LayerNorm into the consuming GEMM epilogue (0: separate pass)
   int defer_reduce = 1;            // split-K partials summed by the consuming norm kernel where the call site allows it
+  int virtual_concat = 0;          // 1: channel concats feeding a ResBlock are read (and written out) by its first GroupNorm kernel (measured neutral)
   int fuse_skip = 1;               // ResBlock 1x1 skip convolution as a second K segment of conv2 (0: GEMM of its own + residual add)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)

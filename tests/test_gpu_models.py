@@ -125,6 +125,7 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
     {"ln_fold": 0},                       # LayerNorm as a separate pass instead of the GEMM-epilogue fold
     {"fuse_skip": 0},                     # skip convolution as its own GEMM + residual add
     {"defer_reduce": 0},                  # split-K always through the reduce kernel
+    {"virtual_concat": 1},                # channel concats read and written out by the consuming GroupNorm kernel
     {"defer_reduce": 1, "force_splits": 4},  # split-K partials summed by the consuming GroupNorm kernel
     {"fuse_skip": 1, "force_splits": 8},  # second K segment under split-K (the last split starts inside it)
     {"producer_stats": 0},                # every norm computes its own statistics (no epilogue partial sums)
@@ -159,18 +160,21 @@ def test_unet64_switches_agree_at_full_size(ctx, diff64):
     cx = rng.standard_normal((77, 768), dtype=np.float32)
     t = host_sampler.get_time_embedding(500.0)
     y_default = diff64.forward(x, cx, t)
-    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}):
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}, {"virtual_concat": 1}):
         old = {k: ctx.get_option(k) for k in opts}
         for k, v in opts.items():
             ctx.set_option(k, v)
         try:
             y = diff64.forward(x, cx, t)
+            # a batch of two takes other slab / tile shapes (e.g. the re-read mode of the fused norm kernels)
+            y2 = diff64.forward(np.stack([x, x]), cx, t)
         finally:
             for k, v in old.items():
                 ctx.set_option(k, v)
         e = relerr(y, y_default)
         print(f"unet64 {opts}: rel_linf vs default plan {e:.2e}")
         assert e < TOL_BATCH
+        assert np.array_equal(y2[0], y2[1]) and relerr(y2[0], y_default) < TOL_BATCH
 
 
 def test_load_weights_blob_path(ctx, golden_small):
