@@ -1589,8 +1589,15 @@ cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsR
   if (!norm_apply_partial_supported(req.C, req.G) || pixels_ll >= (1 << 30)) return cudaErrorInvalidValue;
   const int C4 = req.C / 4, pixels = (int)pixels_ll;
   const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
-  // ~4 blocks per SM over the whole batch; a slab is a multiple of the pixels in flight
-  int slabs = (4 * 148 + N - 1) / N;
+  // blocks over the whole batch (each folds the partial statistics of its image first, a fixed cost);
+  // a slab is a multiple of the pixels in flight
+  static int target = -1;
+  if (target < 0) {
+    const char* v = getenv("TSD_NORM_BLOCKS");  // lab override
+    target = v ? atoi(v) : 4 * 148;
+    if (target < 1) target = 4 * 148;
+  }
+  int slabs = (target + N - 1) / N;
   int slab = (pixels + slabs - 1) / slabs;
   slab = (slab + ppl - 1) / ppl * ppl;
   if (slab < ppl) slab = ppl;
