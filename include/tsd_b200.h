@@ -47,6 +47,7 @@ typedef struct tsd_decoder tsd_decoder;     /* VAE Decoder (vae.mojo:162-250) */
 typedef struct tsd_clip tsd_clip;           /* CLIP text encoder (clip.mojo:56-109) */
 typedef struct tsd_encoder tsd_encoder;     /* VAE Encoder (vae.mojo:70-159) */
 typedef struct tsd_tokenizer tsd_tokenizer; /* Tokenizer (helpers/utils.mojo:228-292) */
+typedef struct tsd_safetensors tsd_safetensors; /* checkpoint file (the reference's weight-loading TODO, README.md:44,55) */
 
 /* ---- context ------------------------------------------------------------------------ */
 int32_t tsd_init(int32_t device, tsd_ctx** out);
@@ -290,6 +291,22 @@ int32_t tsd_tokenizer_encode(const tsd_tokenizer* t, const uint8_t* text, int32_
 int32_t tsd_png_encode(const float* img, int32_t c, int32_t h, int32_t w, uint8_t* out, int64_t cap,
                        int64_t* size);
 int32_t tsd_png_write(const char* path, const float* img, int32_t c, int32_t h, int32_t w);
+
+/* ---- checkpoint files ------------------------------------------------------
+ * The reference has no loader (README.md:44,55 list it as future work); its weights are random.  These entry
+ * points read the safetensors container (uint64 LE header length, JSON header, raw tensor bytes) so that the flat
+ * blobs tsd_*_load_weights expect can be assembled from a checkpoint: F32 / F16 / BF16 / F64 tensors are delivered
+ * as fp32 (exact for F16 / BF16).  Malformed headers, offsets outside the file or sizes that do not match
+ * shape x dtype are TSD_ERR_INVALID. */
+int32_t tsd_safetensors_open(const char* path, tsd_safetensors** out); /* memory-maps the file */
+int32_t tsd_safetensors_from_memory(const void* buf, int64_t size, tsd_safetensors** out); /* copies buf */
+int32_t tsd_safetensors_close(tsd_safetensors* st);
+int32_t tsd_safetensors_count(const tsd_safetensors* st);
+const char* tsd_safetensors_name(const tsd_safetensors* st, int32_t i);
+int32_t tsd_safetensors_find(const tsd_safetensors* st, const char* name); /* index or -1 */
+int32_t tsd_safetensors_info(const tsd_safetensors* st, int32_t i, char dtype[8], int32_t* rank, int64_t shape[8],
+                             int64_t* numel);
+int32_t tsd_safetensors_read_f32(const tsd_safetensors* st, int32_t i, float* out, int64_t cap);
 
 /* ---- tuning probes (synthetic device-resident operands, CUDA-event ms per launch) ------------ */
 int32_t tsd_bench_gemm(tsd_ctx* ctx, int32_t m, int32_t n, int32_t k, int32_t batch, int32_t geglu,

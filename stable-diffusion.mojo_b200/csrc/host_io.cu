@@ -306,3 +306,344 @@ int32_t tsd_png_write(const char* path, const float* img, int32_t c, int32_t h, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// safetensors reader (the reference's stated TODO README.md:44,55: "load the weights").
+// File layout: uint64 little-endian header length N, N bytes of JSON {"name": {"dtype": "F32", "shape": [..],
+// "data_offsets": [begin, end]}, ..., "__metadata__": {...}}, then the tensor bytes (offsets relative to the end
+// of the header).  F32 / F16 / BF16 / F64 tensors are delivered as fp32.
+// ---------------------------------------------------------------------------------------------------------
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+struct tsd_safetensors {
+  struct Entry {
+    std::string name, dtype;
+    std::vector<int64_t> shape;
+    int64_t begin = 0, end = 0, numel = 0;
+  };
+  std::vector<Entry> entries;
+  const uint8_t* base = nullptr;  // start of the tensor bytes
+  int64_t data_size = 0;
+  void* map = nullptr;            // mmap of the whole file, or nullptr
+  size_t map_size = 0;
+  std::vector<uint8_t> owned;     // from_memory copy
+};
+
+namespace {
+
+struct Json {  // minimal recursive-descent parser for the header's subset of JSON
+  const char* p;
+  const char* e;
+  bool ok = true;
+  void ws() {
+    while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+  }
+  bool eat(char c) {
+    ws();
+    if (p < e && *p == c) {
+      ++p;
+      return true;
+    }
+    return false;
+  }
+  bool str(std::string& out) {
+    ws();
+    if (p >= e || *p != '"') return ok = false;
+    ++p;
+    out.clear();
+    while (p < e && *p != '"') {
+      if (*p == '\\') {
+        if (++p >= e) return ok = false;
+        switch (*p) {
+          case 'n': out.push_back('\n'); break;
+          case 't': out.push_back('\t'); break;
+          case 'r': out.push_back('\r'); break;
+          case 'b': out.push_back('\b'); break;
+          case 'f': out.push_back('\f'); break;
+          case 'u': {
+            if (e - p < 5) return ok = false;
+            unsigned v = 0;
+            for (int i = 1; i <= 4; ++i) {
+              const char ch = p[i];
+              v <<= 4;
+              if (ch >= '0' && ch <= '9') v |= ch - '0';
+              else if (ch >= 'a' && ch <= 'f') v |= ch - 'a' + 10;
+              else if (ch >= 'A' && ch <= 'F') v |= ch - 'A' + 10;
+              else return ok = false;
+            }
+            p += 4;
+            if (v < 0x80) out.push_back((char)v);  // UTF-8 encode (BMP; surrogate pairs are kept as two code units)
+            else if (v < 0x800) {
+              out.push_back((char)(0xC0 | (v >> 6)));
+              out.push_back((char)(0x80 | (v & 0x3F)));
+            } else {
+              out.push_back((char)(0xE0 | (v >> 12)));
+              out.push_back((char)(0x80 | ((v >> 6) & 0x3F)));
+              out.push_back((char)(0x80 | (v & 0x3F)));
+            }
+            break;
+          }
+          default: out.push_back(*p);  // \" \\ \/
+        }
+        ++p;
+      } else {
+        out.push_back(*p++);
+      }
+    }
+    if (p >= e) return ok = false;
+    ++p;
+    return true;
+  }
+  bool integer(int64_t& v) {
+    ws();
+    const char* s = p;
+    bool neg = false;
+    if (p < e && *p == '-') {
+      neg = true;
+      ++p;
+    }
+    if (p >= e || *p < '0' || *p > '9') {
+      p = s;
+      return ok = false;
+    }
+    v = 0;
+    while (p < e && *p >= '0' && *p <= '9') {
+      if (v > (INT64_MAX - 9) / 10) return ok = false;
+      v = v * 10 + (*p++ - '0');
+    }
+    if (neg) v = -v;
+    return true;
+  }
+  bool int_array(std::vector<int64_t>& a) {
+    a.clear();
+    if (!eat('[')) return ok = false;
+    if (eat(']')) return true;
+    do {
+      int64_t v;
+      if (!integer(v)) return false;
+      a.push_back(v);
+    } while (eat(','));
+    return eat(']') ? true : (ok = false);
+  }
+  bool skip_value() {  // __metadata__ and unknown keys
+    ws();
+    if (p >= e) return ok = false;
+    if (*p == '"') {
+      std::string s;
+      return str(s);
+    }
+    if (*p == '{' || *p == '[') {
+      const char open = *p, close = open == '{' ? '}' : ']';
+      ++p;
+      if (eat(close)) return true;
+      do {
+        if (open == '{') {
+          std::string k;
+          if (!str(k) || !eat(':')) return ok = false;
+        }
+        if (!skip_value()) return false;
+      } while (eat(','));
+      return eat(close) ? true : (ok = false);
+    }
+    while (p < e && *p != ',' && *p != '}' && *p != ']' && *p != ' ' && *p != '\n') ++p;  // number / true / false / null
+    return true;
+  }
+};
+
+int dtype_size(const std::string& d) {
+  if (d == "F32") return 4;
+  if (d == "F16" || d == "BF16") return 2;
+  if (d == "F64") return 8;
+  return 0;  // I8/I32/... are listed but cannot be read as fp32 parameters
+}
+
+float half_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else {  // subnormal: normalise
+      int sh = 0;
+      while (!(man & 0x400u)) {
+        man <<= 1;
+        ++sh;
+      }
+      man &= 0x3FFu;
+      bits = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | (man << 13);
+    }
+  } else if (exp == 31) {
+    bits = sign | 0x7F800000u | (man << 13);
+  } else {
+    bits = sign | ((exp + 112u) << 23) | (man << 13);
+  }
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
+
+int32_t safetensors_parse(tsd_safetensors* st, const uint8_t* file, int64_t size) {
+  if (size < 8) return TSD_ERR_INVALID;
+  uint64_t hlen = 0;
+  std::memcpy(&hlen, file, 8);
+  if (hlen > (uint64_t)(size - 8) || hlen > (1ull << 30)) return TSD_ERR_INVALID;
+  st->base = file + 8 + hlen;
+  st->data_size = size - 8 - (int64_t)hlen;
+  Json j{reinterpret_cast<const char*>(file + 8), reinterpret_cast<const char*>(file + 8 + hlen)};
+  if (!j.eat('{')) return TSD_ERR_INVALID;
+  if (j.eat('}')) return TSD_OK;
+  do {
+    std::string key;
+    if (!j.str(key) || !j.eat(':')) return TSD_ERR_INVALID;
+    if (key == "__metadata__") {
+      if (!j.skip_value()) return TSD_ERR_INVALID;
+      continue;
+    }
+    tsd_safetensors::Entry en;
+    en.name = key;
+    bool have_d = false, have_s = false, have_o = false;
+    if (!j.eat('{')) return TSD_ERR_INVALID;
+    do {
+      std::string k;
+      if (!j.str(k) || !j.eat(':')) return TSD_ERR_INVALID;
+      if (k == "dtype") have_d = j.str(en.dtype);
+      else if (k == "shape") have_s = j.int_array(en.shape);
+      else if (k == "data_offsets") {
+        std::vector<int64_t> o;
+        have_o = j.int_array(o) && o.size() == 2;
+        if (have_o) {
+          en.begin = o[0];
+          en.end = o[1];
+        }
+      } else if (!j.skip_value()) return TSD_ERR_INVALID;
+      if (!j.ok) return TSD_ERR_INVALID;
+    } while (j.eat(','));
+    if (!j.eat('}') || !have_d || !have_s || !have_o) return TSD_ERR_INVALID;
+    en.numel = 1;
+    for (int64_t d : en.shape) {
+      if (d < 0 || (d > 0 && en.numel > INT64_MAX / d)) return TSD_ERR_INVALID;
+      en.numel *= d;
+    }
+    if (en.begin < 0 || en.end < en.begin || en.end > st->data_size) return TSD_ERR_INVALID;
+    const int es = dtype_size(en.dtype);
+    if (es && en.end - en.begin != en.numel * es) return TSD_ERR_INVALID;
+    st->entries.push_back(std::move(en));
+  } while (j.eat(','));
+  if (!j.eat('}')) return TSD_ERR_INVALID;
+  return TSD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tsd_safetensors_open(const char* path, tsd_safetensors** out) {
+  if (!path || !out) return TSD_ERR_INVALID;
+  *out = nullptr;
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) return TSD_ERR_INVALID;
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || sb.st_size < 8) {
+    ::close(fd);
+    return TSD_ERR_INVALID;
+  }
+  void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (m == MAP_FAILED) return TSD_ERR_OOM;
+  tsd_safetensors* st = new (std::nothrow) tsd_safetensors();
+  if (!st) {
+    munmap(m, (size_t)sb.st_size);
+    return TSD_ERR_OOM;
+  }
+  st->map = m;
+  st->map_size = (size_t)sb.st_size;
+  const int32_t rc = safetensors_parse(st, static_cast<const uint8_t*>(m), (int64_t)sb.st_size);
+  if (rc) {
+    munmap(m, st->map_size);
+    delete st;
+    return rc;
+  }
+  *out = st;
+  return TSD_OK;
+}
+
+int32_t tsd_safetensors_from_memory(const void* buf, int64_t size, tsd_safetensors** out) {
+  if (!buf || !out || size < 8) return TSD_ERR_INVALID;
+  *out = nullptr;
+  tsd_safetensors* st = new (std::nothrow) tsd_safetensors();
+  if (!st) return TSD_ERR_OOM;
+  st->owned.assign(static_cast<const uint8_t*>(buf), static_cast<const uint8_t*>(buf) + size);
+  const int32_t rc = safetensors_parse(st, st->owned.data(), size);
+  if (rc) {
+    delete st;
+    return rc;
+  }
+  *out = st;
+  return TSD_OK;
+}
+
+int32_t tsd_safetensors_close(tsd_safetensors* st) {
+  if (!st) return TSD_ERR_INVALID;
+  if (st->map) munmap(st->map, st->map_size);
+  delete st;
+  return TSD_OK;
+}
+int32_t tsd_safetensors_count(const tsd_safetensors* st) { return st ? (int32_t)st->entries.size() : 0; }
+const char* tsd_safetensors_name(const tsd_safetensors* st, int32_t i) {
+  return (st && i >= 0 && i < (int32_t)st->entries.size()) ? st->entries[i].name.c_str() : nullptr;
+}
+int32_t tsd_safetensors_find(const tsd_safetensors* st, const char* name) {
+  if (!st || !name) return -1;
+  for (size_t i = 0; i < st->entries.size(); ++i)
+    if (st->entries[i].name == name) return (int32_t)i;
+  return -1;
+}
+int32_t tsd_safetensors_info(const tsd_safetensors* st, int32_t i, char dtype[8], int32_t* rank, int64_t shape[8],
+                             int64_t* numel) {
+  if (!st || i < 0 || i >= (int32_t)st->entries.size()) return TSD_ERR_INVALID;
+  const tsd_safetensors::Entry& en = st->entries[i];
+  if (dtype) {
+    std::memset(dtype, 0, 8);
+    std::strncpy(dtype, en.dtype.c_str(), 7);
+  }
+  if (rank) *rank = (int32_t)en.shape.size();
+  if (shape)
+    for (size_t d = 0; d < en.shape.size() && d < 8; ++d) shape[d] = en.shape[d];
+  if (numel) *numel = en.numel;
+  return en.shape.size() > 8 ? TSD_ERR_INVALID : TSD_OK;
+}
+int32_t tsd_safetensors_read_f32(const tsd_safetensors* st, int32_t i, float* out, int64_t cap) {
+  if (!st || !out || i < 0 || i >= (int32_t)st->entries.size()) return TSD_ERR_INVALID;
+  const tsd_safetensors::Entry& en = st->entries[i];
+  if (cap < en.numel) return TSD_ERR_OOM;
+  const uint8_t* src = st->base + en.begin;
+  if (en.dtype == "F32") {
+    std::memcpy(out, src, (size_t)en.numel * 4);
+  } else if (en.dtype == "F16") {
+    for (int64_t k = 0; k < en.numel; ++k) {
+      uint16_t h;
+      std::memcpy(&h, src + 2 * k, 2);
+      out[k] = half_to_float(h);
+    }
+  } else if (en.dtype == "BF16") {
+    for (int64_t k = 0; k < en.numel; ++k) {
+      uint16_t h;
+      std::memcpy(&h, src + 2 * k, 2);
+      const uint32_t bits = (uint32_t)h << 16;
+      std::memcpy(out + k, &bits, 4);
+    }
+  } else if (en.dtype == "F64") {
+    for (int64_t k = 0; k < en.numel; ++k) {
+      double d;
+      std::memcpy(&d, src + 8 * k, 8);
+      out[k] = (float)d;
+    }
+  } else {
+    return TSD_ERR_INVALID;
+  }
+  return TSD_OK;
+}
+
+}  // extern "C"

@@ -138,6 +138,14 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_tokenizer_token", vp, vp, i32, i32p, C.POINTER(C.c_float))
     sig("tsd_tokenizer_find", i32, vp, C.c_char_p, i32)
     sig("tsd_tokenizer_encode", i32, vp, C.c_char_p, i32, i32, i32p, i32, i32p)
+    sig("tsd_safetensors_open", i32, C.c_char_p, C.POINTER(vp))
+    sig("tsd_safetensors_from_memory", i32, C.c_char_p, i64, C.POINTER(vp))
+    sig("tsd_safetensors_close", i32, vp)
+    sig("tsd_safetensors_count", i32, vp)
+    sig("tsd_safetensors_name", C.c_char_p, vp, i32)
+    sig("tsd_safetensors_find", i32, vp, C.c_char_p)
+    sig("tsd_safetensors_info", i32, vp, i32, C.c_char_p, i32p, C.POINTER(i64), C.POINTER(i64))
+    sig("tsd_safetensors_read_f32", i32, vp, i32, fp, i64)
     sig("tsd_png_encode", i32, fp, i32, i32, i32, vp, i64, C.POINTER(i64))
     sig("tsd_png_write", i32, C.c_char_p, fp, i32, i32, i32)
     sig("tsd_decoder_create", i32, vp, i32, i32, i32, C.POINTER(vp))

@@ -550,3 +550,30 @@ def test_generate_from_prompt_string(ctx, tmp_path):
         assert np.array_equal(got, np.floor(img + 0.5).astype(np.uint8).transpose(1, 2, 0))
     finally:
         p.close()
+
+
+# ---- checkpoint export / import (infrastructure) ---------------------------------------
+@pytest.mark.parametrize("dtype,exact", [("F32", True), ("BF16", False)])
+def test_checkpoint_round_trip(ctx, tmp_path, dtype, exact):
+    """A model's parameters written to a safetensors file and loaded into a second handle through
+    tsd_safetensors_* + tsd_decoder_load_weights give the same forward (bit-exact for F32)."""
+    from tsd_b200 import weights as W
+    a = Decoder(ctx, 4, 4)
+    b = Decoder(ctx, 4, 4)
+    try:
+        a.init_random(21)
+        path = tmp_path / "decoder.safetensors"
+        W.export_model(a, path, dtype)
+        rep = W.import_model(b, path)
+        assert rep == {"missing": [], "unused": []}
+        z = np.random.default_rng(2).standard_normal((4, 4, 4)).astype(np.float32) * 0.18215
+        ya, yb = a.forward(z), b.forward(z)
+        if exact:
+            assert np.array_equal(ya, yb)
+        else:
+            assert relerr(yb, ya) < 5e-2 and not np.array_equal(ya, yb)    # bf16 weights: 8-bit mantissa
+        with pytest.raises(TsdError):
+            W.import_model(b, path, name_map={"l1.weight": "no.such.tensor"})
+    finally:
+        a.close()
+        b.close()

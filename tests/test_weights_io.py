@@ -1,0 +1,114 @@
+"""SURVEY section 8 row f2 (infrastructure): the safetensors reader of the C ABI and the blob assembly, on the CPU.
+The reference has no loader and no checkpoint exists offline, so the checks are against numpy: the reader returns
+exactly what the writer stored (F32 bit-exact, F16 / BF16 widened exactly), for every malformed file an error."""
+import json
+import struct
+
+import numpy as np
+import pytest
+
+from tsd_b200 import weights as W
+from tsd_b200._lib import TsdError
+
+
+def tensors(seed=0):
+    rng = np.random.default_rng(seed)
+    t = {"unet.layer1.weight": rng.standard_normal((8, 4, 3, 3)).astype(np.float32),
+         "unet.layer1.bias": rng.standard_normal(8).astype(np.float32),
+         "time_embed.layer1.weight": rng.standard_normal((16, 5)).astype(np.float32),
+         "scalar": np.float32(3.5).reshape(()),
+         "empty": np.zeros((0, 4), np.float32),
+         "specials": np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 6.1e-5, 5.96e-8, 65504.0, 1e-40, -1e38], np.float32)}
+    return t
+
+
+@pytest.mark.parametrize("dtype", ["F32", "F16", "BF16"])
+def test_reader_returns_what_was_written(tmp_path, dtype):
+    t = tensors()
+    p = tmp_path / "w.safetensors"
+    with np.errstate(over="ignore"):                     # 1e38 -> F16 overflows to inf on purpose
+        W.write_safetensors(p, t, dtype, {"note": 'quote " and \\ backslash', "n": 3})
+    for src in (p, p.read_bytes()):                      # memory-mapped file and in-memory copy
+        st = W.SafeTensors(src)
+        assert st.names() == list(t)
+        for name, a in t.items():
+            d, shape = st.info(name)
+            assert d == dtype and shape == a.shape
+            got = st.read(name)
+            if dtype == "F32":
+                want = a
+            elif dtype == "F16":
+                with np.errstate(over="ignore"):
+                    want = a.astype(np.float16).astype(np.float32)
+            else:
+                want = (W._bf16_bits(a).astype(np.uint32) << 16).view(np.float32).reshape(a.shape)
+            assert got.dtype == np.float32 and got.shape == a.shape
+            bits = lambda v: np.asarray(v, np.float32).reshape(-1).view(np.uint32)  # noqa: E731
+            assert np.array_equal(bits(got), bits(want)), (name, dtype)
+        st.close()
+
+
+def test_f64_and_non_float_tensors(tmp_path):
+    a = np.array([1.5, -2.25, 1e300], np.float64)
+    i = np.arange(6, dtype=np.int32)
+    hdr = {"d": {"dtype": "F64", "shape": [3], "data_offsets": [0, 24]},
+           "i": {"dtype": "I32", "shape": [2, 3], "data_offsets": [24, 48]}}
+    hj = json.dumps(hdr).encode()
+    blob = struct.pack("<Q", len(hj)) + hj + a.tobytes() + i.tobytes()
+    st = W.SafeTensors(blob)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(st.read("d"), a.astype(np.float32))
+    assert st.info("i") == ("I32", (2, 3))
+    with pytest.raises(TsdError):
+        st.read("i")                                     # listed, but not a floating-point parameter
+
+
+def test_malformed_files_are_errors(tmp_path):
+    t = {"a": np.arange(6, dtype=np.float32).reshape(2, 3)}
+    p = tmp_path / "w.safetensors"
+    W.write_safetensors(p, t)
+    good = p.read_bytes()
+    (hlen,) = struct.unpack_from("<Q", good)
+    hdr = json.loads(good[8:8 + hlen])
+
+    def rebuild(h, data=good[8 + hlen:]):
+        hj = json.dumps(h).encode()
+        return struct.pack("<Q", len(hj)) + hj + data
+
+    bad = [good[:4], b"", struct.pack("<Q", 1 << 40) + good[8:], good[:9] + b"x" + good[10:],
+           rebuild({"a": {"dtype": "F32", "shape": [2, 3], "data_offsets": [0, 20]}}),      # size != shape x dtype
+           rebuild({"a": {"dtype": "F32", "shape": [2, 3], "data_offsets": [8, 32]}}),      # past the end
+           rebuild({"a": {"dtype": "F32", "shape": [2, 3]}}),                               # no offsets
+           rebuild({"a": {"dtype": "F32", "shape": [2, -3], "data_offsets": [0, 24]}}),
+           rebuild(hdr, good[8 + hlen:-4])]                                                 # truncated data
+    for b in bad:
+        with pytest.raises(TsdError):
+            W.SafeTensors(b)
+    with pytest.raises(TsdError):
+        W.SafeTensors(tmp_path / "missing.safetensors")
+    assert W.SafeTensors(rebuild({})).names() == []
+    assert W.SafeTensors(rebuild({"__metadata__": {"k": "v"}})).names() == []
+
+
+def test_build_blob_from_name_map(tmp_path):
+    t = tensors(3)
+    p = tmp_path / "ckpt.safetensors"
+    W.write_safetensors(p, {"model.diffusion_model.input_blocks.0.0.weight": t["unet.layer1.weight"],
+                            "model.diffusion_model.input_blocks.0.0.bias": t["unet.layer1.bias"],
+                            "time_embed.layer1.weight": t["time_embed.layer1.weight"],
+                            "first_stage_model.unrelated": np.ones(3, np.float32)}, "F16")
+    table = [("unet.layer1.weight", 0, 288), ("unet.layer1.bias", 320, 8), ("time_embed.layer1.weight", 384, 80)]
+    name_map = {"unet.layer1.weight": "model.diffusion_model.input_blocks.0.0.weight",
+                "unet.layer1.bias": "model.diffusion_model.input_blocks.0.0.bias"}
+    st = W.SafeTensors(p)
+    blob, rep = W.build_blob(table, st, name_map)
+    h = lambda a: a.astype(np.float16).astype(np.float32).reshape(-1)  # noqa: E731
+    assert blob.shape == (464,) and rep == {"missing": [], "unused": ["first_stage_model.unrelated"]}
+    assert np.array_equal(blob[:288], h(t["unet.layer1.weight"])) and np.array_equal(blob[320:328], h(t["unet.layer1.bias"]))
+    assert np.array_equal(blob[384:464], h(t["time_embed.layer1.weight"])) and not blob[288:320].any()
+    with pytest.raises(TsdError):                        # a parameter the checkpoint does not hold
+        W.build_blob(table + [("unet.layer2.weight", 464, 4)], st, name_map)
+    _, rep = W.build_blob(table + [("unet.layer2.weight", 464, 4)], st, name_map, strict=False)
+    assert rep["missing"] == ["unet.layer2.weight"]
+    with pytest.raises(TsdError):                        # element count mismatch
+        W.build_blob([("unet.layer1.bias", 0, 9)], st, name_map)
