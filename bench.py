@@ -369,6 +369,35 @@ def run_ours(args):
         pipe.diffusion.close()
         pipe.decoder.close()
 
+    # ---- CFG step (BASELINE configs[2] per-GPU shape: cond + uncond latent in one batch of two) - informational
+    cfg_leg = None
+    if not args.no_image and rank == 0 and world == 1:
+        m2 = Diffusion(ctx, SIDE, SIDE, max_batch=2)
+        m2.init_random(1234)
+        d_lat2 = d_lat0.repeat(2, 1, 1, 1).contiguous()
+        d_eps2 = torch.empty_like(d_lat2)
+        d_ctx2 = torch.cat([d_ctx, torch.zeros_like(d_ctx)]).contiguous()
+        m2.forward_dev(d_lat2.data_ptr(), d_ctx2.data_ptr(), 2, d_temb[0].data_ptr(), 1, 2, d_eps2.data_ptr())
+        ctx.synchronize()
+
+        def cfg_step(i):
+            j = i % LOOP_STEPS
+            m2.forward_dev(d_lat2.data_ptr(), None, 2, d_temb[j].data_ptr(), 1, 2, d_eps2.data_ptr())
+            ctx.sampler_step_dev(d_lat2[0].data_ptr(), d_eps2[0].data_ptr(), d_eps2[1].data_ptr(), 7.5,
+                                 d_noise[j].data_ptr() if ts[j] > 0 else None, coef[j], n_lat, d_lat2[0].data_ptr())
+
+        for i in range(5):
+            cfg_step(i)
+        ctx.synchronize()
+        ctx.timer_start()
+        for i in range(20):
+            cfg_step(i)
+        ms_cfg = ctx.timer_stop() / 20
+        cfg_leg = {"cfg_steps_per_s": 1000.0 / ms_cfg, "ms_per_cfg_step": ms_cfg, "unet_evals_per_s": 2000.0 / ms_cfg,
+                   "note": "one CFG step = UNet on a batch of two (cond, uncond) + combine + sampler step, device-resident",
+                   "finite": bool(torch.isfinite(d_eps2).all().item())}
+        m2.close()
+
     # ---- roofline of the dominant kernel (rank 0): per-launch CUDA events, eager replay of one step
     roof = None
     fam = None
@@ -420,7 +449,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
                     "api": "tsd_diffusion_forward + tsd_sampler_step (host buffers, pinned)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "image_e2e": image, "finite": finite,
+            "image_e2e": image, "cfg_batch2": cfg_leg, "finite": finite,
         }
         print(json.dumps(line), flush=True)
     m.close()
