@@ -771,9 +771,15 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
   TileCfg best = model;
   int rc = TSD_OK;
   const size_t tune_mark = c->arena.mark();
+  static int tune_reps = 0;  // timed runs per candidate (minimum taken); TSD_TUNE_REPS overrides
+  if (tune_reps == 0) {
+    const char* v = getenv("TSD_TUNE_REPS");
+    tune_reps = v ? atoi(v) : 3;
+    if (tune_reps < 1) tune_reps = 3;
+  }
   for (const TileCfg& cand : cands) {
     float ms_c = 1e30f;
-    for (int rep = 0; rep < 3 && !rc; ++rep) {
+    for (int rep = 0; rep < tune_reps && !rc; ++rep) {
       if (c->flush_buf && c->tune_flush) cudaMemsetAsync(c->flush_buf, rep, kFlushBytes, c->stream);
       cudaEventRecord(e0, c->stream);
       rc = run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, 0, 0, flops, nh, &cand, 0);
