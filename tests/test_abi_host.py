@@ -136,3 +136,22 @@ def test_gloo_world2_broadcast_and_gather(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+def test_shipped_tune_plan_is_well_formed():
+    """csrc/tune_b200.txt (read-only plan defaults next to the library): 12 key ints + BN splits cg halo per line,
+    every value inside what the launcher accepts, no duplicate signature."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "stable-diffusion.mojo_b200", "csrc", "tune_b200.txt")
+    keys = set()
+    lines = [ln.split() for ln in open(path) if ln.strip()]
+    assert len(lines) >= 60
+    for v in lines:
+        assert len(v) == 16
+        iv = [int(x) for x in v]
+        bn, splits, cg, halo = iv[12:]
+        assert 16 <= bn <= 256 and bn % 16 == 0 and 1 <= splits <= 16 and cg in (1, 2) and halo in (0, 1)
+        assert iv[0] > 0 and iv[0] % 4 == 0 and iv[6] > 0          # K and N
+        k = tuple(iv[:12])
+        assert k not in keys
+        keys.add(k)
