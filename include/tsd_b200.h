@@ -72,6 +72,8 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *   "ln_fold"          1 = global-statistics LayerNorm folded into the consuming GEMM epilogue [default]
  *   "fuse_skip"        1 = a ResBlock's 1x1 skip convolution is a second K segment of its conv2 GEMM [default],
  *                          0 = a GEMM of its own whose result conv2 adds as a residual
+ *   "conv_stride_tma"  1 = stride-2 3x3 convolutions are implicit GEMMs through a tensor map with element strides
+ *                          [default], 0 = im2col kernel + GEMM
  *   "defer_reduce"     1 = where a split-K GEMM feeds a norm directly, the norm kernel sums the partial tiles
  *                          (no reduce kernel) [default]
  *   "virtual_concat"   1 = the channel concats of the UNet are read (and written out) by the GroupNorm kernel of the

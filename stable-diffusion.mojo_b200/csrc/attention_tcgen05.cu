@@ -28,7 +28,8 @@
 namespace tsd {
 
 int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_elems, const uint32_t* box, int swizzle_atom_32b);
+                  const uint64_t* strides_elems, const uint32_t* box, int swizzle_atom_32b,
+                  const uint32_t* elem_strides);
 
 namespace {
 
@@ -448,7 +449,7 @@ int tmap3(Ctx* c, CUtensorMap* tm, const float* base, int d, int T, long long nb
   uint64_t dims[3] = {(uint64_t)d, (uint64_t)T, (uint64_t)nb};
   uint64_t str[3] = {1, (uint64_t)d, (uint64_t)T * d};
   uint32_t box[3] = {32, (uint32_t)box_rows, 1};
-  return make_tmap_f32(c, tm, base, 3, dims, str, box, atom32);
+  return make_tmap_f32(c, tm, base, 3, dims, str, box, atom32, nullptr);
 }
 
 cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV,

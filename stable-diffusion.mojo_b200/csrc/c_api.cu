@@ -87,7 +87,7 @@ int32_t tsd_init(int32_t device, tsd_ctx** out) {
   h->c = c;
   *out = h;
   // tuning / A-B switches from the environment: TSD_OPT_<option name>=<int>  (same names as tsd_set_option)
-  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "ln_fold", "fuse_skip", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention"};
+  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention"};
   for (const char* name : kEnvOpts) {
     const std::string key = std::string("TSD_OPT_") + name;
     if (const char* v = getenv(key.c_str())) tsd_set_option(h, name, atoi(v));
@@ -130,6 +130,7 @@ static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "norm_v2")) return &h->c->norm_v2;
   if (!strcmp(name, "ln_fold")) return &h->c->ln_fold;
   if (!strcmp(name, "fuse_skip")) return &h->c->fuse_skip;
+  if (!strcmp(name, "conv_stride_tma")) return &h->c->conv_stride_tma;
   if (!strcmp(name, "defer_reduce")) return &h->c->defer_reduce;
   if (!strcmp(name, "virtual_concat")) return &h->c->virtual_concat;
   if (!strcmp(name, "gn_partial")) return &h->c->gn_partial;

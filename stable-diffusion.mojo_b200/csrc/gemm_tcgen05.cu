@@ -696,6 +696,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // convolution accumulated into its second 3x3 convolution (diffusion.mojo:66-72) instead of a GEMM of its own.
       const int it_first = it_begin + role_parity;
       const int taps = p.taps, cin2 = p.cin2;
+      const int cstride = p.cstride, coff = p.coff;
       int tap = it_first / p.chunks_per_tap;
       int kc = (it_first - tap * p.chunks_per_tap) * bk;
       int dy = 0, dx = 0;
@@ -781,8 +782,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (!(debug & 2)) {
           const CUtensorMap* ta = tap >= taps ? &tmA2 : &tmA;
-          tma_a_4d<CG>(sa, ta, fbs, kc, w0 + dx, h0 + dy, c3);
-          if (natoms == 2) tma_a_4d<CG>(sa + a_atom, ta, fbs, kc + 32, w0 + dx, h0 + dy, c3);
+          const int wx = w0 * cstride + dx + coff, hy = h0 * cstride + dy + coff;
+          tma_a_4d<CG>(sa, ta, fbs, kc, wx, hy, c3);
+          if (natoms == 2) tma_a_4d<CG>(sa + a_atom, ta, fbs, kc + 32, wx, hy, c3);
         }
         advance();
         stage += step;

@@ -39,6 +39,7 @@ struct GemmKParams {
   int m_per_batch;  // img_n * H * W : rows of D per batch entry
   // K loop
   int taps, cin, chunks_per_tap, total_iters, splits, iters_per_split;
+  int cstride, coff;       // strided 3x3 convolution: input coordinate = out * cstride + tap offset (-1..1) + coff
   int cin2;                // > 0: second K segment - cin2 channels of a second NHWC operand (tmA2) after the taps
   int a_box_bytes;
   // N tiling

@@ -168,13 +168,13 @@ TimedScope::~TimedScope() {
 // ------------------------------------------------------------------------------------------
 // fp32 tensor, dims innermost-first, strides in elements (stride of dim0 is 1), 128 B swizzle.
 int make_tmap_f32(Ctx* c, CUtensorMap* tm, const float* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_elems, const uint32_t* box, int swizzle_atom_32b) {
+                  const uint64_t* strides_elems, const uint32_t* box, int swizzle_atom_32b, const uint32_t* elem_strides) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;  // traversal stride: the box then holds ceil(box / stride) elements
     if (i > 0) {
       gstr[i - 1] = strides_elems[i] * sizeof(float);
       if (gstr[i - 1] % 16 != 0) return c->fail(TSD_ERR_INVALID, "TMA: stride not a multiple of 16 bytes");
@@ -307,6 +307,9 @@ struct ASpec {
   // multiplied by the weight columns [taps*K, taps*K + K2)
   const float* base2;
   int K2;
+  // strided 3x3 convolution: W / H are the OUTPUT grid, the input is in_W x in_H, output pixel (h, w) reads input
+  // (h * cstride + tap_y - pad_lo, w * cstride + tap_x - pad_lo) through a tensor map with element strides
+  int cstride, pad_lo, in_W, in_H;
 };
 // K steps of the provisional 64-wide kind (tile selection happens before the ring picks 64 or 32)
 static int provisional_iters(const ASpec& A) {
@@ -319,7 +322,7 @@ static int provisional_iters(const ASpec& A) {
 // `ws_splits_plan` > 0 (planning pass): reserve split-K workspace for that many splits.
 // 3x3 / stride 1 / pad 1 convolution over an NHWC image that the halo kernel can take
 static bool conv_halo_eligible(const Ctx* c, const ASpec& A, int N, const GemmKParams& p) {
-  return c->conv_halo > 0 && A.K2 == 0 && A.taps == 9 && A.batch == 1 && A.K % 4 == 0 && A.W >= c->halo_min_w && A.H >= c->halo_min_h &&
+  return c->conv_halo > 0 && A.K2 == 0 && A.cstride <= 1 && A.taps == 9 && A.batch == 1 && A.K % 4 == 0 && A.W >= c->halo_min_w && A.H >= c->halo_min_h &&
          !p.geglu && p.row_bias == nullptr && N >= 16;
 }
 
@@ -344,6 +347,8 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   p.taps = A.taps;
   p.cin = A.K;
   p.cin2 = A.K2;
+  p.cstride = A.cstride > 1 ? A.cstride : 1;
+  p.coff = A.cstride > 1 ? 1 - A.pad_lo : 0;  // tap offsets are -1..1 (pad 1); pad 0 shifts them to 0..2
   p.chunks_per_tap = (A.K + GEMM_BK - 1) / GEMM_BK;  // provisional (K steps of 64): the ring below may pick 32
   p.total_iters = provisional_iters(A);
   long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
@@ -410,7 +415,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     uint64_t dims[4] = {(uint64_t)A.K2, (uint64_t)A.W, (uint64_t)A.H, (uint64_t)A.imgs};
     uint64_t str[4] = {1, (uint64_t)A.K2, (uint64_t)A.K2 * A.W, (uint64_t)A.K2 * A.W * A.H};
     uint32_t box[4] = {32u, (uint32_t)bw, (uint32_t)bh, 1};
-    int rc = make_tmap_f32(c, &tmA2, A.base2, 4, dims, str, box, 0);
+    int rc = make_tmap_f32(c, &tmA2, A.base2, 4, dims, str, box, 0, nullptr);
     if (rc) return rc;
   }
   if (!c->dry_run) {
@@ -422,7 +427,15 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
     if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
     uint32_t box[4] = {32u, (uint32_t)(p.halo ? 16 : bw), (uint32_t)(p.halo ? 18 : bh), 1};
-    int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box, 0);
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (A.cstride > 1) {  // the box spans bw*stride x bh*stride input pixels and keeps every stride-th one
+      dims[1] = (uint64_t)A.in_W;
+      dims[2] = (uint64_t)A.in_H;
+      box[1] = (uint32_t)(bw * A.cstride);
+      box[2] = (uint32_t)(bh * A.cstride);
+      es[1] = es[2] = (uint32_t)A.cstride;
+    }
+    int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box, 0, A.cstride > 1 ? es : nullptr);
     if (rc) return rc;
   }
   if (!c->dry_run) {
@@ -430,7 +443,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
     uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
     uint32_t box[3] = {32u, (uint32_t)((p.geglu || p.cg == 2) ? p.BN / 2 : p.BN), 1};
-    int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box, 0);
+    int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box, 0, nullptr);
     if (rc) return rc;
   }
 
@@ -732,7 +745,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     while (128 % bw) --bw;
     int i = 0;
     key.v[i++] = A.K; key.v[i++] = A.W; key.v[i++] = A.H; key.v[i++] = A.imgs; key.v[i++] = A.batch;
-    key.v[i++] = A.taps + 16 * (A.K2 / 32);
+    key.v[i++] = A.taps + 16 * (A.K2 / 32) + (A.cstride > 1 ? 8192 * A.cstride : 0);
     key.v[i++] = N; key.v[i++] = p.geglu; key.v[i++] = allow_split ? 1 : 0; key.v[i++] = p.residual ? 1 : 0;
     key.v[i++] = (nh && nh->G > 0 && c->producer_stats) ? nh->G : 0; key.v[i++] = c->gemm_cg * 4 + c->conv_halo;
   }
@@ -908,6 +921,30 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
       A.ld_h = (long long)A.W * a.Cin;
       A.ld_img = A.ld_h;
     }
+    NormHint* nh = a.nh;
+    if (nh) nh->imgs = a.N;
+    return run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops, nh);
+  }
+  if (tensor_ok && c->conv_stride_tma && a.k == 3 && (a.pad == 1 || a.pad == 0) && a.stride > 1 && a.stride <= 2 &&
+      a.Cin2 == 0) {
+    // strided convolutions (diffusion.mojo:180,183; vae.mojo:97,100,103 after two_stride_pad) as implicit GEMMs: the
+    // tensor map walks the input with an element stride, a box of (bw*s) x (bh*s) input pixels delivers the bw x bh
+    // pixels one tap needs; out-of-bounds coordinates (either side) are the zero padding
+    ASpec A{};
+    A.base = a.x;
+    A.K = a.Cin;
+    A.W = Wo;
+    A.H = Ho;
+    A.imgs = a.N;
+    A.ld_w = a.Cin;
+    A.ld_h = (long long)a.W * a.Cin;
+    A.ld_img = (long long)a.H * a.W * a.Cin;
+    A.batch = 1;
+    A.taps = 9;
+    A.cstride = a.stride;
+    A.pad_lo = a.pad;
+    A.in_W = a.W;
+    A.in_H = a.H;
     NormHint* nh = a.nh;
     if (nh) nh->imgs = a.N;
     return run_gemm(c, A, a.w, a.Cout, ktot, 0, a.Cout, p, a.force_bn, a.force_splits, flops, nh);

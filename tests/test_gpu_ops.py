@@ -71,6 +71,21 @@ def test_conv2d_bottom_right_padding(ctx, ops, n, cin, h, w, cout, stride):
     assert relerr(ctx.conv2d(xp, wt, b, pad=0, stride=stride), ref) < (TOL_FP32 if cin < 32 else TOL_TF32)
 
 
+def test_conv2d_stride2_both_paths(ctx, ops):
+    """stride-2 3x3 convolution: the strided tensor-map path and the im2col path against the oracle"""
+    rng = np.random.default_rng(5)
+    for (n, cin, h, w, cout, pad, pad_hi) in ((1, 64, 16, 16, 64, 1, None), (2, 96, 12, 20, 32, 1, None),
+                                              (1, 64, 10, 14, 48, 0, 1), (1, 128, 64, 64, 128, 0, 1)):
+        x = rng.standard_normal((n, cin, h, w), dtype=np.float32)
+        wt = (rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32)
+        b = rng.standard_normal(cout, dtype=np.float32)
+        ref = np.stack([ops.conv2d(x[i], wt, b, pad=pad, stride=2, pad_hi=pad_hi) for i in range(n)])
+        for mode in (1, 0):
+            with _Options(ctx, conv_stride_tma=mode):
+                y = ctx.conv2d(x, wt, b, pad=pad, stride=2, pad_hi=pad_hi)
+            assert y.shape == ref.shape and relerr(y, ref) < TOL_TF32, (mode, n, cin, h, w)
+
+
 def test_conv2d_no_bias_and_errors(ctx, ops):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((64, 8, 8), dtype=np.float32)
