@@ -165,3 +165,34 @@ def test_png_validation(tmp_path):
         save_png(tmp_path / "no_such_dir" / "x.png", np.zeros((3, 2, 2), np.float32))
     nan = np.full((1, 1, 2), np.nan, np.float32)
     assert T.png_decode(encode_png(nan))[3] == [b"\0\0"]
+
+
+def test_bpe_random_vocabularies_match_restatement():
+    """Random vocabularies (binary token bytes >= 0x80, score ties, tokens that are concatenations of others) and random
+    byte strings: ids from the C++ encoder == ids from the line-by-line restatement, both str_concat readings."""
+    rnd = random.Random(11)
+    for trial in range(25):
+        alphabet = bytes(rnd.sample(range(1, 256), rnd.randint(3, 12)))           # no NUL: tokens are C strings
+        singles = [bytes([b]) for b in alphabet if bytes([b]) not in (b"'", b'"')]
+        toks = list(dict.fromkeys(singles))
+        while len(toks) < len(singles) + rnd.randint(5, 60):
+            a, b = rnd.choice(toks), rnd.choice(toks)
+            t = (a + b)[:rnd.randint(2, 7)]
+            if t not in toks and t not in (b"\\n", b"\\t"):
+                toks.append(t)
+        rnd.shuffle(toks)
+        scores = [float(rnd.randint(0, 6)) for _ in toks]                          # many ties
+        blob = struct.pack("I", max(len(t) for t in toks))
+        for t, s in zip(toks, scores):
+            blob += struct.pack("fI", s, len(t)) + t
+        prod, ref = P.Tokenizer(blob, len(toks)), T.Tokenizer(len(toks), blob)
+        for t in toks:
+            assert prod.find(t) == ref.find(t)
+        for _ in range(20):
+            text = bytes(rnd.choice(alphabet + b"\x00'") for _ in range(rnd.randint(0, 30)))
+            if b"\x00" in text:
+                text = text.replace(b"\x00", b"")                                   # ctypes passes C strings
+            for as_written in (True, False):
+                want, _ = T.bpe_encode(text, ref, as_written)
+                assert prod.encode(text, concat_as_written=as_written) == want, (trial, text, as_written)
+        prod.close()
