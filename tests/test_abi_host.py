@@ -155,3 +155,26 @@ def test_shipped_tune_plan_is_well_formed():
         k = tuple(iv[:12])
         assert k not in keys
         keys.add(k)
+
+
+def test_host_sampler_strength_matches_oracle():
+    """DDPMSampler.set_strength / add_noise coefficients of the host mirror (sampler.mojo:67-73, 111-124) against the
+    oracle's restatement, including the edge cases strength = 1 (full schedule) and strength -> 0 (nothing left)."""
+    import numpy as np
+    import tsd_oracle as O
+    from tsd_b200 import sampler as S
+    for n in (1, 5, 20, 50):
+        for strength in (1.0, 0.9, 0.8, 0.55, 0.3, 0.04, 0.0):
+            a, b = S.DDPMSampler(), O.DDPMSampler()
+            a.set_inference_timesteps(n)
+            b.set_inference_timesteps(n)
+            a.set_strength(strength)
+            b.set_strength(strength)
+            assert a.start_step == b.start_step == n - int(n * strength)
+            assert np.array_equal(a.timesteps, b.timesteps) and len(a.timesteps) == n - a.start_step
+            if len(a.timesteps):
+                t = int(a.timesteps[0])
+                sa, sb = a.add_noise_coefficients(t)
+                x, nz = np.float64(0.7), np.float64(-1.3)
+                assert abs(float(sa) * x + float(sb) * nz - b.add_noise(x, t, nz)) < 1e-6
+                assert np.allclose(a.coefficient_table(), np.stack([b.coefficients(int(tt)) for tt in b.timesteps]), rtol=1e-6)
