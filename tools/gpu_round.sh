@@ -31,3 +31,9 @@ for f in ${tag}_ncu_gemm_conv320 ${tag}_ncu_attn ${tag}_ncu_norm; do
 done
 ITERS=20 timeout 300 python tools/prof_kernels.py > gpurun_out/kernel_timings_$tag.log 2>&1
 du -sh gpurun_out
+# condensed artefacts for profiles/ (copy them over after reading the numbers):
+python tools/step_launches.py gpurun_out/launches_$tag.csv gpurun_out/${tag}_launches_unet_step > /dev/null 2>&1
+for f in ${tag}_ncu_gemm_conv320 ${tag}_ncu_attn ${tag}_ncu_norm; do
+  python tools/ncu_summary.py gpurun_out/$f.raw.csv gpurun_out/$f > /dev/null 2>&1
+done
+rm -f gpurun_out/*.ncu-rep
