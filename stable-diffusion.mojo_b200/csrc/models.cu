@@ -990,12 +990,13 @@ void Decoder::destroy() {
 
 // Attention_Block.forward, vae.mojo:17-27: GroupNorm(32) -> 1-head self-attention -> + residue
 static int vae_attn_block(Ctx* c, const ParamStore& ps, int attn_in, int attn_out, const float* x, int n,
-                          int H, int W, float* out) {
+                          int H, int W, float* out, const NormHint* xns = nullptr, NormHint* next = nullptr) {
   const int C = 512;
   const long long T = (long long)H * W, M = n * T;
   const size_t mark = c->arena.mark();
   WALLOC(a, M * C);
-  TRY(op_group_norm(c, x, a, n, H, W, C, 32, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1));
+  TRY(op_group_norm(c, x, a, n, H, W, C, 32, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1,
+                    (xns && xns->G == 32 && xns->eps == 1e-5f) ? xns->ready() : nullptr));
   WALLOC(qkv, 3 * M * C);
   TRY(linear(c, a, M, C, ps.w(attn_in), ps.w(attn_in + 1), 3 * C, qkv, C, nullptr, 1, 0, C, M * C));
   WALLOC(o, M * C);
@@ -1004,7 +1005,7 @@ static int vae_attn_block(Ctx* c, const ParamStore& ps, int attn_in, int attn_ou
   at.batch = n; at.heads = 1; at.Tq = (int)T; at.Tk = (int)T; at.d = C; at.O = o;
   at.softmax_axis = c->softmax_axis;
   TRY(op_attention(c, at));
-  TRY(linear(c, o, M, C, ps.w(attn_out), ps.w(attn_out + 1), C, out, C, x, 0));
+  TRY(linear(c, o, M, C, ps.w(attn_out), ps.w(attn_out + 1), C, out, C, x, 0, 0, 0, 0, next));
   c->arena.release_to(mark);
   return TSD_OK;
 }
@@ -1029,40 +1030,66 @@ int Decoder::decode(int n, int rescale) {
   TRY(conv(c, ps, l2, cur, n, H, W, 4, 512, 3, 1, 1, nullptr, 0, nullptr, nxt, 0));
   swap();
   int ri = 0;
-  auto RES = [&]() -> int {
+  // Producer-side norm statistics along the chain (as in the UNet): every GEMM whose output is normalised next leaves
+  // the partial sums for that norm (`groups` of the consumer; 0 = the consumer is not a norm).  cur_ns describes `cur`.
+  NormHint cur_ns;
+  auto make_hint = [&](NormHint& h, int groups, int C, int hh, int ww) -> bool {
+    h = NormHint();
+    if (groups <= 0) return true;
+    h.G = groups;
+    h.eps = 1e-5f;
+    h.imgs = n;
+    h.scratch_elems = norm_scratch_elems(n, (long long)hh * ww, C, groups);
+    h.scratch = c->arena.alloc_n<float2>(h.scratch_elems);  // lives until the next decode resets the arena
+    return h.scratch != nullptr;
+  };
+  auto RES = [&](int next_groups) -> int {
     Act x;
     x.p = cur; x.N = n; x.H = H; x.W = W; x.C = res[ri].cin;
-    int rc = res_block(c, ps, res[ri], x, nullptr, 0, 1e-5f, nxt);
+    x.ns = cur_ns;
+    NormHint out_ns;
+    if (!make_hint(out_ns, next_groups, res[ri].cout, H, W)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+    int rc = res_block(c, ps, res[ri], x, nullptr, 0, 1e-5f, nxt, next_groups > 0 ? &out_ns : nullptr);
+    cur_ns = out_ns;
     ++ri;
     swap();
     return rc;
   };
-  auto UPCONV = [&](int wi, int cin, int cout) -> int {
+  auto UPCONV = [&](int wi, int cin, int cout, int next_groups) -> int {
+    NormHint out_ns;
+    if (!make_hint(out_ns, next_groups, cout, 2 * H, 2 * W)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
     const size_t mark = c->arena.mark();
     WALLOC(up, (long long)n * 4 * H * W * cin);
     LAUNCH(c, launch_upsample2x(cur, up, n, H, W, cin, c->stream), "upsample2x");
     H *= 2;
     W *= 2;
-    TRY(conv(c, ps, wi, up, n, H, W, cin, cout, 3, 1, 1, nullptr, 0, nullptr, nxt, 0));
+    TRY(conv(c, ps, wi, up, n, H, W, cin, cout, 3, 1, 1, nullptr, 0, nullptr, nxt, 0, next_groups > 0 ? &out_ns : nullptr));
     c->arena.release_to(mark);
+    cur_ns = out_ns;
     swap();
     return TSD_OK;
   };
-  TRY(RES());  // l3
-  TRY(vae_attn_block(c, ps, attn_in, attn_out, cur, n, H, W, nxt));  // l4
+  TRY(RES(32));  // l3 -> Attention_Block's GroupNorm(32)
+  {
+    NormHint out_ns;
+    if (!make_hint(out_ns, 16, 512, H, W)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
+    TRY(vae_attn_block(c, ps, attn_in, attn_out, cur, n, H, W, nxt, &cur_ns, &out_ns));  // l4
+    cur_ns = out_ns;
+  }
   swap();
-  for (int i = 0; i < 4; ++i) TRY(RES());  // l5..l8
-  TRY(UPCONV(l10, 512, 512));              // l9, l10
-  for (int i = 0; i < 3; ++i) TRY(RES());  // l11..l13
-  TRY(UPCONV(l15, 512, 512));              // l14, l15
-  for (int i = 0; i < 3; ++i) TRY(RES());  // l16..l18
-  TRY(UPCONV(l20, 256, 256));              // l19, l20
-  for (int i = 0; i < 3; ++i) TRY(RES());  // l21..l23
+  for (int i = 0; i < 4; ++i) TRY(RES(i < 3 ? 16 : 0));   // l5..l8 (l8 feeds the upsample)
+  TRY(UPCONV(l10, 512, 512, 16));                         // l9, l10
+  for (int i = 0; i < 3; ++i) TRY(RES(i < 2 ? 16 : 0));   // l11..l13
+  TRY(UPCONV(l15, 512, 512, 16));                         // l14, l15
+  for (int i = 0; i < 3; ++i) TRY(RES(i < 2 ? 16 : 0));   // l16..l18
+  TRY(UPCONV(l20, 256, 256, 16));                         // l19, l20
+  for (int i = 0; i < 3; ++i) TRY(RES(i < 2 ? 16 : 32));  // l21..l23 (l23 -> l24 GroupNorm(32))
   {
     // l24 GroupNorm(32,128), l25 SiLU, l26 conv 128->3, then rescale/clamp (pipeline.mojo:127)
     const size_t mark = c->arena.mark();
     WALLOC(f, (long long)n * H * W * 128);
-    TRY(op_group_norm(c, cur, f, n, H, W, 128, 32, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1));
+    TRY(op_group_norm(c, cur, f, n, H, W, 128, 32, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1,
+                      (cur_ns.G == 32 && cur_ns.eps == 1e-5f) ? cur_ns.ready() : nullptr));
     TRY(conv(c, ps, l26, f, n, H, W, 128, 3, 3, 1, 1, nullptr, 0, nullptr, nxt, 0));
     c->arena.release_to(mark);
     LAUNCH(c, launch_rescale_to_nchw(nxt, img_out, n, 3, H * W, rescale, c->stream), "rescale_to_nchw");
