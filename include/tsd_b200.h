@@ -143,6 +143,9 @@ int32_t tsd_cross_attention(tsd_ctx* ctx, const float* x, int32_t t, int32_t c, 
 /* Attention core only (config 5 sweep): q (h,tq,d), k,v (h,tk,d) -> out (tq, h*d) merged. */
 int32_t tsd_attention_core(tsd_ctx* ctx, const float* q, const float* k, const float* v, int32_t h,
                            int32_t tq, int32_t tk, int32_t d, float* out);
+/* Same on DEVICE pointers, asynchronous on the context's stream (tsd_synchronize to wait). */
+int32_t tsd_attention_core_dev(tsd_ctx* ctx, const float* q, const float* k, const float* v, int32_t h,
+                               int32_t tq, int32_t tk, int32_t d, float* out);
 /* DDPMSampler.step, sampler.mojo:75-109 (+ CFG combine pipeline.mojo:117-119 when eps_uncond
  * is non-NULL).  Scalars are the schedule values the host sampler computes (see
  * tsd_b200.DDPMSampler): x0 = (x - sqrt_1mab*eps)/sqrt_ab ; out = c0*x0 + c1*x + sigma*noise. */
@@ -249,6 +252,7 @@ int32_t tsd_clip_load_weights(tsd_clip* m, const float* blob, int64_t n_floats);
 int32_t tsd_clip_init_random(tsd_clip* m, uint64_t seed);
 int32_t tsd_clip_param_count(const tsd_clip* m);
 const char* tsd_clip_param_name(const tsd_clip* m, int32_t i, int64_t* offset, int64_t* numel);
+int32_t tsd_clip_get_param(const tsd_clip* m, int32_t i, float* out);
 int32_t tsd_clip_forward(tsd_clip* m, const int32_t* tokens, int32_t n_tokens, float* context);
 int32_t tsd_clip_forward_dev(tsd_clip* m, const int32_t* tokens, int32_t n_tokens, float* context);
 
@@ -316,6 +320,10 @@ int32_t tsd_bench_gemm(tsd_ctx* ctx, int32_t m, int32_t n, int32_t k, int32_t ba
 int32_t tsd_bench_conv(tsd_ctx* ctx, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
                        int32_t k, int32_t stride, int32_t force_bn, int32_t force_splits,
                        int32_t iters, double* ms_out);
+/* attention core (helpers/attention.mojo:46-62) on synthetic N(0,1)-like q,k,v: h heads, tq x tk, head dim d, the
+ * context's softmax_axis / fused_attention options; ms per op (both launches of the fused kernel). */
+int32_t tsd_bench_attention(tsd_ctx* ctx, int32_t h, int32_t tq, int32_t tk, int32_t d, int32_t iters,
+                            double* ms_out);
 
 #if defined(TSD_BUILD)
 #pragma GCC visibility pop

@@ -33,6 +33,20 @@ API int ref_num_threads(void) {
 #endif
 }
 
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the CPU baseline is defined on ALL host cores,
+ * so bench.py sets the team size explicitly.  n <= 0: the number of processors OpenMP sees.  Returns the new size. */
+API int ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  omp_set_dynamic(0);
+  omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 /* Conv2D.forward, helpers/utils.mojo:1738-1811.
  * pad (utils.mojo:1383-1413) then, parallel over out channels (:1809), for every (y, x) of
  * tile_2d (:405-409, :1788-1807), for every in channel (:1771): 3x3 patch * kernel plane,

@@ -54,6 +54,8 @@ def clib():
         L = C.CDLL(_CLIB_PATH)
         fp, i, f = C.c_void_p, C.c_int, C.c_float
         L.ref_num_threads.restype = i
+        L.ref_set_num_threads.argtypes = [i]
+        L.ref_set_num_threads.restype = i
         L.ref_conv2d.argtypes = [fp, i, i, i, fp, fp, i, i, i, i, fp]
         L.ref_matmul.argtypes = [fp, fp, i, i, i, i, fp]
         L.ref_linear.argtypes = [fp, i, i, fp, fp, i, fp]

@@ -454,19 +454,10 @@ int tmap3(Ctx* c, CUtensorMap* tm, const float* base, int d, int T, long long nb
 
 cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV,
                         const AttnKParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
-  static int max_dyn = -1;
-  if (max_dyn < 0) {
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, attn_kernel);
+  int max_dyn = 0;
+  {
+    cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(attn_kernel), -1, &max_dyn);
     if (e != cudaSuccess) return e;
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e != cudaSuccess) return e;
-    const int lim = optin - (int)fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return e;
-    max_dyn = lim;
   }
   if ((long long)smem > max_dyn) return cudaErrorInvalidConfiguration;
   return launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);

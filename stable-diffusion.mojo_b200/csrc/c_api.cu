@@ -443,6 +443,22 @@ int32_t tsd_attention_core(tsd_ctx* h, const float* q, const float* k, const flo
   return hc.finish();
 }
 
+int32_t tsd_attention_core_dev(tsd_ctx* h, const float* q, const float* k, const float* v, int32_t heads,
+                               int32_t tq, int32_t tk, int32_t d, float* out) {
+  if (!h || !q || !k || !v || !out || heads <= 0 || tq <= 0 || tk <= 0 || d <= 0) return TSD_ERR_INVALID;
+  if (d % 4) return h->c->fail(TSD_ERR_INVALID, "attention: head dim must be a multiple of 4");
+  size_t need = (size_t)heads * ((size_t)tq + tk) * 64 + (32u << 20);  // softmax statistics
+  if (!h->c->fused_attention || !attention_fused_supported(d, 0)) need += ((size_t)heads * tq * (tk + 4) + (size_t)heads * d * (tk + 4)) * 4;
+  HostCall hc(h, need);
+  if (!hc.rc) {
+    AttnArgs a;
+    a.Q = q; a.K = k; a.V = v; a.heads = heads; a.Tq = tq; a.Tk = tk; a.d = d; a.O = out;
+    a.softmax_axis = hc.c->softmax_axis;
+    hc.run(op_attention(hc.c, a));
+  }
+  return hc.rc;  // asynchronous: no synchronize
+}
+
 int32_t tsd_self_attention(tsd_ctx* h, const float* x, int32_t t, int32_t cch, int32_t n_heads,
                            const float* w_in, const float* b_in, const float* w_out,
                            const float* b_out, float* out) {
@@ -626,6 +642,42 @@ int32_t tsd_bench_gemm(tsd_ctx* h, int32_t m, int32_t n, int32_t k, int32_t batc
   launch_spin((long long)iters * 12000, c->stream);  // queue the launches behind a spin: events see device time
   cudaEventRecord(e0, c->stream);
   for (int i = 0; i < iters && !hc.rc; ++i) hc.run(op_gemm(c, g));
+  cudaEventRecord(e1, c->stream);
+  int rc = hc.finish();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
+  return rc;
+}
+
+int32_t tsd_bench_attention(tsd_ctx* h, int32_t heads, int32_t tq, int32_t tk, int32_t d, int32_t iters,
+                            double* ms_out) {
+  if (!h || !ms_out || heads <= 0 || tq <= 0 || tk <= 0 || d <= 0 || d % 4 || iters <= 0) return TSD_ERR_INVALID;
+  const size_t nq = (size_t)heads * tq * d, nk = (size_t)heads * tk * d;
+  size_t need = (2 * nq + 2 * nk) * 4 + (size_t)heads * ((size_t)tq + tk) * 64 + (32u << 20);
+  if (!h->c->fused_attention || !attention_fused_supported(d, 0)) need += ((size_t)heads * tq * (tk + 4) + (size_t)heads * d * (tk + 4)) * 4;
+  HostCall hc(h, need);
+  float* q = hc.dev(nq);
+  float* k = hc.dev(nk);
+  float* v = hc.dev(nk);
+  float* o = hc.dev(nq);
+  if (hc.rc) return hc.finish();
+  Ctx* c = hc.c;
+  fill_uniform(c, q, nq, 1, 1.7f);  // variance ~1
+  fill_uniform(c, k, nk, 2, 1.7f);
+  fill_uniform(c, v, nk, 3, 1.7f);
+  AttnArgs a;
+  a.Q = q; a.K = k; a.V = v; a.heads = heads; a.Tq = tq; a.Tk = tk; a.d = d; a.O = o;
+  a.softmax_axis = c->softmax_axis;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 3 && !hc.rc; ++i) hc.run(op_attention(c, a));
+  launch_spin((long long)iters * 25000, c->stream);  // queue the launches behind a spin: events see device time
+  cudaEventRecord(e0, c->stream);
+  for (int i = 0; i < iters && !hc.rc; ++i) hc.run(op_attention(c, a));
   cudaEventRecord(e1, c->stream);
   int rc = hc.finish();
   float ms = 0;

@@ -275,7 +275,8 @@ int32_t tsd_clip_create(tsd_ctx* h, int32_t n_vocab, int32_t n_layers, tsd_clip*
   if (!h || !out) return TSD_ERR_INVALID;
   *out = nullptr;
   Guard g(h);
-  tsd_clip* d = new tsd_clip();
+  tsd_clip* d = new (std::nothrow) tsd_clip();
+  if (!d) return TSD_ERR_OOM;
   d->m.h = h;
   d->m.c = h->c;
   if (n_vocab > 0) d->m.n_vocab = n_vocab;
@@ -316,6 +317,12 @@ const char* tsd_clip_param_name(const tsd_clip* d, int32_t i, int64_t* offset, i
   if (offset) *offset = p.offset;
   if (numel) *numel = p.numel;
   return p.name.c_str();
+}
+int32_t tsd_clip_get_param(const tsd_clip* d, int32_t i, float* out) {
+  if (!d || !out) return TSD_ERR_INVALID;
+  tsd_clip* dd = const_cast<tsd_clip*>(d);
+  Guard g(dd->m.h);
+  return dd->m.ps.get(i, out);
 }
 int32_t tsd_clip_forward(tsd_clip* d, const int32_t* tokens, int32_t n_tokens, float* context) {
   if (!d) return TSD_ERR_INVALID;

@@ -389,7 +389,14 @@ norm_fused_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
       __threadfence();
       atomicAdd(bar + 1, 1u);
     } else {
-      while (*gen == g0) __nanosleep(20);
+      unsigned int spins = 0;
+      while (*gen == g0) {
+        __nanosleep(20);
+        if (++spins > (1u << 24)) {  // bounded: lost co-residency traps instead of hanging the GPU
+          printf("tsd: norm_fused grid barrier timed out (block %d)\n", blockIdx.x);
+          __trap();
+        }
+      }
     }
     __threadfence();
   }
@@ -1262,12 +1269,14 @@ __global__ void softmax_row_kernel(float* __restrict__ S, int Cc_all, int ld, fl
 // ClipEmbedding.forward (clip.mojo:17-20; Embedding.forward, helpers/utils.mojo:2032-2046):
 // out[t][:] = token_table[tokens[t]][:] + position[t][:]
 __global__ void clip_embed_kernel(const int* __restrict__ tokens, const float4* __restrict__ table,
-                                  const float4* __restrict__ pos, float4* __restrict__ out, int T, int d4) {
+                                  const float4* __restrict__ pos, float4* __restrict__ out, int T, int d4, int n_vocab) {
   const long long total = (long long)T * d4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i / d4), c = (int)(i - (long long)t * d4);
-    const float4 a = table[(long long)tokens[t] * d4 + c], b = pos[i];
+    int id = tokens[t];
+    id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);  // device-side token ids (tsd_clip_forward_dev) are not host-validated
+    const float4 a = table[(long long)id * d4 + c], b = pos[i];
     out[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
   }
 }
@@ -1420,11 +1429,9 @@ cudaError_t launch_group_stats(const float* x, int N, long long pixels, int C, i
     const int nb = group_stats_blocks(N, pixels, C);
     const int slab = (int)((pixels + nb - 1) / nb);
     const size_t smem = (size_t)ppl * 2 * C * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(group_stats_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    {
+      cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(group_stats_vec_kernel), 64 * 1024, nullptr);
       if (e != cudaSuccess) return e;
-      attr_set = true;
     }
     dim3 grid((unsigned)nb, N);
     group_stats_vec_kernel<<<grid, GS_THREADS, smem, s>>>(reinterpret_cast<const float4*>(x), pixels, C4, G, cpg, slab,
@@ -1468,11 +1475,13 @@ cudaError_t launch_norm_fused(const float* x, float* y, int N, long long pixels,
   int grid = items < sm_count ? items : sm_count;
   size_t smem = (size_t)ppl * 2 * C * sizeof(float);
   if (smem < (size_t)G * sizeof(float2)) smem = (size_t)G * sizeof(float2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(norm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  {
+    cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(norm_fused_kernel), 64 * 1024, nullptr);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+  }
+  {
+    cudaError_t e = grid_coresident(reinterpret_cast<const void*>(norm_fused_kernel), GS_THREADS, smem, grid);
+    if (e != cudaSuccess) return e;
   }
   { cudaError_t e_ = launch_pdl(norm_fused_kernel, dim3(grid), dim3(GS_THREADS), smem, s, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
                                                    pixels, C4, G, cpg, slabs, slab, items,
@@ -1508,11 +1517,29 @@ static NormFused2Plan norm_fused2_plan(int N, long long pixels, int C, int sm_co
   pl.cache = pl.iters <= maxit;
   return pl;
 }
+// the kernel instantiation and dynamic shared memory a plan launches with
+static const void* norm_fused2_func(const NormFused2Plan& pl);
+static size_t norm_fused2_smem(const NormFused2Plan& pl, int C, int G) {
+  size_t smem = (size_t)pl.ppl * 2 * C * sizeof(float);
+  if (smem < (size_t)G * sizeof(float2)) smem = (size_t)G * sizeof(float2);
+  return smem;
+}
 bool norm_fused2_supported(int N, long long pixels, int C, int G, int sm_count) {
   if (C % 4 || C / 4 > 3 * NF_THREADS || G <= 0 || C % G || pixels >= (1 << 30)) return false;
   if (N > 2 * sm_count) return false;
   const NormFused2Plan pl = norm_fused2_plan(N, pixels, C, sm_count);
-  return pl.subs_per_img <= 32 && (long long)N * pl.subs_per_img + 1 <= kNormBarrierCounters;
+  if (!(pl.subs_per_img <= 32 && (long long)N * pl.subs_per_img + 1 <= kNormBarrierCounters)) return false;
+  // the grid barrier needs every block resident at once: ask the runtime instead of assuming two blocks per SM
+  const void* fn = norm_fused2_func(pl);
+  if (optin_dyn_smem(fn, 64 * 1024, nullptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (grid_coresident(fn, NF_THREADS, norm_fused2_smem(pl, C, G), (long long)N * pl.slabs_per_img) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
 }
 size_t norm_fused2_scratch_bytes(int N, long long pixels, int C, int G, int sm_count) {
   const NormFused2Plan pl = norm_fused2_plan(N, pixels, C, sm_count);
@@ -1561,17 +1588,9 @@ cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long l
   bool cache = pl.cache;
   if ((p.splits > 1 || p.x2 != nullptr) && !cache && p.raw == nullptr) return cudaErrorInvalidValue;  // re-read mode needs the raw tensor
   const int grid = N * pl.slabs_per_img;
-  size_t smem = (size_t)pl.ppl * 2 * C * sizeof(float);
-  if (smem < (size_t)G * sizeof(float2)) smem = (size_t)G * sizeof(float2);
+  const size_t smem = norm_fused2_smem(pl, C, G);  // opt-in limit and co-residency were established by norm_fused2_supported
 #define NF2_LAUNCH(NQ, MAXIT, CACHE)                                                                        \
   do {                                                                                                      \
-    static bool attr_set = false;                                                                           \
-    if (!attr_set) {                                                                                        \
-      cudaError_t e = cudaFuncSetAttribute(norm_fused2_kernel<NQ, MAXIT, CACHE>,                            \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);         \
-      if (e != cudaSuccess) return e;                                                                       \
-      attr_set = true;                                                                                      \
-    }                                                                                                       \
     { cudaError_t e_ = launch_pdl(norm_fused2_kernel<NQ, MAXIT, CACHE>, dim3(grid), dim3(NF_THREADS), smem, s, p); if (e_ != cudaSuccess) return e_; } \
   } while (0)
   if (pl.nq == 1) { if (cache) NF2_LAUNCH(1, 16, true); else NF2_LAUNCH(1, 16, false); }
@@ -1579,6 +1598,12 @@ cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long l
   else { if (cache) NF2_LAUNCH(3, 5, true); else NF2_LAUNCH(3, 5, false); }
 #undef NF2_LAUNCH
   return cudaGetLastError();
+}
+
+static const void* norm_fused2_func(const NormFused2Plan& pl) {
+  if (pl.nq == 1) return pl.cache ? reinterpret_cast<const void*>(norm_fused2_kernel<1, 16, true>) : reinterpret_cast<const void*>(norm_fused2_kernel<1, 16, false>);
+  if (pl.nq == 2) return pl.cache ? reinterpret_cast<const void*>(norm_fused2_kernel<2, 8, true>) : reinterpret_cast<const void*>(norm_fused2_kernel<2, 8, false>);
+  return pl.cache ? reinterpret_cast<const void*>(norm_fused2_kernel<3, 5, true>) : reinterpret_cast<const void*>(norm_fused2_kernel<3, 5, false>);
 }
 
 bool norm_apply_partial_supported(int C, int G) { return C % 4 == 0 && C / 4 <= GS_MAXQ * GS_THREADS && G <= 512; }
@@ -1697,11 +1722,11 @@ cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, flo
 }
 
 cudaError_t launch_clip_embed(const int* tokens, const float* table, const float* pos, float* out, int T, int d,
-                              cudaStream_t s) {
+                              int n_vocab, cudaStream_t s) {
   if (d % 4) return cudaErrorInvalidValue;
   clip_embed_kernel<<<grid_for((long long)T * (d / 4), 256), 256, 0, s>>>(tokens, reinterpret_cast<const float4*>(table),
                                                                         reinterpret_cast<const float4*>(pos),
-                                                                        reinterpret_cast<float4*>(out), T, d / 4);
+                                                                        reinterpret_cast<float4*>(out), T, d / 4, n_vocab);
   return cudaGetLastError();
 }
 

@@ -123,7 +123,7 @@ cudaError_t launch_softmax(float* S, int B, int R, int Cc, int ld, int axis, flo
 
 // keeps the stream busy for `ns` nanoseconds (profiling aid)
 cudaError_t launch_clip_embed(const int* tokens, const float* table, const float* pos, float* out, int T, int d,
-                              cudaStream_t s);
+                              int n_vocab, cudaStream_t s);
 cudaError_t launch_spin(long long ns, cudaStream_t s);
 
 // ---- DDPM step (+ optional CFG combine), sampler.mojo:75-109, pipeline.mojo:117-119 --------

@@ -1171,19 +1171,10 @@ template <int CG>
 static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
                                   const GemmKParams& p, dim3 grid, size_t smem_bytes, cudaStream_t stream) {
   // static + dynamic shared memory must fit the 227 KiB opt-in limit together
-  static int max_dyn = -1;
-  if (max_dyn < 0) {
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tf32_kernel<CG>);
+  int max_dyn = 0;
+  {
+    cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(gemm_tf32_kernel<CG>), -1, &max_dyn);
     if (e != cudaSuccess) return e;
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e != cudaSuccess) return e;
-    const int lim = optin - (int)fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(gemm_tf32_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return e;
-    max_dyn = lim;
   }
   if ((long long)smem_bytes > max_dyn) return cudaErrorInvalidConfiguration;
   cudaLaunchConfig_t cfg{};
@@ -1222,19 +1213,10 @@ size_t halo_smem_bytes(int BN, int cg, int sb) {
 template <int CG>
 static cudaError_t launch_halo_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
                                   size_t smem_bytes, cudaStream_t stream) {
-  static int max_dyn = -1;
-  if (max_dyn < 0) {
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv3x3_halo_kernel<CG>);
+  int max_dyn = 0;
+  {
+    cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(conv3x3_halo_kernel<CG>), -1, &max_dyn);
     if (e != cudaSuccess) return e;
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e != cudaSuccess) return e;
-    const int lim = optin - (int)fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(conv3x3_halo_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return e;
-    max_dyn = lim;
   }
   if ((long long)smem_bytes > max_dyn) return cudaErrorInvalidConfiguration;
   cudaLaunchConfig_t cfg{};
@@ -1363,11 +1345,9 @@ cudaError_t launch_splitk_reduce(const SplitKReduceParams& p, cudaStream_t strea
     const int n4 = p.n_valid >> 2;
     const int ppl = n4 < RK_THREADS ? RK_THREADS / n4 : 1;
     const size_t smem = (size_t)ppl * p.n_valid * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(splitk_reduce_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    {
+      cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(splitk_reduce_stats_kernel), 96 * 1024, nullptr);
       if (e != cudaSuccess) return e;
-      attr_set = true;
     }
     const int blocks = (p.m + p.slab_rows - 1) / p.slab_rows;
     return launch_pdl(splitk_reduce_stats_kernel, dim3(blocks), dim3(RK_THREADS), smem, stream, p);

@@ -428,7 +428,14 @@ struct Json {  // minimal recursive-descent parser for the header's subset of JS
     } while (eat(','));
     return eat(']') ? true : (ok = false);
   }
+  int depth = 0;  // nesting of the value being skipped: the header is attacker-controlled, recursion is capped
   bool skip_value() {  // __metadata__ and unknown keys
+    struct Level {
+      int& d;
+      explicit Level(int& dd) : d(dd) { ++d; }
+      ~Level() { --d; }
+    } level(depth);
+    if (depth > 64) return ok = false;
     ws();
     if (p >= e) return ok = false;
     if (*p == '"') {

@@ -874,7 +874,7 @@ int Diffusion::run_unet_graph(int n, int n_ctx, int n_time) {
   if (!h->use_graph || c->timer) return unet(n, n_ctx, n_time);
   GraphSlot& g = graph;
   const bool valid = g.exec && g.n == n && g.n_ctx == n_ctx && g.n_time == n_time && g.epoch == h->option_epoch &&
-                     g.arena_base == c->arena.base();
+                     g.arena_base == c->arena.base() && g.weights_gen == ps.gen;
   if (!valid) {
     // one eager pass first: validates shapes, initialises per-kernel attributes outside capture
     TRY(unet(n, n_ctx, n_time));
@@ -886,6 +886,7 @@ int Diffusion::run_unet_graph(int n, int n_ctx, int n_time) {
     if (rc) return rc;
     if (rc2) return rc2;
     g.n = n; g.n_ctx = n_ctx; g.n_time = n_time; g.epoch = h->option_epoch; g.arena_base = c->arena.base();
+    g.weights_gen = ps.gen;
     return TSD_OK;  // the eager pass already produced this call's result
   }
   TRY(c->check(cudaGraphLaunch(g.exec, c->stream), "graph launch"));
@@ -1127,7 +1128,7 @@ int Decoder::forward(const float* z, int n, int rescale, float* img, bool host_p
   GraphSlot& g = graph;
   const bool use = h->use_graph && !c->timer;
   const bool valid = g.exec && g.n == n && g.n_ctx == rescale && g.epoch == h->option_epoch &&
-                     g.arena_base == c->arena.base();
+                     g.arena_base == c->arena.base() && g.weights_gen == ps.gen;
   if (!use) {
     TRY(decode(n, rescale));
   } else if (!valid) {
@@ -1139,6 +1140,7 @@ int Decoder::forward(const float* z, int n, int rescale, float* img, bool host_p
     if (rc) return rc;
     if (rc2) return rc2;
     g.n = n; g.n_ctx = rescale; g.epoch = h->option_epoch; g.arena_base = c->arena.base();
+    g.weights_gen = ps.gen;
   } else {
     TRY(c->check(cudaGraphLaunch(g.exec, c->stream), "graph launch"));
     c->launches += g.nodes;
@@ -1290,7 +1292,7 @@ int Encoder::forward(const float* img, const float* noise, int n, int rescale, f
   GraphSlot& g = graph;
   const bool use = h->use_graph && !c->timer;
   const bool valid = g.exec && g.n == n && g.n_ctx == rescale && g.epoch == h->option_epoch &&
-                     g.arena_base == c->arena.base();
+                     g.arena_base == c->arena.base() && g.weights_gen == ps.gen;
   if (!use) {
     TRY(encode(n, rescale));
   } else if (!valid) {
@@ -1302,6 +1304,7 @@ int Encoder::forward(const float* img, const float* noise, int n, int rescale, f
     if (rc) return rc;
     if (rc2) return rc2;
     g.n = n; g.n_ctx = rescale; g.epoch = h->option_epoch; g.arena_base = c->arena.base();
+    g.weights_gen = ps.gen;
   } else {
     TRY(c->check(cudaGraphLaunch(g.exec, c->stream), "graph launch"));
     c->launches += g.nodes;
@@ -1418,9 +1421,12 @@ int generate_latents(Diffusion& m, const tsd_loop_params& lp, const float* laten
     // graph of one step, valid for (nb, ctx rows, cfg, noise?, arena base); replayed `steps` times
     Diffusion::LoopCache& cache = m.loop_cache;
     GraphSlot& g = cache.slot;
+    // (the captured step reads step / coef / time-bias tables / noise at addresses carved behind the UNet region:
+    // those offsets depend on the step count, so `steps` is part of the key; so is the weight generation)
     const bool valid = g.exec && g.n == nb && g.n_ctx == n_ctx_eff && cache.cfg == lp.cfg &&
-                       cache.has_noise == (lp.noise != nullptr) && cache.scale == lp.cfg_scale &&
-                       cache.top == (const void*)top && g.epoch == m.h->option_epoch && g.arena_base == c->arena.base();
+                       cache.has_noise == (lp.noise != nullptr) && cache.scale == lp.cfg_scale && cache.steps == steps &&
+                       cache.top == (const void*)top && g.epoch == m.h->option_epoch && g.arena_base == c->arena.base() &&
+                       g.weights_gen == m.ps.gen;
     int first = 0;
     if (!valid) {
       TRY(one_step());  // eager step 0 (also the warm-up that sets kernel attributes)
@@ -1434,7 +1440,9 @@ int generate_latents(Diffusion& m, const tsd_loop_params& lp, const float* laten
         if (rc2) return rc2;
         cache.cfg = lp.cfg; cache.has_noise = lp.noise != nullptr; cache.scale = lp.cfg_scale;
         cache.top = top;
+        cache.steps = steps;
         g.n = nb; g.n_ctx = n_ctx_eff; g.epoch = m.h->option_epoch; g.arena_base = c->arena.base();
+        g.weights_gen = m.ps.gen;
       }
     }
     for (int i = first; i < steps; ++i) {

@@ -85,6 +85,8 @@ struct GraphSlot {
   cudaGraphExec_t exec = nullptr;
   int n = 0, n_ctx = 0, n_time = 0;
   int epoch = -1;
+  int weights_gen = -1;  // ParamStore::gen the graph was captured with: derived weight buffers (fused skip weights,
+                         // LayerNorm-fold row sums) are only refreshed by an eager pass, so a reload re-captures
   const void* arena_base = nullptr;
   long long nodes = 0;  // kernels per replay (bench gpu_launches accounting)
 };
@@ -112,6 +114,7 @@ struct Diffusion {
   struct LoopCache {
     GraphSlot slot;
     int cfg = 0, has_noise = 0;
+    int steps = 0;  // the loop-lifetime buffers are carved behind tables whose size depends on the step count
     float scale = 0.f;
     const void* top = nullptr;
   } loop_cache;

@@ -103,7 +103,7 @@ int Clip::encode() {
   float* x1 = cw(c, (long long)T * C);
   float* hbuf = cw(c, 4LL * T * C);
   if (!x || !v || !qkv || !o || !x1 || !hbuf) return c->fail(TSD_ERR_OOM, "workspace exhausted (clip)");
-  LAUNCH(c, launch_clip_embed(tokens_dev, ps.w(tok), ps.w(pos), x, T, C, c->stream), "clip_embed");
+  LAUNCH(c, launch_clip_embed(tokens_dev, ps.w(tok), ps.w(pos), x, T, C, n_vocab, c->stream), "clip_embed");
   for (int l = 0; l < n_layers; ++l) {
     const Layer& w = layer[l];
     TRY(clip_layer_norm(c, x, v, T, C));

@@ -1075,16 +1075,22 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
     // one launch: statistics + grid barrier + normalise
     void* scratch = c->arena.alloc(norm_fused_scratch_bytes(N, (long long)H * W, C, G));
     if (!scratch) return c->fail(TSD_ERR_OOM, "group_norm: arena exhausted");
+    bool launched = true;
     if (!c->dry_run) {
       TimedScope ts(c, FAM_NORM, 0);
-      int rc = c->check(launch_norm_fused(x, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
-                                          round_tf32, scratch, c->ticket + 4, c->sm_count, c->stream),
-                        "norm_fused launch");
-      if (rc) return rc;
-      c->launches += 1;
+      const cudaError_t e = launch_norm_fused(x, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
+                                              round_tf32, scratch, c->ticket + 4, c->sm_count, c->stream);
+      if (e == cudaErrorCooperativeLaunchTooLarge) {
+        cudaGetLastError();  // the grid barrier cannot be proven co-resident on this device: two-kernel path below
+        launched = false;
+      } else {
+        int rc = c->check(e, "norm_fused launch");
+        if (rc) return rc;
+        c->launches += 1;
+      }
     }
     c->arena.release_to(mark);
-    return TSD_OK;
+    if (launched) return TSD_OK;
   }
   void* accum = c->arena.alloc(group_stats_scratch_bytes(N, (long long)H * W, C, G));
   float2* stats = c->arena.alloc_n<float2>((size_t)N * G);

@@ -114,6 +114,7 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_cross_attention", i32, vp, fp, i32, i32, fp, i32, i32, i32, fp, fp, fp, fp, fp, fp, fp,
         fp, fp)
     sig("tsd_attention_core", i32, vp, fp, fp, fp, i32, i32, i32, i32, fp)
+    sig("tsd_attention_core_dev", i32, vp, fp, fp, fp, i32, i32, i32, i32, fp)
     sig("tsd_sampler_step", i32, vp, fp, fp, fp, f32, fp, f32, f32, f32, f32, f32, i64, fp)
     sig("tsd_sampler_add_noise", i32, vp, fp, fp, f32, f32, i64, fp)
     sig("tsd_sampler_step_dev", i32, vp, fp, fp, fp, f32, fp, f32, f32, f32, f32, f32, i64, fp)
@@ -175,8 +176,10 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_clip_init_random", i32, vp, C.c_uint64)
     sig("tsd_clip_param_count", i32, vp)
     sig("tsd_clip_param_name", C.c_char_p, vp, i32, c_i64_p, c_i64_p)
+    sig("tsd_clip_get_param", i32, vp, i32, fp)
     sig("tsd_clip_forward", i32, vp, vp, i32, fp)
     sig("tsd_clip_forward_dev", i32, vp, vp, i32, fp)
     sig("tsd_generate_latents", i32, vp, C.POINTER(LoopParams), fp, fp, i32, i32, fp)
     sig("tsd_bench_gemm", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)
+    sig("tsd_bench_attention", i32, vp, i32, i32, i32, i32, i32, c_double_p)
     sig("tsd_bench_conv", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)

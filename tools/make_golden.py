@@ -11,6 +11,10 @@ checked at the full BASELINE sizes, where running the oracle inside a test would
   python tools/make_golden.py encoder    # VAE Encoder at 32x32 / 128x128 images + the img2img start latents
   python tools/make_golden.py encoder64  # VAE Encoder 512x512x3 -> 64x64x4
   python tools/make_golden.py tokenizer  # synthetic tokenizer .bin + known-answer token ids
+  python tools/make_golden.py loop64     # 20-step denoising loop at 64x64 (BASELINE config 2) with the latents after
+                                         # steps 1, 2, 5, 10, 20, and a 4-step CFG 7.5 loop (config 3 per-GPU shape)
+  python tools/make_golden.py decoder64_full  # two distinct 512x512 decodes kept whole (fp16 x scale): batch-16 test
+  python tools/make_golden.py clip12     # the 12-layer, 49408-token CLIP of clip.mojo:71-83
 """
 import os
 import sys
@@ -186,6 +190,71 @@ def tokenizer():
     print("tokenizer golden:", len(keys), "tokens,", len(blob), "bytes")
 
 
+def _loop_trace(ops, W, lat0, context, steps, noise, keep, cfg_context=None, cfg_scale=7.5):
+    """O.generate_latents (pipeline.mojo:86-122) with the latents after the steps listed in `keep` recorded."""
+    sm = O.DDPMSampler()
+    sm.set_inference_timesteps(steps)
+    lat = ops.arr(lat0)
+    out = {}
+    for i, t in enumerate(sm.timesteps):
+        t0 = time.time()
+        temb = O.get_time_embedding(float(t))
+        eps = O.diffusion_forward(ops, W, lat, context, temb)
+        if cfg_context is not None:
+            eps = O.cfg_combine(eps, O.diffusion_forward(ops, W, lat, cfg_context, temb), cfg_scale)
+        lat = sm.step(int(t), lat, eps, ops.arr(noise[i]))
+        if i + 1 in keep:
+            out[i + 1] = np.asarray(lat, np.float64).copy()
+        print(f"  step {i + 1}/{steps}: {time.time() - t0:.1f} s", flush=True)
+    return out
+
+
+def loop64():
+    """BASELINE config 2 (20 steps, no CFG) and config 3's per-GPU shape (CFG 7.5; 4 steps of its 50) at the 64x64
+    latent, fp64.  Inputs are regenerated from their seeds in the test; only the latents are stored."""
+    ops = O.Ops("np", np.float64)
+    W = synth.SynthWeights(synth.diffusion_specs(), UNET_SEED)
+    x, ctx = inputs(61, 64, n_ctx=2)
+    rng = np.random.default_rng(62)
+    noise = rng.standard_normal((20, 4, 64, 64), dtype=np.float32)
+    keep = (1, 2, 5, 10, 20)
+    tr = _loop_trace(ops, W, x, ctx[0], 20, noise, keep)
+    out = {f"lat_step{k}": v for k, v in tr.items()}
+    trc = _loop_trace(ops, W, x, ctx[0], 4, noise[:4], (1, 2, 4), cfg_context=ctx[1], cfg_scale=7.5)
+    out.update({f"cfg_lat_step{k}": v for k, v in trc.items()})
+    np.savez_compressed(os.path.join(G, "loop64.npz"), **out)
+
+
+def decoder64_full():
+    ops = O.Ops("np", np.float64)
+    Wd = synth.SynthWeights(synth.decoder_specs(), DEC_SEED)
+    out = {}
+    for i, seed in enumerate((31, 32)):
+        z = (np.random.default_rng(seed).standard_normal((4, 64, 64)) * 0.18215).astype(np.float32)
+        t0 = time.time()
+        y = O.decoder_forward(ops, Wd, z)
+        print("decoder64 oracle seconds", time.time() - t0, flush=True)
+        scale = float(np.abs(y).max())
+        out[f"y{i}_f16"] = (y / scale).astype(np.float16)   # 2^-11 relative to the image maximum: 40x below the tolerance
+        out[f"y{i}_scale"] = scale
+    np.savez_compressed(os.path.join(G, "decoder64_full.npz"), **out)
+
+
+CLIP12_SEED = 78
+
+
+def clip12():
+    W = synth.SynthWeights(synth.clip_specs(49408, 12), CLIP12_SEED)
+    tokens = np.random.default_rng(5).integers(0, 49408, 77)
+    t0 = time.time()
+    y_ref = O.clip_forward(O.Ops("np", np.float64), W, tokens, n_layers=12)
+    y_int = O.clip_forward(O.Ops("np", np.float64, O.Switches(softmax_axis="key", layernorm="token")), W, tokens,
+                           n_layers=12)
+    print(f"clip12 oracle x2: {time.time() - t0:.1f} s")
+    np.savez_compressed(os.path.join(G, "clip12.npz"), tokens=tokens, y_reference_switches=y_ref.astype(np.float32),
+                        y_intended_switches=y_int.astype(np.float32))
+
+
 if __name__ == "__main__":
     {"tokenizer": tokenizer, "small": small, "unet64": unet64, "decoder64": decoder64, "clip": clip, "encoder": encoder,
-     "encoder64": encoder64}[sys.argv[1]]()
+     "encoder64": encoder64, "loop64": loop64, "decoder64_full": decoder64_full, "clip12": clip12}[sys.argv[1]]()
