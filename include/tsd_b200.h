@@ -192,6 +192,15 @@ int32_t tsd_diffusion_get_param(const tsd_diffusion* m, int32_t i, float* out);
  * n_ctx = 1 (shared) or n; time (n_time,320) with n_time = 1 or n. */
 int32_t tsd_diffusion_forward(tsd_diffusion* m, const float* x, const float* context, int32_t n_ctx,
                               const float* time, int32_t n_time, int32_t n, float* out);
+/* One iteration of the reference denoising loop (pipeline.mojo:107-121) through host buffers in ONE call:
+ * Diffusion.forward (diffusion.mojo:309-318; on [cond; uncond] when cfg != 0), the CFG combine (pipeline.mojo:117-119)
+ * and DDPMSampler.step (sampler.mojo:75-109) with the schedule scalars of tsd_sampler_step.  latents / noise /
+ * latents_out (n,4,H,W); time (320); context rows as tsd_generate_latents: (1|n) without cfg, (2|2n) with cfg, cond
+ * rows first.  The K/V projections of `context` are reused while its bytes do not change (content hash), NULL reuses
+ * the previous context outright.  Transfers per call: latents, time, noise in; latents out. */
+int32_t tsd_diffusion_step(tsd_diffusion* m, const float* latents, const float* context, int32_t n_ctx,
+                           const float* time, const float* noise, int32_t cfg, float cfg_scale, float sqrt_ab,
+                           float sqrt_1mab, float c0, float c1, float sigma, int32_t n, float* latents_out);
 int32_t tsd_diffusion_forward_dev(tsd_diffusion* m, const float* x, const float* context,
                                   int32_t n_ctx, const float* time, int32_t n_time, int32_t n,
                                   float* out);
@@ -313,6 +322,30 @@ int32_t tsd_safetensors_find(const tsd_safetensors* st, const char* name); /* in
 int32_t tsd_safetensors_info(const tsd_safetensors* st, int32_t i, char dtype[8], int32_t* rank, int64_t shape[8],
                              int64_t* numel);
 int32_t tsd_safetensors_read_f32(const tsd_safetensors* st, int32_t i, float* out, int64_t cap);
+
+/* ---- multi-GPU: batch sharding over the GPUs of one box ---------------------------------------
+ * The reference has no distributed code; its only batching hints are pipeline.mojo:12 (a batch of images) and :96-105
+ * (the two CFG halves).  The path shards by independent images: one process per GPU, rank r owns images r, r+R, ...,
+ * every rank holds a full weight replica, the context is broadcast ONCE per prompt and there is no per-step collective.
+ * NCCL (NVLink 5 / NVSwitch) is loaded at run time by tsd_dist_init when nranks > 1.
+ * Bootstrap: rank 0 calls tsd_dist_unique_id and hands the 128 bytes to the other ranks by whatever means the host
+ * program has (argv, a socket, MPI, torch.distributed), or every rank passes id = NULL and a rendezvous file path
+ * (or TSD_DIST_RENDEZVOUS) on a file system they share: rank 0 writes the id there, the others wait for it. */
+#define TSD_DIST_ID_BYTES 128
+typedef struct tsd_dist tsd_dist;
+int32_t tsd_dist_unique_id(uint8_t id[TSD_DIST_ID_BYTES]);
+int32_t tsd_dist_init(tsd_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id, const char* rendezvous_path,
+                      tsd_dist** out);
+int32_t tsd_dist_shutdown(tsd_dist* d);
+int32_t tsd_dist_rank(const tsd_dist* d);
+int32_t tsd_dist_size(const tsd_dist* d);
+/* in place on a HOST buffer: root's n_floats values (the (n_ctx,77,768) context of pipeline.mojo:41-53) reach every rank */
+int32_t tsd_dist_broadcast_context(tsd_dist* d, float* context, int64_t n_floats, int32_t root);
+/* every rank contributes n_floats host values; `all` (root only) receives nranks x n_floats in rank order */
+int32_t tsd_dist_gather(tsd_dist* d, const float* local, int64_t n_floats, float* all, int32_t root);
+/* tsd_dist_broadcast_context(context) followed by tsd_generate_latents on this rank's n latents */
+int32_t tsd_dist_generate(tsd_dist* d, tsd_diffusion* m, const tsd_loop_params* lp, const float* latents_in,
+                          float* context, int32_t n_ctx, int32_t n, int32_t root, float* latents_out);
 
 /* ---- tuning probes (synthetic device-resident operands, CUDA-event ms per launch) ------------ */
 int32_t tsd_bench_gemm(tsd_ctx* ctx, int32_t m, int32_t n, int32_t k, int32_t batch, int32_t geglu,

@@ -421,13 +421,372 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2 softmax role: the same protocol as attn_kernel, with the tensor-memory reads software-pipelined.
+//
+// Measured on the v1 kernel (profiles/r01_ncu_attn.txt, T = 4096, d = 40): 2240 (statistics) / 2917 (apply) cycles per
+// 128 x 128 tile against 1024 cycles of MUFU.EX2 issue.  A tile is 64 KiB of fp32 scores that every softmax thread
+// must pull out of tensor memory (tcgen05.ld, ~64 B/clk per SM) before it can exponentiate them, and in v1 all eight
+// softmax warps did the two phases in lock step: load, wait, compute, (store, wait,) barrier.  Here each warp keeps
+// the load of chunk g+1 in flight while it exponentiates chunk g (two register buffers, loop unrolled by two), runs
+// straight across tile boundaries, and the per-tile all-warp barrier is gone: mu (query axis) is staged in shared
+// memory for every key of the pass once, before the loop.
+// Preconditions (attention_fused picks v1 otherwise): BN in {64, 128}, Ty a multiple of BN, and for the query-axis
+// apply pass Ty * 4 bytes of extra shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
+  // zero instructions: pins the uses of v[] behind the preceding tcgen05.wait::ld in the compiler's schedule
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                    "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
+
+template <int MODE, bool PER_ROW, int NCH, bool TRACE>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t x_full, y_full[2], y_empty[2], v_full[2], v_empty[2];
+  __shared__ __align__(8) uint64_t s_full[2], s_free[2], p_full[2], o_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float2 comb[ATT_BM];
+  constexpr bool apply = MODE == ATT_APPLY;
+  constexpr int BN = NCH * 64;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t dyn0 = smem_u32(smem_dyn);
+  const uint32_t xs = (dyn0 + 1023u) & ~1023u;
+  const uint32_t x_bytes = (uint32_t)p.nbox * ATT_BM * ATT_BOX_ROW_BYTES;
+  const uint32_t ybox = (uint32_t)BN * ATT_BOX_ROW_BYTES;
+  const uint32_t ystage = (uint32_t)p.nbox * ybox;
+  const uint32_t ys = xs + x_bytes;
+  const uint32_t vs = ys + (uint32_t)p.sY * ystage;
+  float* mu_all = reinterpret_cast<float*>(smem_dyn + (vs - dyn0) + (size_t)(apply ? p.sV : 0) * ystage);
+
+  const int xt = blockIdx.x, bh = blockIdx.y, split = blockIdx.z;
+  const int h = bh % p.heads;
+  const int x0 = xt * ATT_BM;
+  const int it0 = split * p.tiles_per_split;
+  int n_it = p.total_tiles - it0;
+  if (n_it > p.tiles_per_split) n_it = p.tiles_per_split;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&x_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&y_full[s], 1);
+      mbar_init(&y_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], ATT_SM_THREADS);
+      mbar_init(&p_full[s], ATT_SM_THREADS);
+    }
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmY);
+    if (apply) prefetch_tensormap(&tmV);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_wait();               // Q/K/V and the statistics come from predecessor kernels
+  pdl_launch_dependents();  // resources are held: the next kernel may start its prologue
+  const uint32_t tmem_o = tmem_base + 256u;  // S0: cols [0,128), S1: [128,256), O: [256, 256+dpad)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&x_full, x_bytes);
+      for (int bx = 0; bx < p.nbox; ++bx)
+        tma_load_3d_s(xs + bx * (ATT_BM * ATT_BOX_ROW_BYTES), &tmX, &x_full, bx * 32, x0, p.x_shared ? h : bh);
+      for (int it = 0; it < n_it; ++it) {
+        const int yrow = (it0 + it) * BN;
+        {
+          const int st = it % p.sY;
+          const uint32_t ph = (uint32_t)(it / p.sY) & 1u;
+          mbar_wait(&y_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&y_full[st], ystage);
+          for (int bx = 0; bx < p.nbox; ++bx)
+            tma_load_3d_s(ys + st * ystage + bx * ybox, &tmY, &y_full[st], bx * 32, yrow, p.y_shared ? h : bh);
+        }
+        if (apply) {
+          const int st = it % p.sV;
+          const uint32_t ph = (uint32_t)(it / p.sV) & 1u;
+          mbar_wait(&v_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&v_full[st], ystage);
+          for (int bx = 0; bx < p.nbox; ++bx)
+            tma_load_3d_s(vs + st * ystage + bx * ybox, &tmV, &v_full[st], bx * 32, yrow, p.v_shared ? h : bh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc(UMMA_FMT_TF32, ATT_BM, (uint32_t)BN, 0, 0);
+      const uint32_t idesc_o = umma_idesc(UMMA_FMT_TF32, ATT_BM, (uint32_t)p.dpad, 0, 1);  // B (= V) MN-major
+      const int ksteps = p.d >> 3;
+      constexpr int pv_steps = BN >> 3;
+      auto issue_pv = [&](int j) {
+        const int bj = j & 1;
+        const int st = j % p.sV;
+        mbar_wait(&p_full[bj], (uint32_t)(j >> 1) & 1u);
+        mbar_wait(&v_full[st], (uint32_t)(j / p.sV) & 1u);
+        tc_fence_after_sync();
+        const uint32_t vb = vs + st * ystage;
+#pragma unroll 4
+        for (int ks = 0; ks < pv_steps; ++ks) {
+          const uint64_t bdesc = umma_smem_desc(vb + ks * 1024, ybox, 512, UMMA_SWIZZLE_128B_BASE32B);
+          umma_tf32_ts(tmem_o, tmem_base + (uint32_t)(bj * 128 + ks * 8), bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+      };
+      mbar_wait(&x_full, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int b = it & 1;
+        const int st = it % p.sY;
+        mbar_wait(&y_full[st], (uint32_t)(it / p.sY) & 1u);
+        if (!apply && it >= 2) mbar_wait(&s_free[b], (uint32_t)((it >> 1) - 1) & 1u);
+        tc_fence_after_sync();
+        const uint32_t yb = ys + st * ystage;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks & 3) * 32u;
+          const uint64_t adesc = umma_smem_desc(xs + (ks >> 2) * (ATT_BM * ATT_BOX_ROW_BYTES) + off, 16, 1024, UMMA_SWIZZLE_128B);
+          const uint64_t bdesc = umma_smem_desc(yb + (ks >> 2) * ybox + off, 16, 1024, UMMA_SWIZZLE_128B);
+          umma_tf32(tmem_base + (uint32_t)(b * 128), adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&y_empty[st]);
+        umma_commit(&s_full[b]);
+        if (apply && it >= 1) issue_pv(it - 1);
+      }
+      if (apply) {
+        issue_pv(n_it - 1);
+        umma_commit(&o_full);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue (warps 2..9) =====================
+    const int sw = warp - 2;        // 0..7
+    const int q = warp & 3;         // lane quadrant
+    const int half = sw >> 2;       // column half: this warp owns columns [cb, cb + 32 * NCH) of every tile
+    const int row = q * 32 + lane;  // S row == TMEM lane
+    const int st = sw * 32 + lane;  // 0..255 among the softmax threads
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool row_ok = x0 + row < p.Tx;
+    const float c = p.c;
+    const int cb = half * (BN / 2);
+    const int total = n_it * NCH;   // 32-column chunks of this warp over the whole pass
+    [[maybe_unused]] long long t_wait_s = 0, t_wait_ld = 0, t_wait_st = 0, t_begin = 0;
+    const bool tr = TRACE && st == 0;
+
+    // load of chunk g into `buf`; at a tile boundary first wait for the tile's scores
+    auto issue = [&](int g, uint32_t (&buf)[32]) {
+      const int it = g / NCH, k = g - it * NCH;
+      if (k == 0) {
+        long long t0 = 0;
+        if (tr) t0 = clock64();
+        mbar_wait(&s_full[it & 1], (uint32_t)(it >> 1) & 1u);
+        tc_fence_after_sync();
+        if (tr) t_wait_s += clock64() - t0;
+      }
+      tmem_ld32(lane_base + (uint32_t)((it & 1) * 128 + cb + k * 32), buf);
+    };
+    auto ld_wait = [&](uint32_t (&buf)[32]) {
+      long long t0 = 0;
+      if (tr) t0 = clock64();
+      tmem_ld_wait();
+      reg_fence32(buf);
+      if (tr) t_wait_ld += clock64() - t0;
+    };
+
+    if constexpr (!apply) {
+      float m = -INFINITY, l = 0.f;
+      auto consume = [&](int g, uint32_t (&v)[32]) {
+        const int it = g / NCH, k = g - it * NCH;
+        float cm0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+        float cm1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+        for (int j = 4; j < 32; j += 4) {
+          cm0 = fmaxf(cm0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+          cm1 = fmaxf(cm1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+        }
+        const float cm = fmaxf(cm0, cm1) * c;  // c > 0
+        if (cm > m) {
+          l *= ex2(m - cm);
+          m = cm;
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          a0 += ex2(fmaf(__uint_as_float(v[j]), c, -m));
+          a1 += ex2(fmaf(__uint_as_float(v[j + 1]), c, -m));
+          a2 += ex2(fmaf(__uint_as_float(v[j + 2]), c, -m));
+          a3 += ex2(fmaf(__uint_as_float(v[j + 3]), c, -m));
+        }
+        l += (a0 + a1) + (a2 + a3);
+        if (k == NCH - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&s_free[it & 1]);  // this thread's reads of S[it & 1] are complete
+        }
+      };
+      uint32_t A[32], B[32];
+      if (tr) t_begin = clock64();
+      if (total > 0) issue(0, A);
+      // reg_fence32 after each issue(): the consumers of the current buffer are pinned BEHIND the next chunk's
+      // tcgen05.ld in the instruction stream (left alone, the compiler sinks the load below the exponentials - the
+      // arithmetic does not depend on it - and the two never overlap)
+      // The next load is issued unconditionally (past the end it re-reads the last chunk into the idle buffer): under
+      // an `if` the compiler moves the whole conditional block below the exponentials.
+      const int last = total - 1;
+      for (int g = 0; g < total; g += 2) {
+        ld_wait(A);
+        issue(g + 1 < total ? g + 1 : last, B);
+        reg_fence32(A);
+        consume(g, A);
+        if (g + 1 < total) {
+          ld_wait(B);
+          issue(g + 2 < total ? g + 2 : last, A);
+          reg_fence32(B);
+          consume(g + 1, B);
+        }
+      }
+      tmem_ld_wait();  // the trailing dummy load
+      // merge the two column halves of each row (half 1 -> shared -> half 0), then store
+      if (half == 1) comb[row] = make_float2(m, l);
+      named_bar_sync(1, ATT_SM_THREADS);
+      if (half == 0 && row_ok) {
+        const float2 o = comb[row];
+        const float M = fmaxf(m, o.x);
+        const float L = l * ex2(m - M) + o.y * ex2(o.x - M);
+        p.part_out[(long long)split * p.part_stride + (long long)bh * p.Tx + x0 + row] = make_float2(M, L);
+      }
+    } else {
+      // P is written with a 2^-11 relative boost so that the tensor core's truncation of the fp32
+      // bit pattern to TF32 acts as round-to-nearest (unbiased), at no instruction cost
+      const float rnd = 7.0436e-4f;  // log2(1 + 2^-11)
+      float mu_row = 0.f;
+      if constexpr (PER_ROW) {
+        if (row_ok) mu_row = merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + x0 + row) - rnd;
+      } else {
+        // mu = max + log2(sum) - rnd of every key column of this pass, once
+        for (int col = st; col < n_it * BN; col += ATT_SM_THREADS) {
+          const int gcol = it0 * BN + col;
+          float mu = INFINITY;  // masked key column: exp2(-inf) = 0
+          if (gcol < p.Ty) mu = merge_partials(p.part_in, p.part_stride, p.mu_splits, (long long)bh * p.Tmu + gcol) - rnd;
+          mu_all[col] = mu;
+        }
+        named_bar_sync(1, ATT_SM_THREADS);
+      }
+      auto consume = [&](int g, uint32_t (&v)[32]) {
+        const int it = g / NCH, k = g - it * NCH;
+        if constexpr (PER_ROW) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(ex2(fmaf(__uint_as_float(v[j]), c, -mu_row)));
+        } else {
+          const float4* mup = reinterpret_cast<const float4*>(mu_all + it * BN + cb + k * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 m4 = mup[j4];
+            v[4 * j4 + 0] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 0]), c, -m4.x)));
+            v[4 * j4 + 1] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 1]), c, -m4.y)));
+            v[4 * j4 + 2] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 2]), c, -m4.z)));
+            v[4 * j4 + 3] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w)));
+          }
+        }
+        tmem_st32(lane_base + (uint32_t)((it & 1) * 128 + cb + k * 32), v);
+        if (k == NCH - 1) {
+          long long t0 = 0;
+          if (tr) t0 = clock64();
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(&p_full[it & 1]);
+          if (tr) t_wait_st += clock64() - t0;
+        }
+      };
+      uint32_t A[32], B[32];
+      if (tr) t_begin = clock64();
+      if (total > 0) issue(0, A);
+      // reg_fence32 after each issue(): the consumers of the current buffer are pinned BEHIND the next chunk's
+      // tcgen05.ld in the instruction stream (left alone, the compiler sinks the load below the exponentials - the
+      // arithmetic does not depend on it - and the two never overlap)
+      // The next load is issued unconditionally (past the end it re-reads the last chunk into the idle buffer): under
+      // an `if` the compiler moves the whole conditional block below the exponentials.
+      const int last = total - 1;
+      for (int g = 0; g < total; g += 2) {
+        ld_wait(A);
+        issue(g + 1 < total ? g + 1 : last, B);
+        reg_fence32(A);
+        consume(g, A);
+        if (g + 1 < total) {
+          ld_wait(B);
+          issue(g + 2 < total ? g + 2 : last, A);
+          reg_fence32(B);
+          consume(g + 1, B);
+        }
+      }
+      tmem_ld_wait();  // the trailing dummy load
+      // ---- epilogue: O (TMEM) -> merged [b][t][h*d + j]  (attention.mojo:61-62) ----
+      mbar_wait(&o_full, 0);
+      tc_fence_after_sync();
+      const int bidx = bh / p.heads;
+      float* orow = p.O + ((long long)bidx * p.Tx + x0 + row) * p.ldo + (long long)h * p.d;
+      const int e0 = (((p.dpad >> 4) + 1) >> 1) * 16;
+      const int ob = half ? e0 : 0, oe = half ? p.dpad : e0;
+      for (int c0 = ob; c0 < oe; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (c0 + 4 * j4 < p.d) {
+              float4 o;
+              if (p.round_out) {
+                o = make_float4(__uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4]))),
+                                __uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4 + 1]))),
+                                __uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4 + 2]))),
+                                __uint_as_float(rna_tf32_bits(__uint_as_float(v[4 * j4 + 3]))));
+              } else {
+                o = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+              }
+              *reinterpret_cast<float4*>(orow + c0 + 4 * j4) = o;
+            }
+          }
+        }
+      }
+    }
+    if (TRACE && st == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0 && blockIdx.z == 0) {
+      const long long t_all = clock64() - t_begin;
+      printf("attn2 trace mode %d block %d: %d tiles of 128x%d, softmax loop %lld clk (%lld per tile): wait scores %lld, wait tmem ld %lld, wait tmem st + arrive %lld\n",
+             MODE, blockIdx.x, n_it, BN, t_all, t_all / (n_it > 0 ? n_it : 1), t_wait_s, t_wait_ld, t_wait_st);
+    }
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 struct AttnPlan {
   int nbox, dpad, BN, sY, sV;
   size_t smem;
 };
 
 // tile of the streamed operand and ring depths that fit the 227 KiB shared-memory budget
-AttnPlan plan_for(int d, int Ty, bool with_v) {
+AttnPlan plan_for(int d, int Ty, bool with_v, size_t extra = 0) {
   AttnPlan pl{};
   pl.nbox = (d + 31) / 32;
   pl.dpad = (d + 15) / 16 * 16;
@@ -436,12 +795,12 @@ AttnPlan plan_for(int d, int Ty, bool with_v) {
   pl.BN = BN;
   const size_t xb = (size_t)pl.nbox * ATT_BM * ATT_BOX_ROW_BYTES;
   const size_t yb = (size_t)pl.nbox * BN * ATT_BOX_ROW_BYTES;
-  const size_t budget = 212 * 1024;
+  const size_t budget = 212 * 1024 - extra;
   pl.sY = 2;
   pl.sV = with_v ? 2 : 0;
   if (xb + (pl.sY + pl.sV) * yb > budget && with_v) pl.sV = 1;
   if (xb + (pl.sY + pl.sV) * yb > budget) pl.sY = 1;
-  pl.smem = xb + (size_t)(pl.sY + pl.sV) * yb + 1024;
+  pl.smem = xb + (size_t)(pl.sY + pl.sV) * yb + extra + 1024;
   return pl;
 }
 
@@ -463,6 +822,30 @@ cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CU
   return launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);
 }
 
+template <int MODE, bool PER_ROW, int NCH, bool TRACE>
+cudaError_t launch_attn2_t(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV, const AttnKParams& p,
+                           dim3 grid, size_t smem, cudaStream_t stream) {
+  int max_dyn = 0;
+  cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(attn2_kernel<MODE, PER_ROW, NCH, TRACE>), -1, &max_dyn);
+  if (e != cudaSuccess) return e;
+  if ((long long)smem > max_dyn) return cudaErrorInvalidConfiguration;
+  return launch_pdl(attn2_kernel<MODE, PER_ROW, NCH, TRACE>, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);
+}
+cudaError_t launch_attn2(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV, const AttnKParams& p,
+                         dim3 grid, size_t smem, cudaStream_t stream, bool trace) {
+  const int nch = p.BN / 64;
+#define TSD_A2(MODE, PR, NCH)                                                                  \
+  (trace ? launch_attn2_t<MODE, PR, NCH, true>(tmX, tmY, tmV, p, grid, smem, stream)           \
+         : launch_attn2_t<MODE, PR, NCH, false>(tmX, tmY, tmV, p, grid, smem, stream))
+  if (p.mode == ATT_STATS) return nch == 2 ? TSD_A2(ATT_STATS, false, 2) : TSD_A2(ATT_STATS, false, 1);
+  if (p.mu_per_row) return nch == 2 ? TSD_A2(ATT_APPLY, true, 2) : TSD_A2(ATT_APPLY, true, 1);
+  return nch == 2 ? TSD_A2(ATT_APPLY, false, 2) : TSD_A2(ATT_APPLY, false, 1);
+#undef TSD_A2
+}
+
+// v2 takes whole tiles of 64 or 128 streamed rows
+bool attn2_ok(const AttnPlan& pl, int Ty) { return (pl.BN == 64 || pl.BN == 128) && Ty % pl.BN == 0; }
+
 }  // namespace
 
 bool attention_fused_supported(int d, int causal) { return !causal && d >= 8 && d % 8 == 0 && d <= 160; }
@@ -477,6 +860,13 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
   const long long kv_nb = kv_shared ? a.heads : BH;
   const float cs = 1.4426950408889634f / sqrtf((float)a.d);
   const bool query_axis = a.softmax_axis == 0;
+  const bool attn_v2 = c->attn_v2 != 0;
+  static int attn_trace_env = -1;  // TSD_ATTN_TRACE=1: in-kernel cycle counts of the v2 softmax loops (lab)
+  if (attn_trace_env < 0) {
+    const char* v = getenv("TSD_ATTN_TRACE");
+    attn_trace_env = v ? atoi(v) : 0;
+  }
+  const bool attn_trace = attn_trace_env != 0;
 
   // ---- pass 1: statistics --------------------------------------------------------------------
   // query axis: one (max, sum) per key column over all queries  -> X = K, Y = Q
@@ -529,13 +919,23 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
     p.c = cs;
     p.part_out = part;
     p.part_stride = (long long)BH * Tx;
-    rc = c->check(launch_attn(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream),
+    const bool v2s = attn_v2 && attn2_ok(sp, Ty);
+    rc = c->check(v2s ? launch_attn2(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream, attn_trace)
+                      : launch_attn(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream),
                   "attn_kernel (stats) launch");
     if (rc) return rc;
     c->launches++;
 
     // ---- pass 2: P = exp2(c S - mu), O = P V ----------------------------------------------------
-    const AttnPlan ap = plan_for(a.d, a.Tk, true);
+    AttnPlan ap = plan_for(a.d, a.Tk, true);
+    bool v2a = attn_v2 && attn2_ok(ap, a.Tk);
+    if (v2a && query_axis) {
+      // mu of every key staged in shared memory once (4 B per key)
+      const size_t mu_bytes = ((size_t)a.Tk * 4 + 1023) / 1024 * 1024;
+      const AttnPlan ap2 = plan_for(a.d, a.Tk, true, mu_bytes);
+      if (mu_bytes <= 32 * 1024 && attn2_ok(ap2, a.Tk)) ap = ap2;
+      else v2a = false;
+    }
     CUtensorMap tmQ, tmK, tmV;
     rc = tmap3(c, &tmQ, a.Q, a.d, a.Tq, BH, ATT_BM);
     if (rc) return rc;
@@ -570,7 +970,8 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
         return TSD_OK;
       }
     }
-    rc = c->check(launch_attn(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream),
+    rc = c->check(v2a && !q.debug ? launch_attn2(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream, attn_trace)
+                                  : launch_attn(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream),
                   "attn_kernel (apply) launch");
     if (rc) return rc;
     c->launches++;

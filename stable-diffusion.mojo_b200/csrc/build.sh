@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -Wno-deprecated-gpu
 [ "${TSD_LAB_TRACE:-0}" = "1" ] && FLAGS+=(-DTSD_LAB_TRACE)
 [ "${TSD_LAB_NOSTORE:-0}" = "1" ] && FLAGS+=(-DTSD_LAB_NOSTORE)
 mkdir -p build
-SRCS=(gemm_tcgen05.cu attention_tcgen05.cu elementwise.cu runtime.cu models.cu models_clip.cu c_api.cu c_api_models.cu host_io.cu)
+SRCS=(gemm_tcgen05.cu attention_tcgen05.cu elementwise.cu runtime.cu models.cu models_clip.cu c_api.cu c_api_models.cu host_io.cu dist_nccl.cu)
 pids=()
 for s in "${SRCS[@]}"; do
   [ -f "$s" ] || continue

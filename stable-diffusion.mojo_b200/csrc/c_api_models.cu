@@ -83,6 +83,19 @@ int32_t tsd_diffusion_forward(tsd_diffusion* d, const float* x, const float* con
   }
   return rc;
 }
+int32_t tsd_diffusion_step(tsd_diffusion* d, const float* latents, const float* context, int32_t n_ctx,
+                           const float* time, const float* noise, int32_t cfg, float cfg_scale, float sqrt_ab,
+                           float sqrt_1mab, float c0, float c1, float sigma, int32_t n, float* latents_out) {
+  if (!d) return TSD_ERR_INVALID;
+  Guard g(d->m.h);
+  const float coef[5] = {sqrt_ab, sqrt_1mab, c0, c1, sigma};
+  int rc = d->m.step_host(latents, context, n_ctx, time, noise, cfg, cfg_scale, coef, n, latents_out);
+  if (rc) {
+    cudaStreamSynchronize(d->m.c->stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
 int32_t tsd_diffusion_forward_dev(tsd_diffusion* d, const float* x, const float* context, int32_t n_ctx,
                                   const float* time, int32_t n_time, int32_t n, float* out) {
   if (!d) return TSD_ERR_INVALID;

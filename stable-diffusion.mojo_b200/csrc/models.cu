@@ -601,6 +601,8 @@ int Diffusion::create() {
   TRY(dmalloc(&ctx_in, B * cfg.context_len * cfg.context_dim));
   TRY(dmalloc(&time_in, B * 320));
   TRY(dmalloc(&temb, B * 1280 * 2));
+  TRY(dmalloc(&noise_in, B * 4 * HW));
+  TRY(dmalloc(&lat_out, B * 4 * HW));
   for (int i = 0; i < 9; ++i) {
     TRY(dmalloc(&kctx[i], B * cfg.context_len * attn[i].C));
     TRY(dmalloc(&vctx[i], B * cfg.context_len * attn[i].C));
@@ -613,7 +615,7 @@ void Diffusion::destroy() {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (graph.exec) cudaGraphExecDestroy(graph.exec);
-  float* bufs[] = {x_in, out_nchw, x_nhwc, eps_nhwc, ctx_in, time_in, temb};
+  float* bufs[] = {x_in, out_nchw, x_nhwc, eps_nhwc, ctx_in, time_in, temb, noise_in, lat_out};
   for (float* b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 9; ++i) {
@@ -915,10 +917,13 @@ int Diffusion::forward_dev(const float* x, const float* context, int n_ctx, cons
   TRY(c->check(cudaMemcpyAsync(x_in, x, n * 4 * HW * sizeof(float), kin, c->stream), "copy x"));
   TRY(c->check(cudaMemcpyAsync(time_in, time, (size_t)n_time * 320 * sizeof(float), kin, c->stream), "copy time"));
   c->arena.reset();
-  if (context) {
+  if (context && host_ptrs) {
+    TRY(upload_context_cached(context, n_ctx));
+  } else if (context) {
     TRY(c->check(cudaMemcpyAsync(ctx_in, context, (size_t)n_ctx * cfg.context_len * cfg.context_dim * sizeof(float),
                                  kin, c->stream), "copy context"));
     TRY(prepare_context(n_ctx));
+    ctx_hash_gen = -1;  // device-side context: the host-content cache no longer describes kctx/vctx
   }
   TRY(prepare_time(n_time, time_in, tbias, 0));
   LAUNCH(c, launch_nchw_to_nhwc(x_in, x_nhwc, n, 4, (int)HW, c->stream), "nchw_to_nhwc");
@@ -927,6 +932,93 @@ int Diffusion::forward_dev(const float* x, const float* context, int n_ctx, cons
   TRY(c->check(cudaMemcpyAsync(out, out_nchw, n * 4 * HW * sizeof(float), kout, c->stream), "copy out"));
   if (host_ptrs) TRY(c->check(cudaStreamSynchronize(c->stream), "diffusion forward sync"));
   return TSD_OK;
+}
+
+// 64-bit content hash of a host buffer (four independent multiply-xorshift lanes over 8-byte words: ~10 GB/s, i.e.
+// ~25 us for a 77x768 context against a 2.5 ms step)
+static uint64_t hash_bytes(const void* p, size_t nbytes) {
+  const uint64_t* w = static_cast<const uint64_t*>(p);
+  const size_t nw = nbytes / 8;
+  uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xBF58476D1CE4E5B9ull, 0x94D049BB133111EBull, 0xD6E8FEB86659FD93ull};
+  size_t i = 0;
+  for (; i + 4 <= nw; i += 4)
+    for (int k = 0; k < 4; ++k) {
+      uint64_t v = (h[k] ^ w[i + k]) * 0xFF51AFD7ED558CCDull;
+      h[k] = v ^ (v >> 29);
+    }
+  for (; i < nw; ++i) {
+    uint64_t v = (h[0] ^ w[i]) * 0xFF51AFD7ED558CCDull;
+    h[0] = v ^ (v >> 29);
+  }
+  uint64_t tail = 0;
+  memcpy(&tail, static_cast<const uint8_t*>(p) + nw * 8, nbytes - nw * 8);
+  uint64_t r = (h[0] ^ tail) * 0xC4CEB9FE1A85EC53ull;
+  for (int k = 1; k < 4; ++k) r = (r ^ (r >> 31) ^ h[k]) * 0xC4CEB9FE1A85EC53ull;
+  return r ^ (r >> 33) ^ nbytes;
+}
+
+int Diffusion::upload_context_cached(const float* context_host, int n_ctx) {
+  const size_t bytes = (size_t)n_ctx * cfg.context_len * cfg.context_dim * sizeof(float);
+  const uint64_t hsh = hash_bytes(context_host, bytes);
+  if (ctx_ready && ctx_hash_gen == ps.gen && ctx_hash_n == n_ctx && ctx_n == n_ctx && ctx_hash == hsh) return TSD_OK;
+  TRY(c->check(cudaMemcpyAsync(ctx_in, context_host, bytes, cudaMemcpyHostToDevice, c->stream), "copy context"));
+  TRY(prepare_context(n_ctx));
+  ctx_hash = hsh;
+  ctx_hash_n = n_ctx;
+  ctx_hash_gen = ps.gen;
+  return TSD_OK;
+}
+
+int Diffusion::step_host(const float* latents, const float* context, int n_ctx, const float* time, const float* noise,
+                         int use_cfg, float cfg_scale, const float coef[5], int n, float* latents_out) {
+  if (!ps.loaded) return c->fail(TSD_ERR_STATE, "diffusion: step before load_weights / init_random");
+  const int nb = use_cfg ? 2 * n : n;
+  if (n <= 0 || nb > cfg.max_batch) return c->fail(TSD_ERR_INVALID, "diffusion step: batch (x2 with cfg) exceeds max_batch");
+  if (!latents || !time || !latents_out) return c->fail(TSD_ERR_INVALID, "diffusion step: null buffer");
+  const int groups = use_cfg ? 2 : 1;
+  if (context && !(n_ctx == groups || n_ctx == nb))
+    return c->fail(TSD_ERR_INVALID, "diffusion step: n_ctx must be (1|n) without cfg, (2|2n) with cfg (cond rows, then uncond rows)");
+  if (!context && !ctx_ready) return c->fail(TSD_ERR_STATE, "diffusion step: no context set");
+  cudaSetDevice(c->device);
+  const size_t need = workspace_bytes(nb);
+  if (need == 0) return TSD_ERR_OOM;
+  if (need > c->arena.capacity()) {
+    cudaStreamSynchronize(c->stream);
+    if (c->arena.reserve(need) != TSD_OK) return c->fail(TSD_ERR_OOM, "diffusion: workspace allocation failed");
+  }
+  cudaStream_t s = c->stream;
+  const size_t HW = (size_t)cfg.latent_h * cfg.latent_w, n_lat = (size_t)n * 4 * HW;
+  TRY(c->check(cudaMemcpyAsync(x_in, latents, n_lat * 4, cudaMemcpyHostToDevice, s), "copy latents"));
+  if (use_cfg) TRY(c->check(cudaMemcpyAsync(x_in + n_lat, x_in, n_lat * 4, cudaMemcpyDeviceToDevice, s), "copy latents"));
+  TRY(c->check(cudaMemcpyAsync(time_in, time, 320 * sizeof(float), cudaMemcpyHostToDevice, s), "copy time"));
+  if (noise) TRY(c->check(cudaMemcpyAsync(noise_in, noise, n_lat * 4, cudaMemcpyHostToDevice, s), "copy noise"));
+  c->arena.reset();
+  if (context) {
+    if (n_ctx == 1 || n_ctx == nb) {
+      TRY(upload_context_cached(context, n_ctx));
+    } else {
+      // (cond, uncond) shared by all images: one row per UNet batch entry, cond rows first
+      const size_t row = (size_t)cfg.context_len * cfg.context_dim;
+      const uint64_t hsh = hash_bytes(context, 2 * row * sizeof(float)) ^ 0x5bd1e995u;
+      if (!(ctx_ready && ctx_hash_gen == ps.gen && ctx_hash_n == -nb && ctx_n == nb && ctx_hash == hsh)) {
+        for (int i = 0; i < nb; ++i)
+          TRY(c->check(cudaMemcpyAsync(ctx_in + (size_t)i * row, context + (size_t)(i / n) * row, row * sizeof(float),
+                                       cudaMemcpyHostToDevice, s), "copy context"));
+        TRY(prepare_context(nb));
+        ctx_hash = hsh;
+        ctx_hash_n = -nb;
+        ctx_hash_gen = ps.gen;
+      }
+    }
+  }
+  TRY(prepare_time(1, time_in, tbias, 0));
+  LAUNCH(c, launch_nchw_to_nhwc(x_in, x_nhwc, nb, 4, (int)HW, s), "nchw_to_nhwc");
+  TRY(run_unet_graph(nb, ctx_n, 1));
+  LAUNCH(c, launch_nhwc_to_nchw(eps_nhwc, out_nchw, nb, 4, (int)HW, s), "nhwc_to_nchw");
+  LAUNCH(c, launch_ddpm_step(x_in, out_nchw, use_cfg ? out_nchw + n_lat : nullptr, cfg_scale, noise ? noise_in : nullptr,
+                             coef[0], coef[1], coef[2], coef[3], coef[4], lat_out, (long long)n_lat, s), "ddpm_step");
+  TRY(c->check(cudaMemcpyAsync(latents_out, lat_out, n_lat * 4, cudaMemcpyDeviceToHost, s), "copy latents out"));
+  return c->check(cudaStreamSynchronize(s), "diffusion step sync");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1386,6 +1478,7 @@ int generate_latents(Diffusion& m, const tsd_loop_params& lp, const float* laten
     }
   }
   c->arena.reset();
+  m.ctx_hash_gen = -1;  // kctx / vctx no longer belong to the context the host-buffer entry points cached
   TRY(m.prepare_context(n_ctx_eff));
   // time embedding MLP and the 9 block projections for every step at once (M = steps)
   {

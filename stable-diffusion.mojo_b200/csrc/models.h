@@ -122,6 +122,12 @@ struct Diffusion {
   int ws_epoch = -1;
   bool ctx_ready = false;
   int ctx_n = 0;
+  // host-buffer entry points: the K/V projections of a context are kept while the caller keeps passing the same
+  // bytes (the reference rebuilds everything per call, pipeline.mojo:83-122; its loop passes one context for all steps)
+  uint64_t ctx_hash = 0;
+  int ctx_hash_n = 0, ctx_hash_gen = -1;
+  float* noise_in = nullptr;  // [max_batch][4][H][W] staging of tsd_diffusion_step
+  float* lat_out = nullptr;
 
   int create();
   void destroy();
@@ -133,6 +139,11 @@ struct Diffusion {
   int forward_dev(const float* x, const float* context, int n_ctx, const float* time, int n_time, int n,
                   float* out, bool host_ptrs);
   int run_unet_graph(int n, int n_ctx, int n_time);
+  // context rows (host) -> ctx_in + kctx/vctx unless the same bytes are already projected
+  int upload_context_cached(const float* context_host, int n_ctx);
+  // one iteration of the reference loop (pipeline.mojo:107-121): Diffusion.forward (x2 with CFG), combine, DDPMSampler.step
+  int step_host(const float* latents, const float* context, int n_ctx, const float* time, const float* noise, int cfg,
+                float cfg_scale, const float coef[5], int n, float* latents_out);
 };
 
 struct Decoder {

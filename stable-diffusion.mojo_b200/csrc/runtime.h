@@ -115,6 +115,7 @@ struct Ctx {
   int sm_count = 148;
   int softmax_axis = 0;     // 0 = query axis (reference Softmax(dim=2), Q3) ; 1 = key axis
   int fused_attention = 1;  // 1 = tcgen05 fused kernel ; 0 = GEMM + softmax + GEMM
+  int attn_v2 = 1;          // fused attention: 1 = software-pipelined softmax role (attn2_kernel) where the shape allows, 0 = attn_kernel
   int layernorm_mode = 0;   // 0 = global statistics (reference, Q5) ; 1 = per token
   int force_bn = 0, force_splits = 0;  // test/tuning overrides for the GEMM tile heuristic
   int force_stages = 0;     // tuning: operand ring depth override

@@ -128,6 +128,7 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_diffusion_get_param", i32, vp, i32, fp)
     sig("tsd_diffusion_forward", i32, vp, fp, fp, i32, fp, i32, i32, fp)
     sig("tsd_diffusion_forward_dev", i32, vp, fp, fp, i32, fp, i32, i32, fp)
+    sig("tsd_diffusion_step", i32, vp, fp, fp, i32, fp, fp, i32, f32, f32, f32, f32, f32, f32, i32, fp)
     sig("tsd_diffusion_profile", i32, vp, fp, fp, i32, fp, i32, i32, fp, c_double_p, c_double_p,
         c_i64_p)
     i32p = C.POINTER(C.c_int32)
@@ -180,6 +181,14 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_clip_forward", i32, vp, vp, i32, fp)
     sig("tsd_clip_forward_dev", i32, vp, vp, i32, fp)
     sig("tsd_generate_latents", i32, vp, C.POINTER(LoopParams), fp, fp, i32, i32, fp)
+    sig("tsd_dist_unique_id", i32, C.c_char_p)
+    sig("tsd_dist_init", i32, vp, i32, i32, C.c_char_p, C.c_char_p, C.POINTER(vp))
+    sig("tsd_dist_shutdown", i32, vp)
+    sig("tsd_dist_rank", i32, vp)
+    sig("tsd_dist_size", i32, vp)
+    sig("tsd_dist_broadcast_context", i32, vp, fp, i64, i32)
+    sig("tsd_dist_gather", i32, vp, fp, i64, fp, i32)
+    sig("tsd_dist_generate", i32, vp, vp, C.POINTER(LoopParams), fp, fp, i32, i32, i32, fp)
     sig("tsd_bench_gemm", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)
     sig("tsd_bench_attention", i32, vp, i32, i32, i32, i32, i32, c_double_p)
     sig("tsd_bench_conv", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)

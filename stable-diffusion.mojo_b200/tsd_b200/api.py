@@ -309,6 +309,29 @@ class Diffusion(_Model):
                                                       time.shape[0], x.shape[0], _p(out)))
         return out[0] if squeeze else out
 
+    def step(self, latents, context, time, coef, noise=None, uncond_context=None, cfg_scale=7.5):
+        """tsd_diffusion_step: one iteration of the reference loop (pipeline.mojo:107-121) in one call - forward
+        (x2 with CFG), combine, DDPMSampler.step.  latents (n,4,H,W); context (77,768) or (n,77,768); coef = the five
+        schedule scalars of the step; noise like latents or None; returns the new latents."""
+        latents = _f32(latents)
+        squeeze = latents.ndim == 3
+        if squeeze:
+            latents = latents[None]
+            noise = None if noise is None else _f32(noise)[None]
+        context = _f32(context)
+        if context.ndim == 2:
+            context = context[None]
+        cfg = uncond_context is not None
+        if cfg:
+            u = _f32(uncond_context)
+            context = np.ascontiguousarray(np.concatenate([context, u[None] if u.ndim == 2 else u], axis=0))
+        nz = None if noise is None else _f32(noise)
+        out = np.empty_like(latents)
+        self.ctx._ck(self.ctx.L.tsd_diffusion_step(self.m, _p(latents), _p(context), context.shape[0],
+                                                   _p(_f32(time).reshape(320)), _p(nz), int(cfg), float(cfg_scale),
+                                                   *[float(v) for v in coef], latents.shape[0], _p(out)))
+        return out[0] if squeeze else out
+
     def forward_dev(self, x_dev, ctx_dev, n_ctx, time_dev, n_time, n, out_dev):
         """tsd_diffusion_forward_dev on raw device addresses (ints), asynchronous on the context's
         stream.  ctx_dev = None reuses the context (and its hoisted K/V projections) of the last call."""

@@ -112,3 +112,66 @@ def barrier():
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+class DistC:
+    """The C ABI's own multi-GPU entry points (tsd_dist_*, csrc/dist_nccl.cu): one NCCL communicator per process, bound at
+    run time, no torch.distributed involved.  `id_bytes` is the 128-byte id of `DistC.unique_id()` (rank 0) handed to the
+    other ranks by the host program, or None with a `rendezvous` file path every rank can reach."""
+
+    def __init__(self, ctx, nranks: int, rank: int, id_bytes: bytes | None = None, rendezvous: str | None = None):
+        import ctypes as C
+        self.ctx, self.nranks, self.rank = ctx, nranks, rank
+        d = C.c_void_p()
+        idp = None if id_bytes is None else C.c_char_p(bytes(id_bytes))
+        ctx._ck(ctx.L.tsd_dist_init(ctx.h, nranks, rank, idp, None if rendezvous is None else rendezvous.encode(), C.byref(d)))
+        self.d = d
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _lib
+        buf = C.create_string_buffer(128)
+        rc = _lib.lib().tsd_dist_unique_id(buf)
+        if rc != 0:
+            raise _lib.TsdError(rc, "tsd_dist_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def broadcast_context(self, context: np.ndarray | None, shape, root: int = 0) -> np.ndarray:
+        buf = np.ascontiguousarray(context, np.float32) if self.rank == root else np.empty(tuple(shape), np.float32)
+        if tuple(buf.shape) != tuple(shape):
+            raise ValueError("context shape mismatch")
+        self.ctx._ck(self.ctx.L.tsd_dist_broadcast_context(self.d, buf.ctypes.data, buf.size, root))
+        return buf
+
+    def gather(self, local: np.ndarray, root: int = 0) -> np.ndarray | None:
+        local = np.ascontiguousarray(local, np.float32)
+        out = np.empty((self.nranks,) + local.shape, np.float32) if self.rank == root else None
+        self.ctx._ck(self.ctx.L.tsd_dist_gather(self.d, local.ctypes.data, local.size,
+                                                None if out is None else out.ctypes.data, root))
+        return out
+
+    def generate(self, diffusion, latents, context, timesteps, time_emb, coef, noise=None, cfg=False, cfg_scale=7.5,
+                 n_ctx: int = 1, root: int = 0):
+        """tsd_dist_generate: the context rows (valid on `root`) are broadcast, then this rank's latents are denoised."""
+        import ctypes as C
+        from . import _lib
+        latents = np.ascontiguousarray(latents, np.float32)
+        row = (77, 768)
+        cbuf = np.ascontiguousarray(context, np.float32) if self.rank == root else np.empty((n_ctx,) + row, np.float32)
+        timesteps = np.ascontiguousarray(timesteps, np.int32)
+        time_emb = np.ascontiguousarray(time_emb, np.float32)
+        coef = np.ascontiguousarray(coef, np.float32)
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+        lp = _lib.LoopParams(len(timesteps), int(cfg), float(cfg_scale), timesteps.ctypes.data_as(_lib.c_i32_p),
+                             time_emb.ctypes.data_as(_lib.c_float_p), coef.ctypes.data_as(_lib.c_float_p),
+                             None if nz is None else nz.ctypes.data_as(_lib.c_float_p))
+        out = np.empty_like(latents)
+        self.ctx._ck(self.ctx.L.tsd_dist_generate(self.d, diffusion.m, C.byref(lp), latents.ctypes.data, cbuf.ctypes.data,
+                                                  cbuf.shape[0], latents.shape[0], root, out.ctypes.data))
+        return out, cbuf
+
+    def close(self):
+        if getattr(self, "d", None):
+            self.ctx.L.tsd_dist_shutdown(self.d)
+            self.d = None

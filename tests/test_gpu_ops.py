@@ -183,6 +183,52 @@ def test_attention_core(ctx, h, tq, tk, d, axis):
     assert relerr(got, ops.attention_core(q, k, v)) < TOL_TF32
 
 
+@pytest.mark.parametrize("axis", ["query", "key"])
+@pytest.mark.parametrize("tk", [4096, 77])
+@pytest.mark.parametrize("d", [40, 80, 160])
+def test_attention_core_sweep_shapes(ctx, d, tk, axis):
+    """BASELINE configs[4] shapes: h = 8, Tq = 4096, Tk in {4096, 77}, d in {40, 80, 160}, both softmax axes, against
+    the fp64 oracle (helpers/attention.mojo:46-62); the T = 4096 self-attention cases run on the software-pipelined
+    attn2_kernel, which is also compared with the first-generation kernel."""
+    h, tq = 8, 4096
+    rng = np.random.default_rng(d * 7 + tk)
+    q = rng.standard_normal((h, tq, d), dtype=np.float32)
+    k = rng.standard_normal((h, tk, d), dtype=np.float32)
+    v = rng.standard_normal((h, tk, d), dtype=np.float32)
+    ops = O.Ops("np", np.float64, O.Switches(softmax_axis=axis))
+    ref = ops.attention_core(q, k, v)
+    ctx.set_option("softmax_axis", 0 if axis == "query" else 1)
+    try:
+        got = ctx.attention_core(q, k, v)
+        ctx.set_option("attn_v2", 0)
+        got_v1 = ctx.attention_core(q, k, v)
+    finally:
+        ctx.set_option("attn_v2", 1)
+        ctx.set_option("softmax_axis", 0)
+    e, e1 = relerr(got, ref), relerr(got_v1, ref)
+    print(f"attention core h=8 tq=4096 tk={tk} d={d} axis={axis}: rel_linf {e:.2e} (v1 kernel {e1:.2e})")
+    assert e < TOL_TF32 and e1 < TOL_TF32
+    assert relerr(got, got_v1) < 1e-4    # same arithmetic, different instruction schedule
+
+
+def test_attention_core_dev_entry(ctx):
+    """tsd_attention_core_dev (device pointers, asynchronous) and tsd_bench_attention."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(3)
+    h, t, d = 8, 512, 40
+    q, k, v = (rng.standard_normal((h, t, d), dtype=np.float32) for _ in range(3))
+    dq, dk, dv = (torch.from_numpy(a).cuda() for a in (q, k, v))
+    out = torch.empty((t, h * d), device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    ctx._ck(ctx.L.tsd_attention_core_dev(ctx.h, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), h, t, t, d, out.data_ptr()))
+    ctx.synchronize()
+    assert relerr(out.cpu().numpy(), ctx.attention_core(q, k, v)) == 0.0
+    ms = C.c_double()
+    ctx._ck(ctx.L.tsd_bench_attention(ctx.h, h, t, t, d, 3, C.byref(ms)))
+    assert 0.0 < ms.value < 50.0
+
+
 def test_self_and_cross_attention(ctx, ops):
     rng = np.random.default_rng(8)
     t, c, hd = 256, 320, 8
