@@ -226,3 +226,34 @@ def test_loop64_golden_first_step_pins_the_oracle():
     lat = sm.step(t, ops.arr(x), eps, ops.arr(noise[0]))
     assert np.abs(lat - g["lat_step1"]).max() < 1e-9 * np.abs(g["lat_step1"]).max()
     assert g["lat_step20"].shape == (4, 64, 64) and g["cfg_lat_step4"].shape == (4, 64, 64)
+
+
+def test_mojo_shim_binds_declared_symbols():
+    """mojo/*.mojo cannot be compiled here (no Mojo toolchain): check instead that every `tsd_*` entry point the shim binds
+    is declared in include/tsd_b200.h, exported by the library, and bound with the header's argument count."""
+    import glob
+    import re
+    header = open(_lib.HEADER).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(tsd_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    L = _lib.lib()
+    bound = {}
+    for path in glob.glob(os.path.join(ROOT, "mojo", "**", "*.mojo"), recursive=True):
+        text = open(path).read()
+        for m in re.finditer(r"get_function\[fn \((.*?)\) -> \w+\]\(\s*\"(tsd_[a-z0-9_]+)\"", text, flags=re.S):
+            args = m.group(1).strip()
+            # Pointer[Handle] etc. contain no commas; count top-level commas only
+            depth, n = 0, 1 if args else 0
+            for ch in args:
+                depth += ch == "["
+                depth -= ch == "]"
+                n += ch == "," and depth == 0
+            bound[m.group(2)] = n
+    assert len(bound) >= 25, sorted(bound)
+    for name, n in sorted(bound.items()):
+        assert name in protos, f"{name} is bound by the Mojo shim but not declared in the header"
+        assert hasattr(L, name), name
+        assert protos[name] == n, f"{name}: header has {protos[name]} arguments, the shim binds {n}"
