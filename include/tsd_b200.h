@@ -357,6 +357,10 @@ int32_t tsd_bench_conv(tsd_ctx* ctx, int32_t n, int32_t h, int32_t w, int32_t ci
  * context's softmax_axis / fused_attention options; ms per op (both launches of the fused kernel). */
 int32_t tsd_bench_attention(tsd_ctx* ctx, int32_t h, int32_t tq, int32_t tk, int32_t d, int32_t iters,
                             double* ms_out);
+/* GroupNorm(G, C) + SiLU on (n, C, H, W) device data: mode 0 stand-alone, 1 normalise-only over the partial statistics a
+ * producing 3x3 convolution left (convolution untimed), 2 convolution + norm as a pair */
+int32_t tsd_bench_norm(tsd_ctx* ctx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t g, int32_t mode,
+                       int32_t iters, double* ms_out);
 
 #if defined(TSD_BUILD)
 #pragma GCC visibility pop

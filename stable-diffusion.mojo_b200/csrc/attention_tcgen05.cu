@@ -449,7 +449,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t x_full, y_full[2], y_empty[2], v_full[2], v_empty[2];
-  __shared__ __align__(8) uint64_t s_full[2], s_free[2], p_full[2], o_full;
+  __shared__ __align__(8) uint64_t s_full[3], s_free[3], p_full[3], o_full;  // three S / P buffers in tensor memory
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float2 comb[ATT_BM];
   constexpr bool apply = MODE == ATT_APPLY;
@@ -481,6 +481,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       mbar_init(&y_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_free[s], ATT_SM_THREADS);
       mbar_init(&p_full[s], ATT_SM_THREADS);
@@ -501,7 +503,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();               // Q/K/V and the statistics come from predecessor kernels
   pdl_launch_dependents();  // resources are held: the next kernel may start its prologue
-  const uint32_t tmem_o = tmem_base + 256u;  // S0: cols [0,128), S1: [128,256), O: [256, 256+dpad)
+  // S / P buffer b of a tile: columns [b * BN, (b + 1) * BN), b = tile % 3; O: [3 * BN, 3 * BN + dpad)
+  const uint32_t tmem_o = tmem_base + (uint32_t)(3 * BN);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -509,67 +512,106 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       mbar_arrive_expect_tx(&x_full, x_bytes);
       for (int bx = 0; bx < p.nbox; ++bx)
         tma_load_3d_s(xs + bx * (ATT_BM * ATT_BOX_ROW_BYTES), &tmX, &x_full, bx * 32, x0, p.x_shared ? h : bh);
+      // K tiles run one ahead of V tiles: S = Q K^T of tile it+1 is issued while P V of tile it-2 is still waiting
+      // for its softmax, so the K load must never queue behind a V slot that frees late
+      auto load_y = [&](int it) {
+        const int st = it % p.sY;
+        const uint32_t ph = (uint32_t)(it / p.sY) & 1u;
+        mbar_wait(&y_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&y_full[st], ystage);
+        for (int bx = 0; bx < p.nbox; ++bx)
+          tma_load_3d_s(ys + st * ystage + bx * ybox, &tmY, &y_full[st], bx * 32, (it0 + it) * BN, p.y_shared ? h : bh);
+      };
+      if (n_it > 0) load_y(0);
       for (int it = 0; it < n_it; ++it) {
-        const int yrow = (it0 + it) * BN;
-        {
-          const int st = it % p.sY;
-          const uint32_t ph = (uint32_t)(it / p.sY) & 1u;
-          mbar_wait(&y_empty[st], ph ^ 1u);
-          mbar_arrive_expect_tx(&y_full[st], ystage);
-          for (int bx = 0; bx < p.nbox; ++bx)
-            tma_load_3d_s(ys + st * ystage + bx * ybox, &tmY, &y_full[st], bx * 32, yrow, p.y_shared ? h : bh);
-        }
+        if (it + 1 < n_it) load_y(it + 1);
         if (apply) {
           const int st = it % p.sV;
           const uint32_t ph = (uint32_t)(it / p.sV) & 1u;
           mbar_wait(&v_empty[st], ph ^ 1u);
           mbar_arrive_expect_tx(&v_full[st], ystage);
           for (int bx = 0; bx < p.nbox; ++bx)
-            tma_load_3d_s(vs + st * ystage + bx * ybox, &tmV, &v_full[st], bx * 32, yrow, p.v_shared ? h : bh);
+            tma_load_3d_s(vs + st * ystage + bx * ybox, &tmV, &v_full[st], bx * 32, (it0 + it) * BN, p.v_shared ? h : bh);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // A lone thread pays 4-6 cycles per dependent instruction and ~90 per mbarrier try_wait: with descriptors rebuilt
+    // per MMA this role took ~100 cycles per instruction (21 per 128 x 128 tile at d = 40) and bounded the apply pass
+    // (trace: the softmax warps waited 625 of 2146 cycles per tile for their scores).  Descriptors are therefore built
+    // once and advanced by adds of compile-time constants; the K loops are unrolled.
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc(UMMA_FMT_TF32, ATT_BM, (uint32_t)BN, 0, 0);
       const uint32_t idesc_o = umma_idesc(UMMA_FMT_TF32, ATT_BM, (uint32_t)p.dpad, 0, 1);  // B (= V) MN-major
       const int ksteps = p.d >> 3;
       constexpr int pv_steps = BN >> 3;
-      auto issue_pv = [&](int j) {
-        const int bj = j & 1;
-        const int st = j % p.sV;
-        mbar_wait(&p_full[bj], (uint32_t)(j >> 1) & 1u);
-        mbar_wait(&v_full[st], (uint32_t)(j / p.sV) & 1u);
+      // descriptor start-address fields are in 16-byte units
+      const uint64_t xdesc0 = umma_smem_desc(xs, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint64_t ydesc0 = umma_smem_desc(ys, 16, 1024, UMMA_SWIZZLE_128B);
+      // V tile: [BN keys][32 floats] boxes read MN-major.  For 32-bit MN-major operands the only legal layout is
+      // SWIZZLE_128B with 32 B atoms: 4-key groups of 512 B (SBO), N atoms (boxes of 32 floats) ybox apart (LBO); one
+      // K = 8 step spans two groups (1024 B).
+      const uint64_t vdesc0 = umma_smem_desc(vs, ybox, 512, UMMA_SWIZZLE_128B_BASE32B);
+      const uint32_t stage_step = ystage >> 4, ybox_step = ybox >> 4;
+      constexpr uint32_t xbox_step = (ATT_BM * ATT_BOX_ROW_BYTES) >> 4;
+      auto issue_pv = [&](int j, int bj, int stv, uint32_t par_p, uint32_t par_v) {
+        mbar_wait(&p_full[bj], par_p);
+        mbar_wait(&v_full[stv], par_v);
         tc_fence_after_sync();
-        const uint32_t vb = vs + st * ystage;
-#pragma unroll 4
-        for (int ks = 0; ks < pv_steps; ++ks) {
-          const uint64_t bdesc = umma_smem_desc(vb + ks * 1024, ybox, 512, UMMA_SWIZZLE_128B_BASE32B);
-          umma_tf32_ts(tmem_o, tmem_base + (uint32_t)(bj * 128 + ks * 8), bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(&v_empty[st]);
+        const uint64_t vd = vdesc0 + (uint64_t)((uint32_t)stv * stage_step);
+        const uint32_t pa = tmem_base + (uint32_t)(bj * BN);
+        umma_tf32_ts(tmem_o, pa, vd, idesc_o, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 1; ks < pv_steps; ++ks) umma_tf32_ts(tmem_o, pa + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 64), idesc_o, 1u);
+        umma_commit(&v_empty[stv]);
       };
       mbar_wait(&x_full, 0);
+      // running tile state: S buffer b = it % 3 with its barrier parity, ring slots and parities of K (sY) and V (sV)
+      int b = 0, sty = 0;
+      uint32_t par_s = 0, par_y = 0;
+      int pj = 0, pb = 0, stv = 0;      // P V bookkeeping of tile pj = it - 2
+      uint32_t par_p = 0, par_v = 0;
+      auto advance_pv = [&]() {
+        ++pj;
+        if (++pb == 3) { pb = 0; par_p ^= 1u; }
+        if (++stv == p.sV) { stv = 0; par_v ^= 1u; }
+      };
       for (int it = 0; it < n_it; ++it) {
-        const int b = it & 1;
-        const int st = it % p.sY;
-        mbar_wait(&y_full[st], (uint32_t)(it / p.sY) & 1u);
-        if (!apply && it >= 2) mbar_wait(&s_free[b], (uint32_t)((it >> 1) - 1) & 1u);
+        // Three S buffers: S of tile `it` is issued as soon as P V of tile it-3 has been (the tensor pipe runs in
+        // order), two tiles ahead of the softmax that consumes it - the P V of a tile, which has to wait for that
+        // tile's exponentials, is then never on the path to the next tile's scores
+        mbar_wait(&y_full[sty], par_y);
+        if (!apply && it >= 3) mbar_wait(&s_free[b], par_s ^ 1u);
         tc_fence_after_sync();
-        const uint32_t yb = ys + st * ystage;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks & 3) * 32u;
-          const uint64_t adesc = umma_smem_desc(xs + (ks >> 2) * (ATT_BM * ATT_BOX_ROW_BYTES) + off, 16, 1024, UMMA_SWIZZLE_128B);
-          const uint64_t bdesc = umma_smem_desc(yb + (ks >> 2) * ybox + off, 16, 1024, UMMA_SWIZZLE_128B);
-          umma_tf32(tmem_base + (uint32_t)(b * 128), adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        const uint64_t yd = ydesc0 + (uint64_t)((uint32_t)sty * stage_step);
+        const uint32_t sd = tmem_base + (uint32_t)(b * BN);
+        int kleft = ksteps;
+        for (int bx = 0; bx < p.nbox; ++bx, kleft -= 4) {
+          const uint64_t xa = xdesc0 + (uint64_t)((uint32_t)bx * xbox_step), ya = yd + (uint64_t)((uint32_t)bx * ybox_step);
+          if (kleft >= 4) {
+            umma_tf32(sd, xa, ya, idesc_s, bx > 0 ? 1u : 0u);
+            umma_tf32(sd, xa + 2, ya + 2, idesc_s, 1u);
+            umma_tf32(sd, xa + 4, ya + 4, idesc_s, 1u);
+            umma_tf32(sd, xa + 6, ya + 6, idesc_s, 1u);
+          } else {
+            for (int kk = 0; kk < kleft; ++kk) umma_tf32(sd, xa + (uint64_t)(2 * kk), ya + (uint64_t)(2 * kk), idesc_s, (bx > 0 || kk > 0) ? 1u : 0u);
+          }
         }
-        umma_commit(&y_empty[st]);
+        umma_commit(&y_empty[sty]);
         umma_commit(&s_full[b]);
-        if (apply && it >= 1) issue_pv(it - 1);
+        if (++b == 3) { b = 0; par_s ^= 1u; }
+        if (++sty == p.sY) { sty = 0; par_y ^= 1u; }
+        if (apply && it >= 2) {
+          issue_pv(pj, pb, stv, par_p, par_v);
+          advance_pv();
+        }
       }
       if (apply) {
-        issue_pv(n_it - 1);
+        while (pj < n_it) {
+          issue_pv(pj, pb, stv, par_p, par_v);
+          advance_pv();
+        }
         umma_commit(&o_full);
       }
     }
@@ -594,11 +636,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (k == 0) {
         long long t0 = 0;
         if (tr) t0 = clock64();
-        mbar_wait(&s_full[it & 1], (uint32_t)(it >> 1) & 1u);
+        mbar_wait(&s_full[it % 3], (uint32_t)(it / 3) & 1u);
         tc_fence_after_sync();
         if (tr) t_wait_s += clock64() - t0;
       }
-      tmem_ld32(lane_base + (uint32_t)((it & 1) * 128 + cb + k * 32), buf);
+      tmem_ld32(lane_base + (uint32_t)((it % 3) * BN + cb + k * 32), buf);
     };
     auto ld_wait = [&](uint32_t (&buf)[32]) {
       long long t0 = 0;
@@ -635,7 +677,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         l += (a0 + a1) + (a2 + a3);
         if (k == NCH - 1) {
           tc_fence_before_sync();
-          mbar_arrive(&s_free[it & 1]);  // this thread's reads of S[it & 1] are complete
+          mbar_arrive(&s_free[it % 3]);  // this thread's reads of this tile's S are complete
         }
       };
       uint32_t A[32], B[32];
@@ -702,13 +744,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             v[4 * j4 + 3] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w)));
           }
         }
-        tmem_st32(lane_base + (uint32_t)((it & 1) * 128 + cb + k * 32), v);
+        tmem_st32(lane_base + (uint32_t)((it % 3) * BN + cb + k * 32), v);
         if (k == NCH - 1) {
           long long t0 = 0;
           if (tr) t0 = clock64();
           tmem_st_wait();
           tc_fence_before_sync();
-          mbar_arrive(&p_full[it & 1]);
+          mbar_arrive(&p_full[it % 3]);
           if (tr) t_wait_st += clock64() - t0;
         }
       };
@@ -743,7 +785,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const int ob = half ? e0 : 0, oe = half ? p.dpad : e0;
       for (int c0 = ob; c0 < oe; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
+        tmem_ld16(lane_base + (uint32_t)(3 * BN + c0), v);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
@@ -843,8 +885,14 @@ cudaError_t launch_attn2(const CUtensorMap& tmX, const CUtensorMap& tmY, const C
 #undef TSD_A2
 }
 
-// v2 takes whole tiles of 64 or 128 streamed rows
-bool attn2_ok(const AttnPlan& pl, int Ty) { return (pl.BN == 64 || pl.BN == 128) && Ty % pl.BN == 0; }
+// v2 takes whole tiles of 64 or 128 streamed rows; its three S / P buffers and the O tile must fit the 512 columns
+bool attn2_ok(const AttnPlan& pl, int Ty) { return (pl.BN == 64 || pl.BN == 128) && Ty % pl.BN == 0 && 3 * pl.BN + pl.dpad <= 512; }
+int attn2_tmem_cols(const AttnPlan& pl, bool apply) {
+  const int need = 3 * pl.BN + (apply ? pl.dpad : 0);
+  int c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
 
 }  // namespace
 
@@ -920,6 +968,7 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
     p.part_out = part;
     p.part_stride = (long long)BH * Tx;
     const bool v2s = attn_v2 && attn2_ok(sp, Ty);
+    if (v2s) p.tmem_cols = attn2_tmem_cols(sp, false);
     rc = c->check(v2s ? launch_attn2(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream, attn_trace)
                       : launch_attn(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream),
                   "attn_kernel (stats) launch");
@@ -970,6 +1019,7 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
         return TSD_OK;
       }
     }
+    if (v2a && !q.debug) q.tmem_cols = attn2_tmem_cols(ap, true);
     rc = c->check(v2a && !q.debug ? launch_attn2(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream, attn_trace)
                                   : launch_attn(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream),
                   "attn_kernel (apply) launch");

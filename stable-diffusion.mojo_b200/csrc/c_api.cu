@@ -689,6 +689,55 @@ int32_t tsd_bench_attention(tsd_ctx* h, int32_t heads, int32_t tq, int32_t tk, i
   return rc;
 }
 
+// Lab: GroupNorm(+SiLU) consumer timed alone.  mode 0: stand-alone (statistics + normalise in one fused launch);
+// mode 1: normalise-only pass over producer-side partial statistics left by a 3x3 convolution (run once, untimed);
+// mode 2: the producer convolution + its consumer norm, timed as a pair.
+int32_t tsd_bench_norm(tsd_ctx* h, int32_t n, int32_t H, int32_t W, int32_t C, int32_t G, int32_t mode, int32_t iters,
+                       double* ms_out) {
+  if (!h || !ms_out || n <= 0 || H <= 0 || W <= 0 || C <= 0 || G <= 0 || iters <= 0) return TSD_ERR_INVALID;
+  const size_t nx = (size_t)n * H * W * C, nw = (size_t)C * 9 * C;
+  HostCall hc(h, (3 * nx + nw + C) * 4 + (size_t)34 * nx * 4 + (256u << 20));
+  float* x = hc.dev(nx);
+  float* w = hc.dev(nw);
+  float* y = hc.dev(nx);
+  float* o = hc.dev(nx);
+  float* bias = hc.dev(C);
+  if (hc.rc) return hc.finish();
+  Ctx* c = hc.c;
+  fill_uniform(c, x, nx, 1, 1.0f);
+  fill_uniform(c, w, nw, 2, 0.02f);
+  fill_uniform(c, bias, C, 3, 0.05f);
+  NormHint nh;
+  nh.G = G; nh.eps = 1e-5f; nh.imgs = n;
+  nh.scratch_elems = norm_scratch_elems(n, (long long)H * W, C, G);
+  nh.scratch = reinterpret_cast<float2*>(hc.dev(2 * nh.scratch_elems));
+  ConvArgs a;
+  a.x = x; a.N = n; a.H = H; a.W = W; a.Cin = C; a.Cout = C; a.k = 3; a.pad = 1; a.stride = 1;
+  a.w = w; a.bias = bias; a.out = y; a.nh = mode >= 1 ? &nh : nullptr;
+  auto consumer = [&]() { return op_group_norm(c, y, o, n, H, W, C, G, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1, mode >= 1 ? nh.ready() : nullptr, nullptr); };
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 3 && !hc.rc; ++i) {
+    hc.run(op_conv2d(c, a));
+    hc.run(consumer());
+  }
+  launch_spin((long long)iters * 20000, c->stream);
+  cudaEventRecord(e0, c->stream);
+  for (int i = 0; i < iters && !hc.rc; ++i) {
+    if (mode == 2) hc.run(op_conv2d(c, a));
+    hc.run(consumer());
+  }
+  cudaEventRecord(e1, c->stream);
+  int rc = hc.finish();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
+  return rc;
+}
+
 int32_t tsd_bench_conv(tsd_ctx* h, int32_t n, int32_t H, int32_t W, int32_t cin, int32_t cout,
                        int32_t k, int32_t stride, int32_t force_bn, int32_t force_splits,
                        int32_t iters, double* ms_out) {

@@ -555,7 +555,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       int n_end = n0 + out_cols;
       if (n_end > n_valid) n_end = n_valid;
       const int g_hi = (n_end - 1) / cpg;
-      float2* dst = p.ns.partial + ((long long)blockIdx.x * p.ns.n_tiles + nt) * p.ns.lg;
+      float2* dst = p.ns.partial + (long long)nt * p.ns.lg * p.ns.slabs_total + blockIdx.x;  // [n-tile][group][slab]
       for (int g = g_lo + ew; g <= g_hi; g += 8) {  // one warp per group: lanes stride over its columns in the tile
         int c_lo = g * cpg - n0, c_hi = (g + 1) * cpg - n0;
         if (c_lo < 0) c_lo = 0;
@@ -571,7 +571,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
           s += __shfl_xor_sync(0xffffffffu, s, o);
           qv += __shfl_xor_sync(0xffffffffu, qv, o);
         }
-        if (lane == 0) dst[g - g_lo] = make_float2(s, qv);
+        if (lane == 0) dst[(long long)(g - g_lo) * p.ns.slabs_total] = make_float2(s, qv);
       }
     }
   }
@@ -1322,7 +1322,7 @@ splitk_reduce_stats_kernel(const SplitKReduceParams p) {
   __syncthreads();
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* dst = p.ns.partial + (long long)blockIdx.x * p.ns.lg;
+    float2* dst = p.ns.partial + blockIdx.x;  // [group][slab]
     for (int g = warp; g < p.ns.G; g += RK_THREADS / 32) {
       float s = 0.f, qv = 0.f;
       for (int cc = g * p.ns.cpg + lane; cc < (g + 1) * p.ns.cpg; cc += 32) {
@@ -1335,7 +1335,7 @@ splitk_reduce_stats_kernel(const SplitKReduceParams p) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         qv += __shfl_xor_sync(0xffffffffu, qv, o);
       }
-      if (lane == 0) dst[g] = make_float2(s, qv);
+      if (lane == 0) dst[(long long)g * p.ns.slabs_total] = make_float2(s, qv);
     }
   }
 }

@@ -3,7 +3,10 @@
 // A kernel that writes an activation [rows][C] (GEMM epilogue, split-K reduction) also writes, per
 // tile it owns (slab of rows x n-tile of BN columns), the partial sums (sum x, sum x^2) of the
 // values it stored, folded to the GROUPS that overlap its column range:
-//   partial[(slab * n_tiles + nt) * lg + (g - first_group(nt))]      (float2, fp32 sums)
+//   partial[((nt * lg) + (g - first_group(nt))) * slabs_total + slab]      (float2, fp32 sums)
+// (slab innermost: the entries of one group are contiguous runs, so the consumer's fold is a coalesced read - with the
+// slab-major layout of round 1 every lane of a fold hit a different 128 B line, and the few hundred blocks of a
+// normalise pass folding the same table serialised on those lines in L2: 8 000 - 20 000 cycles per block, measured)
 // The consumer (norm_apply_partial_kernel) folds the few hundred partials of its image in a fixed
 // order at the top of every block - redundantly, in parallel, from L2 - and normalises:
 //   (x - mean) / (std + eps), biased std       (reference helpers/utils.mojo:1380, 1868-1870)
@@ -21,6 +24,7 @@ struct NormStatsReq {
   int BN = 0, n_tiles = 0;
   int C = 0, G = 0, cpg = 0;
   int slabs_per_img = 0, imgs = 0;
+  int slabs_total = 0;           // imgs * slabs_per_img: the stride between (n-tile, group) rows of the table
   float inv_count = 0.f;         // 1 / elements per (image, group)
   float eps = 0.f;
 };
@@ -29,30 +33,54 @@ struct NormStatsReq {
 // One warp per group; lanes stride over the (slab, n-tile) entries of the group.
 __device__ __forceinline__ void norm_stats_fold(const NormStatsReq& r, int img, int tid, int nthreads, float2* st) {
   const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-  const float2* base = r.partial + (long long)img * r.slabs_per_img * r.n_tiles * r.lg;
-  for (int g0 = warp; g0 < r.G; g0 += 4 * nwarps) {  // 4 groups per pass so that their L2 loads overlap
+  const float2* base = r.partial + (long long)img * r.slabs_per_img;
+  // n / d = umulhi(n, 2^32 / d + 1), exact for n, d < 2^16: integer division by a run-time value costs ~100 cycles
+  // on this part, and this function is a latency chain executed by every block of the consumer
+  const unsigned bn_magic = 0xFFFFFFFFu / (unsigned)r.BN + 1u, cpg_magic = 0xFFFFFFFFu / (unsigned)r.cpg + 1u;
+  for (int g0 = warp; g0 < r.G; g0 += 4 * nwarps) {
+    // Four groups per pass, their entries walked in lock step: a warp issues in order and stalls at the first use of a
+    // loaded value, so one loop nest per group costs one L2 round trip per group and n-tile (measured: 7 000+ cycles
+    // for 32 groups); here up to 16 independent loads are in flight before the first add.
     float fs[4], fq[4];
+    int ent[4], row0[4], nt0s[4], emax = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       fs[k] = fq[k] = 0.f;
+      ent[k] = 0;
+      row0[k] = 0;
+      nt0s[k] = 0;
       const int g = g0 + k * nwarps;
       if (g >= r.G) continue;
-      const int nt0 = (g * r.cpg) / r.BN, nt1 = ((g + 1) * r.cpg - 1) / r.BN;  // n-tiles overlapping the group
-      const int span = nt1 - nt0 + 1;
-      const int entries = r.slabs_per_img * span;
-      for (int k0 = 0; k0 < entries; k0 += 128) {
-        float2 v[4];
+      const int nt0 = (int)__umulhi((unsigned)(g * r.cpg), bn_magic);              // n-tiles overlapping the group
+      const int nt1 = (int)__umulhi((unsigned)((g + 1) * r.cpg - 1), bn_magic);
+      ent[k] = (nt1 - nt0 + 1) * r.slabs_per_img;
+      row0[k] = nt0 * r.lg + (g - (int)__umulhi((unsigned)(nt0 * r.BN), cpg_magic));  // a later tile of the group starts inside it: its entry is row nt * lg
+      nt0s[k] = nt0;
+      emax = ent[k] > emax ? ent[k] : emax;
+    }
+    for (int e0 = lane; e0 < emax; e0 += 128) {
+      float2 v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int e = k0 + j * 32 + lane;
-          v[j] = make_float2(0.f, 0.f);
-          if (e < entries) {
-            const int sl = e / span, nt = nt0 + (e - sl * span);
-            v[j] = __ldcg(base + ((long long)sl * r.n_tiles + nt) * r.lg + (g - (nt * r.BN) / r.cpg));
+          const int e = e0 + 32 * j;
+          v[k][j] = make_float2(0.f, 0.f);
+          if (e < ent[k]) {
+            int t = 0, sl = e, row = row0[k];
+            if (e >= r.slabs_per_img) {  // groups wider than an n-tile only (LayerNorm: one group over every tile)
+              t = e / r.slabs_per_img;
+              sl = e - t * r.slabs_per_img;
+              row = (nt0s[k] + t) * r.lg;
+            }
+            v[k][j] = __ldcg(base + (long long)row * r.slabs_total + sl);
           }
         }
-        fs[k] += (v[0].x + v[1].x) + (v[2].x + v[3].x);
-        fq[k] += (v[0].y + v[1].y) + (v[2].y + v[3].y);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        fs[k] += (v[k][0].x + v[k][1].x) + (v[k][2].x + v[k][3].x);
+        fq[k] += (v[k][0].y + v[k][1].y) + (v[k][2].y + v[k][3].y);
       }
     }
 #pragma unroll

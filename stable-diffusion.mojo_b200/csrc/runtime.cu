@@ -542,6 +542,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
       ns.cpg = cpg;
       ns.slabs_per_img = (int)slabs_per_img;
       ns.imgs = imgs;
+      ns.slabs_total = (int)(imgs * slabs_per_img);
       ns.inv_count = (float)(1.0 / ((double)rows_per_img * cpg));
       ns.eps = nh->eps;
       if (p.splits == 1 || p.fixup) p.ns = ns;

@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
-LIB_PATH = os.path.join(CSRC, "libtsd_b200.so")
+LIB_PATH = os.environ.get("TSD_LIB", os.path.join(CSRC, "libtsd_b200.so"))  # TSD_LIB: lab builds (e.g. the in-kernel trace variant)
 HEADER = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "tsd_b200.h")
 
 c_float_p = C.POINTER(C.c_float)
@@ -191,4 +191,5 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_dist_generate", i32, vp, vp, C.POINTER(LoopParams), fp, fp, i32, i32, i32, fp)
     sig("tsd_bench_gemm", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)
     sig("tsd_bench_attention", i32, vp, i32, i32, i32, i32, i32, c_double_p)
+    sig("tsd_bench_norm", i32, vp, i32, i32, i32, i32, i32, i32, i32, c_double_p)
     sig("tsd_bench_conv", i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_double_p)

@@ -208,7 +208,7 @@ def test_attention_core_sweep_shapes(ctx, d, tk, axis):
     e, e1 = relerr(got, ref), relerr(got_v1, ref)
     print(f"attention core h=8 tq=4096 tk={tk} d={d} axis={axis}: rel_linf {e:.2e} (v1 kernel {e1:.2e})")
     assert e < TOL_TF32 and e1 < TOL_TF32
-    assert relerr(got, got_v1) < 1e-4    # same arithmetic, different instruction schedule
+    assert relerr(got, got_v1) < 1e-3    # same arithmetic in another summation order: P may flip a TF32 ulp (2^-11)
 
 
 def test_attention_core_dev_entry(ctx):
