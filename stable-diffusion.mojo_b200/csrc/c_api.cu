@@ -87,7 +87,7 @@ int32_t tsd_init(int32_t device, tsd_ctx** out) {
   h->c = c;
   *out = h;
   // tuning / A-B switches from the environment: TSD_OPT_<option name>=<int>  (same names as tsd_set_option)
-  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention", "attn_v2"};
+  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention", "attn_v2", "splitk_cluster", "splitk_cluster_max"};
   for (const char* name : kEnvOpts) {
     const std::string key = std::string("TSD_OPT_") + name;
     if (const char* v = getenv(key.c_str())) tsd_set_option(h, name, atoi(v));
@@ -137,6 +137,8 @@ static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "gn_partial")) return &h->c->gn_partial;
   if (!strcmp(name, "gn_partial_max_groups")) return &h->c->gn_partial_max_groups;
   if (!strcmp(name, "splitk_fixup")) return &h->c->splitk_fixup;
+  if (!strcmp(name, "splitk_cluster")) return &h->c->splitk_cluster;
+  if (!strcmp(name, "splitk_cluster_max")) return &h->c->splitk_cluster_max;
   if (!strcmp(name, "pdl")) return &tsd::pdl_enabled();
   if (!strcmp(name, "autotune")) return &h->c->autotune;
   if (!strcmp(name, "conv_halo")) return &h->c->conv_halo;

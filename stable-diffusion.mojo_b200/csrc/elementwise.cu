@@ -918,7 +918,7 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, const float2* __r
 __global__ void __launch_bounds__(GS_THREADS)
 norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, const NormStatsReq req,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float gamma_scalar,
-                          int pixels, int C4, int slab, int silu, int round, int trace) {
+                          int pixels, int C4, int slab, int silu, int round, int trace, int c4_seg) {
   long long t0 = 0, t1 = 0, t2 = 0;
   if (trace) t0 = clock64();
   pdl_wait();
@@ -926,34 +926,47 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
   if (trace) t1 = clock64();
   __shared__ float2 st[512];
   const int n = blockIdx.y;
-  const int TU = C4 < GS_THREADS ? C4 : GS_THREADS;
-  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  // blockIdx.z: channel segment of c4_seg quads (many-group norms: a block then folds only the groups of its segment)
+  const int c4_0 = blockIdx.z * c4_seg;
+  const int C4s = (C4 - c4_0) < c4_seg ? (C4 - c4_0) : c4_seg;  // quads of this segment
+  const int TU = C4s < GS_THREADS ? C4s : GS_THREADS;
+  const int ppl = C4s < GS_THREADS ? GS_THREADS / C4s : 1;
   const int u = threadIdx.x % TU, pl = threadIdx.x / TU;
   int p0 = blockIdx.x * slab, p1 = p0 + slab;
   if (p1 > pixels) p1 = pixels;
-  const float4* base = x + (long long)n * pixels * C4;
-  float4* obase = y + (long long)n * pixels * C4;
+  const float4* base = x + (long long)n * pixels * C4 + c4_0;
+  float4* obase = y + (long long)n * pixels * C4 + c4_0;
+  const int g_begin = norm_fastdiv(c4_0 * 4, req.cpg_magic);
+  const int g_end = norm_fastdiv((c4_0 + C4s) * 4 - 1, req.cpg_magic) + 1;
   // The first NP pixels of this thread are requested BEFORE the statistics are folded: the fold is a latency chain
   // (L2 round trip, shuffles, barrier: 6 000+ cycles measured) that needs no activation data, and the activation loads
   // need no statistics - the two now overlap instead of running back to back.
   constexpr int NP = 3;
   float4 pre[NP][GS_MAXQ];
   const bool active = pl < ppl;
+  auto prefetch = [&]() {
 #pragma unroll
-  for (int k = 0; k < NP; ++k) {
-    const int p = p0 + pl + k * ppl;
+    for (int k = 0; k < NP; ++k) {
+      const int p = p0 + pl + k * ppl;
 #pragma unroll
-    for (int i = 0; i < GS_MAXQ; ++i) {
-      const int qd = u + i * TU;
-      pre[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (active && p < p1 && qd < C4) pre[k][i] = base[(long long)p * C4 + qd];
+      for (int i = 0; i < GS_MAXQ; ++i) {
+        const int qd = u + i * TU;
+        pre[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && p < p1 && qd < C4s) pre[k][i] = base[(long long)p * C4 + qd];
+      }
     }
-  }
-  norm_stats_fold(req, n, threadIdx.x, GS_THREADS, st);
+  };
+  long long trf[3] = {0, 0, 0};
+  // the (tiny) statistics table is requested first, the activation prefetch queues behind it
+  norm_stats_fold(req, n, threadIdx.x, GS_THREADS, st, trace ? trf : nullptr, prefetch, g_begin, g_end);
+  const long long t1b = trace ? clock64() : 0;
   __syncthreads();
   if (trace) t2 = clock64();
+  if (trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    printf("  fold detail: prefetch issue + index math %lld, partial loads %lld, shuffles %lld, finalise %lld, barrier %lld (clk)\n",
+           trf[0] - t1, trf[1] - trf[0], trf[2] - trf[1], t1b - trf[2], t2 - t1b);
   if (!active) return;
-  const unsigned cpg_magic = 0xFFFFFFFFu / (unsigned)req.cpg + 1u;  // c / cpg = umulhi(c, magic), exact for c, cpg < 2^16
+  const unsigned cpg_magic = req.cpg_magic;  // c / cpg = umulhi(c, magic), exact for c, cpg < 2^16
   float mu[GS_MAXQ][4], sc[GS_MAXQ][4], sh[GS_MAXQ][4];
 #pragma unroll
   for (int i = 0; i < GS_MAXQ; ++i) {
@@ -961,9 +974,9 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       mu[i][j] = 0.f; sc[i][j] = 0.f; sh[i][j] = 0.f;
-      if (qd < C4) {
-        const int c = qd * 4 + j;
-        const float2 t = st[__umulhi((unsigned)c, cpg_magic)];
+      if (qd < C4s) {
+        const int c = (c4_0 + qd) * 4 + j;
+        const float2 t = st[norm_fastdiv(c, cpg_magic) - g_begin];
         mu[i][j] = t.x;
         sc[i][j] = t.y * gamma_scalar * (gamma ? gamma[c] : 1.0f);
         sh[i][j] = beta ? beta[c] : 0.0f;
@@ -986,7 +999,7 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
 #pragma unroll
     for (int i = 0; i < GS_MAXQ; ++i) {
       const int qd = u + i * TU;
-      if (p < p1 && qd < C4) emit(pre[k][i], i, (long long)p * C4 + qd);
+      if (p < p1 && qd < C4s) emit(pre[k][i], i, (long long)p * C4 + qd);
     }
   }
 #pragma unroll 2
@@ -994,7 +1007,7 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
 #pragma unroll
     for (int i = 0; i < GS_MAXQ; ++i) {
       const int qd = u + i * TU;
-      if (qd < C4) emit(base[(long long)p * C4 + qd], i, (long long)p * C4 + qd);
+      if (qd < C4s) emit(base[(long long)p * C4 + qd], i, (long long)p * C4 + qd);
     }
   }
   if (trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0)
@@ -1644,14 +1657,30 @@ static int norm_trace_env() {
   return tr;
 }
 
-bool norm_apply_partial_supported(int C, int G) { return C % 4 == 0 && C / 4 <= GS_MAXQ * GS_THREADS && G <= 512; }
+// channel segments of a many-group norm: each block folds at most ~64 groups (0: not expressible)
+static int norm_apply_partial_segments(int C, int G) {
+  if (G <= 64) return 1;
+  const int C4 = C / 4, cpg = C / G;
+  for (int nseg = (G + 63) / 64; nseg <= C4; ++nseg) {
+    if (C4 % nseg) continue;
+    const int ch = (C4 / nseg) * 4;
+    if (ch % cpg == 0 && ch / cpg <= 512) return nseg;
+  }
+  return 0;
+}
+bool norm_apply_partial_supported(int C, int G) {
+  return C % 4 == 0 && C / 4 <= GS_MAXQ * GS_THREADS && G > 0 && C % G == 0 && C < 65536 && norm_apply_partial_segments(C, G) > 0 &&
+         (G <= 512 || norm_apply_partial_segments(C, G) > 1);
+}
 
 cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsReq& req, int N, long long pixels_ll,
                                       const float* gamma, const float* beta, float gamma_scalar, int silu,
                                       int round_tf32, cudaStream_t s) {
   if (!norm_apply_partial_supported(req.C, req.G) || pixels_ll >= (1 << 30)) return cudaErrorInvalidValue;
   const int C4 = req.C / 4, pixels = (int)pixels_ll;
-  const int ppl = C4 < GS_THREADS ? GS_THREADS / C4 : 1;
+  const int nseg = norm_apply_partial_segments(req.C, req.G);
+  const int c4_seg = C4 / nseg;
+  const int ppl = c4_seg < GS_THREADS ? GS_THREADS / c4_seg : 1;
   // blocks over the whole batch (each folds the partial statistics of its image first, a fixed cost);
   // a slab is a multiple of the pixels in flight
   static int target = -1;
@@ -1660,14 +1689,14 @@ cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsR
     target = v ? atoi(v) : 2 * 148;  // two blocks per SM (measured best: 6.7 us for 64 x 64 x 320 against 9.6 at four)
     if (target < 1) target = 2 * 148;
   }
-  int slabs = (target + N - 1) / N;
+  int slabs = (target + N * nseg - 1) / (N * nseg);
   int slab = (pixels + slabs - 1) / slabs;
   slab = (slab + ppl - 1) / ppl * ppl;
   if (slab < ppl) slab = ppl;
   slabs = (pixels + slab - 1) / slab;
-  { cudaError_t e_ = launch_pdl(norm_apply_partial_kernel, dim3(dim3(slabs, N)), dim3(GS_THREADS), 0, s, reinterpret_cast<const float4*>(x),
+  { cudaError_t e_ = launch_pdl(norm_apply_partial_kernel, dim3(slabs, N, nseg), dim3(GS_THREADS), 0, s, reinterpret_cast<const float4*>(x),
                                                                   reinterpret_cast<float4*>(y), req, gamma, beta,
-                                                                  gamma_scalar, pixels, C4, slab, silu, round_tf32, norm_trace_env()); if (e_ != cudaSuccess) return e_; }
+                                                                  gamma_scalar, pixels, C4, slab, silu, round_tf32, norm_trace_env(), c4_seg); if (e_ != cudaSuccess) return e_; }
   return cudaGetLastError();
 }
 

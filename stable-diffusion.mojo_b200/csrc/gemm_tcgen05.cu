@@ -2,6 +2,8 @@
 #include "gemm_tcgen05.cuh"
 
 #include <cstdio>
+#include <map>
+#include <mutex>
 
 #include "pdl.cuh"
 #include "ptx_sm100.cuh"
@@ -116,22 +118,59 @@ __device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t adesc, ui
   }
 }
 // all MMAs issued so far arrive on `bar` when complete; CG == 2: on the same barrier of both CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
 template <int CG>
 __device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
   if constexpr (CG == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
                  : "memory");
   } else {
+    // both CTAs of the pair: cluster ranks 2k and 2k+1 (the cluster may hold several pairs when it also spans K splits)
+    const uint16_t mask = (uint16_t)(3u << (cluster_ctarank() & ~1u));
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
-        "h"((uint16_t)3)
+        "h"(mask)
         : "memory");
   }
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
+__device__ __forceinline__ uint32_t cluster_ctaid_x() {
   uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  asm volatile("mov.u32 %0, %%cluster_ctaid.x;\n" : "=r"(r));
   return r;
+}
+// float2 at shared-window address `laddr` of the CTA with rank `cta` of this cluster (distributed shared memory)
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t laddr, uint32_t cta) {
+  uint32_t raddr;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(cta));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(raddr) : "memory");
+  return v;
+}
+// arrive (release, cluster scope) on the mbarrier at shared-window address `laddr` of CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t laddr, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity))
+    if (++spins > (1u << 26)) mbar_timeout_trap();
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -220,6 +259,8 @@ struct EpilogueCtx {
   int n_iters;          // > 1: two accumulator tiles (even / odd K steps) to be added
   int nt, img, h0, w0, batch, split;
   long long* tr;        // lab trace slots
+  uint32_t red_bar = 0;  // shared address of two mbarriers (count = splits) of the cluster split-K reduction
+  uint32_t pair_rank = 0, cg = 1;
 };
 __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const EpilogueCtx& ec) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -470,26 +511,48 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
     }
     __syncwarp();
   }
+  bool stats_leader = true;  // this CTA writes the statistics of its tile (cluster split-K: the split-0 CTA only)
   if (fixup) {
-    // ---- split-K fix-up: every CTA has stored its raw partial tile; the last one to arrive for this
-    // output tile sums the partials in split order (deterministic) and runs the real epilogue ----
+    // ---- in-kernel split-K reduction: every CTA has stored its raw partial tile (L2-resident).
+    //  fixup 1: the last CTA to arrive for an output tile sums the partials in split order and runs the real epilogue
+    //           (serial tail, measured slower than the separate reduce kernel);
+    //  fixup 2: the `splits` CTAs of a tile form a thread-block CLUSTER (launch attribute, co-scheduled by hardware):
+    //           after a cluster-scope barrier among their epilogue warps each CTA reduces and finishes every
+    //           splits-th 32-column chunk - the reduction runs `splits`-wide, no reduce kernel, no ticket, and the tile's
+    //           norm statistics still come out of this epilogue (column sums gathered through distributed shared memory).
     __shared__ unsigned int fix_last;
     const int te0 = threadIdx.x - 64;
-    named_bar_sync(2, 256);
-    if (te0 == 0) {
+    int c_first = half * 32, c_stride = 64;
+    const int S = p.splits;
+    if (p.fixup == 1) {
+      named_bar_sync(2, 256);
+      if (te0 == 0) {
+        __threadfence();
+        unsigned int* tk = p.tile_tickets + (blockIdx.y * gridDim.x + blockIdx.x);
+        const unsigned int old = atomicAdd(tk, 1u);
+        fix_last = (old == (unsigned int)p.splits - 1) ? 1u : 0u;
+        if (fix_last) *tk = 0u;  // self-resetting: launches on one stream are serialised
+      }
+      named_bar_sync(2, 256);
+      if (!fix_last) return;
       __threadfence();
-      unsigned int* tk = p.tile_tickets + (blockIdx.y * gridDim.x + blockIdx.x);
-      const unsigned int old = atomicAdd(tk, 1u);
-      fix_last = (old == (unsigned int)p.splits - 1) ? 1u : 0u;
-      if (fix_last) *tk = 0u;  // self-resetting: launches on one stream are serialised
+    } else {
+      __threadfence();  // this thread's partial stores are performed before the arrival below is observed
+      named_bar_sync(2, 256);
+      if (te0 < S) mbar_arrive_remote(ec.red_bar, ec.pair_rank + ec.cg * (uint32_t)te0);  // one arrival per CTA of the tile, on each of them
+      mbar_wait_cluster(ec.red_bar, 0);
+      c_first = (split + S * half) * 32;
+      c_stride = 2 * S * 32;
+      stats_leader = split == 0;
+      if (want_stats) {  // columns this CTA does not reduce stay zero in its table
+        for (int i = te0; i < 4 * 256; i += 256) cs[i] = make_float2(0.f, 0.f);
+        named_bar_sync(2, 256);
+      }
     }
-    named_bar_sync(2, 256);
-    if (!fix_last) return;
-    __threadfence();
     const float* cb2 = p.bias ? p.bias + (long long)img * p.bias_img_stride : nullptr;
     const float* ws0 = p.partial;
     const long long ws_split = (long long)p.m_per_batch * p.n_pad;  // floats between splits (batch == 1)
-    for (int c = half * 32; c < out_cols; c += 64) {
+    for (int c = c_first; c < out_cols; c += c_stride) {
       const int n = n0 + c + c4;
       float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), qq = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c + c4 < out_cols && n < n_valid) {
@@ -501,26 +564,41 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
           b4.x -= ln_rmu * w4.x; b4.y -= ln_rmu * w4.y; b4.z -= ln_rmu * w4.z; b4.w -= ln_rmu * w4.w;
           sc = ln_r;
         }
+        // all loads of the chunk first (8 rows x splits), then the sums in split order
+        float4 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow[i] >= 0) t[i] = __ldcg(reinterpret_cast<const float4*>(ws0 + grow[i] * p.n_pad + (long long)nt * p.BN + c + c4));
+        }
+        for (int s2 = 1; s2 < S; ++s2) {
+          float4 u[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow[i] >= 0)
+              u[i] = __ldcg(reinterpret_cast<const float4*>(ws0 + grow[i] * p.n_pad + (long long)nt * p.BN + c + c4 + s2 * ws_split));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            t[i].x += u[i].x; t[i].y += u[i].y; t[i].z += u[i].z; t[i].w += u[i].w;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (grow[i] < 0) continue;
-          const float* src = ws0 + grow[i] * p.n_pad + (long long)nt * p.BN + c + c4;
-          float4 t = __ldcg(reinterpret_cast<const float4*>(src));
-          for (int s = 1; s < p.splits; ++s) {
-            const float4 u = __ldcg(reinterpret_cast<const float4*>(src + s * ws_split));
-            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-          }
-          t.x = fmaf(t.x, sc, b4.x); t.y = fmaf(t.y, sc, b4.y); t.z = fmaf(t.z, sc, b4.z); t.w = fmaf(t.w, sc, b4.w);
+          float4 v4 = t[i];
+          v4.x = fmaf(v4.x, sc, b4.x); v4.y = fmaf(v4.y, sc, b4.y); v4.z = fmaf(v4.z, sc, b4.z); v4.w = fmaf(v4.w, sc, b4.w);
           if (p.residual != nullptr) {
             const float4 rr = *reinterpret_cast<const float4*>(p.residual + grow[i] * p.ldr + n);
-            t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+            v4.x += rr.x; v4.y += rr.y; v4.z += rr.z; v4.w += rr.w;
           }
           if (p.round_tf32) {
-            t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
+            v4.x = round_tf32(v4.x); v4.y = round_tf32(v4.y); v4.z = round_tf32(v4.z); v4.w = round_tf32(v4.w);
           }
-          *reinterpret_cast<float4*>(p.D + grow[i] * p.ldd + n) = t;
-          ss.x += t.x; ss.y += t.y; ss.z += t.z; ss.w += t.w;
-          qq.x = fmaf(t.x, t.x, qq.x); qq.y = fmaf(t.y, t.y, qq.y); qq.z = fmaf(t.z, t.z, qq.z); qq.w = fmaf(t.w, t.w, qq.w);
+          *reinterpret_cast<float4*>(p.D + grow[i] * p.ldd + n) = v4;
+          ss.x += v4.x; ss.y += v4.y; ss.z += v4.z; ss.w += v4.w;
+          qq.x = fmaf(v4.x, v4.x, qq.x); qq.y = fmaf(v4.y, v4.y, qq.y); qq.z = fmaf(v4.z, v4.z, qq.z); qq.w = fmaf(v4.w, v4.w, qq.w);
         }
       }
       if (want_stats) {
@@ -536,6 +614,30 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
           d[0] = make_float2(ss.x, qq.x); d[1] = make_float2(ss.y, qq.y);
           d[2] = make_float2(ss.z, qq.z); d[3] = make_float2(ss.w, qq.w);
         }
+      }
+    }
+    if (p.fixup == 2 && want_stats) {
+      // the column sums of a chunk live in the CTA that reduced it: the split-0 CTA gathers them through distributed
+      // shared memory once every CTA of the tile has finished (second barrier), then writes the tile's statistics
+      named_bar_sync(2, 256);
+      if (te0 == 0) mbar_arrive_remote(ec.red_bar + 8u, ec.pair_rank);  // on the split-0 CTA of this tile
+      if (!stats_leader) return;
+      mbar_wait_cluster(ec.red_bar + 8u, 0);
+      {
+        const int te = te0;
+        float2 tot = make_float2(0.f, 0.f);
+        if (te < out_cols) {
+          const uint32_t owner = ec.pair_rank + ec.cg * (uint32_t)((te >> 5) % S);
+          const uint32_t a0 = smem_u32(cs + te);
+          const float2 a = ld_dsmem_f2(a0, owner), b = ld_dsmem_f2(a0 + 256 * 8, owner), c2 = ld_dsmem_f2(a0 + 512 * 8, owner),
+                       d2 = ld_dsmem_f2(a0 + 768 * 8, owner);
+          tot = make_float2((a.x + b.x) + (c2.x + d2.x), (a.y + b.y) + (c2.y + d2.y));
+        }
+        named_bar_sync(2, 256);  // every remote read of this CTA's own table (owner == self) is done before it is overwritten
+        cs[te] = tot;
+        cs[256 + te] = make_float2(0.f, 0.f);
+        cs[512 + te] = make_float2(0.f, 0.f);
+        cs[768 + te] = make_float2(0.f, 0.f);
       }
     }
   }
@@ -595,12 +697,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t red_bar[2];  // cluster split-K (p.fixup == 2): partial tiles stored / column sums ready
   __shared__ uint32_t tmem_slot;
   __shared__ long long tr[16];  // lab trace (debug bit 3)
   TSD_TRACE(threadIdx.x == 0, 0);
 
   const int warp = threadIdx.x >> 5;
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t rank = (CG == 2) ? cluster_ctaid_x() : 0u;  // position in the CTA pair (the cluster may also span K splits along z)
+  const bool cluster_split = p.fixup == 2;  // the K splits of a tile are the z extent of this CTA's cluster
 
   // 1024 B aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -635,6 +739,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, (n_iters > 1 && GEMM_ROLE_PAIRS > 1) ? 2 : 1);  // one commit per MMA issuer
+    if (cluster_split) {
+      mbar_init(&red_bar[0], (uint32_t)p.splits);
+      mbar_init(&red_bar[1], (uint32_t)p.splits);
+    }
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -652,7 +760,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   tc_fence_before_sync();
-  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before anything arrives on them
+  if (CG == 2 || cluster_split) cluster_sync_all();  // the peers' barriers must exist before anything arrives on them
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
@@ -860,6 +968,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ec.n_iters = n_iters;
     ec.nt = nt; ec.img = img; ec.h0 = h0; ec.w0 = w0; ec.batch = batch; ec.split = split;
     ec.tr = tr;
+    ec.red_bar = smem_u32(&red_bar[0]);
+    ec.pair_rank = rank;
+    ec.cg = CG;
     gemm_epilogue(p, ec);
     tc_fence_before_sync();
   }
@@ -874,7 +985,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
            tr[8] - tr[4], tr[9] - tr[4], tr[10] - tr[4], tr[11] - tr[4], tr[12] - tr[4], tr[13] - tr[4], tr[14] - tr[4]);
 #endif
 
-  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may release TMEM / exit while the pair is in flight
+  // neither CTA of a pair may release TMEM / exit while the pair is in flight; no CTA of a split-K cluster may exit while
+  // the split-0 CTA still reads its column sums through distributed shared memory
+  if (CG == 2 || cluster_split) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after_sync();
     if constexpr (CG == 1) {
@@ -915,7 +1028,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   TSD_TRACE(threadIdx.x == 0, 0);
 
   const int warp = threadIdx.x >> 5;
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t rank = (CG == 2) ? cluster_ctaid_x() : 0u;  // position in the CTA pair (the cluster may also span K splits along z)
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int b_rows = p.BN / CG;
   const uint32_t b_atom = (uint32_t)b_rows * 128;
@@ -1186,11 +1299,23 @@ static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.z = p.fixup == 2 ? p.splits : 1;  // cluster split-K: the K splits of a tile are co-scheduled
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  if (p.fixup == 2 && CG * p.splits > 8) {  // beyond the portable cluster size: opt in once per (kernel, device)
+    static std::mutex mu;
+    static std::map<int, bool> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<CG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+      done[dev] = true;
+    }
+  }
   return cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<CG>, tmA, tmB, tmA2, p);
 }
 

@@ -354,7 +354,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   long long m_tiles = (long long)A.imgs * ((A.H + bh - 1) / bh) * ((A.W + bw - 1) / bw);
   const int nbatch = A.batch;
   const bool allow_split = !p.geglu && nbatch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) &&
-                           p.alpha == 1.0f && (p.ln.partial == nullptr || c->splitk_fixup);
+                           p.alpha == 1.0f && (p.ln.partial == nullptr || c->splitk_fixup || c->splitk_cluster);
   const bool halo_ok = conv_halo_eligible(c, A, N, p);
   TileCfg cfg = use ? *use
                     : choose_tiles(c->sm_count, m_tiles, N, p.total_iters, nbatch, p.geglu != 0, allow_split,
@@ -395,6 +395,11 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     p.total_iters = p.taps * p.chunks_per_tap + A.K2 / p.bk;
   }
   p.splits = std::min(cfg.splits, p.total_iters);
+  if (p.ln.partial != nullptr && !c->splitk_fixup && p.splits > 1) {
+    // a folded LayerNorm needs the reduction inside the kernel: keep the split count within the cluster limit
+    const int max_s = (c->splitk_cluster && !p.halo) ? std::max(1, c->splitk_cluster_max / std::max(1, p.cg)) : 1;
+    p.splits = std::min(p.splits, max_s);
+  }
   p.iters_per_split = (p.total_iters + p.splits - 1) / p.splits;
   p.splits = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;  // no empty split
   p.debug = c->gemm_debug;
@@ -487,10 +492,13 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     p.partial = ws;
     // in-kernel reduction by the last CTA of every output tile (needs the vector epilogue and a ticket per tile)
     const long long tiles = (long long)(p.cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles) * n_tiles;
-    p.fixup = (c->splitk_fixup && tiles <= kTileTickets && N % 4 == 0 && p.ldd % 4 == 0 && (!p.residual || p.ldr % 4 == 0) &&
-               (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)))
-                  ? 1
-                  : 0;
+    const bool vec_epilogue = N % 4 == 0 && p.ldd % 4 == 0 && (!p.residual || p.ldr % 4 == 0) &&
+                              (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+    p.fixup = (c->splitk_fixup && tiles <= kTileTickets && vec_epilogue) ? 1 : 0;
+    // cluster split-K: the splits of a tile are one thread-block cluster (x pair, z splits) and reduce in the kernel
+    if (!p.fixup && c->splitk_cluster && !p.halo && vec_epilogue && nbatch == 1 && p.cg * p.splits <= c->splitk_cluster_max &&
+        p.cg * p.splits <= 16)
+      p.fixup = 2;
     p.tile_tickets = c->tile_tickets;
   } else {
     p.partial = nullptr;
@@ -543,6 +551,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
       ns.slabs_per_img = (int)slabs_per_img;
       ns.imgs = imgs;
       ns.slabs_total = (int)(imgs * slabs_per_img);
+      ns.set_magics();
       ns.inv_count = (float)(1.0 / ((double)rows_per_img * cpg));
       ns.eps = nh->eps;
       if (p.splits == 1 || p.fixup) p.ns = ns;
@@ -719,7 +728,7 @@ static std::vector<TileCfg> tune_candidates(int sm, long long m_tiles, int N, in
 static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb, long long b_bs,
                     int b_rows, GemmKParams p, int force_bn, int force_splits, double flops, NormHint* nh = nullptr) {
   const bool allow_split = !p.geglu && A.batch == 1 && p.row_bias == nullptr && p.split_n >= (1 << 30) && p.alpha == 1.0f &&
-                           (p.ln.partial == nullptr || c->splitk_fixup);
+                           (p.ln.partial == nullptr || c->splitk_fixup || c->splitk_cluster);
   const bool tunable = c->autotune && force_bn <= 0 && force_splits <= 0 && c->gemm_debug == 0 && c->force_stages == 0;
   if (!tunable) return run_gemm_cfg(c, A, B, N, ldb, b_bs, b_rows, p, force_bn, force_splits, flops, nh, nullptr, 0);
   if (c->dry_run) {
@@ -816,7 +825,8 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     // A split-K candidate cannot leave norm statistics in its epilogue: the consumer then runs the
     // stand-alone fused norm (~18 us) instead of the normalise-only pass (~6 us) or, for a folded
     // LayerNorm, instead of nothing at all.  Charge that to the candidate (measured, profiles/).
-    if (nh && nh->G > 0 && c->producer_stats == 1 && cand.splits > 1 && !c->splitk_fixup)
+    const bool in_kernel_reduce = c->splitk_fixup || (c->splitk_cluster && !cand.halo && cand.cg * cand.splits <= c->splitk_cluster_max);
+    if (nh && nh->G > 0 && c->producer_stats == 1 && cand.splits > 1 && !in_kernel_reduce)
       ms_c += (nh->G == 1 && c->ln_fold) ? 0.018f : 0.012f;
     if (ms_c < best_ms) {
       best_ms = ms_c;
@@ -1042,7 +1052,7 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
     c->arena.release_to(mark);
   }
   if (pre != nullptr && pre->partial != nullptr && !upsample && pre->G == G && pre->C == C && pre->imgs == N &&
-      c->gn_partial && G <= c->gn_partial_max_groups && norm_apply_partial_supported(C, G)) {
+      c->gn_partial && (G <= c->gn_partial_max_groups || c->gn_partial_max_groups >= 64) && norm_apply_partial_supported(C, G)) {
     // the producer left per-tile partial sums: one normalise pass that folds them per block
     if (!c->dry_run) {
       TimedScope ts(c, FAM_NORM, 0);

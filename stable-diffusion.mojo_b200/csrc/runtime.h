@@ -125,6 +125,8 @@ struct Ctx {
   int bench_stats_groups = 0;      // lab: tsd_bench_conv / tsd_bench_gemm request norm statistics with this many groups
   unsigned int* tile_tickets = nullptr;  // zero-initialised per-tile arrival counters of the split-K fix-up
   int splitk_fixup = 0;            // 1: split-K partials reduced by the last CTA of each tile (measured slower than the separate reduce kernel: serial tail)
+  int splitk_cluster = 0;          // 1: split-K reduced inside the GEMM by the thread-block cluster of a tile's K splits (cluster size <= splitk_cluster_max); measured: the in-kernel reduction costs about what the reduce kernel does, so it stays off
+  int splitk_cluster_max = 8;      // largest cluster (CTA pair x splits) the in-kernel reduction is used with; 16 needs the non-portable opt-in
   unsigned int* norm_bar = nullptr;  // zero-initialised barrier words of the fused norm (elementwise.cuh)
   TuneCache* tune = nullptr;
   void* flush_buf = nullptr;
