@@ -171,6 +171,11 @@ typedef struct tsd_diffusion_config {
   int32_t context_len;        /* 77 */
   int32_t context_dim;        /* 768 */
   int32_t mojo_alias_time;    /* 0 [default]; 1 reproduces SiLU^k(t_emb) aliasing */
+  int32_t norm_affine;        /* 0 [default]: GroupNorm / LayerNorm own no tensors, as the reference's structs
+                                 (helpers/utils.mojo:1817-1819, 2052-2061); 1: every norm carries a per-channel weight and
+                                 bias (".weight" / ".bias" under the norm's field name, in struct order) - what a real
+                                 checkpoint (README.md:44,55) needs, together with the options softmax_axis = 1,
+                                 layernorm_mode = 1 and norm_eps_mode = 1 */
 } tsd_diffusion_config;
 int32_t tsd_diffusion_create(tsd_ctx* ctx, const tsd_diffusion_config* cfg, tsd_diffusion** out);
 int32_t tsd_diffusion_destroy(tsd_diffusion* m);

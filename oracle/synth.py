@@ -28,6 +28,8 @@ def _splitmix64_scalar(x: int) -> int:
 
 def synth_tensor(seed: int, index: int, numel: int, scale: np.float32) -> np.ndarray:
     """value(j) = float32(int(z >> 40) - 2^23) * float32(scale * 2^-23), z = splitmix64(pseed + j)."""
+    if scale is None:
+        return np.ones(numel, np.float32)
     if float(scale) == 0.0:
         return np.zeros(numel, np.float32)
     pseed = _splitmix64_scalar(seed ^ _splitmix64_scalar(index + 1))
@@ -72,8 +74,15 @@ def _linear(specs, name, fin, fout, bias):
         specs.append((name + ".bias", (fout,), s))
 
 
-def diffusion_specs(context_dim: int = 768):
-    """[(name, reference-layout shape, init scale)] in blob order."""
+def _norm(specs, name, c):
+    # init scale None = the constant 1 (norm weight); the bias is 0
+    specs.append((name + ".weight", (c,), None))
+    specs.append((name + ".bias", (c,), np.float32(0.0)))
+
+
+def diffusion_specs(context_dim: int = 768, norm_affine: bool = False):
+    """[(name, reference-layout shape, init scale)] in blob order.  norm_affine: the per-channel weight / bias of every
+    GroupNorm / LayerNorm, in struct order (tsd_diffusion_config.norm_affine)."""
     sp = []
     _linear(sp, "time_embed.layer1", 320, 1280, True)
     _linear(sp, "time_embed.layer2", 1280, 1280, True)
@@ -90,23 +99,37 @@ def diffusion_specs(context_dim: int = 768):
         elif layer in RES_LAYER:
             i = RES_LAYER.index(layer)
             cin, cout = RES_IN[i], RES_OUT[i]
+            if norm_affine:
+                _norm(sp, base + ".layer1", cin)
             _conv(sp, base + ".layer2", cin, cout, 3)
             _linear(sp, base + ".layer3", 1280, cout, True)
+            if norm_affine:
+                _norm(sp, base + ".layer4", cout)
             _conv(sp, base + ".layer5", cout, cout, 3)
             if cin != cout:
                 _conv(sp, base + ".layer6", cin, cout, 1)
         else:
             c = ATTN_C[ATTN_LAYER.index(layer)]
+            if norm_affine:
+                _norm(sp, base + ".layer1", c)
             _conv(sp, base + ".layer2", c, c, 1)
+            if norm_affine:
+                _norm(sp, base + ".layer3", c)
             _linear(sp, base + ".layer4.in_proj", c, 3 * c, False)
             _linear(sp, base + ".layer4.out_proj", c, c, True)
+            if norm_affine:
+                _norm(sp, base + ".layer5", c)
             _linear(sp, base + ".layer6.q_proj", c, c, False)
             _linear(sp, base + ".layer6.k_proj", context_dim, c, False)
             _linear(sp, base + ".layer6.v_proj", context_dim, c, False)
             _linear(sp, base + ".layer6.out_proj", c, c, True)
+            if norm_affine:
+                _norm(sp, base + ".layer7", c)
             _linear(sp, base + ".layer8", c, 8 * c, True)
             _linear(sp, base + ".layer9", 4 * c, c, True)
             _conv(sp, base + ".layer10", c, c, 1)
+    if norm_affine:
+        _norm(sp, "final.layer1", 320)
     _conv(sp, "final.layer2", 320, 4, 3)
     return sp
 
@@ -252,6 +275,9 @@ def random_blob(specs, seed: int, bias_scale: float = 1.0) -> np.ndarray:
     parts = []
     for name, shape, scale in specs:
         n = int(np.prod(shape))
+        if scale is None:   # norm weight: around 1
+            parts.append((1.0 + 0.3 * (rng.random(n, dtype=np.float32) * 2 - 1)).astype(np.float32))
+            continue
         s = float(scale)
         if s == 0.0:
             s = 0.05 * bias_scale

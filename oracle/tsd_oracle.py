@@ -38,6 +38,7 @@ class Switches:
     softmax_axis: str = "query"      # Q3: "query" (reference Softmax(dim=2)) | "key" (standard)
     layernorm: str = "global"        # Q5: "global" (GroupNorm(1,C) over the whole tensor) | "token"
     mojo_alias_time: bool = False    # Q2: SiLU^k(t_emb) aliasing, off by default
+    norm_eps_inside: bool = False    # Q6: False = (x-mean)/(std+eps) as the reference; True = (x-mean)/sqrt(var+eps)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -148,11 +149,12 @@ class Ops:
         return self.arr(a) @ self.arr(b)
 
     # GroupNorm.forward, helpers/utils.mojo:1845-1885; (x-mean)/(std+eps), biased std, gamma=1 (Q6)
-    def group_norm(self, x, groups, eps=1e-5):
+    def group_norm(self, x, groups, eps=1e-5, gamma=None, beta=None):
+        """gamma / beta: optional per-channel vectors (the reference has a scalar gamma = 1 and never adds beta)."""
         c = x.shape[0]
         if c % groups:
             raise ValueError("Number of channels does not evenly divide the number of groups")
-        if self.backend == "c32":
+        if self.backend == "c32" and gamma is None and beta is None and not self.sw.norm_eps_inside:
             x = _f32(x)
             out = np.empty_like(x)
             clib().ref_groupnorm(_p(x), c, int(np.prod(x.shape[1:])), groups, eps, _p(out))
@@ -160,19 +162,32 @@ class Ops:
         x = self.arr(x)
         g = x.reshape(groups, -1)
         mean = g.mean(axis=1, keepdims=True)
-        std = np.sqrt(((g - mean) ** 2).mean(axis=1, keepdims=True))
-        return ((g - mean) / (std + self.dtype(eps))).reshape(x.shape)
+        var = ((g - mean) ** 2).mean(axis=1, keepdims=True)
+        den = np.sqrt(var + self.dtype(eps)) if self.sw.norm_eps_inside else np.sqrt(var) + self.dtype(eps)
+        out = ((g - mean) / den).reshape(x.shape)
+        bshape = (c,) + (1,) * (x.ndim - 1)
+        if gamma is not None:
+            out = out * self.arr(gamma).reshape(bshape)
+        if beta is not None:
+            out = out + self.arr(beta).reshape(bshape)
+        return out
 
     # LayerNorm.forward = GroupNorm(1, C) on the (C,T,1) Matrix, helpers/utils.mojo:2052-2061 (Q5).
     # x is token-major (T,C); statistics are layout independent in the default mode.
-    def layer_norm(self, x):
+    def layer_norm(self, x, gamma=None, beta=None):
         if self.sw.layernorm == "global":
             t, c = x.shape
-            return self.group_norm(np.ascontiguousarray(x.T).reshape(c, t, 1), 1, 1e-5).reshape(c, t).T
+            return self.group_norm(np.ascontiguousarray(x.T).reshape(c, t, 1), 1, 1e-5, gamma, beta).reshape(c, t).T
         x = self.arr(x)
         mean = x.mean(axis=1, keepdims=True)
-        std = np.sqrt(((x - mean) ** 2).mean(axis=1, keepdims=True))
-        return (x - mean) / (std + self.dtype(1e-5))
+        var = ((x - mean) ** 2).mean(axis=1, keepdims=True)
+        den = np.sqrt(var + self.dtype(1e-5)) if self.sw.norm_eps_inside else np.sqrt(var) + self.dtype(1e-5)
+        out = (x - mean) / den
+        if gamma is not None:
+            out = out * self.arr(gamma)[None, :]
+        if beta is not None:
+            out = out + self.arr(beta)[None, :]
+        return out
 
     def silu(self, x):  # SiLU.forward, helpers/utils.mojo:1892-1902
         if self.backend == "c32":
@@ -294,16 +309,23 @@ def time_embedding_mlp(ops: Ops, W, t):
     return ops.linear(h, W["time_embed.layer2.weight"], W["time_embed.layer2.bias"])[0]
 
 
+def _affine(W, name):
+    """(weight, bias) of a norm when the weight set carries them (norm_affine models), else (None, None)."""
+    if (name + ".weight") in W:
+        return W[name + ".weight"], W[name + ".bias"]
+    return None, None
+
+
 def unet_res_block(ops: Ops, W, base, x, time_act, cin, cout):
     """Unet_Residual_Block.forward, diffusion.mojo:54-72.  time_act = the vector fed to layer3
     (SiLU(t_emb), or SiLU^k under mojo_alias_time)."""
     x = x[:cin]
-    out = ops.group_norm(x, 32, 1e-5)
+    out = ops.group_norm(x, 32, 1e-5, *_affine(W, base + ".layer1"))
     out = ops.silu(out)
     out = ops.conv2d(out, W[base + ".layer2.weight"], W[base + ".layer2.bias"], pad=1)
     tb = ops.linear(ops.arr(time_act)[None, :], W[base + ".layer3.weight"], W[base + ".layer3.bias"])[0]
     merged = out + ops.arr(tb)[:, None, None]
-    merged = ops.group_norm(merged, 32, 1e-5)
+    merged = ops.group_norm(merged, 32, 1e-5, *_affine(W, base + ".layer4"))
     merged = ops.silu(merged)
     merged = ops.conv2d(merged, W[base + ".layer5.weight"], W[base + ".layer5.bias"], pad=1)
     if cin != cout:
@@ -315,22 +337,22 @@ def unet_attn_block(ops: Ops, W, base, x, context, n_heads=8):
     """Unet_Attention_Block.forward, diffusion.mojo:112-147; x (C,H,W), context (77,768)."""
     c, h, w = x.shape
     residue_long = ops.arr(x)
-    out = ops.group_norm(x, 32, 1e-6)
+    out = ops.group_norm(x, 32, 1e-6, *_affine(W, base + ".layer1"))
     out = ops.conv2d(out, W[base + ".layer2.weight"], W[base + ".layer2.bias"])
     seq = np.ascontiguousarray(out.reshape(c, h * w).T)         # (T,C) token-major view of :118-123
     rs = seq
-    seq = ops.layer_norm(seq)
+    seq = ops.layer_norm(seq, *_affine(W, base + ".layer3"))
     seq = ops.self_attention(seq, n_heads, W[base + ".layer4.in_proj.weight"], None,
                              W[base + ".layer4.out_proj.weight"], W[base + ".layer4.out_proj.bias"])
     seq = seq + rs
     rs = seq
-    seq = ops.layer_norm(seq)
+    seq = ops.layer_norm(seq, *_affine(W, base + ".layer5"))
     seq = ops.cross_attention(seq, context, n_heads, W[base + ".layer6.q_proj.weight"], None,
                               W[base + ".layer6.k_proj.weight"], None, W[base + ".layer6.v_proj.weight"], None,
                               W[base + ".layer6.out_proj.weight"], W[base + ".layer6.out_proj.bias"])
     seq = seq + rs
     rs = seq
-    seq = ops.layer_norm(seq)
+    seq = ops.layer_norm(seq, *_affine(W, base + ".layer7"))
     hcat = ops.linear(seq, W[base + ".layer8.weight"], W[base + ".layer8.bias"])     # (T,8C)
     half = hcat.shape[1] // 2
     seq = hcat[:, :half] * ops.gelu(np.ascontiguousarray(hcat[:, half:]))            # chunk(2,2) :138-141
@@ -381,7 +403,7 @@ def diffusion_forward(ops: Ops, W, x, context, time):
     out = att(7, res(7, out))                       # skip2 dead (Q9)
     out = att(8, res(8, cat(out, skip1)))
     del skip2, skip4
-    out = ops.group_norm(out, 320, 1e-5)            # GroupNorm(320, 320): Q11
+    out = ops.group_norm(out, 320, 1e-5, *_affine(W, "final.layer1"))   # GroupNorm(320, 320): Q11
     out = ops.silu(out)
     return ops.conv2d(out, W["final.layer2.weight"], W["final.layer2.bias"], pad=1)
 

@@ -119,6 +119,7 @@ int32_t tsd_synchronize(tsd_ctx* h) {
 static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "softmax_axis")) return &h->c->softmax_axis;
   if (!strcmp(name, "layernorm_mode")) return &h->c->layernorm_mode;
+  if (!strcmp(name, "norm_eps_mode")) return &h->c->norm_eps_mode;
   if (!strcmp(name, "fused_attention")) return &h->c->fused_attention;
   if (!strcmp(name, "attn_v2")) return &h->c->attn_v2;
   if (!strcmp(name, "cuda_graph")) return &h->use_graph;

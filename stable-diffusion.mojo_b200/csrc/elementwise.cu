@@ -284,7 +284,7 @@ group_stats_vec_kernel(const float4* __restrict__ x, long long pixels, int C4, i
       double var = dq / count - mean * mean;
       if (var < 0.0) var = 0.0;
       // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
-      stats[i] = make_float2((float)mean, (float)(1.0 / (sqrt(var) + (double)eps)));
+      stats[i] = make_float2((float)mean, (float)norm_rstd(var, (double)eps));
     }
   }
 }
@@ -431,7 +431,7 @@ norm_fused_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
           double var = dq / count - mean * mean;
           if (var < 0.0) var = 0.0;
           // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
-          st[g] = make_float2((float)mean, (float)(1.0 / (sqrt(var) + (double)eps)));
+          st[g] = make_float2((float)mean, (float)norm_rstd(var, (double)eps));
         }
       }
       __syncthreads();
@@ -552,9 +552,20 @@ norm_fused2_kernel(const NormFused2Params p) {
     }
     float4 a = p.x[row * p.ldx4 + qd];
     if (p.splits > 1) {
-      for (int s = 1; s < p.splits; ++s) {
-        const float4 t = p.x[row * p.ldx4 + qd + s * p.split_stride4];
-        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      // every split's tile is requested before the first add (a warp issues in order: load -> add -> load -> add
+      // costs one L2 round trip per split); the sum stays in split order
+      const float4* src = p.x + row * p.ldx4 + qd;
+      for (int s0 = 1; s0 < p.splits; s0 += 4) {
+        float4 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (s0 + k < p.splits) t[k] = src[(long long)(s0 + k) * p.split_stride4];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a.x += t[k].x; a.y += t[k].y; a.z += t[k].z; a.w += t[k].w;
+        }
       }
       if (p.bias) {
         const float4 b = *reinterpret_cast<const float4*>(p.bias + (long long)n * p.bias_img_stride + qd * 4);
@@ -754,7 +765,7 @@ norm_fused2_kernel(const NormFused2Params p) {
         double var = (double)mine.y * (double)p.inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
         // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
-        st[g] = make_float2((float)mean, 1.0f / (sqrtf((float)var) + p.eps));
+        st[g] = make_float2((float)mean, norm_rstd((float)var, p.eps));
       }
     }
   }
@@ -861,7 +872,7 @@ __global__ void group_stats_finalize_kernel(const double* __restrict__ accum, in
   double var = accum[2 * i + 1] / count - mean * mean;
   if (var < 0.0) var = 0.0;
   // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
-  double inv = 1.0 / (sqrt(var) + (double)eps);
+  double inv = norm_rstd(var, (double)eps);
   stats[i] = make_float2((float)mean, (float)inv);
 }
 
@@ -1002,7 +1013,7 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
       if (p < p1 && qd < C4s) emit(pre[k][i], i, (long long)p * C4 + qd);
     }
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int p = p0 + pl + NP * ppl; p < p1; p += ppl) {
 #pragma unroll
     for (int i = 0; i < GS_MAXQ; ++i) {
@@ -1689,7 +1700,13 @@ cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsR
     target = v ? atoi(v) : 2 * 148;  // two blocks per SM (measured best: 6.7 us for 64 x 64 x 320 against 9.6 at four)
     if (target < 1) target = 2 * 148;
   }
-  int slabs = (target + N * nseg - 1) / (N * nseg);
+  // small tensors (the UNet's <= 5 MB activations) are latency chains: two blocks per SM; the decoder's tensors of tens
+  // to thousands of MB need loads in flight to fill HBM: up to eight blocks per SM
+  const long long bytes = 4ll * N * pixels_ll * req.C;
+  int tgt = target;
+  if (bytes > (256ll << 20)) tgt = 8 * target / 2;
+  else if (bytes > (32ll << 20)) tgt = 4 * target / 2;
+  int slabs = (tgt + N * nseg - 1) / (N * nseg);
   int slab = (pixels + slabs - 1) / slabs;
   slab = (slab + ppl - 1) / ppl * ppl;
   if (slab < ppl) slab = ppl;

@@ -172,6 +172,12 @@ int ParamStore::add_linear(const std::string& name, int in_f, int out_f, bool bi
   if (bias) add(name + ".bias", P_VEC, out_f, 1, 1, s);
   return i;
 }
+int ParamStore::add_norm(const std::string& name, int channels) {
+  int i = add(name + ".weight", P_VEC, channels, 1, 1, 0.0f);
+  params[i].init_const = 1.0f;
+  add(name + ".bias", P_VEC, channels, 1, 1, 0.0f);
+  return i;
+}
 int ParamStore::allocate() {
   if (block) return TSD_OK;
   // every tensor starts 256 B aligned (TMA base alignment is 16 B)
@@ -248,7 +254,8 @@ int ParamStore::init_random(uint64_t seed) {
   for (size_t i = 0; i < params.size(); ++i) {
     Param& p = params[i];
     if (p.init_scale == 0.0f) {
-      TRY(c->check(cudaMemsetAsync(p.dev, 0, p.numel * sizeof(float), c->stream), "memset"));
+      if (p.init_const != 0.0f) TRY(c->check(launch_fill_uniform(p.dev, p.numel, 1, p.init_const, p.init_const, c->stream), "fill"));
+      else TRY(c->check(cudaMemsetAsync(p.dev, 0, p.numel * sizeof(float), c->stream), "memset"));
       continue;
     }
     const uint64_t pseed = splitmix64(seed ^ splitmix64((uint64_t)i + 1));
@@ -415,7 +422,7 @@ int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, co
   WALLOC(h1, px * w.cin);
   const NormStatsReq* xs = (x.ns.G == w.groups && x.ns.eps == eps && x.C == w.cin) ? x.ns.ready() : nullptr;
   const bool xmatch = x.ns.G == w.groups && x.ns.eps == eps && x.C == w.cin;
-  TRY(op_group_norm(c, x.p, h1, N, H, W, w.cin, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, xs,
+  TRY(op_group_norm(c, x.p, h1, N, H, W, w.cin, w.groups, eps, ps.gamma(w.gn1), ps.beta(w.gn1), 1.0f, 1, 0, 1, xs,
                     xmatch ? x.ns.deferred() : nullptr));
   WALLOC(h2, px * w.cout);
   NormHint mid;
@@ -428,7 +435,7 @@ int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, co
   if (!mid.scratch) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
   TRY(conv(c, ps, w.conv1, h1, N, H, W, w.cin, w.cout, 3, 1, 1, tbias, tbias_stride, nullptr, h2, 0, &mid));
   WALLOC(h3, px * w.cout);
-  TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, nullptr, nullptr, 1.0f, 1, 0, 1, mid.ready(), mid.deferred()));
+  TRY(op_group_norm(c, h2, h3, N, H, W, w.cout, w.groups, eps, ps.gamma(w.gn2), ps.beta(w.gn2), 1.0f, 1, 0, 1, mid.ready(), mid.deferred()));
   const float* r = x.p;
   if (w.cin != w.cout && c->fuse_skip && w.cin % 64 == 0 && w.cout % 64 == 0) {
     // res_conv_layer (1x1, diffusion.mojo:66-70 / vae.mojo:64-66) rides in the K loop of conv2: one GEMM over
@@ -450,10 +457,11 @@ int res_block(Ctx* c, const ParamStore& ps, const ResBlockW& w, const Act& x, co
 }
 
 // LayerNorm.forward = GroupNorm(1, C) over the whole (C,T) tensor of one image (Q5), or per token
-static int layer_norm(Ctx* c, const float* x, float* y, int N, long long T, int C, const NormStatsReq* pre = nullptr) {
+static int layer_norm(Ctx* c, const float* x, float* y, int N, long long T, int C, const NormStatsReq* pre = nullptr,
+                      const float* gamma = nullptr, const float* beta = nullptr) {
   if (c->layernorm_mode == 0)
-    return op_group_norm(c, x, y, N, (int)T, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1, pre);
-  return op_group_norm(c, x, y, (int)(N * T), 1, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1);
+    return op_group_norm(c, x, y, N, (int)T, 1, C, 1, 1e-5f, gamma, beta, 1.0f, 0, 0, 1, pre);
+  return op_group_norm(c, x, y, (int)(N * T), 1, 1, C, 1, 1e-5f, gamma, beta, 1.0f, 0, 0, 1);
 }
 
 // Unet_Attention_Block.forward, diffusion.mojo:112-147
@@ -464,7 +472,7 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   const size_t mark = c->arena.mark();
   WALLOC(a, M * C);
   const NormStatsReq* xs = (x.ns.G == 32 && x.ns.eps == 1e-6f) ? x.ns.ready() : nullptr;
-  TRY(op_group_norm(c, x.p, a, N, x.H, x.W, C, 32, 1e-6f, nullptr, nullptr, 1.0f, 0, 0, 1, xs,
+  TRY(op_group_norm(c, x.p, a, N, x.H, x.W, C, 32, 1e-6f, ps.gamma(w.gn), ps.beta(w.gn), 1.0f, 0, 0, 1, xs,
                     (x.ns.G == 32 && x.ns.eps == 1e-6f) ? x.ns.deferred() : nullptr));
   // LayerNorm with global statistics (Q5) = one group per image: the producing GEMMs fold the sums
   NormHint ln;
@@ -478,19 +486,21 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   TRY(linear(c, a, M, C, ps.w(w.conv_in), ps.w(w.conv_in + 1), C, u, C, nullptr, 0, 0, 0, 0, &ln));
   WALLOC(v, M * C);
   // LayerNorm folded into the consuming GEMM's epilogue when its statistics came with the producer
-  auto ln_then_linear = [&](const float* src, int wi, const float* bias, int Nout, float* dst, long long ldd, int geglu,
-                            int split_n, long long split_stride) -> int {
-    if (c->ln_fold && ln.ready() && T % 128 == 0) {
+  // (a LayerNorm with per-channel weight / bias - norm_affine models - is not a scalar scale and shift: it runs as
+  // its own pass)
+  auto ln_then_linear = [&](const float* src, int lni, int wi, const float* bias, int Nout, float* dst, long long ldd,
+                            int geglu, int split_n, long long split_stride) -> int {
+    if (c->ln_fold && ln.ready() && T % 128 == 0 && lni < 0) {
       const float* ws = const_cast<ParamStore&>(ps).rowsum(wi);
       if (!ws) return c->fail(TSD_ERR_OOM, "rowsum");
       const NormStatsReq req = ln.req;  // the producer of `src` filled it; the next producer will overwrite ln
       return linear(c, src, M, C, ps.w(wi), bias, Nout, dst, ldd, nullptr, 1, geglu, split_n, split_stride, nullptr, &req, ws);
     }
-    TRY(layer_norm(c, src, v, N, T, C, ln.ready()));
+    TRY(layer_norm(c, src, v, N, T, C, ln.ready(), ps.gamma(lni), ps.beta(lni)));
     return linear(c, v, M, C, ps.w(wi), bias, Nout, dst, ldd, nullptr, 1, geglu, split_n, split_stride);
   };
   WALLOC(qkv, 3 * M * C);
-  TRY(ln_then_linear(u, w.in_proj, nullptr, 3 * C, qkv, C, 0, C, M * C));
+  TRY(ln_then_linear(u, w.ln1, w.in_proj, nullptr, 3 * C, qkv, C, 0, C, M * C));
   WALLOC(o, M * C);
   {
     AttnArgs at;
@@ -502,7 +512,7 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   WALLOC(u2, M * C);
   TRY(linear(c, o, M, C, ps.w(w.out_proj), ps.w(w.out_proj + 1), C, u2, C, u, 0, 0, 0, 0, &ln));
   float* q = qkv;
-  TRY(ln_then_linear(u2, w.q, nullptr, C, q, C, 0, 0, 0));
+  TRY(ln_then_linear(u2, w.ln2, w.q, nullptr, C, q, C, 0, 0, 0));
   {
     AttnArgs at;
     at.Q = q; at.K = kctx; at.V = vctx;
@@ -515,7 +525,7 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   TRY(linear(c, o, M, C, ps.w(w.o), ps.w(w.o + 1), C, u3, C, u2, 0, 0, 0, 0, &ln));
   WALLOC(g, M * 4 * C);
   // GEGLU: Linear(C -> 8C), chunk(2,2), out * gelu(gate)  (diffusion.mojo:138-141)
-  TRY(ln_then_linear(u3, w.geglu1, ps.w(w.geglu1 + 1), 8 * C, g, 4 * C, 1, 0, 0));
+  TRY(ln_then_linear(u3, w.ln3, w.geglu1, ps.w(w.geglu1 + 1), 8 * C, g, 4 * C, 1, 0, 0));
   float* u4 = u;  // u is dead after u2
   TRY(linear(c, g, M, 4 * C, ps.w(w.geglu2), ps.w(w.geglu2 + 1), C, u4, C, u3, 1));
   if (next) next->imgs = N;
@@ -563,8 +573,12 @@ int Diffusion::create() {
       w.cin = kResIn[ri];
       w.cout = kResOut[ri];
       w.groups = 32;
+      // struct order of Unet_Residual_Block (diffusion.mojo:25-30): layer1 GroupNorm, layer2 conv, layer3 linear,
+      // layer4 GroupNorm, layer5 conv, layer6 conv
+      if (cfg.norm_affine) w.gn1 = ps.add_norm(base + ".layer1", w.cin);
       w.conv1 = ps.add_conv(base + ".layer2", w.cin, w.cout, 3);
       w.lin_t = ps.add_linear(base + ".layer3", 1280, w.cout, true);
+      if (cfg.norm_affine) w.gn2 = ps.add_norm(base + ".layer4", w.cout);
       w.conv2 = ps.add_conv(base + ".layer5", w.cout, w.cout, 3);
       // layer6 (1x1 skip conv) is allocated by the reference for every block but only used
       // when in != out (diffusion.mojo:42, 70-72): unused tensors are not part of the blob
@@ -575,19 +589,26 @@ int Diffusion::create() {
       w.C = kAttnC[ai];
       w.heads = 8;
       const int C = w.C;
+      // struct order of Unet_Attention_Block (diffusion.mojo:76-85): layer1 GroupNorm, layer2 conv, layer3 LayerNorm,
+      // layer4 self-attention, layer5 LayerNorm, layer6 cross-attention, layer7 LayerNorm, layer8, layer9, layer10
+      if (cfg.norm_affine) w.gn = ps.add_norm(base + ".layer1", C);
       w.conv_in = ps.add_conv(base + ".layer2", C, C, 1);
+      if (cfg.norm_affine) w.ln1 = ps.add_norm(base + ".layer3", C);
       w.in_proj = ps.add_linear(base + ".layer4.in_proj", C, 3 * C, false);
       w.out_proj = ps.add_linear(base + ".layer4.out_proj", C, C, true);
+      if (cfg.norm_affine) w.ln2 = ps.add_norm(base + ".layer5", C);
       w.q = ps.add_linear(base + ".layer6.q_proj", C, C, false);
       w.k = ps.add_linear(base + ".layer6.k_proj", cfg.context_dim, C, false);
       w.v = ps.add_linear(base + ".layer6.v_proj", cfg.context_dim, C, false);
       w.o = ps.add_linear(base + ".layer6.out_proj", C, C, true);
+      if (cfg.norm_affine) w.ln3 = ps.add_norm(base + ".layer7", C);
       w.geglu1 = ps.add_linear(base + ".layer8", C, 8 * C, true);
       w.geglu2 = ps.add_linear(base + ".layer9", 4 * C, C, true);
       w.conv_out = ps.add_conv(base + ".layer10", C, C, 1);
       ++ai;
     }
   }
+  if (cfg.norm_affine) final_gn = ps.add_norm("final.layer1", 320);
   final_conv = ps.add_conv("final.layer2", 320, 4, 3);
 
   const size_t B = cfg.max_batch, HW = (size_t)cfg.latent_h * cfg.latent_w;
@@ -823,7 +844,7 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
   // UNet_Output_Layer: GroupNorm(320 groups) -> SiLU -> conv 320->4 (diffusion.mojo:280, 287-291)
   Act f = act(320, H, W);
   NEED(f);
-  TRY(op_group_norm(c, a23.p, f.p, n, H, W, 320, 320, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1,
+  TRY(op_group_norm(c, a23.p, f.p, n, H, W, 320, 320, 1e-5f, ps.gamma(final_gn), ps.beta(final_gn), 1.0f, 1, 0, 1,
                     (a23.ns.G == 320) ? a23.ns.ready() : nullptr));
   TRY(conv(c, ps, final_conv, f.p, n, H, W, 320, 4, 3, 1, 1, nullptr, 0, nullptr, eps_nhwc, 0));
 #undef NEED

@@ -27,6 +27,7 @@ struct Param {
   long long numel = 0;
   long long offset = 0;      // float offset in the reference-order blob
   float init_scale = 0.f;    // synthetic init: U(-s, s)
+  float init_const = 0.f;    // synthetic init when init_scale == 0: this value (norm weights: 1)
   float* dev = nullptr;
 };
 
@@ -42,6 +43,10 @@ struct ParamStore {
   int add_conv(const std::string& name, int cin, int cout, int k);
   // linear (weight[, bias]) -> index of the weight
   int add_linear(const std::string& name, int in_f, int out_f, bool bias);
+  // per-channel norm (weight = 1, bias = 0 at synthetic init) -> index of the weight; bias is index + 1
+  int add_norm(const std::string& name, int channels);
+  const float* gamma(int i) const { return i >= 0 ? params[i].dev : nullptr; }
+  const float* beta(int i) const { return i >= 0 ? params[i + 1].dev : nullptr; }
   int allocate();
   int load(const float* blob, long long n_floats);
   int init_random(uint64_t seed);
@@ -73,12 +78,14 @@ struct Act {
 struct ResBlockW {
   int cin = 0, cout = 0;
   int conv1 = -1, lin_t = -1, conv2 = -1, skip = -1;  // param indices of the weights
+  int gn1 = -1, gn2 = -1;  // per-channel norm weights (norm_affine models only)
   int groups = 32;
 };
 struct AttnBlockW {
   int heads = 8, C = 0;
   int conv_in = -1, in_proj = -1, out_proj = -1, q = -1, k = -1, v = -1, o = -1, geglu1 = -1, geglu2 = -1,
       conv_out = -1;
+  int gn = -1, ln1 = -1, ln2 = -1, ln3 = -1;  // per-channel norm weights (norm_affine models only)
 };
 
 struct GraphSlot {
@@ -96,7 +103,7 @@ struct Diffusion {
   Ctx* c = nullptr;
   tsd_diffusion_config cfg{};
   ParamStore ps;
-  int te1 = -1, te2 = -1, conv_in = -1, final_conv = -1, down1 = -1, down2 = -1;
+  int te1 = -1, te2 = -1, conv_in = -1, final_conv = -1, down1 = -1, down2 = -1, final_gn = -1;
   ResBlockW res[9];
   AttnBlockW attn[9];
   // persistent device buffers (fixed addresses -> CUDA-graph friendly)

@@ -18,6 +18,15 @@
 
 namespace tsd {
 
+// 1 / (std + eps) as the reference computes it (helpers/utils.mojo:1868-1870), or - eps < 0, the
+// "norm_eps_mode" option used with real checkpoints - the usual 1 / sqrt(var + |eps|)
+__host__ __device__ __forceinline__ float norm_rstd(float var, float eps) {
+  return eps >= 0.f ? 1.0f / (sqrtf(var) + eps) : 1.0f / sqrtf(var - eps);
+}
+__host__ __device__ __forceinline__ double norm_rstd(double var, double eps) {
+  return eps >= 0.0 ? 1.0 / (sqrt(var) + eps) : 1.0 / sqrt(var - eps);
+}
+
 struct NormStatsReq {
   float2* partial = nullptr;     // (nullptr: no statistics available)
   int lg = 0;                    // entries per tile = max groups overlapping BN columns
@@ -128,7 +137,7 @@ __device__ __forceinline__ void norm_stats_fold(const NormStatsReq& r, int img, 
       const double mean = (double)ms * (double)r.inv_count;
       double var = (double)mq * (double)r.inv_count - mean * mean;
       if (var < 0.0) var = 0.0;
-      st[g - g_begin] = make_float2((float)mean, 1.0f / (sqrtf((float)var) + r.eps));
+      st[g - g_begin] = make_float2((float)mean, norm_rstd((float)var, r.eps));
     }
   }
   if (!hooked) after_issue();  // threads without a table entry of their own

@@ -553,7 +553,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
       ns.slabs_total = (int)(imgs * slabs_per_img);
       ns.set_magics();
       ns.inv_count = (float)(1.0 / ((double)rows_per_img * cpg));
-      ns.eps = nh->eps;
+      ns.eps = c->norm_eps_mode ? -fabsf(nh->eps) : nh->eps;
       if (p.splits == 1 || p.fixup) p.ns = ns;
       else rp.ns = ns;
       nh->req = ns;
@@ -1013,6 +1013,7 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
                   const float* gamma, const float* beta, float gamma_scalar, int silu, int upsample,
                   int round_tf32, const NormStatsReq* pre, const NormHint::Deferred* def) {
   if (G <= 0 || C % G) return c->fail(TSD_ERR_INVALID, "group_norm: channels not divisible by groups");
+  if (c->norm_eps_mode) eps = -fabsf(eps);  // kernels read a negative eps as "inside the square root" (norm_rstd)
   if (def != nullptr && def->ws != nullptr) {
     // the producer was a split-K GEMM that left its partial tiles: sum them, add bias / residual, write the raw
     // output (x) and normalise in one launch

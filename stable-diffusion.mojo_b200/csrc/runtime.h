@@ -117,6 +117,7 @@ struct Ctx {
   int fused_attention = 1;  // 1 = tcgen05 fused kernel ; 0 = GEMM + softmax + GEMM
   int attn_v2 = 1;          // fused attention: 1 = software-pipelined softmax role (attn2_kernel) where the shape allows, 0 = attn_kernel
   int layernorm_mode = 0;   // 0 = global statistics (reference, Q5) ; 1 = per token
+  int norm_eps_mode = 0;    // 0 = (x - mean) / (std + eps) (reference, Q6) ; 1 = (x - mean) / sqrt(var + eps)
   int force_bn = 0, force_splits = 0;  // test/tuning overrides for the GEMM tile heuristic
   int force_stages = 0;     // tuning: operand ring depth override
   int gemm_cg = 0;          // tuning: 0 = model decides, 1 = single CTAs, 2 = CTA pairs (cta_group::2)

@@ -36,6 +36,7 @@ class DiffusionConfig(C.Structure):
         ("context_len", C.c_int32),
         ("context_dim", C.c_int32),
         ("mojo_alias_time", C.c_int32),
+        ("norm_affine", C.c_int32),
     ]
 
 

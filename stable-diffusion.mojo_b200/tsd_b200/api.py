@@ -285,10 +285,12 @@ class Diffusion(_Model):
     _prefix = "diffusion"
 
     def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1, context_len=77, context_dim=768,
-                 mojo_alias_time=False):
+                 mojo_alias_time=False, norm_affine=False):
+        """norm_affine: every GroupNorm / LayerNorm carries a per-channel weight and bias (what a real checkpoint needs;
+        the reference's norm structs own no tensors, so the default is off)."""
         self.ctx = ctx
         self.cfg = _lib.DiffusionConfig(latent_h, latent_w, max_batch, context_len, context_dim,
-                                        int(mojo_alias_time))
+                                        int(mojo_alias_time), int(norm_affine))
         m = C.c_void_p()
         ctx._ck(ctx.L.tsd_diffusion_create(ctx.h, C.byref(self.cfg), C.byref(m)))
         self.m = m

@@ -6,10 +6,15 @@
   checkpoint and a name map {parameter name of this library: tensor name in the file}.
 * `export_model` / `import_model`: a model's parameters to / from a safetensors file under this library's names.
 
-What is NOT here: a verified name map for `segmind/tiny-sd`.  No checkpoint exists offline to check one against, and
-the reference's structs own no GroupNorm / LayerNorm affine tensors (helpers/utils.mojo:1825-1872, 2052-2061), so a
-real checkpoint's norm weights have nowhere to go without extending the model; `missing` / `unused` in the report of
-`build_blob` make both visible instead of hiding them."""
+* `tiny_sd_unet_name_map`: this library's UNet parameter names -> diffusers-convention tensor names (the layout
+  `segmind/tiny-sd` ships in: `down_blocks.N.resnets.M.conv1.weight`, `...attentions.M.transformer_blocks.0.attn1.to_q.weight`,
+  ...), for a model created with `norm_affine=True` (a real checkpoint's GroupNorm / LayerNorm weights need a home; the
+  reference's norm structs own no tensors, helpers/utils.mojo:1825-1872, 2052-2061).  A fused tensor of this library
+  (self-attention `in_proj` = to_q | to_k | to_v) maps to a LIST of file tensors concatenated along their first axis.
+  The map follows the reference's 23-layer topology (diffusion.mojo:175-201); no checkpoint exists offline, so it is
+  tested against a synthetic file with those names, not against the published weights - `missing` / `unused` in the
+  report of `build_blob` show what a real file does not cover (e.g. the upsamplers' convolutions, which the reference's
+  `Upsample` does not have).  Run such a model with softmax_axis = 1, layernorm_mode = 1, norm_eps_mode = 1."""
 from __future__ import annotations
 
 import ctypes as C
@@ -110,14 +115,15 @@ def build_blob(param_table, source: SafeTensors, name_map: dict | None = None, s
     used, missing = set(), []
     for name, off, numel in param_table:
         src = (name_map or {}).get(name, name)
-        if src not in source:
+        parts = list(src) if isinstance(src, (list, tuple)) else [src]   # a list: tensors concatenated along axis 0
+        if any(p not in source for p in parts):
             missing.append(name)
             continue
-        t = source.read(src)
+        t = np.concatenate([source.read(p).reshape(-1) for p in parts])
         if t.size != numel:
             raise TsdError(1, f"checkpoint tensor {src} has {t.size} elements, parameter {name} needs {numel}")
-        blob[off:off + numel] = t.reshape(-1)
-        used.add(src)
+        blob[off:off + numel] = t
+        used.update(parts)
     if strict and missing:
         raise TsdError(1, f"checkpoint lacks {len(missing)} parameters, first: {missing[0]}")
     return blob, {"missing": missing, "unused": [n for n in source.names() if n not in used]}
@@ -139,3 +145,50 @@ def import_model(model, path, name_map: dict | None = None, strict: bool = True)
         st.close()
     model.load_weights(blob)
     return report
+
+
+# reference layer number (diffusion.mojo:175-201) -> diffusers block path, for the 23-layer topology of the reference
+_RES_PATH = {2: "down_blocks.0.resnets.0", 5: "down_blocks.1.resnets.0", 8: "down_blocks.2.resnets.0",
+             10: "up_blocks.0.resnets.0", 12: "up_blocks.0.resnets.1", 15: "up_blocks.1.resnets.0",
+             17: "up_blocks.1.resnets.1", 20: "up_blocks.2.resnets.0", 22: "up_blocks.2.resnets.1"}
+_ATTN_PATH = {3: "down_blocks.0.attentions.0", 6: "down_blocks.1.attentions.0", 9: "down_blocks.2.attentions.0",
+              11: "up_blocks.0.attentions.0", 13: "up_blocks.0.attentions.1", 16: "up_blocks.1.attentions.0",
+              18: "up_blocks.1.attentions.1", 21: "up_blocks.2.attentions.0", 23: "up_blocks.2.attentions.1"}
+_RES_FIELD = {"layer1": "norm1", "layer2": "conv1", "layer3": "time_emb_proj", "layer4": "norm2", "layer5": "conv2",
+              "layer6": "conv_shortcut"}
+_ATTN_FIELD = {"layer1": "norm", "layer2": "proj_in", "layer3": "transformer_blocks.0.norm1",
+               "layer4.out_proj": "transformer_blocks.0.attn1.to_out.0", "layer5": "transformer_blocks.0.norm2",
+               "layer6.q_proj": "transformer_blocks.0.attn2.to_q", "layer6.k_proj": "transformer_blocks.0.attn2.to_k",
+               "layer6.v_proj": "transformer_blocks.0.attn2.to_v", "layer6.out_proj": "transformer_blocks.0.attn2.to_out.0",
+               "layer7": "transformer_blocks.0.norm3", "layer8": "transformer_blocks.0.ff.net.0.proj",
+               "layer9": "transformer_blocks.0.ff.net.2", "layer10": "proj_out"}
+
+
+def tiny_sd_unet_name_map(param_names) -> dict:
+    """{parameter name of a norm_affine Diffusion: diffusers tensor name, or a list of names to concatenate}."""
+    out = {}
+    for name in param_names:
+        stem, kind = name.rsplit(".", 1)             # ".weight" / ".bias"
+        if stem.startswith("time_embed.layer"):
+            out[name] = f"time_embedding.linear_{stem[-1]}.{kind}"
+        elif stem == "unet.layer1":
+            out[name] = f"conv_in.{kind}"
+        elif stem in ("unet.layer4", "unet.layer7"):
+            out[name] = f"down_blocks.{0 if stem.endswith('4') else 1}.downsamplers.0.conv.{kind}"
+        elif stem == "final.layer1":
+            out[name] = f"conv_norm_out.{kind}"
+        elif stem == "final.layer2":
+            out[name] = f"conv_out.{kind}"
+        elif stem.startswith("unet.layer"):
+            layer, field = stem[len("unet.layer"):].split(".", 1)
+            layer = int(layer)
+            if layer in _RES_PATH:
+                out[name] = f"{_RES_PATH[layer]}.{_RES_FIELD[field]}.{kind}"
+            elif field == "layer4.in_proj":          # to_q | to_k | to_v stacked along the output axis (attention.mojo:29)
+                base = f"{_ATTN_PATH[layer]}.transformer_blocks.0.attn1"
+                out[name] = [f"{base}.to_q.{kind}", f"{base}.to_k.{kind}", f"{base}.to_v.{kind}"]
+            else:
+                out[name] = f"{_ATTN_PATH[layer]}.{_ATTN_FIELD[field]}.{kind}"
+        else:
+            raise KeyError(name)
+    return out

@@ -408,3 +408,21 @@ def test_encoder_golden_reproduced(opsc):
     sm.set_strength(0.6)
     assert np.array_equal(sm.timesteps, g["i2i_timesteps"])
     assert relerr(sm.add_noise(g["z16"], sm.timesteps[0], g["i2i_start_noise"].astype(np.float64)), g["i2i_start"]) < 1e-14
+
+
+def test_affine_norms_and_eps_mode_match_torch():
+    """Row f2: per-channel norm weights and the standard eps placement (norm_eps_inside) of the oracle against
+    torch.nn.functional - what a real checkpoint needs on top of the reference's scalar-gamma (x - mean) / (std + eps)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(3)
+    ops = O.Ops("np", np.float64, O.Switches(layernorm="token", norm_eps_inside=True))
+    x = rng.standard_normal((32, 6, 5))
+    g, b = rng.standard_normal(32), rng.standard_normal(32)
+    want = F.group_norm(torch.from_numpy(x)[None], 8, torch.from_numpy(g), torch.from_numpy(b), 1e-5)[0].numpy()
+    assert np.abs(ops.group_norm(x, 8, 1e-5, g, b) - want).max() < 1e-12
+    seq = rng.standard_normal((11, 32))
+    want = F.layer_norm(torch.from_numpy(seq), (32,), torch.from_numpy(g), torch.from_numpy(b), 1e-5).numpy()
+    assert np.abs(ops.layer_norm(seq, g, b) - want).max() < 1e-12
+    ref = O.Ops("np", np.float64)                       # reference placement differs, by construction
+    assert np.abs(ref.group_norm(x, 8, 1e-1) - ops.group_norm(x, 8, 1e-1)).max() > 1e-3

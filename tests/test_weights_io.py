@@ -112,3 +112,44 @@ def test_build_blob_from_name_map(tmp_path):
     assert rep["missing"] == ["unet.layer2.weight"]
     with pytest.raises(TsdError):                        # element count mismatch
         W.build_blob([("unet.layer1.bias", 0, 9)], st, name_map)
+
+
+def test_tiny_sd_name_map_round_trip(tmp_path):
+    """A synthetic checkpoint under diffusers-convention names (the layout segmind/tiny-sd ships in) assembles, through
+    tiny_sd_unet_name_map, into exactly the blob a norm_affine Diffusion expects: every parameter is found, the fused
+    self-attention in_proj is rebuilt from to_q | to_k | to_v, conv kernels keep OIHW, and the tensors the reference's
+    topology has no home for (upsampler convolutions) are reported as unused instead of being dropped silently."""
+    import synth
+    specs = synth.diffusion_specs(norm_affine=True)
+    blob = synth.random_blob(specs, 21)
+    ours = synth.BlobWeights(specs, blob)
+    table, off = [], 0
+    for name, shape, _ in specs:
+        n = int(np.prod(shape))
+        table.append((name, off, n))
+        off += n
+    nm = W.tiny_sd_unet_name_map([t[0] for t in table])
+    assert len(nm) == len(table) and len(set(map(str, nm.values()))) == len(nm)     # one-to-one
+    assert nm["unet.layer2.layer1.weight"] == "down_blocks.0.resnets.0.norm1.weight"
+    assert nm["unet.layer23.layer8.bias"] == "up_blocks.2.attentions.1.transformer_blocks.0.ff.net.0.proj.bias"
+    assert nm["unet.layer4.weight"] == "down_blocks.0.downsamplers.0.conv.weight"
+    assert nm["final.layer1.bias"] == "conv_norm_out.bias"
+    file_tensors = {}
+    for name, shape, _ in specs:
+        src = nm[name]
+        if isinstance(src, list):                       # split the fused projection the way the file stores it
+            parts = np.split(ours[name], len(src), axis=0)
+            for s_, p_ in zip(src, parts):
+                file_tensors[s_] = p_
+        elif src.endswith("proj_in.weight") or src.endswith("proj_out.weight"):
+            file_tensors[src] = ours[name].reshape(shape[0], shape[1])   # tiny-sd stores the 1x1 projections as linears
+        else:
+            file_tensors[src] = ours[name]
+    file_tensors["up_blocks.0.upsamplers.0.conv.weight"] = np.zeros((4, 4, 3, 3), np.float32)   # no counterpart (Q8)
+    path = tmp_path / "tiny_sd_like.safetensors"
+    W.write_safetensors(path, file_tensors)
+    st = W.SafeTensors(path)
+    got, report = W.build_blob(table, st, nm)
+    st.close()
+    assert np.array_equal(got, blob)
+    assert report["missing"] == [] and report["unused"] == ["up_blocks.0.upsamplers.0.conv.weight"]
