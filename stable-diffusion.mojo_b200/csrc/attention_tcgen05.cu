@@ -435,6 +435,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
 // Preconditions (attention_fused picks v1 otherwise): BN in {64, 128}, Ty a multiple of BN, and for the query-axis
 // apply pass Ty * 4 bytes of extra shared memory.
 // ------------------------------------------------------------------------------------------
+// 2^x for x <= ~0 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, below the 2^-11 rounding P takes on its way into the tensor core),
+// exponent added to the bit pattern.  MUFU.EX2 retires one warp instruction per ~10.4 cycles per scheduler on this part
+// (measured, tools/lab/ubench.cu), which bounds both softmax passes; every fourth exponential taken here shortens the
+// MUFU queue by a quarter while the FMA pipe (otherwise one FFMA per element) stays below it.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);                    // keeps the result a normal number (values this small do not matter)
+  const float y = x + 12582912.0f;          // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+  const float n = y - 12582912.0f;
+  const float f = x - n;
+  float p = fmaf(f, 0.05517157f, 0.24261111f);
+  p = fmaf(p, f, 0.69326103f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
+}
+
 __device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
   // zero instructions: pins the uses of v[] behind the preceding tcgen05.wait::ld in the compiler's schedule
   asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
@@ -443,7 +459,7 @@ __device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
                     "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
 }
 
-template <int MODE, bool PER_ROW, int NCH, bool TRACE>
+template <int MODE, bool PER_ROW, int NCH, bool TRACE, bool POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
              const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
@@ -501,7 +517,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  pdl_wait();               // Q/K/V and the statistics come from predecessor kernels
+  // Statistics pass: Q / K come from the predecessor kernel - everybody waits.  Apply pass: its stream predecessor is
+  // the statistics pass of the same attention op, which itself waited for every earlier kernel BEFORE it allowed this
+  // launch (pdl_wait precedes pdl_launch_dependents in every thread of it), so Q / K / V are complete and visible the
+  // moment this kernel runs: the producer and the MMA issuer start at once, only the softmax warps - readers of the
+  // statistics, writers of O - wait.
+  if (!apply || warp >= 2) pdl_wait();
   pdl_launch_dependents();  // resources are held: the next kernel may start its prologue
   // S / P buffer b of a tile: columns [b * BN, (b + 1) * BN), b = tile % 3; O: [3 * BN, 3 * BN + dpad)
   const uint32_t tmem_o = tmem_base + (uint32_t)(3 * BN);
@@ -672,7 +693,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           a0 += ex2(fmaf(__uint_as_float(v[j]), c, -m));
           a1 += ex2(fmaf(__uint_as_float(v[j + 1]), c, -m));
           a2 += ex2(fmaf(__uint_as_float(v[j + 2]), c, -m));
-          a3 += ex2(fmaf(__uint_as_float(v[j + 3]), c, -m));
+          a3 += POLY ? ex2_poly(fmaf(__uint_as_float(v[j + 3]), c, -m)) : ex2(fmaf(__uint_as_float(v[j + 3]), c, -m));
         }
         l += (a0 + a1) + (a2 + a3);
         if (k == NCH - 1) {
@@ -732,7 +753,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const int it = g / NCH, k = g - it * NCH;
         if constexpr (PER_ROW) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(ex2(fmaf(__uint_as_float(v[j]), c, -mu_row)));
+          for (int j = 0; j < 32; ++j) {
+            const float xj = fmaf(__uint_as_float(v[j]), c, -mu_row);
+            v[j] = __float_as_uint((POLY && (j & 3) == 3) ? ex2_poly(xj) : ex2(xj));
+          }
         } else {
           const float4* mup = reinterpret_cast<const float4*>(mu_all + it * BN + cb + k * 32);
 #pragma unroll
@@ -741,7 +765,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             v[4 * j4 + 0] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 0]), c, -m4.x)));
             v[4 * j4 + 1] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 1]), c, -m4.y)));
             v[4 * j4 + 2] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 2]), c, -m4.z)));
-            v[4 * j4 + 3] = __float_as_uint(ex2(fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w)));
+            const float x3 = fmaf(__uint_as_float(v[4 * j4 + 3]), c, -m4.w);
+            v[4 * j4 + 3] = __float_as_uint(POLY ? ex2_poly(x3) : ex2(x3));
           }
         }
         tmem_st32(lane_base + (uint32_t)((it % 3) * BN + cb + k * 32), v);
@@ -864,21 +889,25 @@ cudaError_t launch_attn(const CUtensorMap& tmX, const CUtensorMap& tmY, const CU
   return launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);
 }
 
-template <int MODE, bool PER_ROW, int NCH, bool TRACE>
+template <int MODE, bool PER_ROW, int NCH, bool TRACE, bool POLY>
 cudaError_t launch_attn2_t(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV, const AttnKParams& p,
                            dim3 grid, size_t smem, cudaStream_t stream) {
   int max_dyn = 0;
-  cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(attn2_kernel<MODE, PER_ROW, NCH, TRACE>), -1, &max_dyn);
+  cudaError_t e = optin_dyn_smem(reinterpret_cast<const void*>(attn2_kernel<MODE, PER_ROW, NCH, TRACE, POLY>), -1, &max_dyn);
   if (e != cudaSuccess) return e;
   if ((long long)smem > max_dyn) return cudaErrorInvalidConfiguration;
-  return launch_pdl(attn2_kernel<MODE, PER_ROW, NCH, TRACE>, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);
+  return launch_pdl(attn2_kernel<MODE, PER_ROW, NCH, TRACE, POLY>, grid, dim3(ATT_THREADS), smem, stream, tmX, tmY, tmV, p);
 }
 cudaError_t launch_attn2(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmV, const AttnKParams& p,
-                         dim3 grid, size_t smem, cudaStream_t stream, bool trace) {
+                         dim3 grid, size_t smem, cudaStream_t stream, bool trace, bool poly) {
   const int nch = p.BN / 64;
-#define TSD_A2(MODE, PR, NCH)                                                                  \
-  (trace ? launch_attn2_t<MODE, PR, NCH, true>(tmX, tmY, tmV, p, grid, smem, stream)           \
-         : launch_attn2_t<MODE, PR, NCH, false>(tmX, tmY, tmV, p, grid, smem, stream))
+  // POLY (every fourth exponential as an FMA-pipe polynomial, ex2_poly) is compiled out: measured on B200 it does not
+  // shorten either pass (T = 4096, d = 40: 122.6 us without, 123.2 us with) - the statistics loop is bound by
+  // instruction issue (~5 instructions per score), not by the MUFU queue, and the polynomial adds six more.
+  (void)poly;
+#define TSD_A2(MODE, PR, NCH)                                                                                    \
+  (trace ? launch_attn2_t<MODE, PR, NCH, true, false>(tmX, tmY, tmV, p, grid, smem, stream)                        \
+         : launch_attn2_t<MODE, PR, NCH, false, false>(tmX, tmY, tmV, p, grid, smem, stream))
   if (p.mode == ATT_STATS) return nch == 2 ? TSD_A2(ATT_STATS, false, 2) : TSD_A2(ATT_STATS, false, 1);
   if (p.mu_per_row) return nch == 2 ? TSD_A2(ATT_APPLY, true, 2) : TSD_A2(ATT_APPLY, true, 1);
   return nch == 2 ? TSD_A2(ATT_APPLY, false, 2) : TSD_A2(ATT_APPLY, false, 1);
@@ -969,7 +998,7 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
     p.part_stride = (long long)BH * Tx;
     const bool v2s = attn_v2 && attn2_ok(sp, Ty);
     if (v2s) p.tmem_cols = attn2_tmem_cols(sp, false);
-    rc = c->check(v2s ? launch_attn2(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream, attn_trace)
+    rc = c->check(v2s ? launch_attn2(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream, attn_trace, c->attn_poly != 0)
                       : launch_attn(tmX, tmY, tmY, p, dim3(x_tiles, BH, splits), sp.smem, c->stream),
                   "attn_kernel (stats) launch");
     if (rc) return rc;
@@ -1020,7 +1049,7 @@ int attention_fused(Ctx* c, const AttnArgs& a) {
       }
     }
     if (v2a && !q.debug) q.tmem_cols = attn2_tmem_cols(ap, true);
-    rc = c->check(v2a && !q.debug ? launch_attn2(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream, attn_trace)
+    rc = c->check(v2a && !q.debug ? launch_attn2(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream, attn_trace, c->attn_poly != 0)
                                   : launch_attn(tmQ, tmK, tmV, q, dim3((a.Tq + ATT_BM - 1) / ATT_BM, BH, 1), ap.smem, c->stream),
                   "attn_kernel (apply) launch");
     if (rc) return rc;

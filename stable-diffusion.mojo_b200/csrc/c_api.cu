@@ -87,7 +87,7 @@ int32_t tsd_init(int32_t device, tsd_ctx** out) {
   h->c = c;
   *out = h;
   // tuning / A-B switches from the environment: TSD_OPT_<option name>=<int>  (same names as tsd_set_option)
-  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention", "attn_v2", "splitk_cluster", "splitk_cluster_max"};
+  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention", "attn_v2", "attn_poly", "splitk_cluster", "splitk_cluster_max"};
   for (const char* name : kEnvOpts) {
     const std::string key = std::string("TSD_OPT_") + name;
     if (const char* v = getenv(key.c_str())) tsd_set_option(h, name, atoi(v));
@@ -122,6 +122,7 @@ static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "norm_eps_mode")) return &h->c->norm_eps_mode;
   if (!strcmp(name, "fused_attention")) return &h->c->fused_attention;
   if (!strcmp(name, "attn_v2")) return &h->c->attn_v2;
+  if (!strcmp(name, "attn_poly")) return &h->c->attn_poly;
   if (!strcmp(name, "cuda_graph")) return &h->use_graph;
   if (!strcmp(name, "force_bn")) return &h->c->force_bn;
   if (!strcmp(name, "force_splits")) return &h->c->force_splits;

@@ -115,6 +115,7 @@ struct Ctx {
   int sm_count = 148;
   int softmax_axis = 0;     // 0 = query axis (reference Softmax(dim=2), Q3) ; 1 = key axis
   int fused_attention = 1;  // 1 = tcgen05 fused kernel ; 0 = GEMM + softmax + GEMM
+  int attn_poly = 0;        // lab switch, compiled out (FMA-pipe polynomial for every fourth exponential: measured no gain)
   int attn_v2 = 1;          // fused attention: 1 = software-pipelined softmax role (attn2_kernel) where the shape allows, 0 = attn_kernel
   int layernorm_mode = 0;   // 0 = global statistics (reference, Q5) ; 1 = per token
   int norm_eps_mode = 0;    // 0 = (x - mean) / (std + eps) (reference, Q6) ; 1 = (x - mean) / sqrt(var + eps)

@@ -797,3 +797,19 @@ def test_checkpoint_round_trip(ctx, tmp_path, dtype, exact):
     finally:
         a.close()
         b.close()
+
+
+def test_dist_c_abi_two_gpus():
+    """tsd_dist_init / tsd_dist_broadcast_context / tsd_dist_generate / tsd_dist_gather over NCCL with two ranks
+    (tests/dist_c_abi_check.py under torchrun as a plain launcher).  Needs two GPUs: skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    port = 29500 + os.getpid() % 400
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(os.path.dirname(__file__), "dist_c_abi_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DIST_C_ABI_OK" in r.stdout
