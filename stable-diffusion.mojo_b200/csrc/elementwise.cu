@@ -926,6 +926,10 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, const float2* __r
 // block first folds the partials of its image to (mean, 1/(std+eps)) per group (a few hundred
 // float2 from L2), then a thread owns up to three fixed channel quads (coalesced float4 along C)
 // and walks the pixels of its slab, `ppl` pixels in flight per block - no index divisions.
+// NQ = channel quads per thread (1 for C <= 1024 per segment).  One instantiation per NQ keeps the code a launch touches
+// small: these kernels run a few microseconds between GEMMs whose own code evicts them from the instruction caches, so
+// every launch starts cold and pays for each 128 B line of straight-line code it walks through.
+template <int NQ>
 __global__ void __launch_bounds__(GS_THREADS)
 norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, const NormStatsReq req,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float gamma_scalar,
@@ -953,14 +957,14 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
   // (L2 round trip, shuffles, barrier: 6 000+ cycles measured) that needs no activation data, and the activation loads
   // need no statistics - the two now overlap instead of running back to back.
   constexpr int NP = 3;
-  float4 pre[NP][GS_MAXQ];
+  float4 pre[NP][NQ];
   const bool active = pl < ppl;
   auto prefetch = [&]() {
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
       const int p = p0 + pl + k * ppl;
 #pragma unroll
-      for (int i = 0; i < GS_MAXQ; ++i) {
+      for (int i = 0; i < NQ; ++i) {
         const int qd = u + i * TU;
         pre[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active && p < p1 && qd < C4s) pre[k][i] = base[(long long)p * C4 + qd];
@@ -978,9 +982,9 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
            trf[0] - t1, trf[1] - trf[0], trf[2] - trf[1], t1b - trf[2], t2 - t1b);
   if (!active) return;
   const unsigned cpg_magic = req.cpg_magic;  // c / cpg = umulhi(c, magic), exact for c, cpg < 2^16
-  float mu[GS_MAXQ][4], sc[GS_MAXQ][4], sh[GS_MAXQ][4];
+  float mu[NQ][4], sc[NQ][4], sh[NQ][4];
 #pragma unroll
-  for (int i = 0; i < GS_MAXQ; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qd = u + i * TU;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1000,7 +1004,7 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (silu) o[j] = silu_f(o[j]);
-      if (round) o[j] = rna_tf32(o[j]);
+      if (round) o[j] = __uint_as_float((__float_as_uint(o[j]) + 0x1000u) & 0xffffe000u);  // round to nearest (ties away) at TF32 precision: the bits cvt.rna.tf32 gives for finite values, two instructions
     }
     obase[idx] = make_float4(o[0], o[1], o[2], o[3]);
   };
@@ -1008,7 +1012,7 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
   for (int k = 0; k < NP; ++k) {
     const int p = p0 + pl + k * ppl;
 #pragma unroll
-    for (int i = 0; i < GS_MAXQ; ++i) {
+    for (int i = 0; i < NQ; ++i) {
       const int qd = u + i * TU;
       if (p < p1 && qd < C4s) emit(pre[k][i], i, (long long)p * C4 + qd);
     }
@@ -1016,7 +1020,7 @@ norm_apply_partial_kernel(const float4* __restrict__ x, float4* __restrict__ y, 
 #pragma unroll 4
   for (int p = p0 + pl + NP * ppl; p < p1; p += ppl) {
 #pragma unroll
-    for (int i = 0; i < GS_MAXQ; ++i) {
+    for (int i = 0; i < NQ; ++i) {
       const int qd = u + i * TU;
       if (qd < C4s) emit(base[(long long)p * C4 + qd], i, (long long)p * C4 + qd);
     }
@@ -1711,9 +1715,14 @@ cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsR
   slab = (slab + ppl - 1) / ppl * ppl;
   if (slab < ppl) slab = ppl;
   slabs = (pixels + slab - 1) / slab;
-  { cudaError_t e_ = launch_pdl(norm_apply_partial_kernel, dim3(slabs, N, nseg), dim3(GS_THREADS), 0, s, reinterpret_cast<const float4*>(x),
-                                                                  reinterpret_cast<float4*>(y), req, gamma, beta,
-                                                                  gamma_scalar, pixels, C4, slab, silu, round_tf32, norm_trace_env(), c4_seg); if (e_ != cudaSuccess) return e_; }
+  const int nq = (c4_seg + GS_THREADS - 1) / GS_THREADS;
+#define TSD_NAP(NQ)                                                                                                        \
+  launch_pdl(norm_apply_partial_kernel<NQ>, dim3(slabs, N, nseg), dim3(GS_THREADS), 0, s, reinterpret_cast<const float4*>(x), \
+             reinterpret_cast<float4*>(y), req, gamma, beta, gamma_scalar, pixels, C4, slab, silu, round_tf32,             \
+             norm_trace_env(), c4_seg)
+  const cudaError_t e_ = nq <= 1 ? TSD_NAP(1) : (nq == 2 ? TSD_NAP(2) : TSD_NAP(3));
+#undef TSD_NAP
+  if (e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
