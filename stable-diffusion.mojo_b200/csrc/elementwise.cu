@@ -829,6 +829,209 @@ norm_fused2_kernel(const NormFused2Params p) {
            t4 - t3, clock64() - t4, gridDim.x);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Cluster GroupNorm: ONE thread-block cluster per (image, group).  The CTAs of a cluster split the pixels of the
+// group; each keeps its slab of the group (cpg channels x its pixels) in shared memory, reduces (sum, sum^2) over the
+// block, exchanges the partials through distributed shared memory (one cluster barrier - a few hundred cycles where
+// the grid barrier of norm_fused2 costs ~9K) and normalises out of shared memory.  Groups never talk to each other,
+// so there is no grid-wide synchronisation and no co-residency requirement beyond what a cluster launch guarantees.
+// The source is a plain activation, the split-K partials of a GEMM (+bias, +residual; `raw` receives the reduced
+// tensor: this kernel IS the reduction) or a channel concat of two tensors (`raw` receives the concatenation).
+// V = floats per access (4 when cpg % 4 == 0, else 2); fixed summation orders (bit-reproducible).
+// ------------------------------------------------------------------------------------------
+constexpr int NC_THREADS = 256;
+struct NormClusterParams {
+  const float* x;
+  int splits;
+  long long split_stride;  // floats between splits
+  int ldx;                 // row stride of the source (floats)
+  const float* bias;
+  int bias_img_stride;
+  const float* residual;
+  float* raw;
+  const float* x2;
+  int c_a;
+  float* y;
+  int pixels, C, G, cpg;
+  int cs, ppc;             // CTAs per cluster, pixels per CTA
+  int hc, ppl;             // vectors per pixel of the group (cpg / V), pixel lanes per pass (NC_THREADS / hc)
+  float inv_count, eps;
+  const float* gamma;
+  const float* beta;
+  float gamma_scalar;
+  int silu, round;
+};
+
+template <int V> struct NcVec;
+template <> struct NcVec<2> { using T = float2; };
+template <> struct NcVec<4> { using T = float4; };
+
+__device__ __forceinline__ uint32_t nc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float2 nc_ld_remote_f2(const void* local, uint32_t cta) {
+  const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t raddr;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(cta));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(raddr) : "memory");
+  return v;
+}
+
+template <int V>
+__global__ void __launch_bounds__(NC_THREADS)
+norm_cluster_kernel(const NormClusterParams p) {
+  using VT = typename NcVec<V>::T;
+  extern __shared__ __align__(16) float nc_sm[];  // the slab: [ppc][hc] vectors, thread-private entries
+  __shared__ float2 warp_part[NC_THREADS / 32];
+  __shared__ float2 cta_part;   // read by the other CTAs of the cluster
+  __shared__ float2 stat_s;     // (mean, 1 / (std + eps))
+  const uint32_t rank = nc_cluster_rank();
+  const int cluster = blockIdx.x / p.cs;
+  const int n = cluster / p.G, g = cluster - n * p.G;
+  const int u = threadIdx.x % p.hc, pl = threadIdx.x / p.hc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = (int)rank * p.ppc;
+  int p1 = p0 + p.ppc;
+  if (p1 > p.pixels) p1 = p.pixels;
+  const int c0 = g * p.cpg + u * V;  // first channel of this thread's vector
+  const bool active = pl < p.ppl;
+  VT* slab = reinterpret_cast<VT*>(nc_sm);
+
+  // per-channel affine terms do not depend on the producer: fetch them before the dependency wait
+  float ga[V], be[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    ga[j] = p.gamma_scalar * ((p.gamma && active) ? p.gamma[c0 + j] : 1.0f);
+    be[j] = (p.beta && active) ? p.beta[c0 + j] : 0.0f;
+  }
+  pdl_wait();
+
+  float bias_v[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) bias_v[j] = (p.bias && active) ? p.bias[(long long)n * p.bias_img_stride + c0 + j] : 0.0f;
+
+  auto ldv = [&](const float* q) -> VT { return *reinterpret_cast<const VT*>(q); };
+  auto add = [&](VT& a, const VT& b) {
+    a.x += b.x; a.y += b.y;
+    if constexpr (V == 4) { a.z += b.z; a.w += b.w; }
+  };
+  auto load = [&](int px) -> VT {
+    const long long row = (long long)n * p.pixels + px;
+    VT a;
+    if (p.x2 != nullptr) {
+      a = c0 < p.c_a ? ldv(p.x + row * p.c_a + c0) : ldv(p.x2 + row * (p.C - p.c_a) + (c0 - p.c_a));
+    } else if (p.splits > 1) {
+      const float* src = p.x + row * p.ldx + c0;
+      a = ldv(src);
+      for (int s0 = 1; s0 < p.splits; s0 += 4) {  // every split requested before the first add; sum in split order
+        VT t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (V == 4) t[k] = make_float4(0.f, 0.f, 0.f, 0.f); else t[k] = make_float2(0.f, 0.f);
+          if (s0 + k < p.splits) t[k] = ldv(src + (long long)(s0 + k) * p.split_stride);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) add(a, t[k]);
+      }
+    } else {
+      a = ldv(p.x + row * p.ldx + c0);
+    }
+    if (p.splits > 1 || p.bias != nullptr || p.residual != nullptr) {
+      a.x += bias_v[0]; a.y += bias_v[1];
+      if constexpr (V == 4) { a.z += bias_v[2]; a.w += bias_v[3]; }
+      if (p.residual) add(a, ldv(p.residual + row * p.C + c0));
+    }
+    if (p.raw) *reinterpret_cast<VT*>(p.raw + row * p.C + c0) = a;
+    return a;
+  };
+
+  // ---- phase 1: slab -> shared memory, (sum, sum^2) ----
+  float s = 0.f, q = 0.f;
+  if (active) {
+    int it = 0;
+    int px = p0 + pl;
+    for (; px + p.ppl < p1; px += 2 * p.ppl, it += 2) {  // two pixels per trip: both rows' loads are in flight together
+      const VT a = load(px), b = load(px + p.ppl);
+      slab[(it * p.ppl + pl) * p.hc + u] = a;
+      slab[((it + 1) * p.ppl + pl) * p.hc + u] = b;
+      s += a.x; q = fmaf(a.x, a.x, q); s += a.y; q = fmaf(a.y, a.y, q);
+      if constexpr (V == 4) { s += a.z; q = fmaf(a.z, a.z, q); s += a.w; q = fmaf(a.w, a.w, q); }
+      s += b.x; q = fmaf(b.x, b.x, q); s += b.y; q = fmaf(b.y, b.y, q);
+      if constexpr (V == 4) { s += b.z; q = fmaf(b.z, b.z, q); s += b.w; q = fmaf(b.w, b.w, q); }
+    }
+    if (px < p1) {
+      const VT a = load(px);
+      slab[(it * p.ppl + pl) * p.hc + u] = a;
+      s += a.x; q = fmaf(a.x, a.x, q); s += a.y; q = fmaf(a.y, a.y, q);
+      if constexpr (V == 4) { s += a.z; q = fmaf(a.z, a.z, q); s += a.w; q = fmaf(a.w, a.w, q); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) warp_part[warp] = make_float2(s, q);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float2 t = warp_part[0];
+#pragma unroll
+    for (int w = 1; w < NC_THREADS / 32; ++w) { t.x += warp_part[w].x; t.y += warp_part[w].y; }
+    cta_part = t;
+  }
+  // ---- exchange inside the cluster ----
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  if (threadIdx.x == 0) {
+    float2 t = nc_ld_remote_f2(&cta_part, 0);
+    for (int r = 1; r < p.cs; ++r) {
+      const float2 o = nc_ld_remote_f2(&cta_part, (uint32_t)r);
+      t.x += o.x; t.y += o.y;
+    }
+    const double mean = (double)t.x * (double)p.inv_count;
+    double var = (double)t.y * (double)p.inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    // reference: (x - mean) / (std + eps), biased std  (helpers/utils.mojo:1380, 1868-1870)
+    stat_s = make_float2((float)mean, norm_rstd((float)var, p.eps));
+  }
+  __syncthreads();
+  // the second barrier keeps every CTA (and its shared memory) alive until all remote reads are done
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  pdl_launch_dependents();
+
+  // ---- phase 2: normalise out of shared memory ----
+  if (active) {
+    const float mu = stat_s.x, rstd = stat_s.y;
+    float sc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) sc[j] = rstd * ga[j];
+    float* obase = p.y + (long long)n * p.pixels * p.C + c0;
+    int it = 0;
+#pragma unroll 2
+    for (int px = p0 + pl; px < p1; px += p.ppl, ++it) {
+      const VT a = slab[(it * p.ppl + pl) * p.hc + u];
+      float o[V];
+      o[0] = (a.x - mu) * sc[0] + be[0];
+      o[1] = (a.y - mu) * sc[1] + be[1];
+      if constexpr (V == 4) { o[2] = (a.z - mu) * sc[2] + be[2]; o[3] = (a.w - mu) * sc[3] + be[3]; }
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        if (p.silu) o[j] = silu_f(o[j]);
+        if (p.round) o[j] = rna_tf32(o[j]);
+      }
+      VT out;
+      out.x = o[0]; out.y = o[1];
+      if constexpr (V == 4) { out.z = o[2]; out.w = o[3]; }
+      *reinterpret_cast<VT*>(obase + (long long)px * p.C) = out;
+    }
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 // General path: one block per (n, g).
 __global__ void group_stats_general_kernel(const float* __restrict__ x, long long pixels, int C,
                                            int G, int cpg, double* __restrict__ accum) {
@@ -1664,6 +1867,102 @@ static const void* norm_fused2_func(const NormFused2Plan& pl) {
   if (pl.nq == 1) return pl.cache ? reinterpret_cast<const void*>(norm_fused2_kernel<1, 16, true>) : reinterpret_cast<const void*>(norm_fused2_kernel<1, 16, false>);
   if (pl.nq == 2) return pl.cache ? reinterpret_cast<const void*>(norm_fused2_kernel<2, 8, true>) : reinterpret_cast<const void*>(norm_fused2_kernel<2, 8, false>);
   return pl.cache ? reinterpret_cast<const void*>(norm_fused2_kernel<3, 5, true>) : reinterpret_cast<const void*>(norm_fused2_kernel<3, 5, false>);
+}
+
+
+// ---- cluster GroupNorm ----
+struct NormClusterPlan {
+  int v, hc, ppl, cs, ppc;
+  size_t smem;
+  bool ok;
+};
+static NormClusterPlan norm_cluster_plan(int N, long long pixels, int C, int G) {
+  NormClusterPlan pl{};
+  if (G <= 0 || C % G || pixels <= 0 || pixels >= (1 << 30)) return pl;
+  const int cpg = C / G;
+  if (cpg % 2 || C % 4) return pl;
+  pl.v = cpg % 4 == 0 ? 4 : 2;
+  pl.hc = cpg / pl.v;
+  if (pl.hc > NC_THREADS) return pl;
+  pl.ppl = NC_THREADS / pl.hc;
+  const long long clusters = (long long)N * G;
+  if (clusters > (1 << 20)) return pl;
+  // smallest cluster that fills the device (>= 256 CTAs) and whose slab fits shared memory; <= 8 (portable size)
+  const size_t limit = 200 * 1024;
+  for (int cs = 1; cs <= 8; cs *= 2) {
+    const long long ppc = (pixels + cs - 1) / cs;
+    const size_t smem = (size_t)((ppc + pl.ppl - 1) / pl.ppl * pl.ppl) * cpg * sizeof(float);
+    if (smem > limit) continue;
+    pl.cs = cs;
+    pl.ppc = (int)ppc;
+    pl.smem = smem;
+    pl.ok = true;
+    if (clusters * cs >= 256 || ppc <= 2 * pl.ppl) break;
+  }
+  if (pl.ok && clusters * pl.cs < 64) pl.ok = false;  // too few CTAs to be worth it (LayerNorm of one image)
+  return pl;
+}
+bool norm_cluster_supported(int N, long long pixels, int C, int G) {
+  const NormClusterPlan pl = norm_cluster_plan(N, pixels, C, G);
+  if (!pl.ok) return false;
+  const void* fn = pl.v == 4 ? reinterpret_cast<const void*>(norm_cluster_kernel<4>) : reinterpret_cast<const void*>(norm_cluster_kernel<2>);
+  if (optin_dyn_smem(fn, 200 * 1024, nullptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+cudaError_t launch_norm_cluster(const NormFused2Src& src, float* y, int N, long long pixels, int C, int G, float eps,
+                                const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
+                                cudaStream_t s) {
+  if (!norm_cluster_supported(N, pixels, C, G)) return cudaErrorInvalidValue;
+  const NormClusterPlan pl = norm_cluster_plan(N, pixels, C, G);
+  NormClusterParams p{};
+  p.x = src.x;
+  p.splits = src.splits > 1 ? src.splits : 1;
+  p.split_stride = src.split_stride;
+  p.ldx = src.splits > 1 ? src.ldx : C;
+  p.bias = src.bias;
+  p.bias_img_stride = src.bias_img_stride;
+  p.residual = src.residual;
+  p.raw = src.raw;
+  p.x2 = src.x2;
+  p.c_a = src.c_a;
+  if (src.x2 != nullptr && (src.splits > 1 || src.c_a <= 0 || src.c_a >= C || src.c_a % pl.v || (C - src.c_a) % pl.v)) return cudaErrorInvalidValue;
+  if (p.splits > 1 && (src.ldx % pl.v || src.split_stride % pl.v)) return cudaErrorInvalidValue;
+  p.y = y;
+  p.pixels = (int)pixels;
+  p.C = C;
+  p.G = G;
+  p.cpg = C / G;
+  p.cs = pl.cs;
+  p.ppc = pl.ppc;
+  p.hc = pl.hc;
+  p.ppl = pl.ppl;
+  p.inv_count = (float)(1.0 / ((double)pixels * (C / G)));
+  p.eps = eps;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.gamma_scalar = gamma_scalar;
+  p.silu = silu;
+  p.round = round_tf32;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((long long)N * G * pl.cs));
+  cfg.blockDim = dim3(NC_THREADS);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = (unsigned)pl.cs;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = pl.v == 4 ? cudaLaunchKernelEx(&cfg, norm_cluster_kernel<4>, p) : cudaLaunchKernelEx(&cfg, norm_cluster_kernel<2>, p);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
 }
 
 static int norm_trace_env() {

@@ -62,6 +62,11 @@ size_t norm_fused2_scratch_bytes(int N, long long pixels, int C, int G, int sm_c
 cudaError_t launch_norm_fused2(const NormFused2Src& src, float* y, int N, long long pixels, int C, int G, float eps,
                                const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
                                void* scratch, unsigned int* barrier_words, int sm_count, cudaStream_t s);
+// cluster GroupNorm: one thread-block cluster per (image, group), slab in shared memory, no grid barrier, no scratch
+bool norm_cluster_supported(int N, long long pixels, int C, int G);
+cudaError_t launch_norm_cluster(const NormFused2Src& src, float* y, int N, long long pixels, int C, int G, float eps,
+                                const float* gamma, const float* beta, float gamma_scalar, int silu, int round_tf32,
+                                cudaStream_t s);
 bool norm_apply_partial_supported(int C, int G);
 cudaError_t launch_norm_apply_partial(const float* x, float* y, const NormStatsReq& req, int N, long long pixels,
                                       const float* gamma, const float* beta, float gamma_scalar, int silu,

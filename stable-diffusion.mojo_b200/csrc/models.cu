@@ -769,7 +769,8 @@ int Diffusion::unet(int n, int n_ctx, int n_time) {
     out_ = act(a.C + b.C, a.H, a.W);
     if (!out_.p) return c->fail(TSD_ERR_OOM, "workspace exhausted (unet activation)");
     if (c->virtual_concat && a.C % 4 == 0 && b.C % 4 == 0 &&
-        norm_fused2_supported(a.N, (long long)a.H * a.W, a.C + b.C, 32, c->sm_count)) {
+        ((c->norm_cluster && norm_cluster_supported(a.N, (long long)a.H * a.W, a.C + b.C, 32)) ||
+         norm_fused2_supported(a.N, (long long)a.H * a.W, a.C + b.C, 32, c->sm_count))) {
       // every concat of the UNet feeds a ResBlock whose first GroupNorm(32, eps 1e-5) is its first reader: that
       // kernel reads the two tensors and writes the concatenation (for the block's convolutions) as a by-product
       out_.ns.G = 32;
@@ -892,19 +893,32 @@ static int capture_end(Ctx* c, GraphSlot* slot) {
   return rc;
 }
 
+// Everything of a forward that works on the handle's own fixed buffers: time-embedding MLP + the nine block linears
+// (time_in -> tbias), NCHW -> NHWC of the latents (x_in -> x_nhwc), the UNet, NHWC -> NCHW of the result (eps_nhwc ->
+// out_nchw).  One captured graph replays all of it: the six small launches around the UNet no longer pay a stream-launch
+// gap each.
+int Diffusion::core(int n, int n_ctx, int n_time) {
+  const int HW = cfg.latent_h * cfg.latent_w;
+  TRY(prepare_time(n_time, time_in, tbias, 0));
+  LAUNCH(c, launch_nchw_to_nhwc(x_in, x_nhwc, n, 4, HW, c->stream), "nchw_to_nhwc");
+  TRY(unet(n, n_ctx, n_time));
+  LAUNCH(c, launch_nhwc_to_nchw(eps_nhwc, out_nchw, n, 4, HW, c->stream), "nhwc_to_nchw");
+  return TSD_OK;
+}
+
 int Diffusion::run_unet_graph(int n, int n_ctx, int n_time) {
   c->arena.reset();
-  if (!h->use_graph || c->timer) return unet(n, n_ctx, n_time);
+  if (!h->use_graph || c->timer) return core(n, n_ctx, n_time);
   GraphSlot& g = graph;
   const bool valid = g.exec && g.n == n && g.n_ctx == n_ctx && g.n_time == n_time && g.epoch == h->option_epoch &&
                      g.arena_base == c->arena.base() && g.weights_gen == ps.gen;
   if (!valid) {
     // one eager pass first: validates shapes, initialises per-kernel attributes outside capture
-    TRY(unet(n, n_ctx, n_time));
+    TRY(core(n, n_ctx, n_time));
     TRY(c->check(cudaStreamSynchronize(c->stream), "unet eager pass"));
     c->arena.reset();
     TRY(capture_begin(c));
-    int rc = unet(n, n_ctx, n_time);
+    int rc = core(n, n_ctx, n_time);
     int rc2 = capture_end(c, &g);
     if (rc) return rc;
     if (rc2) return rc2;
@@ -946,10 +960,7 @@ int Diffusion::forward_dev(const float* x, const float* context, int n_ctx, cons
     TRY(prepare_context(n_ctx));
     ctx_hash_gen = -1;  // device-side context: the host-content cache no longer describes kctx/vctx
   }
-  TRY(prepare_time(n_time, time_in, tbias, 0));
-  LAUNCH(c, launch_nchw_to_nhwc(x_in, x_nhwc, n, 4, (int)HW, c->stream), "nchw_to_nhwc");
   TRY(run_unet_graph(n, ctx_n, n_time));
-  LAUNCH(c, launch_nhwc_to_nchw(eps_nhwc, out_nchw, n, 4, (int)HW, c->stream), "nhwc_to_nchw");
   TRY(c->check(cudaMemcpyAsync(out, out_nchw, n * 4 * HW * sizeof(float), kout, c->stream), "copy out"));
   if (host_ptrs) TRY(c->check(cudaStreamSynchronize(c->stream), "diffusion forward sync"));
   return TSD_OK;
@@ -1032,10 +1043,7 @@ int Diffusion::step_host(const float* latents, const float* context, int n_ctx, 
       }
     }
   }
-  TRY(prepare_time(1, time_in, tbias, 0));
-  LAUNCH(c, launch_nchw_to_nhwc(x_in, x_nhwc, nb, 4, (int)HW, s), "nchw_to_nhwc");
   TRY(run_unet_graph(nb, ctx_n, 1));
-  LAUNCH(c, launch_nhwc_to_nchw(eps_nhwc, out_nchw, nb, 4, (int)HW, s), "nhwc_to_nchw");
   LAUNCH(c, launch_ddpm_step(x_in, out_nchw, use_cfg ? out_nchw + n_lat : nullptr, cfg_scale, noise ? noise_in : nullptr,
                              coef[0], coef[1], coef[2], coef[3], coef[4], lat_out, (long long)n_lat, s), "ddpm_step");
   TRY(c->check(cudaMemcpyAsync(latents_out, lat_out, n_lat * 4, cudaMemcpyDeviceToHost, s), "copy latents out"));

@@ -143,6 +143,7 @@ struct Diffusion {
   int prepare_time(int n_time, const float* time_dev /*[n_time][320]*/, float* const* tb_out,
                    int rows_stride);              // time embedding MLP + 9 ResBlock time linears
   int unet(int n, int n_ctx, int n_time);         // x_nhwc -> eps_nhwc (uses kctx/vctx/tbias)
+  int core(int n, int n_ctx, int n_time);         // time_in, x_in -> out_nchw: time MLP + layout changes + unet
   int forward_dev(const float* x, const float* context, int n_ctx, const float* time, int n_time, int n,
                   float* out, bool host_ptrs);
   int run_unet_graph(int n, int n_ctx, int n_time);

@@ -1017,8 +1017,34 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
   if (def != nullptr && def->ws != nullptr) {
     // the producer was a split-K GEMM that left its partial tiles: sum them, add bias / residual, write the raw
     // output (x) and normalise in one launch
-    if (upsample || def->raw != x || def->C != C || def->rows != (long long)N * H * W ||
-        !norm_fused2_supported(N, (long long)H * W, C, G, c->sm_count))
+    if (upsample || def->raw != x || def->C != C || def->rows != (long long)N * H * W)
+      return c->fail(TSD_ERR_STATE, "group_norm: deferred split-K reduction does not match its consumer");
+    NormFused2Src dsrc;
+    dsrc.x = def->ws;
+    dsrc.splits = def->splits;
+    dsrc.split_stride = def->split_stride;
+    dsrc.ldx = def->ld;
+    dsrc.bias = def->bias;
+    dsrc.bias_img_stride = def->bias_img_stride;
+    dsrc.residual = def->residual;
+    dsrc.raw = def->raw;
+    dsrc.x2 = def->x2;
+    dsrc.c_a = def->c_a;
+    if (c->norm_cluster && norm_cluster_supported(N, (long long)H * W, C, G) &&
+        (def->splits <= 1 || (def->ld % 4 == 0 && def->split_stride % 4 == 0)) &&
+        (def->x2 == nullptr || (def->c_a % 4 == 0 && (C - def->c_a) % 4 == 0))) {
+      // one cluster per (image, group): no grid barrier, no scratch
+      if (!c->dry_run) {
+        TimedScope ts(c, FAM_NORM, 0);
+        int rc = c->check(launch_norm_cluster(dsrc, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
+                                              round_tf32, c->stream),
+                          "norm_cluster (split-K source) launch");
+        if (rc) return rc;
+        c->launches += 1;
+      }
+      return TSD_OK;
+    }
+    if (!norm_fused2_supported(N, (long long)H * W, C, G, c->sm_count))
       return c->fail(TSD_ERR_STATE, "group_norm: deferred split-K reduction does not match its consumer");
     const size_t mark = c->arena.mark();
     void* scratch = c->arena.alloc(norm_fused2_scratch_bytes(N, (long long)H * W, C, G, c->sm_count));
@@ -1060,6 +1086,19 @@ int op_group_norm(Ctx* c, const float* x, float* y, int N, int H, int W, int C, 
       int rc = c->check(launch_norm_apply_partial(x, y, *pre, N, (long long)H * W, gamma, beta, gamma_scalar, silu,
                                                   round_tf32, c->stream),
                         "norm_apply_partial launch");
+      if (rc) return rc;
+      c->launches += 1;
+    }
+    return TSD_OK;
+  }
+  if (!upsample && c->norm_cluster && norm_cluster_supported(N, (long long)H * W, C, G)) {
+    if (!c->dry_run) {
+      TimedScope ts(c, FAM_NORM, 0);
+      NormFused2Src src;
+      src.x = x;
+      int rc = c->check(launch_norm_cluster(src, y, N, (long long)H * W, C, G, eps, gamma, beta, gamma_scalar, silu,
+                                            round_tf32, c->stream),
+                        "norm_cluster launch");
       if (rc) return rc;
       c->launches += 1;
     }

@@ -141,9 +141,10 @@ struct Ctx {
   int gn_partial_max_groups = 64;  // ... only up to this many groups (every block folds all groups of its image)
   int ln_fold = 1;                 // fold global-statistics LayerNorm into the consuming GEMM epilogue (0: separate pass)
   int defer_reduce = 1;            // split-K partials summed by the consuming norm kernel where the call site allows it
-  int virtual_concat = 0;          // 1: channel concats feeding a ResBlock are read (and written out) by its first GroupNorm kernel (measured neutral)
+  int virtual_concat = 1;          // 1: channel concats feeding a ResBlock are read (and written out) by its first GroupNorm kernel (+0.5 % with the cluster norm)
   int conv_stride_tma = 1;         // stride-2 3x3 convolutions as implicit GEMMs through a strided tensor map (0: im2col + GEMM)
   int fuse_skip = 1;               // ResBlock 1x1 skip convolution as a second K segment of conv2 (0: GEMM of its own + residual add)
+  int norm_cluster = 1;            // 1: GroupNorm with one thread-block cluster per (image, group) where the slab fits shared memory
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;

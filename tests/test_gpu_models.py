@@ -126,7 +126,9 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
     {"fuse_skip": 0},                     # skip convolution as its own GEMM + residual add
     {"conv_stride_tma": 0},               # stride-2 convolutions through im2col + GEMM
     {"defer_reduce": 0},                  # split-K always through the reduce kernel
-    {"virtual_concat": 1},                # channel concats read and written out by the consuming GroupNorm kernel
+    {"virtual_concat": 0},                # explicit concat kernel instead of the consuming GroupNorm reading both tensors
+    {"norm_cluster": 0},                  # grid-barrier norm kernels instead of one cluster per (image, group)
+    {"norm_cluster": 0, "virtual_concat": 1},
     {"defer_reduce": 1, "force_splits": 4},  # split-K partials summed by the consuming GroupNorm kernel
     {"fuse_skip": 1, "force_splits": 8},  # second K segment under split-K (the last split starts inside it)
     {"producer_stats": 0},                # every norm computes its own statistics (no epilogue partial sums)
@@ -161,7 +163,7 @@ def test_unet64_switches_agree_at_full_size(ctx, diff64):
     cx = rng.standard_normal((77, 768), dtype=np.float32)
     t = host_sampler.get_time_embedding(500.0)
     y_default = diff64.forward(x, cx, t)
-    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"conv_stride_tma": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}, {"virtual_concat": 1}):
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"conv_stride_tma": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}, {"virtual_concat": 0}, {"norm_cluster": 0}, {"norm_cluster": 0, "norm_v2": 1}):
         old = {k: ctx.get_option(k) for k in opts}
         for k, v in opts.items():
             ctx.set_option(k, v)

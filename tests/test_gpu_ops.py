@@ -342,13 +342,15 @@ def test_linear_autotune_is_stable(ctx, ops):
     assert relerr(y0, ops.linear(x[0], w, None)[None]) < TOL_TF32
 
 
-@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("path", ["fused", "v2", "cluster"])
 @pytest.mark.parametrize("c,h,w,g,eps", [(320, 16, 16, 32, 1e-5), (1920, 16, 16, 32, 1e-5), (320, 8, 8, 320, 1e-5),
-                                         (640, 32, 32, 1, 1e-5), (128, 64, 64, 32, 1e-6)])
-def test_groupnorm_fused_kernels(ctx, ops, v2, c, h, w, g, eps):
-    """both single-launch norm kernels (grid barrier v1, register-resident two-level barrier v2)"""
+                                         (640, 32, 32, 1, 1e-5), (128, 64, 64, 32, 1e-6), (960, 64, 64, 32, 1e-5),
+                                         (320, 64, 64, 32, 1e-5), (1280, 8, 8, 32, 1e-5), (96, 5, 7, 16, 1e-5)])
+def test_groupnorm_fused_kernels(ctx, ops, path, c, h, w, g, eps):
+    """the single-launch norm kernels: grid barrier v1, register-resident two-level barrier v2, and the
+    cluster-per-(image, group) kernel (shapes it does not take - odd channels per group, one group - fall through)"""
     rng = np.random.default_rng(c + h)
     x = (rng.standard_normal((c, h, w)) * 2 + 0.5).astype(np.float32)
-    with _Options(ctx, norm_v2=v2):
+    with _Options(ctx, norm_v2=int(path == "v2"), norm_cluster=int(path == "cluster")):
         y = ctx.groupnorm(x, g, eps)
     assert relerr(y, ops.group_norm(x, g, eps)) < TOL_FP32

@@ -1,0 +1,36 @@
+"""Launches each hot kernel at its BASELINE shape once (for `ncu --set full -k regex:...`); `what` selects the group.
+  gemm     conv 320->320 @64x64 (the most frequent UNet GEMM), shipped tile plan
+  attn     attention core h=8 T=4096 d=40: attn2_kernel statistics + apply, then the Tk=77 cross-attention (attn_kernel)
+  norm     one eager UNet step (norm_apply_partial / norm_fused2 / norm_fused / gemv_multi are picked by -k)
+  decoder  conv 256->256 @512x512 (VAE decoder l20 shape)"""
+import os
+import sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "stable-diffusion.mojo_b200"))
+from tsd_b200.api import Context, Diffusion  # noqa: E402
+
+what = sys.argv[1]
+ctx = Context(0)
+if what == "gemm":
+    ctx.bench_conv(1, 64, 64, 320, 320, 3, 1, iters=2)
+elif what == "decoder":
+    ctx.bench_conv(1, 512, 512, 256, 256, 3, 1, iters=2)
+elif what == "attn":
+    rng = np.random.default_rng(0)
+    for tk in (4096, 77):
+        q = rng.standard_normal((8, 4096, 40), dtype=np.float32)
+        k = rng.standard_normal((8, tk, 40), dtype=np.float32)
+        v = rng.standard_normal((8, tk, 40), dtype=np.float32)
+        ctx.attention_core(q, k, v)
+else:
+    ctx.set_option("cuda_graph", 0)
+    m = Diffusion(ctx, 64, 64, max_batch=1)
+    m.init_random(1234)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((4, 64, 64), dtype=np.float32)
+    cx = rng.standard_normal((77, 768), dtype=np.float32)
+    t = np.concatenate([np.ones(160, np.float32), np.zeros(160, np.float32)])
+    m.forward(x, cx, t)
+    m.forward(x, cx, t)
+ctx.synchronize()
