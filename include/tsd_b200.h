@@ -218,6 +218,15 @@ int32_t tsd_diffusion_profile(tsd_diffusion* m, const float* x_dev, const float*
 /* ---- VAE decoder, vae.mojo:221-250 (+ rescale/clamp pipeline.mojo:127 when rescale != 0) --- */
 int32_t tsd_decoder_create(tsd_ctx* ctx, int32_t latent_h, int32_t latent_w, int32_t max_batch,
                            tsd_decoder** out);
+/* Model flags of the *_create_ex entry points.  TSD_MODEL_NORM_AFFINE: every GroupNorm / LayerNorm of the model owns
+ * a per-channel weight and bias (what real checkpoints carry; the reference's norms have none, helpers/utils.mojo:1833,
+ * 1871-1873).  The extra parameters follow their block's tensors in the blob: Res_Block "<l>.groupnorm1", "<l>.groupnorm2"
+ * after its convolutions, Attention_Block "<l>.groupnorm" after out_proj, the output norm ("l24" decoder, "l16" encoder)
+ * before the last convolutions; CLIP "player<k>.layer1", "player<k>.layer3" after each layer's linears and "layernorm"
+ * last.  tsd_*_param_name lists them.  flags = 0 is exactly tsd_*_create. */
+#define TSD_MODEL_NORM_AFFINE 1u
+int32_t tsd_decoder_create_ex(tsd_ctx* ctx, int32_t latent_h, int32_t latent_w, int32_t max_batch, uint32_t flags,
+                              tsd_decoder** out);
 int32_t tsd_decoder_destroy(tsd_decoder* m);
 int64_t tsd_decoder_num_params(const tsd_decoder* m);
 int32_t tsd_decoder_load_weights(tsd_decoder* m, const float* blob, int64_t n_floats);
@@ -239,6 +248,8 @@ int32_t tsd_decoder_forward_dev(tsd_decoder* m, const float* z, int32_t n, int32
  * rescale((0,255),(-1,1)), pipeline.mojo:71).  noise, z: (n,4,H,W).  Parameters in struct order l1..l19. */
 int32_t tsd_encoder_create(tsd_ctx* ctx, int32_t latent_h, int32_t latent_w, int32_t max_batch,
                            tsd_encoder** out);
+int32_t tsd_encoder_create_ex(tsd_ctx* ctx, int32_t latent_h, int32_t latent_w, int32_t max_batch, uint32_t flags,
+                              tsd_encoder** out);
 int32_t tsd_encoder_destroy(tsd_encoder* m);
 int64_t tsd_encoder_num_params(const tsd_encoder* m);
 int32_t tsd_encoder_load_weights(tsd_encoder* m, const float* blob, int64_t n_floats);
@@ -260,6 +271,7 @@ int32_t tsd_encoder_forward_dev(tsd_encoder* m, const float* img, const float* n
  * tokens: up to 77 int32 ids, zero-padded to 77 as clip.mojo:90-92 does; context: [77][768] fp32.
  * "softmax_axis" / "layernorm_mode" apply as in the UNet; the causal mask is the standard triu(1). */
 int32_t tsd_clip_create(tsd_ctx* ctx, int32_t n_vocab, int32_t n_layers, tsd_clip** out);
+int32_t tsd_clip_create_ex(tsd_ctx* ctx, int32_t n_vocab, int32_t n_layers, uint32_t flags, tsd_clip** out);
 int32_t tsd_clip_destroy(tsd_clip* m);
 int64_t tsd_clip_num_params(const tsd_clip* m);
 int32_t tsd_clip_load_weights(tsd_clip* m, const float* blob, int64_t n_floats);

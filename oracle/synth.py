@@ -134,7 +134,8 @@ def diffusion_specs(context_dim: int = 768, norm_affine: bool = False):
     return sp
 
 
-def decoder_specs():
+def decoder_specs(norm_affine: bool = False):
+    """norm_affine: per-channel weight / bias of every GroupNorm (TSD_MODEL_NORM_AFFINE order, include/tsd_b200.h)."""
     sp = []
 
     def res(name, cin, cout):
@@ -142,12 +143,17 @@ def decoder_specs():
         _conv(sp, name + ".conv2", cout, cout, 3)
         if cin != cout:
             _conv(sp, name + ".res_conv_layer", cin, cout, 1)
+        if norm_affine:
+            _norm(sp, name + ".groupnorm1", cin)
+            _norm(sp, name + ".groupnorm2", cout)
 
     _conv(sp, "l1", 4, 4, 1)
     _conv(sp, "l2", 4, 512, 3)
     res("l3", 512, 512)
     _linear(sp, "l4.attention.in_proj", 512, 1536, True)
     _linear(sp, "l4.attention.out_proj", 512, 512, True)
+    if norm_affine:
+        _norm(sp, "l4.groupnorm", 512)
     for n in ("l5", "l6", "l7", "l8"):
         res(n, 512, 512)
     _conv(sp, "l10", 512, 512, 3)
@@ -161,11 +167,13 @@ def decoder_specs():
     res("l21", 256, 128)
     res("l22", 128, 128)
     res("l23", 128, 128)
+    if norm_affine:
+        _norm(sp, "l24", 128)
     _conv(sp, "l26", 128, 3, 3)
     return sp
 
 
-def encoder_specs():
+def encoder_specs(norm_affine: bool = False):
     """VAE Encoder (vae.mojo:71-112) in struct-declaration order."""
     sp = []
 
@@ -174,6 +182,9 @@ def encoder_specs():
         _conv(sp, name + ".conv2", cout, cout, 3)
         if cin != cout:
             _conv(sp, name + ".res_conv_layer", cin, cout, 1)
+        if norm_affine:
+            _norm(sp, name + ".groupnorm1", cin)
+            _norm(sp, name + ".groupnorm2", cout)
 
     _conv(sp, "l1", 3, 128, 3)
     res("l2", 128, 128)
@@ -189,13 +200,18 @@ def encoder_specs():
         res(n, 512, 512)
     _linear(sp, "l14.attention.in_proj", 512, 1536, True)
     _linear(sp, "l14.attention.out_proj", 512, 512, True)
+    if norm_affine:
+        _norm(sp, "l14.groupnorm", 512)
     res("l15", 512, 512)
+    if norm_affine:
+        _norm(sp, "l16", 512)
     _conv(sp, "l18", 512, 8, 3)
     _conv(sp, "l19", 8, 8, 1)
     return sp
 
 
-def clip_specs(n_vocab: int = 49408, n_layers: int = 12, n_embed: int = 768, n_tokens: int = 77):
+def clip_specs(n_vocab: int = 49408, n_layers: int = 12, n_embed: int = 768, n_tokens: int = 77,
+               norm_affine: bool = False):
     """CLIP text encoder (clip.mojo:5-15, 23-34, 56-87) in struct-declaration order.  The embedding
     table and the position embedding are stored flat (device kind P_VEC); LayerNorm owns no tensor."""
     sp = [("embedding.token_embedding.weight", (n_vocab * n_embed,), np.float32(1.0)),
@@ -206,6 +222,11 @@ def clip_specs(n_vocab: int = 49408, n_layers: int = 12, n_embed: int = 768, n_t
         _linear(sp, b + ".layer2.out_proj", n_embed, n_embed, True)
         _linear(sp, b + ".layer4", n_embed, 4 * n_embed, True)
         _linear(sp, b + ".layer5", 4 * n_embed, n_embed, True)
+        if norm_affine:
+            _norm(sp, b + ".layer1", n_embed)
+            _norm(sp, b + ".layer3", n_embed)
+    if norm_affine:
+        _norm(sp, "layernorm", n_embed)
     return sp
 
 

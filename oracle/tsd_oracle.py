@@ -288,17 +288,17 @@ def clip_forward(ops: Ops, W, tokens, n_embed=768, n_tokens=77, n_heads=12, n_la
     for l in range(1, n_layers + 1):
         b = f"player{l}"
         residue = x
-        h = ops.layer_norm(x)                                                # :38-41
+        h = ops.layer_norm(x, *_affine(W, b + ".layer1"))                    # :38-41
         h = ops.self_attention(h, n_heads, W[b + ".layer2.in_proj.weight"], W[b + ".layer2.in_proj.bias"],
                                W[b + ".layer2.out_proj.weight"], W[b + ".layer2.out_proj.bias"], causal=True)  # :42
         x = h + residue                                                      # :43
         residue = x
-        h = ops.layer_norm(x)                                                # :45-47
+        h = ops.layer_norm(x, *_affine(W, b + ".layer3"))                    # :45-47
         h = ops.linear(h, W[b + ".layer4.weight"], W[b + ".layer4.bias"])    # :48
         h = ops.quick_gelu(h)                                                # :49-50
         h = ops.linear(h, W[b + ".layer5.weight"], W[b + ".layer5.bias"])    # :51
         x = h + residue                                                      # :52
-    return ops.layer_norm(x)                                                 # :106-108
+    return ops.layer_norm(x, *_affine(W, "layernorm"))                       # :106-108
 
 
 
@@ -410,10 +410,10 @@ def diffusion_forward(ops: Ops, W, x, context, time):
 
 def vae_res_block(ops: Ops, W, base, x, cin, cout):
     """Res_Block.forward, vae.mojo:57-67 (GroupNorm(16,.), Q17)."""
-    out = ops.group_norm(x, 16, 1e-5)
+    out = ops.group_norm(x, 16, 1e-5, *_affine(W, base + ".groupnorm1"))
     out = ops.silu(out)
     out = ops.conv2d(out, W[base + ".conv1.weight"], W[base + ".conv1.bias"], pad=1)
-    out = ops.group_norm(out, 16, 1e-5)
+    out = ops.group_norm(out, 16, 1e-5, *_affine(W, base + ".groupnorm2"))
     out = ops.silu(out)
     out = ops.conv2d(out, W[base + ".conv2.weight"], W[base + ".conv2.bias"], pad=1)
     res = ops.arr(x)
@@ -425,7 +425,7 @@ def vae_res_block(ops: Ops, W, base, x, cin, cout):
 def vae_attn_block(ops: Ops, W, x, name="l4"):
     """Attention_Block.forward, vae.mojo:17-27: GroupNorm(32) -> 1-head self-attention -> + residue."""
     c, h, w = x.shape
-    out = ops.group_norm(x, 32, 1e-5)
+    out = ops.group_norm(x, 32, 1e-5, *_affine(W, name + ".groupnorm"))
     seq = np.ascontiguousarray(out.reshape(c, h * w).T)
     seq = ops.self_attention(seq, 1, W[name + ".attention.in_proj.weight"], W[name + ".attention.in_proj.bias"],
                              W[name + ".attention.out_proj.weight"], W[name + ".attention.out_proj.bias"])
@@ -449,7 +449,7 @@ def encoder_forward(ops: Ops, W, x, noise):
         out = vae_res_block(ops, W, n, out, 512, 512)
     out = vae_attn_block(ops, W, out, "l14")
     out = vae_res_block(ops, W, "l15", out, 512, 512)
-    out = ops.group_norm(out, 32, 1e-5)
+    out = ops.group_norm(out, 32, 1e-5, *_affine(W, "l16"))
     out = ops.silu(out)
     out = ops.conv2d(out, W["l18.weight"], W["l18.bias"], pad=1)
     out = ops.conv2d(out, W["l19.weight"], W["l19.bias"])
@@ -512,7 +512,7 @@ def decoder_forward(ops: Ops, W, z, rescale=False):
     out = vae_res_block(ops, W, "l21", out, 256, 128)
     out = vae_res_block(ops, W, "l22", out, 128, 128)
     out = vae_res_block(ops, W, "l23", out, 128, 128)
-    out = ops.group_norm(out, 32, 1e-5)
+    out = ops.group_norm(out, 32, 1e-5, *_affine(W, "l24"))
     out = ops.silu(out)
     out = ops.conv2d(out, W["l26.weight"], W["l26.bias"], pad=1)
     return rescale_image(out) if rescale else out

@@ -141,9 +141,14 @@ int32_t tsd_diffusion_profile(tsd_diffusion* d, const float* x_dev, const float*
 
 // ---- Decoder ---------------------------------------------------------------------------------
 int32_t tsd_decoder_create(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32_t max_batch, tsd_decoder** out) {
+  return tsd_decoder_create_ex(h, latent_h, latent_w, max_batch, 0, out);
+}
+int32_t tsd_decoder_create_ex(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32_t max_batch, uint32_t flags,
+                              tsd_decoder** out) {
   if (!h || !out) return TSD_ERR_INVALID;
   *out = nullptr;
   Guard g(h);
+  if (flags & ~(uint32_t)TSD_MODEL_NORM_AFFINE) return h->c->fail(TSD_ERR_INVALID, "decoder: unknown flag");
   tsd_decoder* d = new (std::nothrow) tsd_decoder();
   if (!d) return h->c->fail(TSD_ERR_OOM, "decoder: host allocation failed");
   d->m.h = h;
@@ -151,6 +156,7 @@ int32_t tsd_decoder_create(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32
   d->m.latent_h = latent_h;
   d->m.latent_w = latent_w;
   d->m.max_batch = max_batch;
+  d->m.norm_affine = (flags & TSD_MODEL_NORM_AFFINE) ? 1 : 0;
   int rc = d->m.create();
   if (rc) {
     d->m.destroy();
@@ -212,9 +218,14 @@ int32_t tsd_decoder_forward_dev(tsd_decoder* d, const float* z, int32_t n, int32
 
 // ---- VAE Encoder (vae.mojo:70-159) ---------------------------------------------------------------------------------
 int32_t tsd_encoder_create(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32_t max_batch, tsd_encoder** out) {
+  return tsd_encoder_create_ex(h, latent_h, latent_w, max_batch, 0, out);
+}
+int32_t tsd_encoder_create_ex(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32_t max_batch, uint32_t flags,
+                              tsd_encoder** out) {
   if (!h || !out) return TSD_ERR_INVALID;
   *out = nullptr;
   Guard g(h);
+  if (flags & ~(uint32_t)TSD_MODEL_NORM_AFFINE) return h->c->fail(TSD_ERR_INVALID, "encoder: unknown flag");
   tsd_encoder* d = new (std::nothrow) tsd_encoder();
   if (!d) return h->c->fail(TSD_ERR_OOM, "encoder: host allocation failed");
   d->m.h = h;
@@ -222,6 +233,7 @@ int32_t tsd_encoder_create(tsd_ctx* h, int32_t latent_h, int32_t latent_w, int32
   d->m.latent_h = latent_h;
   d->m.latent_w = latent_w;
   d->m.max_batch = max_batch;
+  d->m.norm_affine = (flags & TSD_MODEL_NORM_AFFINE) ? 1 : 0;
   int rc = d->m.create();
   if (rc) {
     d->m.destroy();
@@ -285,15 +297,20 @@ int32_t tsd_encoder_forward_dev(tsd_encoder* d, const float* img, const float* n
 
 // ---- CLIP text encoder (clip.mojo:56-109) ------------------------------------------------------
 int32_t tsd_clip_create(tsd_ctx* h, int32_t n_vocab, int32_t n_layers, tsd_clip** out) {
+  return tsd_clip_create_ex(h, n_vocab, n_layers, 0, out);
+}
+int32_t tsd_clip_create_ex(tsd_ctx* h, int32_t n_vocab, int32_t n_layers, uint32_t flags, tsd_clip** out) {
   if (!h || !out) return TSD_ERR_INVALID;
   *out = nullptr;
   Guard g(h);
+  if (flags & ~(uint32_t)TSD_MODEL_NORM_AFFINE) return h->c->fail(TSD_ERR_INVALID, "clip: unknown flag");
   tsd_clip* d = new (std::nothrow) tsd_clip();
   if (!d) return TSD_ERR_OOM;
   d->m.h = h;
   d->m.c = h->c;
   if (n_vocab > 0) d->m.n_vocab = n_vocab;
   if (n_layers > 0) d->m.n_layers = n_layers;
+  d->m.norm_affine = (flags & TSD_MODEL_NORM_AFFINE) ? 1 : 0;
   int rc = d->m.create();
   if (rc) {
     d->m.destroy();

@@ -1065,12 +1065,17 @@ int Decoder::create() {
     w.conv1 = ps.add_conv(b + ".conv1", cin, cout, 3);
     w.conv2 = ps.add_conv(b + ".conv2", cout, cout, 3);
     if (cin != cout) w.skip = ps.add_conv(b + ".res_conv_layer", cin, cout, 1);
+    if (norm_affine) {
+      w.gn1 = ps.add_norm(b + ".groupnorm1", cin);
+      w.gn2 = ps.add_norm(b + ".groupnorm2", cout);
+    }
   };
   l1 = ps.add_conv("l1", 4, 4, 1);
   l2 = ps.add_conv("l2", 4, 512, 3);
   add_res("l3", 512, 512);
   attn_in = ps.add_linear("l4.attention.in_proj", 512, 1536, true);
   attn_out = ps.add_linear("l4.attention.out_proj", 512, 512, true);
+  if (norm_affine) attn_gn = ps.add_norm("l4.groupnorm", 512);
   add_res("l5", 512, 512);
   add_res("l6", 512, 512);
   add_res("l7", 512, 512);
@@ -1087,6 +1092,7 @@ int Decoder::create() {
   add_res("l21", 256, 128);
   add_res("l22", 128, 128);
   add_res("l23", 128, 128);
+  if (norm_affine) out_gn = ps.add_norm("l24", 128);
   l26 = ps.add_conv("l26", 128, 3, 3);
 
   const size_t B = max_batch, hw = (size_t)latent_h * latent_w;
@@ -1111,13 +1117,13 @@ void Decoder::destroy() {
 }
 
 // Attention_Block.forward, vae.mojo:17-27: GroupNorm(32) -> 1-head self-attention -> + residue
-static int vae_attn_block(Ctx* c, const ParamStore& ps, int attn_in, int attn_out, const float* x, int n,
+static int vae_attn_block(Ctx* c, const ParamStore& ps, int attn_in, int attn_out, int attn_gn, const float* x, int n,
                           int H, int W, float* out, const NormHint* xns = nullptr, NormHint* next = nullptr) {
   const int C = 512;
   const long long T = (long long)H * W, M = n * T;
   const size_t mark = c->arena.mark();
   WALLOC(a, M * C);
-  TRY(op_group_norm(c, x, a, n, H, W, C, 32, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1,
+  TRY(op_group_norm(c, x, a, n, H, W, C, 32, 1e-5f, ps.gamma(attn_gn), ps.beta(attn_gn), 1.0f, 0, 0, 1,
                     (xns && xns->G == 32 && xns->eps == 1e-5f) ? xns->ready() : nullptr));
   WALLOC(qkv, 3 * M * C);
   TRY(linear(c, a, M, C, ps.w(attn_in), ps.w(attn_in + 1), 3 * C, qkv, C, nullptr, 1, 0, C, M * C));
@@ -1195,7 +1201,7 @@ int Decoder::decode(int n, int rescale) {
   {
     NormHint out_ns;
     if (!make_hint(out_ns, 16, 512, H, W)) return c->fail(TSD_ERR_OOM, "workspace exhausted (norm statistics)");
-    TRY(vae_attn_block(c, ps, attn_in, attn_out, cur, n, H, W, nxt, &cur_ns, &out_ns));  // l4
+    TRY(vae_attn_block(c, ps, attn_in, attn_out, attn_gn, cur, n, H, W, nxt, &cur_ns, &out_ns));  // l4
     cur_ns = out_ns;
   }
   swap();
@@ -1210,7 +1216,7 @@ int Decoder::decode(int n, int rescale) {
     // l24 GroupNorm(32,128), l25 SiLU, l26 conv 128->3, then rescale/clamp (pipeline.mojo:127)
     const size_t mark = c->arena.mark();
     WALLOC(f, (long long)n * H * W * 128);
-    TRY(op_group_norm(c, cur, f, n, H, W, 128, 32, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1,
+    TRY(op_group_norm(c, cur, f, n, H, W, 128, 32, 1e-5f, ps.gamma(out_gn), ps.beta(out_gn), 1.0f, 1, 0, 1,
                       (cur_ns.G == 32 && cur_ns.eps == 1e-5f) ? cur_ns.ready() : nullptr));
     TRY(conv(c, ps, l26, f, n, H, W, 128, 3, 3, 1, 1, nullptr, 0, nullptr, nxt, 0));
     c->arena.release_to(mark);
@@ -1287,6 +1293,10 @@ int Encoder::create() {
     w.conv1 = ps.add_conv(b + ".conv1", cin, cout, 3);
     w.conv2 = ps.add_conv(b + ".conv2", cout, cout, 3);
     if (cin != cout) w.skip = ps.add_conv(b + ".res_conv_layer", cin, cout, 1);
+    if (norm_affine) {
+      w.gn1 = ps.add_norm(b + ".groupnorm1", cin);
+      w.gn2 = ps.add_norm(b + ".groupnorm2", cout);
+    }
   };
   l1 = ps.add_conv("l1", 3, 128, 3);
   add_res("l2", 128, 128);
@@ -1303,7 +1313,9 @@ int Encoder::create() {
   add_res("l13", 512, 512);
   attn_in = ps.add_linear("l14.attention.in_proj", 512, 1536, true);
   attn_out = ps.add_linear("l14.attention.out_proj", 512, 512, true);
+  if (norm_affine) attn_gn = ps.add_norm("l14.groupnorm", 512);
   add_res("l15", 512, 512);
+  if (norm_affine) out_gn = ps.add_norm("l16", 512);
   l18 = ps.add_conv("l18", 512, 8, 3);
   l19 = ps.add_conv("l19", 8, 8, 1);
 
@@ -1366,14 +1378,14 @@ int Encoder::encode(int n, int rescale) {
   TRY(RES());  // l9
   TRY(DOWN(l10, 512));
   for (int i = 0; i < 3; ++i) TRY(RES());  // l11..l13
-  TRY(vae_attn_block(c, ps, attn_in, attn_out, cur, n, H, W, nxt));  // l14
+  TRY(vae_attn_block(c, ps, attn_in, attn_out, attn_gn, cur, n, H, W, nxt));  // l14
   swap();
   TRY(RES());  // l15
   {
     // l16 GroupNorm(32,512), l17 SiLU, l18 conv 512->8, l19 conv 1x1 8->8, metrics_evals (vae.mojo:118-129)
     const size_t mark = c->arena.mark();
     WALLOC(f, (long long)n * H * W * 512);
-    TRY(op_group_norm(c, cur, f, n, H, W, 512, 32, 1e-5f, nullptr, nullptr, 1.0f, 1, 0, 1));
+    TRY(op_group_norm(c, cur, f, n, H, W, 512, 32, 1e-5f, ps.gamma(out_gn), ps.beta(out_gn), 1.0f, 1, 0, 1));
     WALLOC(m8, (long long)n * H * W * 8);
     TRY(conv(c, ps, l18, f, n, H, W, 512, 8, 3, 1, 1, nullptr, 0, nullptr, m8, 0));
     TRY(conv(c, ps, l19, m8, n, H, W, 8, 8, 1, 0, 1, nullptr, 0, nullptr, nxt, 0));

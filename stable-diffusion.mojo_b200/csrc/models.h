@@ -160,6 +160,8 @@ struct Decoder {
   int latent_h = 0, latent_w = 0, max_batch = 1;
   ParamStore ps;
   int l1 = -1, l2 = -1, l10 = -1, l15 = -1, l20 = -1, l26 = -1, attn_in = -1, attn_out = -1;
+  int norm_affine = 0;           // 1: every GroupNorm owns a per-channel weight and bias (real checkpoints)
+  int attn_gn = -1, out_gn = -1; // norm_affine only: Attention_Block's GroupNorm, l24
   ResBlockW res[14];  // l3, l5..l8, l11..l13, l16..l18, l21..l23
   float* z_in = nullptr;     // [max_batch][4][h][w]
   float* img_out = nullptr;  // [max_batch][3][8h][8w]
@@ -182,6 +184,8 @@ struct Encoder {
   int latent_h = 0, latent_w = 0, max_batch = 1;
   ParamStore ps;
   int l1 = -1, l4 = -1, l7 = -1, l10 = -1, l18 = -1, l19 = -1, attn_in = -1, attn_out = -1;
+  int norm_affine = 0;           // 1: every GroupNorm owns a per-channel weight and bias (real checkpoints)
+  int attn_gn = -1, out_gn = -1; // norm_affine only: Attention_Block's GroupNorm, l16
   ResBlockW res[10];  // l2 l3 l5 l6 l8 l9 l11 l12 l13 l15
   float* img_in = nullptr;    // [max_batch][3][8h][8w]
   float* noise_in = nullptr;  // [max_batch][4][h][w]
@@ -206,8 +210,11 @@ struct Clip {
   int n_vocab = 49408, n_embed = 768, n_tokens = 77, n_heads = 12, n_layers = 12;  // clip.mojo:71-83
   ParamStore ps;
   int tok = -1, pos = -1;
+  int norm_affine = 0;  // 1: every LayerNorm owns a per-channel weight and bias (real checkpoints)
+  int final_ln = -1;
   struct Layer {
     int in_proj = -1, out_proj = -1, fc1 = -1, fc2 = -1;
+    int ln1 = -1, ln2 = -1;  // norm_affine only
   } layer[kMaxLayers];
   int* tokens_dev = nullptr;
   float* out_dev = nullptr;  // [n_tokens][n_embed]

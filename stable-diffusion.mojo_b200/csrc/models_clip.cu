@@ -53,7 +53,12 @@ int Clip::create() {
     layer[l].out_proj = ps.add_linear(b + ".layer2.out_proj", n_embed, n_embed, true);
     layer[l].fc1 = ps.add_linear(b + ".layer4", n_embed, 4 * n_embed, true);
     layer[l].fc2 = ps.add_linear(b + ".layer5", 4 * n_embed, n_embed, true);
+    if (norm_affine) {  // real checkpoints: layer_norm1 / layer_norm2 weight + bias
+      layer[l].ln1 = ps.add_norm(b + ".layer1", n_embed);
+      layer[l].ln2 = ps.add_norm(b + ".layer3", n_embed);
+    }
   }
+  if (norm_affine) final_ln = ps.add_norm("layernorm", n_embed);
   if (cudaMalloc(&tokens_dev, sizeof(int) * n_tokens) != cudaSuccess ||
       cudaMalloc(&out_dev, sizeof(float) * (size_t)n_tokens * n_embed) != cudaSuccess)
     return c->fail(TSD_ERR_OOM, "clip: buffer allocation failed");
@@ -87,9 +92,9 @@ static int clip_linear(Ctx* c, const float* x, int M, int K, const float* w, con
 }
 
 // LayerNorm.forward (helpers/utils.mojo:2052-2061) on a (T, C) sequence, both modes
-static int clip_layer_norm(Ctx* c, const float* x, float* y, int T, int C) {
-  if (c->layernorm_mode == 0) return op_group_norm(c, x, y, 1, T, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1);
-  return op_group_norm(c, x, y, T, 1, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 1);
+static int clip_layer_norm(Ctx* c, const float* x, float* y, int T, int C, const float* gamma, const float* beta, int round_tf32 = 1) {
+  if (c->layernorm_mode == 0) return op_group_norm(c, x, y, 1, T, 1, C, 1, 1e-5f, gamma, beta, 1.0f, 0, 0, round_tf32);
+  return op_group_norm(c, x, y, T, 1, 1, C, 1, 1e-5f, gamma, beta, 1.0f, 0, 0, round_tf32);
 }
 
 // CLIP.forward, clip.mojo:88-109: tokens_dev -> out_dev
@@ -106,7 +111,7 @@ int Clip::encode() {
   LAUNCH(c, launch_clip_embed(tokens_dev, ps.w(tok), ps.w(pos), x, T, C, n_vocab, c->stream), "clip_embed");
   for (int l = 0; l < n_layers; ++l) {
     const Layer& w = layer[l];
-    TRY(clip_layer_norm(c, x, v, T, C));
+    TRY(clip_layer_norm(c, x, v, T, C, ps.gamma(w.ln1), ps.beta(w.ln1)));
     // Self_Attention.forward with causal_mask (helpers/attention.mojo:26-65): in_proj, chunk, raw head split
     TRY(clip_linear(c, v, T, C, ps.w(w.in_proj), ps.w(w.in_proj + 1), 3 * C, qkv, nullptr, 1, C, (long long)T * C));
     AttnArgs at;
@@ -116,14 +121,13 @@ int Clip::encode() {
     at.causal = 1;
     TRY(op_attention(c, at));
     TRY(clip_linear(c, o, T, C, ps.w(w.out_proj), ps.w(w.out_proj + 1), C, x1, x, 0));
-    TRY(clip_layer_norm(c, x1, v, T, C));
+    TRY(clip_layer_norm(c, x1, v, T, C, ps.gamma(w.ln2), ps.beta(w.ln2)));
     TRY(clip_linear(c, v, T, C, ps.w(w.fc1), ps.w(w.fc1 + 1), 4 * C, hbuf, nullptr, 0));
     LAUNCH(c, launch_unary(hbuf, hbuf, 4LL * T * C, UNARY_QUICKGELU, 1.0f, c->stream), "quick_gelu");
     TRY(clip_linear(c, hbuf, T, 4 * C, ps.w(w.fc2), ps.w(w.fc2 + 1), C, x, x1, 0));
   }
   // final LayerNorm; un-rounded (this is the model output, not a GEMM operand)
-  if (c->layernorm_mode == 0) TRY(op_group_norm(c, x, out_dev, 1, T, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 0));
-  else TRY(op_group_norm(c, x, out_dev, T, 1, 1, C, 1, 1e-5f, nullptr, nullptr, 1.0f, 0, 0, 0));
+  TRY(clip_layer_norm(c, x, out_dev, T, C, ps.gamma(final_ln), ps.beta(final_ln), 0));
   c->arena.release_to(mark);
   return TSD_OK;
 }

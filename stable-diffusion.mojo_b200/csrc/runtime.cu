@@ -827,7 +827,7 @@ static int run_gemm(Ctx* c, const ASpec& A, const float* B, int N, long long ldb
     // LayerNorm, instead of nothing at all.  Charge that to the candidate (measured, profiles/).
     const bool in_kernel_reduce = c->splitk_fixup || (c->splitk_cluster && !cand.halo && cand.cg * cand.splits <= c->splitk_cluster_max);
     if (nh && nh->G > 0 && c->producer_stats == 1 && cand.splits > 1 && !in_kernel_reduce)
-      ms_c += (nh->G == 1 && c->ln_fold) ? 0.018f : 0.012f;
+      ms_c += (nh->G == 1 && c->ln_fold) ? 0.018f : (c->norm_cluster && nh->G >= 16 ? c->tune_defer_penalty_us * 1e-3f : 0.012f);
     if (ms_c < best_ms) {
       best_ms = ms_c;
       best = cand;

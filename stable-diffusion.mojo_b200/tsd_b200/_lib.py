@@ -152,6 +152,7 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_png_encode", i32, fp, i32, i32, i32, vp, i64, C.POINTER(i64))
     sig("tsd_png_write", i32, C.c_char_p, fp, i32, i32, i32)
     sig("tsd_decoder_create", i32, vp, i32, i32, i32, C.POINTER(vp))
+    sig("tsd_decoder_create_ex", i32, vp, i32, i32, i32, C.c_uint32, C.POINTER(vp))
     sig("tsd_decoder_destroy", i32, vp)
     sig("tsd_decoder_num_params", i64, vp)
     sig("tsd_decoder_load_weights", i32, vp, fp, i64)
@@ -162,6 +163,7 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_decoder_forward", i32, vp, fp, i32, i32, fp)
     sig("tsd_decoder_forward_dev", i32, vp, fp, i32, i32, fp)
     sig("tsd_encoder_create", i32, vp, i32, i32, i32, C.POINTER(vp))
+    sig("tsd_encoder_create_ex", i32, vp, i32, i32, i32, C.c_uint32, C.POINTER(vp))
     sig("tsd_encoder_destroy", i32, vp)
     sig("tsd_encoder_num_params", i64, vp)
     sig("tsd_encoder_load_weights", i32, vp, fp, i64)
@@ -172,6 +174,7 @@ def _declare(L: C.CDLL) -> None:
     sig("tsd_encoder_forward", i32, vp, fp, fp, i32, i32, fp)
     sig("tsd_encoder_forward_dev", i32, vp, fp, fp, i32, i32, fp)
     sig("tsd_clip_create", i32, vp, i32, i32, C.POINTER(vp))
+    sig("tsd_clip_create_ex", i32, vp, i32, i32, C.c_uint32, C.POINTER(vp))
     sig("tsd_clip_destroy", i32, vp)
     sig("tsd_clip_num_params", i64, vp)
     sig("tsd_clip_load_weights", i32, vp, fp, i64)

@@ -13,6 +13,8 @@ import numpy as np
 from . import _lib
 from ._lib import TsdError
 
+MODEL_NORM_AFFINE = 1  # TSD_MODEL_NORM_AFFINE (include/tsd_b200.h)
+
 
 def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
@@ -376,10 +378,11 @@ class Clip(_Model):
     """tsd_clip: CLIP text encoder (clip.mojo:56-109): token ids -> the (77, 768) context."""
     _prefix = "clip"
 
-    def __init__(self, ctx: Context, n_vocab: int = 0, n_layers: int = 0):
+    def __init__(self, ctx: Context, n_vocab: int = 0, n_layers: int = 0, norm_affine=False):
         self.ctx = ctx
         m = C.c_void_p()
-        ctx._ck(ctx.L.tsd_clip_create(ctx.h, int(n_vocab), int(n_layers), C.byref(m)))
+        ctx._ck(ctx.L.tsd_clip_create_ex(ctx.h, int(n_vocab), int(n_layers), MODEL_NORM_AFFINE if norm_affine else 0,
+                                         C.byref(m)))
         self.m = m
 
     def forward(self, tokens) -> np.ndarray:
@@ -394,11 +397,12 @@ class Decoder(_Model):
     """tsd_decoder: VAE Decoder (vae.mojo:162-250)."""
     _prefix = "decoder"
 
-    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1):
+    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1, norm_affine=False):
         self.ctx = ctx
         self.shape = (latent_h, latent_w)
         m = C.c_void_p()
-        ctx._ck(ctx.L.tsd_decoder_create(ctx.h, latent_h, latent_w, max_batch, C.byref(m)))
+        ctx._ck(ctx.L.tsd_decoder_create_ex(ctx.h, latent_h, latent_w, max_batch, MODEL_NORM_AFFINE if norm_affine else 0,
+                                            C.byref(m)))
         self.m = m
 
     def forward(self, z, rescale=False):
@@ -421,11 +425,12 @@ class Encoder(_Model):
     rescale((0,255),(-1,1)) (pipeline.mojo:71) - and noise (4,h,w) -> latent (4,h,w)."""
     _prefix = "encoder"
 
-    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1):
+    def __init__(self, ctx: Context, latent_h=64, latent_w=64, max_batch=1, norm_affine=False):
         self.ctx = ctx
         self.shape = (latent_h, latent_w)
         m = C.c_void_p()
-        ctx._ck(ctx.L.tsd_encoder_create(ctx.h, latent_h, latent_w, max_batch, C.byref(m)))
+        ctx._ck(ctx.L.tsd_encoder_create_ex(ctx.h, latent_h, latent_w, max_batch, MODEL_NORM_AFFINE if norm_affine else 0,
+                                            C.byref(m)))
         self.m = m
 
     def forward(self, x, noise, rescale=False):

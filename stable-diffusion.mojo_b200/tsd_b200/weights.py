@@ -192,3 +192,80 @@ def tiny_sd_unet_name_map(param_names) -> dict:
         else:
             raise KeyError(name)
     return out
+
+
+# ---- VAE (diffusers AutoencoderKL names) and CLIP text encoder (transformers CLIPTextModel names) ----
+_VAE_RES_FIELD = {"conv1": "conv1", "conv2": "conv2", "res_conv_layer": "conv_shortcut", "groupnorm1": "norm1",
+                  "groupnorm2": "norm2"}
+# reference struct field (vae.mojo:163-188 decoder, :71-112 encoder) -> diffusers module path
+_VAE_DECODER_PATH = {"l1": "post_quant_conv", "l2": "decoder.conv_in", "l3": "decoder.mid_block.resnets.0",
+                     "l4": "decoder.mid_block.attentions.0", "l5": "decoder.mid_block.resnets.1",
+                     "l6": "decoder.up_blocks.0.resnets.0", "l7": "decoder.up_blocks.0.resnets.1",
+                     "l8": "decoder.up_blocks.0.resnets.2", "l10": "decoder.up_blocks.0.upsamplers.0.conv",
+                     "l11": "decoder.up_blocks.1.resnets.0", "l12": "decoder.up_blocks.1.resnets.1",
+                     "l13": "decoder.up_blocks.1.resnets.2", "l15": "decoder.up_blocks.1.upsamplers.0.conv",
+                     "l16": "decoder.up_blocks.2.resnets.0", "l17": "decoder.up_blocks.2.resnets.1",
+                     "l18": "decoder.up_blocks.2.resnets.2", "l20": "decoder.up_blocks.2.upsamplers.0.conv",
+                     "l21": "decoder.up_blocks.3.resnets.0", "l22": "decoder.up_blocks.3.resnets.1",
+                     "l23": "decoder.up_blocks.3.resnets.2", "l24": "decoder.conv_norm_out", "l26": "decoder.conv_out"}
+_VAE_ENCODER_PATH = {"l1": "encoder.conv_in", "l2": "encoder.down_blocks.0.resnets.0", "l3": "encoder.down_blocks.0.resnets.1",
+                     "l4": "encoder.down_blocks.0.downsamplers.0.conv", "l5": "encoder.down_blocks.1.resnets.0",
+                     "l6": "encoder.down_blocks.1.resnets.1", "l7": "encoder.down_blocks.1.downsamplers.0.conv",
+                     "l8": "encoder.down_blocks.2.resnets.0", "l9": "encoder.down_blocks.2.resnets.1",
+                     "l10": "encoder.down_blocks.2.downsamplers.0.conv", "l11": "encoder.down_blocks.3.resnets.0",
+                     "l12": "encoder.down_blocks.3.resnets.1", "l13": "encoder.mid_block.resnets.0",
+                     "l14": "encoder.mid_block.attentions.0", "l15": "encoder.mid_block.resnets.1",
+                     "l16": "encoder.conv_norm_out", "l18": "encoder.conv_out", "l19": "quant_conv"}
+
+
+def _vae_name_map(param_names, paths) -> dict:
+    out = {}
+    for name in param_names:
+        stem, kind = name.rsplit(".", 1)
+        layer, _, field = stem.partition(".")
+        base = paths[layer]
+        if not field:
+            out[name] = f"{base}.{kind}"
+        elif field == "attention.in_proj":      # to_q | to_k | to_v stacked along the output axis (attention.mojo:29)
+            out[name] = [f"{base}.to_q.{kind}", f"{base}.to_k.{kind}", f"{base}.to_v.{kind}"]
+        elif field == "attention.out_proj":
+            out[name] = f"{base}.to_out.0.{kind}"
+        elif field == "groupnorm":
+            out[name] = f"{base}.group_norm.{kind}"
+        else:
+            out[name] = f"{base}.{_VAE_RES_FIELD[field]}.{kind}"
+    return out
+
+
+def tiny_sd_vae_decoder_name_map(param_names) -> dict:
+    """{parameter name of a TSD_MODEL_NORM_AFFINE Decoder: AutoencoderKL tensor name (or names to concatenate)}."""
+    return _vae_name_map(param_names, _VAE_DECODER_PATH)
+
+
+def tiny_sd_vae_encoder_name_map(param_names) -> dict:
+    """{parameter name of a TSD_MODEL_NORM_AFFINE Encoder: AutoencoderKL tensor name (or names to concatenate)}."""
+    return _vae_name_map(param_names, _VAE_ENCODER_PATH)
+
+
+def tiny_sd_clip_name_map(param_names) -> dict:
+    """{parameter name of a TSD_MODEL_NORM_AFFINE Clip: CLIPTextModel tensor name (or names to concatenate)}.
+    The token table and the position embedding are stored flat on our side: build_blob only needs equal sizes."""
+    field = {"layer2.out_proj": "self_attn.out_proj", "layer4": "mlp.fc1", "layer5": "mlp.fc2", "layer1": "layer_norm1",
+             "layer3": "layer_norm2"}
+    out = {}
+    for name in param_names:
+        if name == "embedding.token_embedding.weight":
+            out[name] = "text_model.embeddings.token_embedding.weight"
+        elif name == "embedding.position_embedding":
+            out[name] = "text_model.embeddings.position_embedding.weight"
+        elif name.startswith("layernorm."):
+            out[name] = "text_model.final_layer_norm." + name.rsplit(".", 1)[1]
+        else:
+            stem, kind = name.rsplit(".", 1)
+            layer, f = stem.split(".", 1)
+            base = f"text_model.encoder.layers.{int(layer[len('player'):]) - 1}"
+            if f == "layer2.in_proj":
+                out[name] = [f"{base}.self_attn.{p}_proj.{kind}" for p in "qkv"]
+            else:
+                out[name] = f"{base}.{field[f]}.{kind}"
+    return out

@@ -3,6 +3,7 @@ Decoder.forward - against the fp64 oracle at sizes it finishes in seconds, again
 full-size goldens (BASELINE config 2 shapes), and through size-independent properties.
 Tolerance for TF32 model-level outputs: max|a-b|/max|b| <= 2e-2; measured
 values are printed."""
+import ctypes
 import os
 
 import numpy as np
@@ -11,7 +12,7 @@ import pytest
 import synth
 import tsd_oracle as O
 from conftest import GOLDEN, relerr
-from tsd_b200.api import Decoder, Diffusion, Encoder
+from tsd_b200.api import Clip, Decoder, Diffusion, Encoder
 from tsd_b200._lib import TsdError
 from tsd_b200.pipeline import Pipeline
 from tsd_b200 import sampler as host_sampler
@@ -317,6 +318,61 @@ def dec8(ctx):
     m.init_random(DEC_SEED)
     yield m
     m.close()
+
+
+@pytest.mark.parametrize("intended", [1, 0])
+def test_vae_and_clip_norm_affine(ctx, intended):
+    """Row f2 for the VAE and the text encoder: TSD_MODEL_NORM_AFFINE models (tsd_{decoder,encoder,clip}_create_ex) own a
+    per-channel weight and bias for every GroupNorm / LayerNorm; random ones (weights around 1, non-zero biases) against
+    the fp64 oracle, with the switches a real checkpoint needs and with the reference-faithful ones."""
+    sw = O.Switches(softmax_axis="key", layernorm="token", norm_eps_inside=True) if intended else O.Switches()
+    opts = {"softmax_axis": intended, "layernorm_mode": intended, "norm_eps_mode": intended}
+    ops64 = O.Ops("np", np.float64, sw)
+    rng = np.random.default_rng(40 + intended)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        specs = synth.decoder_specs(norm_affine=True)
+        blob = synth.random_blob(specs, 51)
+        m = Decoder(ctx, 4, 4, max_batch=1, norm_affine=True)
+        assert m.num_params() == synth.num_params(specs) == 49_467_159 + 2 * 11_520
+        assert [t[0] for t in m.param_table()] == [s[0] for s in specs]
+        m.load_weights(blob)
+        z = rng.standard_normal((4, 4, 4), dtype=np.float32)
+        e = relerr(m.forward(z), O.decoder_forward(ops64, synth.BlobWeights(specs, blob), z))
+        print(f"decoder 4x4 latent, norm_affine, intended={intended}: rel_linf vs fp64 oracle {e:.2e}")
+        assert e < TOL_MODEL
+        m.close()
+
+        specs = synth.encoder_specs(norm_affine=True)
+        blob = synth.random_blob(specs, 52)
+        m = Encoder(ctx, 4, 4, max_batch=1, norm_affine=True)
+        assert m.num_params() == synth.num_params(specs)
+        assert [t[0] for t in m.param_table()] == [s[0] for s in specs]
+        m.load_weights(blob)
+        img = rng.uniform(-1, 1, (3, 32, 32)).astype(np.float32)
+        noise = rng.standard_normal((4, 4, 4), dtype=np.float32)
+        e = relerr(m.forward(img, noise), O.encoder_forward(ops64, synth.BlobWeights(specs, blob), img, noise))
+        print(f"encoder 32x32 image, norm_affine, intended={intended}: rel_linf vs fp64 oracle {e:.2e}")
+        assert e < TOL_MODEL
+        m.close()
+
+        specs = synth.clip_specs(1000, 3, norm_affine=True)
+        blob = synth.random_blob(specs, 53)
+        m = Clip(ctx, 1000, 3, norm_affine=True)
+        assert m.num_params() == synth.num_params(specs)
+        assert [t[0] for t in m.param_table()] == [s[0] for s in specs]
+        m.load_weights(blob)
+        tokens = rng.integers(1, 1000, 29)
+        e = relerr(m.forward(tokens), O.clip_forward(ops64, synth.BlobWeights(specs, blob), tokens, n_layers=3))
+        print(f"clip 3 layers, norm_affine, intended={intended}: rel_linf vs fp64 oracle {e:.2e}")
+        assert e < TOL_MODEL
+        m.close()
+    finally:
+        for k in opts:
+            ctx.set_option(k, 0)
+    with pytest.raises(TsdError):
+        ctx._ck(ctx.L.tsd_decoder_create_ex(ctx.h, 4, 4, 1, 2, ctypes.byref(ctypes.c_void_p())))  # unknown flag
 
 
 def test_decoder8_matches_oracle_golden(dec8, golden_small):

@@ -153,3 +153,48 @@ def test_tiny_sd_name_map_round_trip(tmp_path):
     st.close()
     assert np.array_equal(got, blob)
     assert report["missing"] == [] and report["unused"] == ["up_blocks.0.upsamplers.0.conv.weight"]
+
+
+@pytest.mark.parametrize("which", ["decoder", "encoder", "clip"])
+def test_tiny_sd_vae_and_clip_name_maps_round_trip(tmp_path, which):
+    """The VAE (diffusers AutoencoderKL names) and the text encoder (transformers CLIPTextModel names) of a
+    segmind/tiny-sd style checkpoint assemble into the blobs of TSD_MODEL_NORM_AFFINE models: one-to-one maps, fused
+    in_proj rebuilt from q | k | v, nothing missing, nothing unused."""
+    import synth
+    specs, mapper = {"decoder": (synth.decoder_specs(norm_affine=True), W.tiny_sd_vae_decoder_name_map),
+                     "encoder": (synth.encoder_specs(norm_affine=True), W.tiny_sd_vae_encoder_name_map),
+                     "clip": (synth.clip_specs(300, 2, norm_affine=True), W.tiny_sd_clip_name_map)}[which]
+    blob = synth.random_blob(specs, 23)
+    ours = synth.BlobWeights(specs, blob)
+    table, off = [], 0
+    for name, shape, _ in specs:
+        n = int(np.prod(shape))
+        table.append((name, off, n))
+        off += n
+    nm = mapper([t[0] for t in table])
+    assert len(nm) == len(table) and len(set(map(str, nm.values()))) == len(nm)
+    if which == "decoder":
+        assert nm["l4.groupnorm.weight"] == "decoder.mid_block.attentions.0.group_norm.weight"
+        assert nm["l16.res_conv_layer.bias"] == "decoder.up_blocks.2.resnets.0.conv_shortcut.bias"
+        assert nm["l24.bias"] == "decoder.conv_norm_out.bias" and nm["l1.weight"] == "post_quant_conv.weight"
+    elif which == "encoder":
+        assert nm["l19.weight"] == "quant_conv.weight" and nm["l10.bias"] == "encoder.down_blocks.2.downsamplers.0.conv.bias"
+        assert nm["l14.attention.out_proj.weight"] == "encoder.mid_block.attentions.0.to_out.0.weight"
+    else:
+        assert nm["player2.layer2.in_proj.bias"] == [f"text_model.encoder.layers.1.self_attn.{p}_proj.bias" for p in "qkv"]
+        assert nm["layernorm.weight"] == "text_model.final_layer_norm.weight"
+    file_tensors = {}
+    for name, shape, _ in specs:
+        src = nm[name]
+        if isinstance(src, list):
+            for s_, p_ in zip(src, np.split(ours[name], len(src), axis=0)):
+                file_tensors[s_] = p_
+        else:
+            file_tensors[src] = ours[name]
+    path = tmp_path / f"{which}.safetensors"
+    W.write_safetensors(path, file_tensors)
+    st = W.SafeTensors(path)
+    got, report = W.build_blob(table, st, nm)
+    st.close()
+    assert np.array_equal(got, blob)
+    assert report == {"missing": [], "unused": []}
