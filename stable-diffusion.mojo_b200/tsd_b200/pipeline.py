@@ -17,7 +17,7 @@ from .tokenizer import Tokenizer, prompt_tokens
 class Pipeline:
     def __init__(self, ctx: Context, image_size: int = 512, max_images: int = 1, cfg: bool = True, seed: int = 0,
                  weights=None, with_clip: bool = False, clip_vocab: int = 0, clip_layers: int = 0,
-                 tokenizer=None, tokenizer_vocab: int = 49408, concat_as_written: bool = True):
+                 tokenizer=None, tokenizer_vocab: int = 49408, concat_as_written: bool = True, norm_affine: bool = False):
         if image_size % 32:
             raise ValueError("image_size must be a multiple of 32 (latent side a multiple of 4)")
         self.ctx = ctx
@@ -25,9 +25,11 @@ class Pipeline:
         self.side = image_size // 8
         self.cfg = cfg
         self.max_images = max_images
-        self.diffusion = Diffusion(ctx, self.side, self.side, max_batch=max_images * (2 if cfg else 1))
-        self.decoder = Decoder(ctx, self.side, self.side, max_batch=max_images)
-        self.clip = Clip(ctx, clip_vocab, clip_layers) if with_clip else None
+        # norm_affine: every norm of every model owns per-channel weights (real checkpoints; weights.tiny_sd_*_name_map)
+        self.norm_affine = norm_affine
+        self.diffusion = Diffusion(ctx, self.side, self.side, max_batch=max_images * (2 if cfg else 1), norm_affine=norm_affine)
+        self.decoder = Decoder(ctx, self.side, self.side, max_batch=max_images, norm_affine=norm_affine)
+        self.clip = Clip(ctx, clip_vocab, clip_layers, norm_affine=norm_affine) if with_clip else None
         self.encoder = None
         # Tokenizer(49408, read_file("tokenizer_clip.bin")), pipeline.mojo:32-37: a path, the file's bytes or a Tokenizer
         self.tokenizer = tokenizer if tokenizer is None or isinstance(tokenizer, Tokenizer) else Tokenizer(tokenizer, tokenizer_vocab)
@@ -58,7 +60,7 @@ class Pipeline:
     def _encoder(self):
         """The reference builds Encoder() only when an input image is given (pipeline.mojo:66-67)."""
         if self.encoder is None:
-            self.encoder = Encoder(self.ctx, self.side, self.side, max_batch=self.max_images)
+            self.encoder = Encoder(self.ctx, self.side, self.side, max_batch=self.max_images, norm_affine=self.norm_affine)
             if self._weights is None or len(self._weights) < 4:
                 self.encoder.init_random(self._seed + 3)
             else:

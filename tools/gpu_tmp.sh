@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_models.py -m gpu -x -q -s -k "norm_affine or decoder8 or clip_matches or encoder_matches" 2>&1 | tail -15
+TSD_LIB=$PWD/stable-diffusion.mojo_b200/csrc/libtsd_b200_trace.so timeout 300 python tools/lab/gemm_trace.py 2>&1 | tail -40
