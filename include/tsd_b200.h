@@ -60,6 +60,8 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *   "layernorm_mode"   0 = one mean/std over the whole (C,T) tensor, as reference
  *                          LayerNorm = GroupNorm(1,C) (utils.mojo:2052-2061) [default]
  *                      1 = per token
+ *   "norm_eps_mode"    0 = (x - mean) / (std + eps), as reference GroupNorm.forward (utils.mojo:1868-1870) [default]
+ *                      1 = (x - mean) / sqrt(var + eps) (what real checkpoints were trained with)
  *   "fused_attention"  1 = fused tcgen05 attention kernel [default], 0 = GEMM+softmax+GEMM
  *   "cuda_graph"       1 = replay model forwards from a captured CUDA graph [default], 0 = eager
  * Execution-plan knobs (never change semantics; results agree to TF32 rounding level):
@@ -77,8 +79,14 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *   "defer_reduce"     1 = where a split-K GEMM feeds a norm directly, the norm kernel sums the partial tiles
  *                          (no reduce kernel) [default]
  *   "virtual_concat"   1 = the channel concats of the UNet are read (and written out) by the GroupNorm kernel of the
- *                          ResBlock they feed instead of a concat kernel of their own; 0 [default] (measured neutral)
- *   "norm_v2"          0/1 = which single-launch fused norm kernel serves the remaining norms
+ *                          ResBlock they feed instead of a concat kernel of their own [default]; 0 = concat kernel
+ *   "norm_cluster"     1 = GroupNorm by one thread-block cluster per (image, group), slab in shared memory, statistics
+ *                          exchanged through distributed shared memory [default]; 0 = grid-barrier kernels only
+ *   "norm_v2"          0/1 = which grid-barrier fused norm kernel serves the shapes the cluster kernel does not take
+ *   "attn_v2"          1 = attention kernel with three S/P buffers in tensor memory [default], 0 = round-1 kernel
+ *   "splitk_cluster"   1 = split-K partials reduced inside the GEMM through distributed shared memory (cluster over
+ *                          the splits); 0 [default] (measured slower than partial tiles + consumer-side reduction)
+ *   "tune_defer_penalty_us"  autotuner: microseconds charged to a split-K candidate whose consumer sums the partials
  *   "splitk_fixup"     1 = split-K partials reduced in-kernel by the last CTA of each tile, 0 = reduce kernel [default]
  *   "pdl"              1 = programmatic dependent launch between the kernels of a graph [default]
  *   "force_bn" / "force_splits" / "force_stages" / "gemm_debug" / "halo_min_w" / "halo_min_h" /
