@@ -772,8 +772,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // round trip and the instruction issue of a single thread (~40 clk per MMA, ~65 per TMA) are what
   // bounds small-N tiles, so they are spread over two threads.  The two issuers accumulate into two
   // separate TMEM tiles (no ordering between them is needed); the epilogue adds them.
-  const int role_parity = warp >= 10 ? 1 : 0;
+  const int role_parity = (GEMM_ROLE_PAIRS > 1 && warp >= 10) ? 1 : 0;
   const int n_par = (n_iters > 1 && GEMM_ROLE_PAIRS > 1) ? 2 : 1;  // issuers / producers with work
+  // GEMM_B_PRODUCER: warp 0 = A boxes + barrier arming, warp 10 = B boxes (both walk every K step)
+  const bool do_a = !GEMM_B_PRODUCER || warp == 0, do_b = !GEMM_B_PRODUCER || warp == 10;
   if ((warp == 0 || warp == 10) && role_parity < n_par) {
     // ===================== TMA producer (K steps it = parity, parity + 2, ...) =====================
     if (elect_one()) {
@@ -858,13 +860,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       // Weights do not depend on the predecessor kernel: the B halves of the first ring pass are
       // requested BEFORE the programmatic-dependency wait, so their HBM latency overlaps its tail.
+      // (With a separate B producer the barrier is armed by the A producer in the main loop; bytes that land before
+      // the expect_tx only drive the transaction count negative, the phase cannot complete before the arrival.)
       int pre_end = role_parity;  // iterations < pre_end (of this parity) already have their B tile in flight
       if (p.b_static && !(debug & 4)) {
         pre_end = n_iters < num_stages ? n_iters : num_stages;
         int kc2 = kc, tap2 = tap, kb2 = kb, cin_cur2 = cin_cur;
-        for (int it = role_parity; it < pre_end; it += step) {
+        for (int it = role_parity; it < pre_end && do_b; it += step) {
           const uint32_t fb2 = full0 + 8u * it;
-          if (CG == 1 || rank == 0) mbar_expect_tx_a(fb2, tx);
+          if (!GEMM_B_PRODUCER && (CG == 1 || rank == 0)) mbar_expect_tx_a(fb2, tx);
           load_b(smem_base + it * stage_bytes, fb2 & fb_mask, kb2);
           for (int s = 0; s < step; ++s) {
             kc2 += bk;
@@ -883,12 +887,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint32_t fb = full0 + 8u * stage, eb = empty0 + 8u * stage;
         const uint32_t fbs = fb & fb_mask;
-        if (it >= pre_end) {
+        if (GEMM_B_PRODUCER) {
+          if (it >= num_stages || (do_b && it >= pre_end)) mbar_wait_a(eb, phase ^ 1u);  // the first ring pass finds every slot free
+          if (do_a && (CG == 1 || rank == 0)) mbar_expect_tx_a(fb, tx);
+          if (do_b && it >= pre_end && !(debug & 4)) load_b(sa, fbs, kb);
+        } else if (it >= pre_end) {
           mbar_wait_a(eb, phase ^ 1u);
           if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, tx);
           if (!(debug & 4)) load_b(sa, fbs, kb);
         }
-        if (!(debug & 2)) {
+        if (do_a && !(debug & 2)) {
           const CUtensorMap* ta = tap >= taps ? &tmA2 : &tmA;
           const int wx = w0 * cstride + dx + coff, hy = h0 * cstride + dy + coff;
           tma_a_4d<CG>(sa, ta, fbs, kc, wx, hy, c3);
@@ -901,9 +909,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           phase ^= 1u;
         }
       }
-      TSD_TRACE(role_parity == 0, 2);
+      TSD_TRACE(role_parity == 0 && do_a, 2);
     }
-  } else if ((warp == 1 || warp == 11) && role_parity < n_par) {
+  } else if ((warp == 1 || (GEMM_ROLE_PAIRS > 1 && warp == 11)) && role_parity < n_par) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
     if ((CG == 1 || rank == 0) && elect_one()) {
       const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, GEMM_BM * CG, (uint32_t)p.BN, 0, 0);

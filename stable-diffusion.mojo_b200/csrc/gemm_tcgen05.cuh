@@ -30,7 +30,11 @@ constexpr int GEMM_BK = 64;        // preferred K step (fp32 elements) = two 128
 // bandwidth, not by instruction issue) and the 12-warp CTA caps registers at 168 (epilogue spills),
 // so 1 is used; the two-pair path stays for wider tiles / other precisions.
 constexpr int GEMM_ROLE_PAIRS = 1;
-constexpr int GEMM_THREADS = 320 + 64 * (GEMM_ROLE_PAIRS - 1);  // warps 0/10 TMA producers, 1/11 MMA issuers (1: TMEM alloc), 2..9 epilogue
+// With one role pair, warp 10 is a second TMA producer: warp 0 issues the A (activation) boxes and arms the barrier,
+// warp 10 issues the B (weight) boxes.  A lone thread sustains one TMA request per 180-420 clk (tools/lab/l2bench.cu),
+// and a K step of 64 is four requests: the under-filled small-M GEMMs of the UNet were bound by that chain.
+constexpr int GEMM_B_PRODUCER = GEMM_ROLE_PAIRS == 1 ? 1 : 0;
+constexpr int GEMM_THREADS = 320 + 64 * (GEMM_ROLE_PAIRS - 1) + 32 * GEMM_B_PRODUCER;  // warps 0/10 TMA producers, 1/11 MMA issuers (1: TMEM alloc), 2..9 epilogue
 constexpr int GEMM_MAX_STAGES = 6;
 
 struct GemmKParams {
