@@ -82,6 +82,39 @@ __device__ __forceinline__ void tma_a_4d(uint32_t dst, const void* tmap, uint32_
         : "memory");
   }
 }
+// merged K atoms: coordinate 0 is always 0 (the 32 channels of a chunk), the last coordinate is the chunk index
+template <int CG>
+__device__ __forceinline__ void tma_a_5d(uint32_t dst, const void* tmap, uint32_t bar, int c1, int c2, int c3, int c4) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_b_4d(uint32_t dst, const void* tmap, uint32_t bar, int c1, int c2, int c3) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
 template <int CG>
 __device__ __forceinline__ void tma_b_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
   if constexpr (CG == 1) {
@@ -799,6 +832,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         brow0 = nt * p.BN + (int)rank * b_rows;
       }
       const bool two_b = geglu && CG == 1;
+      const bool kmerge = p.kmerge != 0;
       const int step = n_par;
       // (tap, channel chunk) of this thread's first iteration; afterwards advanced incrementally
       // Second K segment (p.cin2 > 0): after the taps over the first operand, `cin2` more channels of a second
@@ -845,7 +879,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t fb_mask = (CG == 2) ? 0xFEFFFFFFu : 0xFFFFFFFFu;  // CG == 2: signal the leader's barrier
       auto load_b = [&](uint32_t sa_, uint32_t fbs_, int kb_) {
         const uint32_t sb = sa_ + natoms * a_atom;
-        if (!two_b) {
+        if (kmerge) {
+          tma_b_4d<CG>(sb, &tmB, fbs_, brow0, batch, kb_ >> 5);
+        } else if (!two_b) {
           tma_b_3d<CG>(sb, &tmB, fbs_, kb_, brow0, batch);
           if (natoms == 2) tma_b_3d<CG>(sb + b_atom, &tmB, fbs_, kb_ + 32, brow0, batch);
         } else {
@@ -899,8 +935,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (do_a && !(debug & 2)) {
           const CUtensorMap* ta = tap >= taps ? &tmA2 : &tmA;
           const int wx = w0 * cstride + dx + coff, hy = h0 * cstride + dy + coff;
-          tma_a_4d<CG>(sa, ta, fbs, kc, wx, hy, c3);
-          if (natoms == 2) tma_a_4d<CG>(sa + a_atom, ta, fbs, kc + 32, wx, hy, c3);
+          if (kmerge) {
+            tma_a_5d<CG>(sa, ta, fbs, wx, hy, c3, kc >> 5);
+          } else {
+            tma_a_4d<CG>(sa, ta, fbs, kc, wx, hy, c3);
+            if (natoms == 2) tma_a_4d<CG>(sa + a_atom, ta, fbs, kc + 32, wx, hy, c3);
+          }
         }
         advance();
         stage += step;

@@ -70,6 +70,8 @@ struct GemmKParams {
   int n_pad;
   int fixup;               // split-K: the last CTA of every output tile reduces the partials and runs the epilogue
   unsigned int* tile_tickets;  // [grid.x * grid.y] zero-initialised, self-resetting arrival counters (fixup)
+  int kmerge;              // 1: a K step of 64 is ONE TMA request per operand (tensor maps carry the 32-channel chunk index as
+                           //    an extra outermost dimension, box extent 2): half the requests of the single-thread producers
   int debug;               // lab only (Ctx::gemm_debug)
   int cg;                  // 1, or 2 = CTA pairs over consecutive M tiles (cluster 2x1x1, grid.x even)
   NormStatsReq ns;         // producer-side GroupNorm statistics of D (ns.partial == nullptr: off)

@@ -415,24 +415,34 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   const int n_out = p.geglu ? N / 2 : N;
   const int n_tiles = (((p.geglu ? n_out : p.n_pad)) + out_cols_per_tile - 1) / out_cols_per_tile;
 
+  // merged K atoms: one TMA request per operand and K step of 64 (the chunk index becomes an extra outermost
+  // dimension of the tensor maps).  Needs whole 32-channel chunks everywhere (no out-of-bounds fill inside a chunk),
+  // full 128-row A boxes (the second atom must land a_atom bytes after the first) and one B box per atom.
+  p.kmerge = (c->gemm_kmerge && !p.halo && p.bk == 64 && A.K % 32 == 0 && A.K2 % 32 == 0 && bw * bh == GEMM_BM &&
+              !(p.geglu && p.cg == 1)) ? 1 : 0;
   CUtensorMap tmA, tmB, tmA2;
   if (!c->dry_run && A.K2 > 0) {
-    uint64_t dims[4] = {(uint64_t)A.K2, (uint64_t)A.W, (uint64_t)A.H, (uint64_t)A.imgs};
-    uint64_t str[4] = {1, (uint64_t)A.K2, (uint64_t)A.K2 * A.W, (uint64_t)A.K2 * A.W * A.H};
-    uint32_t box[4] = {32u, (uint32_t)bw, (uint32_t)bh, 1};
-    int rc = make_tmap_f32(c, &tmA2, A.base2, 4, dims, str, box, 0, nullptr);
+    uint64_t dims[5] = {(uint64_t)A.K2, (uint64_t)A.W, (uint64_t)A.H, (uint64_t)A.imgs, 1};
+    uint64_t str[5] = {1, (uint64_t)A.K2, (uint64_t)A.K2 * A.W, (uint64_t)A.K2 * A.W * A.H, 32};
+    uint32_t box[5] = {32u, (uint32_t)bw, (uint32_t)bh, 1, 2};
+    if (p.kmerge) {
+      dims[4] = (uint64_t)(A.K2 / 32);
+      dims[0] = 32;
+    }
+    int rc = make_tmap_f32(c, &tmA2, A.base2, p.kmerge ? 5 : 4, dims, str, box, 0, nullptr);
     if (rc) return rc;
   }
   if (!c->dry_run) {
-    uint64_t dims[4] = {(uint64_t)A.K, (uint64_t)A.W, (uint64_t)A.H,
-                        (uint64_t)(A.batch > 1 ? A.batch : A.imgs)};
-    uint64_t str[4] = {1, (uint64_t)A.ld_w, (uint64_t)A.ld_h,
-                       (uint64_t)(A.batch > 1 ? A.ld_batch : A.ld_img)};
+    uint64_t dims[5] = {(uint64_t)A.K, (uint64_t)A.W, (uint64_t)A.H,
+                        (uint64_t)(A.batch > 1 ? A.batch : A.imgs), (uint64_t)(A.K / 32)};
+    uint64_t str[5] = {1, (uint64_t)A.ld_w, (uint64_t)A.ld_h,
+                       (uint64_t)(A.batch > 1 ? A.ld_batch : A.ld_img), 32};
+    if (p.kmerge) dims[0] = 32;
     if (dims[3] == 1) str[3] = (uint64_t)A.ld_h * A.H;  // unused but must be a valid stride
     if (dims[2] == 1) str[2] = (uint64_t)A.ld_w * A.W;
     if (dims[3] == 1 && str[3] < str[2]) str[3] = str[2];
-    uint32_t box[4] = {32u, (uint32_t)(p.halo ? 16 : bw), (uint32_t)(p.halo ? 18 : bh), 1};
-    uint32_t es[4] = {1, 1, 1, 1};
+    uint32_t box[5] = {32u, (uint32_t)(p.halo ? 16 : bw), (uint32_t)(p.halo ? 18 : bh), 1, 2};
+    uint32_t es[5] = {1, 1, 1, 1, 1};
     if (A.cstride > 1) {  // the box spans bw*stride x bh*stride input pixels and keeps every stride-th one
       dims[1] = (uint64_t)A.in_W;
       dims[2] = (uint64_t)A.in_H;
@@ -440,15 +450,16 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
       box[2] = (uint32_t)(bh * A.cstride);
       es[1] = es[2] = (uint32_t)A.cstride;
     }
-    int rc = make_tmap_f32(c, &tmA, A.base, 4, dims, str, box, 0, A.cstride > 1 ? es : nullptr);
+    int rc = make_tmap_f32(c, &tmA, A.base, p.kmerge ? 5 : 4, dims, str, box, 0, A.cstride > 1 ? es : nullptr);
     if (rc) return rc;
   }
   if (!c->dry_run) {
     const int ktot = A.taps * A.K + A.K2;
-    uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch};
-    uint64_t str[3] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows)};
-    uint32_t box[3] = {32u, (uint32_t)((p.geglu || p.cg == 2) ? p.BN / 2 : p.BN), 1};
-    int rc = make_tmap_f32(c, &tmB, B, 3, dims, str, box, 0, nullptr);
+    uint64_t dims[4] = {(uint64_t)ktot, (uint64_t)b_rows, (uint64_t)nbatch, (uint64_t)(ktot / 32)};
+    uint64_t str[4] = {1, (uint64_t)ldb, (uint64_t)(nbatch > 1 ? b_bs : (long long)ldb * b_rows), 32};
+    uint32_t box[4] = {32u, (uint32_t)((p.geglu || p.cg == 2) ? p.BN / 2 : p.BN), 1, 2};
+    if (p.kmerge) dims[0] = 32;
+    int rc = make_tmap_f32(c, &tmB, B, p.kmerge ? 4 : 3, dims, str, box, 0, nullptr);
     if (rc) return rc;
   }
 

@@ -146,6 +146,7 @@ struct Ctx {
   int fuse_skip = 1;               // ResBlock 1x1 skip convolution as a second K segment of conv2 (0: GEMM of its own + residual add)
   int norm_cluster = 1;            // 1: GroupNorm with one thread-block cluster per (image, group) where the slab fits shared memory
   int tune_defer_penalty_us = 3;   // autotuner: cost charged to a split-K candidate whose GroupNorm consumer is the cluster kernel (it sums the partials)
+  int gemm_kmerge = 1;             // 1: one TMA request per operand and K step of 64 where the shapes allow (A/B switch)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;
