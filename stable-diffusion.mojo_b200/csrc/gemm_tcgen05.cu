@@ -184,6 +184,13 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t laddr, uint32_t cta) {
   return v;
 }
 // arrive (release, cluster scope) on the mbarrier at shared-window address `laddr` of CTA `cta` of this cluster
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t laddr, uint32_t cta) {
+  uint32_t raddr;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(cta));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t laddr, uint32_t cta) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(cta));
@@ -413,11 +420,18 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
   // re-read the kernel parameters from the constant bank and branched on them in every chunk (a chain of ~6 dependent
   // constant loads, ~300 cycles per chunk with only two epilogue warps per scheduler to hide them).
   enum : uint32_t { F_FULL = 1, F_RES = 2, F_ROUND = 4, F_STATS = 8, F_GEGLU = 16, F_TWOACC = 32, F_PLAIN = 64,
-                    F_PARTIAL = 128, F_ROUTED = 256, F_VEC = 512, F_B4 = 1024, F_STATS1 = 2048 };
+                    F_PARTIAL = 128, F_ROUTED = 256, F_VEC = 512, F_B4 = 1024, F_STATS1 = 2048, F_SMEMTILE = 4096 };
+  // cluster split-K through distributed shared memory (p.fixup == 3): the raw partial tile of this CTA stays in its own
+  // shared memory ([128 rows][BN rounded up to 32, + 4] floats behind the staging area of the idle operand ring); the CTAs of the tile read
+  // each other's tiles with ld.shared::cluster after a cluster barrier - no partial tile ever reaches L2 / HBM
+  const bool dsm = fixup && p.fixup == 3;
+  const int ldt = ((p.BN + 31) & ~31) + 4;  // whole 32-column chunks (the last one may be partly padding) + 4: conflict-free rows
+  float* const tile = reinterpret_cast<float*>(smem_ring + GEMM_DSM_TILE_OFFSET);
   uint32_t flags = (rows_full ? F_FULL : 0u) | (rbase != nullptr ? F_RES : 0u) | (round_out ? F_ROUND : 0u) |
                    (want_stats ? F_STATS : 0u) | (geglu ? F_GEGLU : 0u) | (two_acc ? F_TWOACC : 0u) |
                    (plain ? F_PLAIN : 0u) | (partial ? F_PARTIAL : 0u) | (routed ? F_ROUTED : 0u) |
-                   (vec_ok ? F_VEC : 0u) | ((!geglu && !partial) ? F_B4 : 0u) | (stats_pass1 ? F_STATS1 : 0u);
+                   (vec_ok ? F_VEC : 0u) | ((!geglu && !partial) ? F_B4 : 0u) | (stats_pass1 ? F_STATS1 : 0u) |
+                   (dsm ? F_SMEMTILE : 0u);
   asm volatile("mov.b32 %0, %0;\n" : "+r"(flags));
   const float sc_store = (!geglu && !partial && ln_fold) ? ln_r : 1.0f;
   const long long partial_col0 = (long long)nt * p.BN;
@@ -469,6 +483,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       }
     }
     TSD_TRACE(threadIdx.x == 64 && c == 0, 10);
+    if (flags & F_SMEMTILE) {  // thread = row: 32 consecutive floats of this row, quarter-warps hit distinct banks (ldt % 32 == 4)
+      uint4* trow_s = reinterpret_cast<uint4*>(tile + (q * 32 + lane) * ldt + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) trow_s[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      continue;
+    }
     uint4* srow = reinterpret_cast<uint4*>(stg + lane * ST);
 #pragma unroll
     for (int j = 0; j < 8; ++j) srow[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -570,7 +590,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
       if (!fix_last) return;
       __threadfence();
     } else {
-      __threadfence();  // this thread's partial stores are performed before the arrival below is observed
+      if (!dsm) __threadfence();  // this thread's partial stores are performed before the arrival below is observed
       named_bar_sync(2, 256);
       if (te0 < S) mbar_arrive_remote(ec.red_bar, ec.pair_rank + ec.cg * (uint32_t)te0);  // one arrival per CTA of the tile, on each of them
       mbar_wait_cluster(ec.red_bar, 0);
@@ -599,6 +619,22 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         }
         // all loads of the chunk first (8 rows x splits), then the sums in split order
         float4 t[8];
+        if (dsm) {
+          // this lane's 8 rows of the chunk in the tile of split s2: CTA rank pair_rank + cg * s2 of the cluster
+          const uint32_t a0 = smem_u32(tile + (q * 32 + sub) * ldt + c + c4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = ld_dsmem_f4(a0 + (uint32_t)(i * 4 * ldt) * 4u, ec.pair_rank);
+          for (int s2 = 1; s2 < S; ++s2) {
+            float4 u[8];
+            const uint32_t owner = ec.pair_rank + ec.cg * (uint32_t)s2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = ld_dsmem_f4(a0 + (uint32_t)(i * 4 * ldt) * 4u, owner);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              t[i].x += u[i].x; t[i].y += u[i].y; t[i].z += u[i].z; t[i].w += u[i].w;
+            }
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -616,6 +652,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
           for (int i = 0; i < 8; ++i) {
             t[i].x += u[i].x; t[i].y += u[i].y; t[i].z += u[i].z; t[i].w += u[i].w;
           }
+        }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -649,7 +686,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, const Epilog
         }
       }
     }
-    if (p.fixup == 2 && want_stats) {
+    if (p.fixup >= 2 && want_stats) {
       // the column sums of a chunk live in the CTA that reduced it: the split-0 CTA gathers them through distributed
       // shared memory once every CTA of the tile has finished (second barrier), then writes the tile's statistics
       named_bar_sync(2, 256);
@@ -729,6 +766,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t fullb_bar[GEMM_MAX_B_STAGES];   // deep weight ring (p.b_stages > 0)
+  __shared__ __align__(8) uint64_t emptyb_bar[GEMM_MAX_B_STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ __align__(8) uint64_t red_bar[2];  // cluster split-K (p.fixup == 2): partial tiles stored / column sums ready
   __shared__ uint32_t tmem_slot;
@@ -737,7 +776,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = (CG == 2) ? cluster_ctaid_x() : 0u;  // position in the CTA pair (the cluster may also span K splits along z)
-  const bool cluster_split = p.fixup == 2;  // the K splits of a tile are the z extent of this CTA's cluster
+  const bool cluster_split = p.fixup >= 2;  // the K splits of a tile are the z extent of this CTA's cluster
 
   // 1024 B aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -765,11 +804,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_iters = it_end - it_begin;
   const int num_stages = p.num_stages;
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), accum_a = smem_u32(&accum_bar);
+  const uint32_t fullb0 = smem_u32(&fullb_bar[0]), emptyb0 = smem_u32(&emptyb_bar[0]);
+  const int nb_stages = GEMM_B_PRODUCER ? p.b_stages : 0;      // > 0: separate rings
+  const uint32_t a_stage = natoms * a_atom, b_stage = natoms * b_atom;
+  const uint32_t b_ring = smem_base + (uint32_t)num_stages * a_stage;  // deep mode: the weight ring follows the A ring
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < nb_stages; ++s) {
+      mbar_init(&fullb_bar[s], 1);
+      mbar_init(&emptyb_bar[s], 1);
     }
     mbar_init(&accum_bar, (n_iters > 1 && GEMM_ROLE_PAIRS > 1) ? 2 : 1);  // one commit per MMA issuer
     if (cluster_split) {
@@ -877,8 +924,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = role_parity % num_stages;
       uint32_t phase = (uint32_t)(role_parity / num_stages) & 1u;
       const uint32_t fb_mask = (CG == 2) ? 0xFEFFFFFFu : 0xFFFFFFFFu;  // CG == 2: signal the leader's barrier
-      auto load_b = [&](uint32_t sa_, uint32_t fbs_, int kb_) {
-        const uint32_t sb = sa_ + natoms * a_atom;
+      auto load_b = [&](uint32_t sb, uint32_t fbs_, int kb_) {
         if (kmerge) {
           tma_b_4d<CG>(sb, &tmB, fbs_, brow0, batch, kb_ >> 5);
         } else if (!two_b) {
@@ -894,6 +940,51 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       };
+      if (nb_stages > 0) {
+        // ---- separate rings: warp 10 streams the weight boxes through their own (deep) ring, warp 0 the A boxes ----
+        if (do_b) {
+          const bool stat = p.b_static && !(debug & 4);
+          if (!stat) pdl_wait();  // B is an activation: it belongs to the predecessor (static weights need no wait at all)
+          int t = 0;
+          uint32_t ph = 0;
+          for (int it = 0; it < n_iters; ++it) {
+            const uint32_t fb = fullb0 + 8u * t;
+            if (it >= nb_stages) mbar_wait_a(emptyb0 + 8u * t, ph ^ 1u);
+            if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, (uint32_t)CG * b_tx);
+            if (!(debug & 4)) load_b(b_ring + (uint32_t)t * b_stage, fb & fb_mask, kb);
+            advance();
+            if (++t == nb_stages) {
+              t = 0;
+              ph ^= 1u;
+            }
+          }
+        } else {
+          pdl_wait();
+          for (int it = 0; it < n_iters; ++it) {
+            const uint32_t sa = smem_base + (uint32_t)stage * a_stage;
+            const uint32_t fb = full0 + 8u * stage;
+            const uint32_t fbs = fb & fb_mask;
+            if (it >= num_stages) mbar_wait_a(empty0 + 8u * stage, phase ^ 1u);
+            if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, (uint32_t)CG * a_tx);
+            if (!(debug & 2)) {
+              const CUtensorMap* ta = tap >= taps ? &tmA2 : &tmA;
+              const int wx = w0 * cstride + dx + coff, hy = h0 * cstride + dy + coff;
+              if (kmerge) {
+                tma_a_5d<CG>(sa, ta, fbs, wx, hy, c3, kc >> 5);
+              } else {
+                tma_a_4d<CG>(sa, ta, fbs, kc, wx, hy, c3);
+                if (natoms == 2) tma_a_4d<CG>(sa + a_atom, ta, fbs, kc + 32, wx, hy, c3);
+              }
+            }
+            advance();
+            if (++stage == num_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          TSD_TRACE(true, 2);
+        }
+      } else {
       // Weights do not depend on the predecessor kernel: the B halves of the first ring pass are
       // requested BEFORE the programmatic-dependency wait, so their HBM latency overlaps its tail.
       // (With a separate B producer the barrier is armed by the A producer in the main loop; bytes that land before
@@ -905,7 +996,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = role_parity; it < pre_end && do_b; it += step) {
           const uint32_t fb2 = full0 + 8u * it;
           if (!GEMM_B_PRODUCER && (CG == 1 || rank == 0)) mbar_expect_tx_a(fb2, tx);
-          load_b(smem_base + it * stage_bytes, fb2 & fb_mask, kb2);
+          load_b(smem_base + it * stage_bytes + natoms * a_atom, fb2 & fb_mask, kb2);
           for (int s = 0; s < step; ++s) {
             kc2 += bk;
             kb2 += bk;
@@ -926,11 +1017,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (GEMM_B_PRODUCER) {
           if (it >= num_stages || (do_b && it >= pre_end)) mbar_wait_a(eb, phase ^ 1u);  // the first ring pass finds every slot free
           if (do_a && (CG == 1 || rank == 0)) mbar_expect_tx_a(fb, tx);
-          if (do_b && it >= pre_end && !(debug & 4)) load_b(sa, fbs, kb);
+          if (do_b && it >= pre_end && !(debug & 4)) load_b(sa + natoms * a_atom, fbs, kb);
         } else if (it >= pre_end) {
           mbar_wait_a(eb, phase ^ 1u);
           if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, tx);
-          if (!(debug & 4)) load_b(sa, fbs, kb);
+          if (!(debug & 4)) load_b(sa + natoms * a_atom, fbs, kb);
         }
         if (do_a && !(debug & 2)) {
           const CUtensorMap* ta = tap >= taps ? &tmA2 : &tmA;
@@ -950,6 +1041,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       TSD_TRACE(role_parity == 0 && do_a, 2);
+      }  // shared ring
     }
   } else if ((warp == 1 || (GEMM_ROLE_PAIRS > 1 && warp == 11)) && role_parity < n_par) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
@@ -962,9 +1054,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.debug & 1) nk_last = 0;
       const int nk_full = (p.debug & 1) ? 0 : bk / 8;
       int chunk = (it_begin + role_parity) % chunks;
+      const bool deep = nb_stages > 0;  // separate A / B rings
       const uint64_t adesc0 = umma_smem_desc(smem_base, 16, 1024, UMMA_SWIZZLE_128B);
-      const uint64_t bdesc0 = umma_smem_desc(smem_base + natoms * a_atom, 16, 1024, UMMA_SWIZZLE_128B);
-      const uint32_t stage_step = stage_bytes >> 4, a_step = a_atom >> 4, b_step = b_atom >> 4;
+      const uint64_t bdesc0 = umma_smem_desc(deep ? b_ring : smem_base + natoms * a_atom, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint32_t a_step = a_atom >> 4, b_step = b_atom >> 4;
+      const uint32_t a_stage_step = (deep ? a_stage : stage_bytes) >> 4, b_stage_step = (deep ? b_stage : stage_bytes) >> 4;
+      int tb = 0;
+      uint32_t phb = 0;
       const uint32_t tmem_acc = tmem_d + (uint32_t)(role_parity * p.acc_stride);  // this issuer's accumulator tile
       int stage = role_parity % num_stages;
       uint32_t phase = (uint32_t)(role_parity / num_stages) & 1u;
@@ -973,10 +1069,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nk = (chunk == chunks - 1) ? nk_last : nk_full;
         chunk += step;
         while (chunk >= chunks) chunk -= chunks;
-        const uint32_t soff = (uint32_t)stage * stage_step;
         mbar_wait_a(full0 + 8u * stage, phase);
+        if (deep) mbar_wait_a(fullb0 + 8u * tb, phb);
         tc_fence_after_sync();
-        const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
+        const uint64_t ad = adesc0 + (uint32_t)stage * a_stage_step, bd = bdesc0 + (uint32_t)(deep ? tb : stage) * b_stage_step;
         if (nk == 8) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -998,6 +1094,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         umma_commit_cg<CG>(empty0 + 8u * stage);  // smem slot reusable (in both CTAs) once these MMAs retire
+        if (deep) {
+          umma_commit_cg<CG>(emptyb0 + 8u * tb);
+          if (++tb == nb_stages) {
+            tb = 0;
+            phb ^= 1u;
+          }
+        }
         stage += step;
         if (stage >= num_stages) {
           stage -= num_stages;
@@ -1304,10 +1407,14 @@ __global__ void splitk_reduce_kernel(const SplitKReduceParams p) {
 
 static size_t gemm_stage_bytes(int BN, int cg, int bk) { return (size_t)(bk / 32) * ((size_t)GEMM_BM * 128 + (size_t)(BN / cg) * 128); }
 
-size_t gemm_smem_bytes(int BN, int num_stages, int cg, int bk) {
+size_t gemm_smem_bytes(int BN, int num_stages, int cg, int bk, int b_stages, int dsm_tile) {
   size_t ring = (size_t)num_stages * gemm_stage_bytes(BN, cg, bk);
+  if (b_stages > 0)  // separate rings: num_stages A stages + b_stages B stages
+    ring = (size_t)(bk / 32) * ((size_t)num_stages * GEMM_BM * 128 + (size_t)b_stages * (BN / cg) * 128);
   const size_t staging = 8 * 32 * 36 * 4 + 4 * 256 * 8;  // epilogue staging tiles + column statistics live in the (then idle) ring
   if (ring < staging) ring = staging;
+  const size_t tile = (size_t)GEMM_DSM_TILE_OFFSET + (size_t)GEMM_BM * (((BN + 31) & ~31) + 4) * 4;  // cluster split-K: raw partial tile
+  if (dsm_tile && ring < tile) ring = tile;
   return ring + 1024;
 }
 
@@ -1347,12 +1454,12 @@ static cudaError_t launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = p.fixup == 2 ? p.splits : 1;  // cluster split-K: the K splits of a tile are co-scheduled
+  attr[0].val.clusterDim.z = p.fixup >= 2 ? p.splits : 1;  // cluster split-K: the K splits of a tile are co-scheduled
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (p.fixup == 2 && CG * p.splits > 8) {  // beyond the portable cluster size: opt in once per (kernel, device)
+  if (p.fixup >= 2 && CG * p.splits > 8) {  // beyond the portable cluster size: opt in once per (kernel, device)
     static std::mutex mu;
     static std::map<int, bool> done;
     int dev = 0;

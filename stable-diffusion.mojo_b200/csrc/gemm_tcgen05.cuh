@@ -36,6 +36,8 @@ constexpr int GEMM_ROLE_PAIRS = 1;
 constexpr int GEMM_B_PRODUCER = GEMM_ROLE_PAIRS == 1 ? 1 : 0;
 constexpr int GEMM_THREADS = 320 + 64 * (GEMM_ROLE_PAIRS - 1) + 32 * GEMM_B_PRODUCER;  // warps 0/10 TMA producers, 1/11 MMA issuers (1: TMEM alloc), 2..9 epilogue
 constexpr int GEMM_MAX_STAGES = 6;
+constexpr int GEMM_MAX_B_STAGES = 24;
+constexpr int GEMM_DSM_TILE_OFFSET = 48 * 1024;  // cluster split-K (fixup 3): the raw partial tile sits behind the epilogue staging area  // deep weight ring (GemmKParams::b_stages)
 
 struct GemmKParams {
   // output-pixel tiling (plain GEMM: H = 1, W = M, bw = 128, bh = 1)
@@ -70,6 +72,9 @@ struct GemmKParams {
   int n_pad;
   int fixup;               // split-K: the last CTA of every output tile reduces the partials and runs the epilogue
   unsigned int* tile_tickets;  // [grid.x * grid.y] zero-initialised, self-resetting arrival counters (fixup)
+  int b_stages;            // > 0: the B (weight) operand has its own ring of this depth behind the A ring (num_stages deep), with its
+                           //      own barriers: narrow tiles stream many small weight boxes from HBM, and a ring sized for the
+                           //      32 KiB A boxes keeps too few of them in flight to cover the DRAM latency
   int kmerge;              // 1: a K step of 64 is ONE TMA request per operand (tensor maps carry the 32-channel chunk index as
                            //    an extra outermost dimension, box extent 2): half the requests of the single-thread producers
   int debug;               // lab only (Ctx::gemm_debug)
@@ -107,7 +112,7 @@ int halo_pick_sb(int BN, int cg);
 size_t halo_smem_bytes(int BN, int cg, int sb);
 cudaError_t launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid,
                              size_t smem_bytes, cudaStream_t stream);
-size_t gemm_smem_bytes(int BN, int num_stages, int cg, int bk);
+size_t gemm_smem_bytes(int BN, int num_stages, int cg, int bk, int b_stages = 0, int dsm_tile = 0);
 void gemm_pick_ring(int BN, int cg, int* bk, int* stages);
 
 }  // namespace tsd

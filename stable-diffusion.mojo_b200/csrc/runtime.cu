@@ -403,6 +403,22 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
   p.iters_per_split = (p.total_iters + p.splits - 1) / p.splits;
   p.splits = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;  // no empty split
   p.debug = c->gemm_debug;
+  // Deep weight ring: narrow tiles (B stage <= half an A stage) with more K steps than the shared ring holds give the
+  // weights their own ring - typically the whole K extent of the tile, requested before the dependency wait.
+  p.b_stages = 0;
+  if (GEMM_B_PRODUCER && c->gemm_deep_b && !p.halo && p.bk == 64 && c->force_stages == 0) {
+    const size_t a_stage = 2 * (size_t)GEMM_BM * 128, b_stage = 2 * (size_t)(p.BN / p.cg) * 128;
+    const size_t budget = 223 * 1024;
+    if (2 * b_stage <= a_stage && p.iters_per_split > p.num_stages) {
+      const int sa = 4;
+      long long sb = (long long)((budget - sa * a_stage) / b_stage);
+      sb = std::min<long long>(sb, std::min(GEMM_MAX_B_STAGES, p.iters_per_split));
+      if (sb >= 2 * p.num_stages || sb >= p.iters_per_split) {
+        p.num_stages = sa;
+        p.b_stages = (int)sb;
+      }
+    }
+  }
   // the epilogue reads TMEM in 32-column chunks: keep the last (partial) chunk inside the allocation
   const int tmem_need = p.geglu ? p.BN + 16 : p.BN + ((p.BN & 31) ? 16 : 0);
   p.acc_stride = (tmem_need + 31) / 32 * 32;
@@ -507,9 +523,11 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
                               (!p.bias || ((p.bias_img_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
     p.fixup = (c->splitk_fixup && tiles <= kTileTickets && vec_epilogue) ? 1 : 0;
     // cluster split-K: the splits of a tile are one thread-block cluster (x pair, z splits) and reduce in the kernel
+    // (splitk_cluster 1: partial tiles through L2, reduced by the cluster; 2: partial tiles stay in shared memory and cross
+    // the cluster through DSMEM - then a consumer norm that can sum the partials for free keeps priority)
     if (!p.fixup && c->splitk_cluster && !p.halo && vec_epilogue && nbatch == 1 && p.cg * p.splits <= c->splitk_cluster_max &&
-        p.cg * p.splits <= 16)
-      p.fixup = 2;
+        p.cg * p.splits <= 16 && !(c->splitk_cluster >= 2 && can_defer))
+      p.fixup = c->splitk_cluster >= 2 ? 3 : 2;
     p.tile_tickets = c->tile_tickets;
   } else {
     p.partial = nullptr;
@@ -577,7 +595,7 @@ static int run_gemm_cfg(Ctx* c, const ASpec& A, const float* B, int N, long long
     TimedScope ts(c, FAM_GEMM, flops);
     int rc = p.halo ? c->check(launch_conv_halo(tmA, tmB, p, grid, halo_smem_bytes(p.BN, p.cg, p.num_stages), c->stream),
                                "conv3x3_halo_kernel launch")
-                    : c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg, p.bk), c->stream,
+                    : c->check(launch_gemm_tf32(tmA, tmB, p, grid, gemm_smem_bytes(p.BN, p.num_stages, p.cg, p.bk, p.b_stages, p.fixup == 3), c->stream,
                                               A.K2 > 0 ? &tmA2 : nullptr),
                                "gemm_tf32_kernel launch");
     if (rc) return rc;

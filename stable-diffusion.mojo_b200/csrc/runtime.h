@@ -147,6 +147,7 @@ struct Ctx {
   int norm_cluster = 1;            // 1: GroupNorm with one thread-block cluster per (image, group) where the slab fits shared memory
   int tune_defer_penalty_us = 3;   // autotuner: cost charged to a split-K candidate whose GroupNorm consumer is the cluster kernel (it sums the partials)
   int gemm_kmerge = 1;             // 1: one TMA request per operand and K step of 64 where the shapes allow (A/B switch)
+  int gemm_deep_b = 0;             // 1: narrow GEMM tiles stream their weights through a separate, deeper ring (A/B switch)
   int norm_v2 = 0;                 // 0: previous fused norm kernel (A/B switch)
   int producer_stats = 1;          // 0: never fold norm statistics into GEMM epilogues (A/B switch)
   KernelTimer* timer = nullptr;

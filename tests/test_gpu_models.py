@@ -139,6 +139,8 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
     {"autotune": 0, "conv_halo": 2, "halo_min_w": 8, "halo_min_h": 8},  # halo convolution kernel everywhere
     {"gemm_cg": 1},                       # single CTAs only (no cta_group::2 pairs)
     {"splitk_fixup": 1},                  # split-K reduced in-kernel by the last CTA of each tile
+    {"splitk_cluster": 2, "force_splits": 4},  # ... by the cluster of a tile's splits through distributed shared memory
+    {"splitk_cluster": 1, "force_splits": 2},  # ... by that cluster with the partial tiles in L2
 ])
 def test_unet8_execution_switches(ctx, diff8, golden_small, opts):
     """Every execution-plan switch computes the same UNet step (to TF32 rounding level): the

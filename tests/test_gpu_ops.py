@@ -310,6 +310,28 @@ def test_conv2d_tile_variants(ctx, ops, cg, bn, splits):
     assert relerr(y, ref) < TOL_TF32
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("cg,bn,splits", [(1, 80, 2), (1, 160, 4), (2, 80, 3), (1, 64, 8), (2, 160, 4), (1, 256, 5), (2, 32, 4)])
+def test_splitk_inside_a_cluster(ctx, ops, mode, cg, bn, splits):
+    """split-K reduced inside the GEMM by the thread-block cluster of a tile's splits: partial tiles through L2
+    (splitk_cluster = 1) or kept in shared memory and read across the cluster with ld.shared::cluster (= 2);
+    a 3x3 convolution (ragged last chunk: 300 channels) and linears with ragged M / N"""
+    rng = np.random.default_rng(300 + bn + splits + mode)
+    x = rng.standard_normal((300, 32, 32), dtype=np.float32)
+    wt = (rng.standard_normal((320, 300, 3, 3)) / np.sqrt(2700)).astype(np.float32)
+    b = rng.standard_normal(320, dtype=np.float32)
+    xs = rng.standard_normal((200, 1280), dtype=np.float32)
+    ws = (rng.standard_normal((328, 1280)) / np.sqrt(1280)).astype(np.float32)
+    bs = rng.standard_normal(328, dtype=np.float32)
+    with _Options(ctx, autotune=0, gemm_cg=cg, force_bn=bn, force_splits=splits, splitk_cluster=mode, splitk_cluster_max=16):
+        y = ctx.conv2d(x, wt, b, pad=1)
+        ys = ctx.linear(xs, ws, bs)
+        y2 = ctx.conv2d(x, wt, b, pad=1)
+    assert relerr(y, ops.conv2d(x, wt, b, 1, 1)) < TOL_TF32
+    assert relerr(ys, ops.linear(xs, ws, bs)) < TOL_TF32
+    assert np.array_equal(y, y2)   # fixed summation order
+
+
 @pytest.mark.parametrize("n,cin,h,w,cout,bn,splits,cg", [
     (1, 32, 32, 32, 32, 0, 0, 1), (1, 320, 32, 32, 320, 160, 1, 2), (1, 320, 32, 32, 320, 80, 2, 2),
     (2, 96, 40, 24, 48, 0, 0, 0),      # ragged edges, two images

@@ -1,14 +1,13 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "conv or linear or matmul or gemm" 2>&1 | tail -5
-timeout 900 python -m pytest tests/test_gpu_models.py -m gpu -x -q -k "unet or decoder8 or encoder_matches" 2>&1 | tail -3
 run() { python bench.py --no-image --no-cpu --steps 40 --warmup 5 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['e2e']['value'], d['roofline']['families_ms'])"; }
-runv() { python bench.py --config vae16 --no-cpu 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('vae16', d['value'], d['clocks'])"; }
-run; TSD_OPT_gemm_kmerge=0 run; run; runv; TSD_OPT_gemm_kmerge=0 runv
+        d=json.loads(l); print(d['value'], d['e2e']['value'], d['roofline']['families_ms'], d['gpu_launches'])"; }
+echo base; run
+echo "cluster2, shipped plans"; TSD_OPT_splitk_cluster=2 run
+export TSD_TUNE_DEFAULTS=0 TSD_TUNE_REPS=5 TSD_OPT_splitk_cluster=2
+for i in 1 2; do
+export TSD_TUNE_CACHE=gpurun_out/tune_r02_dsm$i.txt; rm -f $TSD_TUNE_CACHE
+echo "cluster2 fresh tune $i"; run; run
+done
