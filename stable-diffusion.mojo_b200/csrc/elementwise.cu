@@ -1876,6 +1876,15 @@ struct NormClusterPlan {
   size_t smem;
   bool ok;
 };
+static int norm_cluster_target_ctas() {  // lab: TSD_NORM_CLUSTER_CTAS overrides the CTA count a plan aims for
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TSD_NORM_CLUSTER_CTAS");
+    v = e ? atoi(e) : 256;
+    if (v < 1) v = 256;
+  }
+  return v;
+}
 static NormClusterPlan norm_cluster_plan(int N, long long pixels, int C, int G) {
   NormClusterPlan pl{};
   if (G <= 0 || C % G || pixels <= 0 || pixels >= (1 << 30)) return pl;
@@ -1897,7 +1906,7 @@ static NormClusterPlan norm_cluster_plan(int N, long long pixels, int C, int G) 
     pl.ppc = (int)ppc;
     pl.smem = smem;
     pl.ok = true;
-    if (clusters * cs >= 256 || ppc <= 2 * pl.ppl) break;
+    if (clusters * cs >= norm_cluster_target_ctas() || ppc <= 2 * pl.ppl) break;
   }
   if (pl.ok && clusters * pl.cs < 64) pl.ok = false;  // too few CTAs to be worth it (LayerNorm of one image)
   return pl;

@@ -36,6 +36,10 @@ def ops():
     (1, 96, 12, 20, 48, 3, 1, 1),      # ragged tile edges (W not a divisor of 128)
     (1, 4, 8, 8, 4, 1, 0, 1),          # VAE l1
     (3, 36, 5, 7, 20, 3, 1, 1),        # odd everything
+    (1, 320, 64, 64, 320, 3, 1, 1),    # the most frequent UNet convolution at the BASELINE latent (shipped tile plan)
+    (1, 960, 64, 64, 320, 3, 1, 1),    # up-block conv1 after the skip concat at 64x64
+    (2, 640, 32, 32, 640, 3, 1, 1),    # CFG batch of two at the 32x32 level
+    (1, 256, 128, 128, 256, 3, 1, 1),  # VAE decoder level (multi-wave grid)
 ])
 def test_conv2d(ctx, ops, n, cin, h, w, cout, k, pad, stride):
     rng = np.random.default_rng(cin * 1000 + cout + h)
