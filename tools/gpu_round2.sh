@@ -16,7 +16,7 @@ done
 timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; echo "ref exit=$?"
 # launch list of the step graph (per-launch device time; cold-cache and serialised: compare shares)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 250 -c 900 --csv \
-  --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-image --no-cpu > gpurun_out/ncu_bench_$tag.log 2>&1; echo "ncu list exit=$?"
+  --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-image --no-cpu --no-timeline > gpurun_out/ncu_bench_$tag.log 2>&1; echo "ncu list exit=$?"
 cap() {  # name, kernel regex, launch-skip, count, group, extra ncu flags
   timeout 600 ncu --set full --clock-control none --import-source on $6 -k "regex:$2" --launch-skip $3 -c $4 \
     -o gpurun_out/${tag}_ncu_$1 python tools/prof_r02.py $5 > gpurun_out/prof_$1_$tag.log 2>&1; echo "ncu $1 exit=$?"
@@ -34,6 +34,7 @@ cap gemv_multi gemv_multi 0 1 step "$R"
 # DRAM / L2->SM bytes and duration of EVERY launch of one warmed-up eager step
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__m_xbar2l1tex_read_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
   --clock-control none --profile-from-start off --csv --log-file gpurun_out/${tag}_step_traffic.csv python tools/prof_r02.py step > /dev/null 2>&1; echo "ncu traffic exit=$?"
+VERBOSE=1 timeout 300 python tools/lab/graph_timeline.py > gpurun_out/${tag}_graph_timeline.txt 2>&1
 ITERS=20 timeout 300 python tools/prof_kernels.py > gpurun_out/kernel_timings_$tag.log 2>&1
 ITERS=20 timeout 300 python tools/attn_lab.py > gpurun_out/attn_lab_$tag.txt 2>&1
 python tools/step_launches.py gpurun_out/launches_$tag.csv gpurun_out/${tag}_launches_unet_step > /dev/null 2>&1

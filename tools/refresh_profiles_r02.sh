@@ -10,6 +10,7 @@ cp $g/bench_ref_$tag.json profiles/${tag}_bench_ref.json
 cp $g/pytest_$tag.log profiles/${tag}_pytest_gpu.txt
 cp $g/kernel_timings_$tag.log profiles/${tag}_kernel_timings.log
 cp $g/attn_lab_$tag.txt profiles/${tag}_attn_lab.txt
+cp $g/${tag}_graph_timeline.txt profiles/${tag}_graph_timeline.txt
 cp $g/${tag}_launches_unet_step.csv $g/${tag}_launches_unet_step_summary.txt profiles/
 for k in gemm_conv320 decoder_conv256 attn2 cross_attn norm_apply_partial norm_cluster gemv_multi; do
   cp $g/${tag}_ncu_$k.json $g/${tag}_ncu_$k.txt profiles/
