@@ -87,7 +87,7 @@ int32_t tsd_init(int32_t device, tsd_ctx** out) {
   h->c = c;
   *out = h;
   // tuning / A-B switches from the environment: TSD_OPT_<option name>=<int>  (same names as tsd_set_option)
-  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "norm_cluster", "gemm_kmerge", "gemm_deep_b", "tune_defer_penalty_us", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention", "attn_v2", "attn_poly", "splitk_cluster", "splitk_cluster_max"};
+  static const char* kEnvOpts[] = {"producer_stats", "norm_v2", "norm_cluster", "gemm_kmerge", "gemm_deep_b", "fuse_ffn_out", "tune_defer_penalty_us", "ln_fold", "fuse_skip", "conv_stride_tma", "defer_reduce", "virtual_concat", "gn_partial", "gn_partial_max_groups", "splitk_fixup", "pdl", "autotune", "conv_halo", "halo_min_w", "halo_min_h", "tune_verbose", "tune_flush", "gemm_cg", "force_bn", "force_splits", "fused_attention", "attn_v2", "attn_poly", "splitk_cluster", "splitk_cluster_max"};
   for (const char* name : kEnvOpts) {
     const std::string key = std::string("TSD_OPT_") + name;
     if (const char* v = getenv(key.c_str())) tsd_set_option(h, name, atoi(v));
@@ -134,6 +134,7 @@ static int* option_slot(tsd_ctx* h, const char* name) {
   if (!strcmp(name, "norm_cluster")) return &h->c->norm_cluster;
   if (!strcmp(name, "gemm_kmerge")) return &h->c->gemm_kmerge;
   if (!strcmp(name, "gemm_deep_b")) return &h->c->gemm_deep_b;
+  if (!strcmp(name, "fuse_ffn_out")) return &h->c->fuse_ffn_out;
   if (!strcmp(name, "tune_defer_penalty_us")) return &h->c->tune_defer_penalty_us;
   if (!strcmp(name, "ln_fold")) return &h->c->ln_fold;
   if (!strcmp(name, "fuse_skip")) return &h->c->fuse_skip;

@@ -199,6 +199,10 @@ void ParamStore::free_all() {
     if (r) cudaFree(r);
   rowsum_dev.clear();
   rowsum_gen.clear();
+  for (float* r : ffn_dev)
+    if (r) cudaFree(r);
+  ffn_dev.clear();
+  ffn_gen.clear();
   for (float* r : fskip_dev)
     if (r) cudaFree(r);
   fskip_dev.clear();
@@ -314,6 +318,63 @@ __global__ void fuse_skip_weights_kernel(const float* __restrict__ w1, const flo
       out[i] = b1[o] + b2[o];
     }
   }
+}
+
+// out[o][k] = sum_j wc[o][j] * w2[j][k] for k < K2 (the product of the two weight matrices, fp32), wc[o][k - K2] behind it;
+// out[O * (K2 + C) + o] = sum_j wc[o][j] * b2[j] + bc[o].  One thread per output element, 16 x 16 tiles through shared memory.
+__global__ void fuse_ffn_weights_kernel(const float* __restrict__ wc, const float* __restrict__ bc,
+                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                        float* __restrict__ out, int C, int K2) {
+  __shared__ float ta[16][17], tb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int o = blockIdx.y * 16 + ty, k = blockIdx.x * 16 + tx;
+  const int K = K2 + C;
+  // column K2 + C (one extra tile column) carries the bias product
+  float acc = 0.f;
+  for (int j0 = 0; j0 < C; j0 += 16) {
+    ta[ty][tx] = (o < C && j0 + tx < C) ? wc[(long long)o * C + j0 + tx] : 0.f;
+    float bv = 0.f;
+    if (j0 + ty < C) {
+      if (k < K2) bv = w2[(long long)(j0 + ty) * K2 + k];
+      else if (k == K) bv = b2[j0 + ty];
+    }
+    tb[ty][tx] = bv;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaf(ta[ty][j], tb[j][tx], acc);
+    __syncthreads();
+  }
+  if (o >= C) return;
+  if (k < K2) out[(long long)o * K + k] = rna_tf32(acc);
+  else if (k < K) out[(long long)o * K + k] = wc[(long long)o * C + (k - K2)];  // already TF32-rounded at load
+  else if (k == K) out[(long long)C * K + o] = acc + bc[o];
+}
+
+int ParamStore::fused_ffn_out(int w2, int wc, const float** w, const float** b) {
+  if (ffn_dev.size() != params.size()) {
+    ffn_dev.assign(params.size(), nullptr);
+    ffn_gen.assign(params.size(), -1);
+  }
+  const Param& p2 = params[w2];
+  const Param& pc = params[wc];
+  const int C = pc.O, K2 = p2.I * p2.KK;
+  if (p2.O != C || pc.I * pc.KK != C) return c->fail(TSD_ERR_INVALID, "fused ffn out: shapes do not chain");
+  const size_t elems = (size_t)C * (K2 + C);
+  if (!ffn_dev[wc]) {
+    if (cudaMalloc(&ffn_dev[wc], sizeof(float) * (elems + C)) != cudaSuccess) {
+      cudaGetLastError();
+      return c->fail(TSD_ERR_OOM, "fused ffn out weights: allocation failed");
+    }
+  }
+  if (ffn_gen[wc] != gen && !c->dry_run) {
+    const dim3 grid((K2 + C) / 16 + 1, (C + 15) / 16), block(16, 16);
+    fuse_ffn_weights_kernel<<<grid, block, 0, c->stream>>>(pc.dev, params[wc + 1].dev, p2.dev, params[w2 + 1].dev, ffn_dev[wc], C, K2);
+    TRY(c->check(cudaGetLastError(), "fuse_ffn_weights launch"));
+    ffn_gen[wc] = gen;
+  }
+  *w = ffn_dev[wc];
+  *b = ffn_dev[wc] + elems;
+  return TSD_OK;
 }
 
 int ParamStore::fused_skip(int conv_w, int skip_w, const float** w, const float** b) {
@@ -526,9 +587,20 @@ static int attn_block(Ctx* c, const ParamStore& ps, const AttnBlockW& w, const A
   WALLOC(g, M * 4 * C);
   // GEGLU: Linear(C -> 8C), chunk(2,2), out * gelu(gate)  (diffusion.mojo:138-141)
   TRY(ln_then_linear(u3, w.ln3, w.geglu1, ps.w(w.geglu1 + 1), 8 * C, g, 4 * C, 1, 0, 0));
+  if (next) next->imgs = N;
+  if (c->fuse_ffn_out && C % 64 == 0) {
+    // geglu2 (4C -> C, + u3) and conv_out (1x1, C -> C, + x) have nothing between them (diffusion.mojo:141-146):
+    //   out = (g W2^T + b2 + u3) Wc^T + bc + x = [g | u3] [Wc W2 | Wc]^T + (Wc b2 + bc) + x
+    // is ONE GEMM over K = 4C + C (second K segment = u3) with weights merged once per weight load - same FLOPs, one
+    // launch and one activation round trip fewer per attention block
+    const float *wm = nullptr, *bm = nullptr;
+    TRY(const_cast<ParamStore&>(ps).fused_ffn_out(w.geglu2, w.conv_out, &wm, &bm));
+    TRY(conv(c, ps, w.conv_out, g, N, x.H, x.W, 4 * C, C, 1, 0, 1, bm, 0, x.p, out, 0, next, -1, u3, C, wm));
+    c->arena.release_to(mark);
+    return TSD_OK;
+  }
   float* u4 = u;  // u is dead after u2
   TRY(linear(c, g, M, 4 * C, ps.w(w.geglu2), ps.w(w.geglu2 + 1), C, u4, C, u3, 1));
-  if (next) next->imgs = N;
   TRY(linear(c, u4, M, C, ps.w(w.conv_out), ps.w(w.conv_out + 1), C, out, C, x.p, 0, 0, 0, 0, next));
   c->arena.release_to(mark);
   return TSD_OK;

@@ -61,6 +61,10 @@ struct ParamStore {
   // the two biases: the operands of the fused ResBlock tail (conv2 + skip convolution in one GEMM).  Built on first
   // use after every (re)load, keyed by the conv weight's index.
   int fused_skip(int conv_w, int skip_w, const float** w, const float** b);
+  // [conv_out . geglu2 | conv_out] and conv_out . b2 + b_out: the two linears that end an attention block as ONE GEMM
+  int fused_ffn_out(int w2, int wc, const float** w, const float** b);
+  std::vector<float*> ffn_dev;
+  std::vector<int> ffn_gen;
   std::vector<float*> fskip_dev;
   std::vector<int> fskip_gen;
   int gen = 0;  // bumped by load / init_random

@@ -926,8 +926,8 @@ int op_conv2d(Ctx* c, const ConvArgs& a) {
   // rows of w past Cout are out of bounds for the B tensor map and read as zeros
   const bool tensor_ok = a.Cin >= 32 && a.Cin % 4 == 0 && (a.Cout % 4 == 0 || a.Cout < 16);
   const double flops = 2.0 * a.N * Ho * (double)Wo * a.Cout * ktot;
-  if (a.Cin2 > 0 && !(tensor_ok && sym && a.k == 3 && a.pad == 1 && a.stride == 1 && a.x2))
-    return c->fail(TSD_ERR_INVALID, "conv2d: the fused second operand needs the 3x3 / stride 1 tensor-core path");
+  if (a.Cin2 > 0 && !(tensor_ok && sym && ((a.k == 3 && a.pad == 1) || (a.k == 1 && a.pad == 0)) && a.stride == 1 && a.x2))
+    return c->fail(TSD_ERR_INVALID, "conv2d: the fused second operand needs the 3x3 or 1x1 stride-1 tensor-core path");
   GemmKParams p{};
   p.D = a.out;
   p.ldd = a.Cout;

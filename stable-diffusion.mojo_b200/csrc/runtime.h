@@ -143,6 +143,7 @@ struct Ctx {
   int defer_reduce = 1;            // split-K partials summed by the consuming norm kernel where the call site allows it
   int virtual_concat = 1;          // 1: channel concats feeding a ResBlock are read (and written out) by its first GroupNorm kernel (+0.5 % with the cluster norm)
   int conv_stride_tma = 1;         // stride-2 3x3 convolutions as implicit GEMMs through a strided tensor map (0: im2col + GEMM)
+  int fuse_ffn_out = 1;            // the two linears that end an attention block (geglu2, conv_out) as one GEMM with merged weights
   int fuse_skip = 1;               // ResBlock 1x1 skip convolution as a second K segment of conv2 (0: GEMM of its own + residual add)
   int norm_cluster = 1;            // 1: GroupNorm with one thread-block cluster per (image, group) where the slab fits shared memory
   int tune_defer_penalty_us = 3;   // autotuner: cost charged to a split-K candidate whose GroupNorm consumer is the cluster kernel (it sums the partials)

@@ -125,6 +125,7 @@ def test_unet_unfused_attention_path_agrees(ctx, diff8, golden_small):
 @pytest.mark.parametrize("opts", [
     {"ln_fold": 0},                       # LayerNorm as a separate pass instead of the GEMM-epilogue fold
     {"fuse_skip": 0},                     # skip convolution as its own GEMM + residual add
+    {"fuse_ffn_out": 0},                  # geglu2 and conv_out of an attention block as two GEMMs instead of one merged one
     {"conv_stride_tma": 0},               # stride-2 convolutions through im2col + GEMM
     {"defer_reduce": 0},                  # split-K always through the reduce kernel
     {"virtual_concat": 0},                # explicit concat kernel instead of the consuming GroupNorm reading both tensors
@@ -166,7 +167,7 @@ def test_unet64_switches_agree_at_full_size(ctx, diff64):
     cx = rng.standard_normal((77, 768), dtype=np.float32)
     t = host_sampler.get_time_embedding(500.0)
     y_default = diff64.forward(x, cx, t)
-    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"conv_stride_tma": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}, {"virtual_concat": 0}, {"norm_cluster": 0}, {"norm_cluster": 0, "norm_v2": 1}):
+    for opts in ({"ln_fold": 0}, {"producer_stats": 0, "ln_fold": 0}, {"pdl": 0, "autotune": 0}, {"splitk_fixup": 1}, {"fuse_skip": 0}, {"fuse_ffn_out": 0}, {"conv_stride_tma": 0}, {"defer_reduce": 0}, {"defer_reduce": 1, "force_splits": 3}, {"virtual_concat": 0}, {"norm_cluster": 0}, {"norm_cluster": 0, "norm_v2": 1}):
         old = {k: ctx.get_option(k) for k in opts}
         for k, v in opts.items():
             ctx.set_option(k, v)
