@@ -74,6 +74,10 @@ int32_t tsd_synchronize(tsd_ctx* ctx);
  *   "ln_fold"          1 = global-statistics LayerNorm folded into the consuming GEMM epilogue [default]
  *   "fuse_skip"        1 = a ResBlock's 1x1 skip convolution is a second K segment of its conv2 GEMM [default],
  *                          0 = a GEMM of its own whose result conv2 adds as a residual
+ *   "fuse_ffn_out"     1 = the two linears that end an attention block (geglu2, conv_out: diffusion.mojo:141-146) run as one
+ *                          GEMM over K = 4C + C with weights merged at load [default], 0 = two GEMMs
+ *   "gemm_kmerge"      1 = one TMA request per operand and K step of 64 [default]; "gemm_deep_b" 1 = separate deep weight
+ *                          ring for narrow tiles (0 [default], measured slower)
  *   "conv_stride_tma"  1 = stride-2 3x3 convolutions are implicit GEMMs through a tensor map with element strides
  *                          [default], 0 = im2col kernel + GEMM
  *   "defer_reduce"     1 = where a split-K GEMM feeds a norm directly, the norm kernel sums the partial tiles
